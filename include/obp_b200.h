@@ -1,0 +1,162 @@
+/*
+ * obp_b200.h — C-ABI of the B200-native operator-backpropagation engine.
+ *
+ * The reference (Qiskit/qiskit-addon-obp, pure Python) has no FFI of its own: its hot path calls
+ * numpy and the Rust extension `qiskit._accelerate` through Python.  The drop-in boundary is
+ * therefore the body of the reference's gate loop (qiskit_addon_obp/backpropagation.py:171-258);
+ * each entry point below names the reference call it replaces.  The Python driver in
+ * qiskit_addon_obp_b200/backpropagation.py binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns an int status (0 = OK, <0 = error),
+ *     never throws; obp_last_error() gives the message.
+ *   - a context owns one observable: a device-resident term table of packed symplectic keys
+ *     (W = ceil(n_qubits/64) words of x and of z per term, qubit j -> bit j%64 of word j/64, the
+ *     little-endian column order of SparsePauliOp.paulis.x[:, j]) and complex128 coefficients.
+ *   - host buffers are caller-owned and only read/written during the call.
+ *   - every call synchronises its stream before returning unless stated otherwise, so a Python
+ *     signal handler (max_seconds, backpropagation.py:138-142) runs between calls.
+ */
+#ifndef OBP_B200_H
+#define OBP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBP_OK 0
+#define OBP_ERR_BADARG (-1)
+#define OBP_ERR_CUDA (-2)
+#define OBP_ERR_OOM (-3)
+#define OBP_ERR_CAPACITY (-4) /* term table full: state is undefined, call obp_restore() */
+#define OBP_ERR_UNSUPPORTED (-5)
+
+#define OBP_MAX_WORDS 32 /* up to 2048 qubits */
+
+typedef struct obp_ctx obp_ctx;
+
+/* ---- gate programs -------------------------------------------------------------------------
+ * One obp_op is one gate of a slice after the host has decomposed it the way the reference does
+ * (SparsePauliOp.from_operator(Operator(gate)), backpropagation.py:213) and classified it.
+ */
+enum {
+  OBP_OP_CLIFFORD = 1, /* Pauli-transfer matrix is a signed permutation (incl. Pauli gates)   */
+  OBP_OP_ROTATION = 2  /* U = u0*I + u1*G with G a Pauli on <= 4 qubits (rx, rzz, t, p, ...)  */
+};
+
+#define OBP_FLAG_EXACT_COUNTERS 1u /* produce the reference's simplify counters for this op */
+
+typedef struct {
+  int32_t kind;        /* OBP_OP_*                                                            */
+  int32_t n_qubits;    /* qubits the gate acts on: 1..2 (Clifford), 1..4 (rotation)           */
+  int32_t qubit[4];    /* global qubit indices                                                */
+  uint32_t flags;      /* OBP_FLAG_*                                                          */
+  uint32_t n_components; /* k = Pauli terms of the gate's decomposition (raw rows = n*k*k)    */
+  /* Clifford: local Pauli code v = x0 | z0<<1 | x1<<2 | z1<<3 of a term on the gate's qubits   */
+  uint64_t lut;        /* image code of v in bits [4v, 4v+4)                                  */
+  uint32_t sign_mask;  /* bit v set: U^dag sigma_v U = -sigma_lut[v]                          */
+  uint32_t group_size; /* |D|, D = {U_j xor U_l}: keys of the k*k raw rows of one term        */
+  uint64_t group_elems;/* the group_size-1 non-identity members of D, 4-bit codes             */
+  double row_scale;    /* |u_j * conj(u_l)| (uniform for a Clifford): raw-row magnitude / |c| */
+  /* rotation */
+  uint32_t gen_local;  /* generator code: bit 2j = x, bit 2j+1 = z on qubit[j]                */
+  uint32_t reserved;
+  double u0[2];        /* coefficient of I  (re, im), e.g. cos(theta/2)                       */
+  double u1[2];        /* coefficient of G  (re, im), e.g. -i sin(theta/2)                    */
+} obp_op;
+
+/* Counters of the last op of a program, in the vocabulary of SimplifyMetadata
+ * (qiskit_addon_obp/utils/simplify.py:26-40, 128-152). Valid when the op carried
+ * OBP_FLAG_EXACT_COUNTERS; n_in / n_out / n_dense / updates are always valid. */
+typedef struct {
+  uint64_t n_in;          /* terms at entry of the last op                                    */
+  uint64_t raw_rows;      /* n_in * k * k  (SliceMetadata.raw_num_paulis)                     */
+  uint64_t num_unique;    /* distinct keys among the raw rows that passed the zero filter     */
+  uint64_t num_duplicate; /* surviving raw rows - num_unique                                  */
+  uint64_t num_trimmed;   /* filtered raw rows + merged keys with |sum| <= atol               */
+  double sum_trimmed[2];  /* sum of the trimmed merged coefficients                           */
+  uint64_t n_out;         /* live terms after the program                                     */
+  uint64_t n_dense;       /* rows in the dense table incl. tombstones                         */
+  uint64_t updates;       /* sum over ops of the live term count at op entry                  */
+} obp_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Create a context on CUDA device `device` for `n_qubits`-qubit observables with room for
+ * `capacity` terms. */
+int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out);
+void obp_destroy(obp_ctx* ctx);
+/* Message of the last failing call on ctx (ctx == NULL: of the last failing obp_create). */
+const char* obp_last_error(const obp_ctx* ctx);
+/* Run all work of ctx on an existing CUDA stream (cudaStream_t); NULL = the context's own. */
+int obp_set_stream(obp_ctx* ctx, void* cuda_stream);
+/* Free and total bytes of device memory (cudaMemGetInfo) — used to size the table. */
+int obp_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes);
+/* Bytes of device memory a context of this shape allocates per term of capacity. */
+uint64_t obp_bytes_per_term(int n_qubits);
+
+/* ---- table I/O ----------------------------------------------------------------------------- */
+
+/* Upload n rows (x_words/z_words: [n][W] row-major, coeffs: [n][2]) and merge duplicate keys.
+ * atol >= 0: full simplify semantics (utils/simplify.py:115-165: zero filter, merge, zero filter)
+ * with counters in *stats; atol < 0: merge only, nothing trimmed.  Replaces the observable that
+ * reduce_op() hands to the loop (backpropagation.py:114) and simplify() itself. */
+int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
+             uint64_t n, double atol, obp_stats* stats);
+/* Number of live terms (len(observable)). */
+int obp_count(obp_ctx* ctx, uint64_t* n);
+/* Compact and copy the live terms to host arrays with room for max_rows rows. */
+int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coeffs,
+                 uint64_t max_rows, uint64_t* n);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+
+/* Conjugate the observable by n_ops gates in order, merging duplicates and trimming |c| <= atol
+ * after every gate.  Replaces apply_op_to(...) + simplify(...) per gate
+ * (backpropagation.py:210-237; utils/operations.py:100-107; utils/simplify.py:80-169). */
+int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats);
+
+/* <0|O|0> on one qubit then simplify: apply_reset_to (utils/operations.py:194-225). */
+int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats);
+
+/* Pauli-Lindblad damping then simplify: apply_ple_to (utils/operations.py:228-275).
+ * gen_x/gen_z: [n_gens][W] global-width generators, factors[g] = exp(-2*rate_g). */
+int obp_apply_damping(obp_ctx* ctx, const uint64_t* gen_x, const uint64_t* gen_z,
+                      const double* factors, int32_t n_gens, double atol, obp_stats* stats);
+
+/* Error-budget truncation: truncate_binary_search (utils/truncating.py:144-204).
+ * Returns the incurred error and the number of removed terms. */
+int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double* slice_error,
+                 uint64_t* n_removed, uint64_t* n_out);
+
+/* Distinct keys over several observables: _observable_oversized (backpropagation.py:419-428). */
+int obp_union_count(obp_ctx* const* ctxs, int32_t n_ctx, uint64_t* n_distinct);
+
+/* Commit / roll back: the deepcopy at backpropagation.py:279-280 and the discarded slice of
+ * :266-275.  obp_snapshot copies the live terms aside; obp_restore brings them back. */
+int obp_snapshot(obp_ctx* ctx);
+int obp_restore(obp_ctx* ctx);
+
+/* Grow the table to hold new_capacity terms (contents preserved). */
+int obp_reserve(obp_ctx* ctx, uint64_t new_capacity);
+
+/* ---- measurement --------------------------------------------------------------------------- */
+
+enum { OBP_K_ROTATE = 0, OBP_K_CLIFFORD = 1, OBP_K_TRUNCATE = 2, OBP_K_COMPACT = 3,
+       OBP_K_INDEX = 4, OBP_K_OTHER = 5, OBP_K_COUNT = 6 };
+
+typedef struct {
+  uint64_t launches[OBP_K_COUNT];  /* kernel launches per class since the last reset           */
+  double ms[OBP_K_COUNT];          /* CUDA-event time per class (only while profiling is on)   */
+  uint64_t term_updates[OBP_K_COUNT]; /* live terms at entry summed over launches (x gates)    */
+} obp_profile;
+
+int obp_profile_enable(obp_ctx* ctx, int32_t on);
+int obp_profile_get(obp_ctx* ctx, obp_profile* out, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBP_B200_H */

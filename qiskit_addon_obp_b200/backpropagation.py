@@ -1,0 +1,411 @@
+"""``backpropagate`` — the reference's driver loop with the per-gate work on the GPU engine.
+
+Mirrors ``/root/reference/qiskit_addon_obp/backpropagation.py:48-311``: same signature, same
+validation messages, same slice/observable/gate order, same light-cone rule, same per-slice
+metadata, same commit/rollback and stopping behaviour.  What changes is where the work runs: each
+observable is a device-resident :class:`~qiskit_addon_obp_b200.engine.TermTable`; the applied gates
+of a slice are classified on the host (:mod:`.gates`) and executed as one gate program
+(``obp_apply_ops``), followed by the error-budget truncation (``obp_truncate``).
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+import signal
+import sys
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import engine
+from .engine import OBP_FLAG_EXACT_COUNTERS, OP_DTYPE, CapacityError, TermTable
+from .gates import program_for
+from .ir import QuantumCircuit, SparsePauliOp, topological_op_order
+from .utils.metadata import OBPMetadata, SliceMetadata
+from .utils.simplify import OperatorBudget
+from .utils.truncating import TruncationErrorBudget
+
+LOGGER = logging.getLogger(__name__)
+
+
+class TimeoutException(Exception):
+    """Raised by the ``max_seconds`` alarm (``backpropagation.py:42``)."""
+
+
+class RunInfo:
+    """Work counters of the last :func:`backpropagate` call (used by ``bench.py``)."""
+
+    updates = 0  # term-gate updates: sum over applied gates of the term count at gate entry
+    applied_gates = 0
+    profile: dict | None = None
+
+
+last_run = RunInfo()
+
+
+def _default_capacity(num_qubits: int, operator_budget: OperatorBudget, n_obs: int, device: int) -> int:
+    env = os.environ.get("OBP_B200_CAPACITY")
+    if env:
+        return int(env)
+    free, _ = engine.device_memory(device)
+    per_term = int(engine.lib().obp_bytes_per_term(num_qubits))
+    limit = max(1 << 16, int(0.6 * free / per_term / max(1, n_obs)))
+    if operator_budget.max_paulis is not None:
+        want = max(1 << 20, 8 * int(operator_budget.max_paulis))
+    else:
+        want = 1 << 22
+    return int(min(want, limit, 0xFFFF0000))
+
+
+def backpropagate(
+    observables,
+    slices: Sequence[QuantumCircuit],
+    *,
+    truncation_error_budget: TruncationErrorBudget | None = None,
+    operator_budget: OperatorBudget | None = None,
+    max_seconds: int | None = None,
+):
+    """Backpropagate ``slices`` (in reverse order) onto ``observables``.
+
+    Returns ``(observables, remaining_slices, OBPMetadata)`` exactly like the reference; a single
+    observable in gives a single observable out (``backpropagation.py:307-309``).
+    """
+    from . import qiskit_adapter
+
+    observables, slices_ir, restore_types = qiskit_adapter.to_ir(observables, slices)
+
+    operator_budget = operator_budget or OperatorBudget()
+    truncation_error_budget = truncation_error_budget or TruncationErrorBudget()
+    single = isinstance(observables, SparsePauliOp)
+    obs_in: list[SparsePauliOp] = [observables] if single else list(observables)
+
+    _validate_input_options(obs_in, slices_ir, operator_budget)
+    if not operator_budget.simplify:
+        raise NotImplementedError(
+            "OperatorBudget(simplify=False) keeps the k*k raw rows of every gate unmerged; the "
+            "device path always merges. Use the default simplify=True."
+        )
+
+    atol = SparsePauliOp.atol if operator_budget.atol is None else float(operator_budget.atol)
+    num_qubits = slices_ir[0].num_qubits
+    n_obs = len(obs_in)
+    # reduce_op (utils/operations.py:176-181): support set, error for a pure identity observable
+    qargs = [_support(o) for o in obs_in]
+    device = engine.default_device()
+    capacity = _default_capacity(num_qubits, operator_budget, n_obs, device)
+
+    metadata = OBPMetadata(
+        truncation_error_budget=truncation_error_budget,
+        operator_budget=operator_budget,
+        num_slices=len(slices_ir),
+        backpropagation_history=[],
+        num_backpropagated_slices=0,
+    )
+    info = RunInfo()
+    tables: list[TermTable] = []
+    lengths = [len(o) for o in obs_in]  # len(observables_tmp[i]) as the reference sees it
+    # a table only exists once a gate touches its observable: until then the reference carries the
+    # input rows along unchanged (duplicates and zeros included)
+    loaded = [False] * n_obs
+    loaded_committed = [False] * n_obs
+    trunc_active = truncation_error_budget.is_active()
+
+    if max_seconds is not None:
+        if sys.platform == "win32":
+            raise RuntimeError("The `max_seconds` argument is not available on Windows.")
+
+        def handle_timeout(signum, frame):
+            raise TimeoutException()
+
+        signal.signal(signal.SIGALRM, handle_timeout)
+        signal.alarm(max_seconds)
+
+    try:
+        for i in range(n_obs):
+            tables.append(TermTable(num_qubits, max(capacity, 2 * len(obs_in[i])), device))
+        try:
+            for slice_ in slices_ir[::-1]:
+                sm = SliceMetadata(
+                    slice_errors=[0.0] * n_obs,
+                    raw_num_paulis=[0] * n_obs,
+                    num_unique_paulis=list(lengths),
+                    num_duplicate_paulis=[0] * n_obs,
+                    num_trimmed_paulis=[0] * n_obs,
+                    sum_trimmed_coeffs=[0] * n_obs,
+                    num_truncated_paulis=[0] * n_obs,
+                    num_paulis=[0] * n_obs,
+                    sum_paulis=None,
+                    num_qwc_groups=None,
+                )
+                metadata.backpropagation_history.append(sm)
+                op_nodes = topological_op_order(slice_)[::-1]
+                overflowed = False
+                for i in range(n_obs):
+                    applied = []
+                    support = set(qargs[i])
+                    for node in op_nodes:
+                        if node.name == "barrier":
+                            continue
+                        if support.isdisjoint(node.qubits):
+                            continue  # outside the light cone (backpropagation.py:183)
+                        applied.append(node)
+                        if node.name != "reset":
+                            support.update(node.qubits)
+                    non_trivial = bool(applied)
+                    sidx = metadata.num_backpropagated_slices
+                    if non_trivial:
+                        if not loaded[i]:
+                            tables[i].load(obs_in[i])
+                            tables[i].snapshot()
+                            loaded[i] = True
+                        while True:
+                            try:
+                                _run_slice(tables[i], applied, atol, sm, i, info)
+                                if trunc_active:
+                                    budget = metadata.left_over_error_budget(i, sidx)
+                                    err, removed = tables[i].truncate(
+                                        budget, truncation_error_budget.p_norm, truncation_error_budget.tol
+                                    )
+                                    sm.slice_errors[i] = err
+                                    sm.num_truncated_paulis[i] = int(removed)
+                                break
+                            except CapacityError:
+                                # the table overflowed mid-slice: roll back to the committed state
+                                tables[i].restore()
+                                if (
+                                    operator_budget.max_paulis is not None
+                                    and not trunc_active
+                                    and tables[i].capacity > operator_budget.max_paulis
+                                ):
+                                    # without truncation the term count cannot come back under
+                                    # max_paulis within this slice: the slice is oversized
+                                    overflowed = True
+                                    break
+                                _grow(tables[i])
+                        if overflowed:
+                            sm.sum_paulis = tables[i].capacity
+                            break
+                        qargs[i] = sorted(support)
+                        lengths[i] = len(tables[i])
+                    if trunc_active and non_trivial:
+                        lengths[i] = len(tables[i])
+                        LOGGER.info(
+                            f"[{sidx:3}] Accumulated error for the {i}-th observable: "
+                            f"{metadata.accumulated_error(i, sidx + 1):.10f}"
+                        )
+                    sm.num_paulis[i] = lengths[i]
+                    LOGGER.info(
+                        f"[{metadata.num_backpropagated_slices:3}] size of the {i}-th observable: "
+                        f"{sm.num_paulis[i]}"
+                    )
+                if overflowed:
+                    LOGGER.info(
+                        f"[{metadata.num_backpropagated_slices:3}] Too many Pauli terms: more than "
+                        f"{sm.sum_paulis} (device table capacity reached mid-slice)"
+                    )
+                    break
+                if operator_budget.is_active() and _observable_oversized(
+                    tables, loaded, obs_in, operator_budget, metadata.num_backpropagated_slices, sm
+                ):
+                    break
+                # commit (backpropagation.py:279-285): the snapshot is the deepcopy of the reference
+                for i in range(n_obs):
+                    if loaded[i]:
+                        tables[i].snapshot()
+                loaded_committed = list(loaded)
+                metadata.num_backpropagated_slices += 1
+        except TimeoutException:
+            LOGGER.warning("Reached the specified max_seconds timeout!")
+        finally:
+            if max_seconds is not None:
+                signal.alarm(0)
+
+        LOGGER.info(f"Backpropagated {metadata.num_backpropagated_slices} DAG multi-graph slices")
+        n_done = metadata.num_backpropagated_slices
+        slices_out = slices[:-n_done]  # same `[:-0]` quirk as backpropagation.py:300
+        obs_out = []
+        for i in range(n_obs):
+            if not loaded_committed[i]:
+                obs_out.append(obs_in[i].copy())
+                continue
+            # after a break or a timeout the table holds an uncommitted slice: roll it back
+            if len(metadata.backpropagation_history) != n_done:
+                tables[i].restore()
+            obs_out.append(tables[i].download())
+    finally:
+        for t in tables:
+            t.close()
+
+    last_run.updates = info.updates
+    last_run.applied_gates = info.applied_gates
+    obs_out = [restore_types(o) for o in obs_out]
+    return (obs_out[0] if single else obs_out), slices_out, metadata
+
+
+def _grow(table: TermTable) -> None:
+    """Double the table, bounded by free device memory."""
+    free, _ = engine.device_memory(table.device)
+    per_term = int(engine.lib().obp_bytes_per_term(table.num_qubits))
+    new_cap = min(2 * table.capacity, 0xFFFF0000)
+    if new_cap <= table.capacity or (new_cap - table.capacity) * per_term > 0.9 * free:
+        raise MemoryError(
+            f"observable outgrew the device table ({table.capacity} terms) and it cannot be doubled"
+        )
+    table.reserve(new_cap)
+
+
+def _run_slice(table: TermTable, applied, atol: float, sm: SliceMetadata, i: int, info: RunInfo) -> None:
+    """Execute the applied gates of one slice on one observable and record the last gate's counters."""
+    seg: list[np.ndarray] = []
+    stats = None
+    last_idx = len(applied) - 1
+
+    def flush():
+        nonlocal seg, stats
+        if seg:
+            stats = table.apply_ops(np.concatenate(seg), atol)
+            info.updates += int(stats.updates)
+            seg = []
+
+    for k, node in enumerate(applied):
+        if node.name == "reset":
+            flush()
+            stats = table.apply_reset(node.qubits[0], atol)
+            info.updates += int(stats.updates)
+        elif node.name == "LayerError":
+            flush()
+            ple = node.ple
+            if ple is None:
+                raise RuntimeError(
+                    "Expected the LayerError circuit instruction to have a 'ple' "
+                    "attribute but `None` was found."
+                )
+            gens = SparsePauliOp(list(ple.generators))
+            gx = np.zeros((len(gens), table.num_qubits), dtype=bool)
+            gz = np.zeros((len(gens), table.num_qubits), dtype=bool)
+            gx[:, list(node.qubits)] = gens.x
+            gz[:, list(node.qubits)] = gens.z
+            stats = table.apply_damping(gx, gz, np.exp(-2 * np.asarray(ple.rates, dtype=float)), atol)
+            info.updates += int(stats.updates)
+        else:
+            prog = program_for(node)
+            rec = prog.template.copy()
+            rec["qubit"][0, : prog.n_qubits] = node.qubits
+            if k == last_idx:
+                rec["flags"] = OBP_FLAG_EXACT_COUNTERS
+            seg.append(rec)
+        info.applied_gates += 1
+    flush()
+    # the slice reports the counters of its last applied gate (backpropagation.py:218-237)
+    sm.raw_num_paulis[i] = int(stats.raw_rows)
+    sm.num_unique_paulis[i] = int(stats.num_unique)
+    sm.num_duplicate_paulis[i] = int(stats.num_duplicate)
+    sm.num_trimmed_paulis[i] = int(stats.num_trimmed)
+    s = complex(stats.sum_trimmed[0], stats.sum_trimmed[1])
+    sm.sum_trimmed_coeffs[i] = s if s != 0 else 0.0
+
+
+def _support(op: SparsePauliOp) -> list[int]:
+    qargs = [int(q) for q in np.logical_or(op.x, op.z).any(axis=0).nonzero()[0]]
+    if qargs == []:
+        raise ValueError("Input operator may not be the identity operator.")
+    return qargs
+
+
+def _distinct_labels(ops: list[SparsePauliOp]) -> SparsePauliOp:
+    """Coefficient-free union of the rows of several host operators, first-appearance order."""
+    x = np.concatenate([o.x for o in ops], axis=0)
+    z = np.concatenate([o.z for o in ops], axis=0)
+    keys = np.concatenate([np.packbits(x, axis=1), np.packbits(z, axis=1)], axis=1)
+    _, first = np.unique(keys, axis=0, return_index=True)
+    first.sort()
+    return SparsePauliOp((x[first], z[first]), np.ones(len(first)))
+
+
+def _observable_oversized(tables, loaded, obs_in, operator_budget, slice_id, sm) -> bool:
+    """``backpropagation.py:409-442``: distinct keys / QWC groups over all observables."""
+    from .utils.qwc import qwc_group_count
+
+    max_paulis, max_qwc = operator_budget.max_paulis, operator_budget.max_qwc_groups
+    if all(loaded):
+        dev_tables = list(tables)
+        host_ops: list[SparsePauliOp] = []
+    else:
+        dev_tables = [t for t, l in zip(tables, loaded) if l]
+        host_ops = [o for o, l in zip(obs_in, loaded) if not l]
+    union = None
+
+    def union_op() -> SparsePauliOp:
+        nonlocal union
+        if union is None:
+            union = _distinct_labels([t.download() for t in dev_tables] + host_ops)
+        return union
+
+    if max_paulis is not None:
+        if not host_ops and all(not t.zero_operator for t in dev_tables):
+            sm.sum_paulis = engine.union_count(dev_tables)
+        else:
+            sm.sum_paulis = len(union_op())
+        if sm.sum_paulis > max_paulis:
+            LOGGER.info(f"[{slice_id:3}] Too many Pauli terms: {sm.sum_paulis}")
+            return True
+    if max_qwc is not None:
+        sm.num_qwc_groups = qwc_group_count(union_op())
+        if sm.num_qwc_groups > max_qwc:
+            LOGGER.info(
+                f"[{slice_id:3}] Too many qubit-wise commuting Pauli groups: {sm.num_qwc_groups}"
+            )
+            return True
+    return False
+
+
+def _validate_input_options(obs, slices, operator_budget: OperatorBudget) -> None:
+    """``backpropagation.py:314-375`` — same checks, same messages."""
+    from .utils.qwc import qwc_group_count
+
+    num_qubits = slices[0].num_qubits
+    for i, s in enumerate(slices):
+        if s.num_qubits != num_qubits:
+            raise ValueError(
+                "All slices must be defined on the same number of qubits. "
+                f"slices[0] contains {num_qubits} qubits, but slices[{i}] contains "
+                f"{s.num_qubits} qubits."
+            )
+    obs_qubits = obs[0].num_qubits
+    for i, o in enumerate(obs):
+        if o.num_qubits != obs_qubits:
+            raise ValueError(
+                "Input observables must all act on the same number of qubits. "
+                f"observables[0] acts on {obs_qubits} qubits, but observables[{i}]"
+                f" acts on {o.num_qubits} qubits."
+            )
+    if obs_qubits != num_qubits:
+        raise ValueError(
+            "The input observables must be defined on the same number of qubits as the "
+            "circuit slices."
+        )
+    max_paulis, max_qwc = operator_budget.max_paulis, operator_budget.max_qwc_groups
+    if max_paulis is not None and max_paulis < 1:
+        raise ValueError("Limiting the number of Pauli terms to less than 1 does not make sense.")
+    if max_qwc is not None and max_qwc < 1:
+        raise ValueError(
+            "Limiting the number of qubit-wise commmuting Pauli groups to less than 1 does not "
+            "make sense."
+        )
+    if operator_budget.is_active():
+        allp = _distinct_labels(list(obs))
+        if max_paulis is not None and len(allp) > max_paulis:
+            raise ValueError(
+                f"You specified a maximum number of Pauli terms of {max_paulis}, but the "
+                f"provided observables already exceed this threshold with a total of "
+                f"{len(allp)} terms."
+            )
+        if max_qwc is not None:
+            groups = qwc_group_count(allp)
+            if groups > max_qwc:
+                raise ValueError(
+                    f"You specified a maximum number of qubit-wise commuting Pauli groups of "
+                    f"{max_qwc}, but the provided observables already exceed this threshold "
+                    f"with a total of {groups} terms."
+                )

@@ -1,0 +1,1184 @@
+// obp_b200.cu — host side of the C-ABI in include/obp_b200.h: context, gate programs, truncation,
+// compaction, snapshot.  Kernels live in obp_kernels.cuh.  Built for sm_100a only.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "obp_kernels.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int klass;
+};
+
+struct Snapshot {
+  ulonglong2* xz[OBP_MAX_WORDS] = {nullptr};
+  double2* coef = nullptr;
+  u64* hash = nullptr;
+  u64 cap = 0;
+  u64 n = 0;
+  bool valid = false;
+  std::vector<u64> hx, hz;
+};
+
+}  // namespace
+
+struct obp_ctx {
+  int device = 0, nq = 0, W = 0, n_sm = 148;
+  u64 cap = 0, T = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  ulonglong2* xz[OBP_MAX_WORDS] = {nullptr};
+  double2* coef = nullptr;
+  u64* hash = nullptr;
+  u64* index = nullptr;
+  ulonglong2* spare16 = nullptr;
+  u64* spare8 = nullptr;
+  unsigned* dest = nullptr;
+  unsigned* blk = nullptr;
+  DevState* d_st = nullptr;
+  OpStat* d_ops = nullptr;
+  int ops_alloc = 0;
+  double* d_partial = nullptr;
+  double* d_scalar = nullptr;
+  u64* d_cols = nullptr;
+  u64* d_gens = nullptr;
+  double* d_factors = nullptr;
+  int gens_alloc = 0;
+  DevState* h_st = nullptr;    // pinned
+  OpStat* h_ops = nullptr;     // pinned, ops_alloc entries
+  double* h_scalar = nullptr;  // pinned
+  // GF(2)-linear hash frame: h(key) = XOR of hx[q] over x bits and hz[q] over z bits.  Clifford
+  // gates re-express the frame (columns of the touched qubits) so stored row hashes stay valid.
+  std::vector<u64> hx, hz;
+  bool cols_dirty = true;
+  u64 epoch = 1;
+  u64 n_live = 0, n_dense = 0;
+  Snapshot snap;
+  obp_ctx* scratch = nullptr;  // union-count scratch table
+  // profiling
+  bool prof_on = false;
+  obp_profile prof;
+  std::vector<EventPair> ev_pending, ev_free;
+  std::string err;
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+};
+
+#define CU(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return ctx->fail(e__ == cudaErrorMemoryAllocation ? OBP_ERR_OOM : OBP_ERR_CUDA,          \
+                       std::string(#call) + ": " + cudaGetErrorString(e__));                   \
+  } while (0)
+
+namespace {
+
+inline u64 splitmix64(u64& s) {
+  u64 z = (s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+inline u64 next_pow2(u64 v) {
+  u64 p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+Tab make_tab(const obp_ctx* c) {
+  Tab t;
+  for (int w = 0; w < OBP_MAX_WORDS; ++w) t.xz[w] = c->xz[w];
+  t.coef = c->coef;
+  t.hash = c->hash;
+  t.index = c->index;
+  t.mask = c->T - 1;
+  t.cap = c->cap;
+  t.W = c->W;
+  t.st = c->d_st;
+  t.ops = c->d_ops;
+  return t;
+}
+
+inline int grid_for(const obp_ctx* c, u64 rows, int per_sm = 8) {
+  u64 g = (rows + OBP_BS - 1) / OBP_BS;
+  if (g < 1) g = 1;
+  const u64 mx = (u64)c->n_sm * per_sm;
+  return (int)std::min(g, mx);
+}
+
+// RAII launch bracket: counts the launch and, while profiling, records an event pair.
+struct Bracket {
+  obp_ctx* c;
+  int klass;
+  EventPair ep{};
+  bool timed = false;
+  Bracket(obp_ctx* c_, int k) : c(c_), klass(k) {
+    c->prof.launches[k]++;
+    if (c->prof_on) {
+      if (!c->ev_free.empty()) {
+        ep = c->ev_free.back();
+        c->ev_free.pop_back();
+      } else {
+        cudaEventCreate(&ep.a);
+        cudaEventCreate(&ep.b);
+      }
+      ep.klass = k;
+      cudaEventRecord(ep.a, c->stream);
+      timed = true;
+    }
+  }
+  ~Bracket() {
+    if (timed) {
+      cudaEventRecord(ep.b, c->stream);
+      c->ev_pending.push_back(ep);
+    }
+  }
+};
+
+void resolve_events(obp_ctx* c) {
+  for (auto& ep : c->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) c->prof.ms[ep.klass] += ms;
+    c->ev_free.push_back(ep);
+  }
+  c->ev_pending.clear();
+}
+
+int sync_state(obp_ctx* ctx) {
+  CU(cudaMemcpyAsync(ctx->h_st, ctx->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  resolve_events(ctx);
+  ctx->n_live = ctx->h_st->n_live;
+  ctx->n_dense = ctx->h_st->n_scan;
+  if (ctx->h_st->error) {
+    const unsigned e = ctx->h_st->error;
+    ctx->h_st->error = 0;
+    cudaMemsetAsync(&ctx->d_st->error, 0, sizeof(unsigned), ctx->stream);
+    return ctx->fail(OBP_ERR_CAPACITY, (e & OBP_ERR_BIT_CAP) ? "term table capacity exceeded"
+                                                              : "hash index full");
+  }
+  return OBP_OK;
+}
+
+int ensure_ops(obp_ctx* ctx, int n) {
+  if (n <= ctx->ops_alloc) return OBP_OK;
+  int na = std::max(n, std::max(256, ctx->ops_alloc * 2));
+  if (ctx->d_ops) cudaFree(ctx->d_ops);
+  if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
+  ctx->d_ops = nullptr;
+  ctx->h_ops = nullptr;
+  ctx->ops_alloc = 0;
+  CU(cudaMalloc(&ctx->d_ops, sizeof(OpStat) * na));
+  CU(cudaMallocHost(&ctx->h_ops, sizeof(OpStat) * na));
+  ctx->ops_alloc = na;
+  return OBP_OK;
+}
+
+int upload_cols(obp_ctx* ctx) {
+  if (!ctx->cols_dirty) return OBP_OK;
+  std::vector<u64> cols((size_t)2 * 64 * ctx->W, 0);
+  for (int q = 0; q < ctx->nq; ++q) {
+    cols[q] = ctx->hx[q];
+    cols[(size_t)ctx->W * 64 + q] = ctx->hz[q];
+  }
+  CU(cudaMemcpyAsync(ctx->d_cols, cols.data(), cols.size() * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // cols is a stack-owned buffer
+  ctx->cols_dirty = false;
+  return OBP_OK;
+}
+
+void init_frame(obp_ctx* ctx) {
+  u64 seed = 0x0B9B200C0FFEEull;
+  ctx->hx.resize(ctx->nq);
+  ctx->hz.resize(ctx->nq);
+  for (int q = 0; q < ctx->nq; ++q) {
+    ctx->hx[q] = splitmix64(seed);
+    ctx->hz[q] = splitmix64(seed);
+  }
+  ctx->cols_dirty = true;
+}
+
+// (re)build the index from the live rows (no duplicates expected)
+int rebuild_index(obp_ctx* ctx) {
+  CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  Bracket b(ctx, OBP_K_INDEX);
+  k_index_build<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), 0, -1.0, ctx->epoch, -1);
+  CU(cudaGetLastError());
+  return OBP_OK;
+}
+
+// stable compaction of all columns + index rebuild; leaves n_dense == n_live
+int compact(obp_ctx* ctx) {
+  if (ctx->n_dense == 0) return OBP_OK;
+  const u64 nb = (ctx->n_dense + OBP_CHUNK - 1) / OBP_CHUNK;
+  Tab t = make_tab(ctx);
+  {
+    Bracket b(ctx, OBP_K_COMPACT);
+    k_live_count<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(t, ctx->blk);
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk, nb, ctx->d_st);
+    k_dest<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(t, ctx->blk, ctx->dest);
+    const int g = grid_for(ctx, ctx->n_dense);
+    for (int w = 0; w < ctx->W; ++w) {
+      k_scatter16<<<g, OBP_BS, 0, ctx->stream>>>(ctx->xz[w], ctx->spare16, ctx->dest, ctx->d_st);
+      std::swap(ctx->xz[w], ctx->spare16);
+    }
+    k_scatter16<<<g, OBP_BS, 0, ctx->stream>>>((const ulonglong2*)ctx->coef, ctx->spare16, ctx->dest, ctx->d_st);
+    {
+      ulonglong2* old = (ulonglong2*)ctx->coef;
+      ctx->coef = (double2*)ctx->spare16;
+      ctx->spare16 = old;
+    }
+    k_scatter8<<<g, OBP_BS, 0, ctx->stream>>>(ctx->hash, ctx->spare8, ctx->dest, ctx->d_st);
+    std::swap(ctx->hash, ctx->spare8);
+    k_set_counts<<<1, 1, 0, ctx->stream>>>(ctx->d_st);
+    CU(cudaGetLastError());
+  }
+  ctx->n_dense = ctx->n_live;  // n_live is exact on the host at every call site
+  return rebuild_index(ctx);
+}
+
+int set_counts(obp_ctx* ctx, u64 n) {
+  DevState s;
+  memset(&s, 0, sizeof(s));
+  s.n_scan = s.n_append = s.n_live = n;
+  *ctx->h_st = s;
+  CU(cudaMemcpyAsync(ctx->d_st, ctx->h_st, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->n_live = ctx->n_dense = n;
+  return OBP_OK;
+}
+
+int alloc_table(obp_ctx* ctx, u64 cap) {
+  ctx->cap = cap;
+  ctx->T = next_pow2(std::max<u64>(2 * cap, 1024));
+  for (int w = 0; w < ctx->W; ++w) CU(cudaMalloc(&ctx->xz[w], cap * sizeof(ulonglong2)));
+  CU(cudaMalloc(&ctx->coef, cap * sizeof(double2)));
+  CU(cudaMalloc(&ctx->hash, cap * sizeof(u64)));
+  CU(cudaMalloc(&ctx->index, ctx->T * sizeof(u64)));
+  CU(cudaMalloc(&ctx->spare16, cap * sizeof(ulonglong2)));
+  CU(cudaMalloc(&ctx->spare8, cap * sizeof(u64)));
+  CU(cudaMalloc(&ctx->dest, cap * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->blk, ((cap + OBP_CHUNK - 1) / OBP_CHUNK + 1) * sizeof(unsigned)));
+  CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  return OBP_OK;
+}
+
+void free_table(obp_ctx* ctx) {
+  for (int w = 0; w < OBP_MAX_WORDS; ++w) {
+    if (ctx->xz[w]) cudaFree(ctx->xz[w]);
+    ctx->xz[w] = nullptr;
+  }
+  cudaFree(ctx->coef);
+  cudaFree(ctx->hash);
+  cudaFree(ctx->index);
+  cudaFree(ctx->spare16);
+  cudaFree(ctx->spare8);
+  cudaFree(ctx->dest);
+  cudaFree(ctx->blk);
+  ctx->coef = nullptr;
+  ctx->hash = nullptr;
+  ctx->index = nullptr;
+  ctx->spare16 = nullptr;
+  ctx->spare8 = nullptr;
+  ctx->dest = nullptr;
+  ctx->blk = nullptr;
+}
+
+void free_snapshot(Snapshot& s) {
+  for (int w = 0; w < OBP_MAX_WORDS; ++w) {
+    if (s.xz[w]) cudaFree(s.xz[w]);
+    s.xz[w] = nullptr;
+  }
+  if (s.coef) cudaFree(s.coef);
+  if (s.hash) cudaFree(s.hash);
+  s.coef = nullptr;
+  s.hash = nullptr;
+  s.cap = 0;
+  s.valid = false;
+}
+
+// ---- Clifford bookkeeping -----------------------------------------------------------------------
+
+// local columns of the hash frame for a gate on qubits q[0..nq): order x0, z0, x1, z1
+void frame_update(obp_ctx* ctx, const obp_op& op) {
+  const int nb = 2 * op.n_qubits;
+  u64 old_col[4], new_col[4];
+  for (int j = 0; j < op.n_qubits; ++j) {
+    old_col[2 * j] = ctx->hx[op.qubit[j]];
+    old_col[2 * j + 1] = ctx->hz[op.qubit[j]];
+  }
+  // new column j = XOR of old columns over the bits of the preimage of basis vector e_j
+  for (int j = 0; j < nb; ++j) {
+    unsigned pre = 0;
+    for (unsigned v = 0; v < (1u << nb); ++v)
+      if (((op.lut >> (4 * v)) & 15ull) == (1ull << j)) pre = v;
+    u64 c = 0;
+    for (int i = 0; i < nb; ++i)
+      if (pre & (1u << i)) c ^= old_col[i];
+    new_col[j] = c;
+  }
+  for (int j = 0; j < op.n_qubits; ++j) {
+    ctx->hx[op.qubit[j]] = new_col[2 * j];
+    ctx->hz[op.qubit[j]] = new_col[2 * j + 1];
+  }
+  ctx->cols_dirty = true;
+}
+
+bool lut_is_linear_bijection(const obp_op& op) {
+  const int nb = 2 * op.n_qubits;
+  unsigned seen = 0;
+  for (unsigned v = 0; v < (1u << nb); ++v) {
+    const unsigned img = (unsigned)((op.lut >> (4 * v)) & 15ull);
+    if (img >= (1u << nb)) return false;
+    seen |= 1u << img;
+    unsigned lin = 0;
+    for (int i = 0; i < nb; ++i)
+      if (v & (1u << i)) lin ^= (unsigned)((op.lut >> (4 * (1u << i))) & 15ull);
+    if (lin != img) return false;
+  }
+  return seen == ((nb == 4) ? 0xFFFFu : 0xFu);
+}
+
+struct PendingBatch {
+  CliffBatch b;
+  int n_ops = 0;
+  void reset() {
+    b.ng = 0;
+    b.nslots = 0;
+    b.scale = 1e300;
+    n_ops = 0;
+  }
+  int slot_of_word(int w) {
+    for (int s = 0; s < b.nslots; ++s)
+      if (b.word_of_slot[s] == w) return s;
+    b.word_of_slot[b.nslots] = w;
+    return b.nslots++;
+  }
+};
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+uint64_t obp_bytes_per_term(int n_qubits) {
+  const u64 W = (u64)std::max(1, (n_qubits + 63) / 64);
+  // key columns + coef + hash + spare16 + spare8 + dest + index (T >= 2*cap, up to 4*cap)
+  return 16 * W + 16 + 8 + 16 + 8 + 4 + 32;
+}
+
+int obp_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes) {
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_create_error = "obp_device_memory: cudaSetDevice failed";
+    return OBP_ERR_CUDA;
+  }
+  size_t f = 0, t = 0;
+  if (cudaMemGetInfo(&f, &t) != cudaSuccess) {
+    g_create_error = "obp_device_memory: cudaMemGetInfo failed";
+    return OBP_ERR_CUDA;
+  }
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return OBP_OK;
+}
+
+int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
+  if (!out || n_qubits < 1 || n_qubits > 64 * OBP_MAX_WORDS || capacity < 1 || capacity >= 0xffffffffull) {
+    g_create_error = "obp_create: bad argument";
+    return OBP_ERR_BADARG;
+  }
+  obp_ctx* ctx = new obp_ctx();
+  auto bail = [&](int code) {
+    g_create_error = ctx->err;
+    obp_destroy(ctx);
+    return code;
+  };
+  ctx->device = device;
+  ctx->nq = n_qubits;
+  ctx->W = (n_qubits + 63) / 64;
+  memset(&ctx->prof, 0, sizeof(ctx->prof));
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return bail(OBP_ERR_CUDA);
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    ctx->err = "obp_b200 requires an sm_100a (Blackwell B200) device";
+    return bail(OBP_ERR_UNSUPPORTED);
+  }
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    ctx->err = "cudaStreamCreate failed";
+    return bail(OBP_ERR_CUDA);
+  }
+  ctx->stream = ctx->own_stream;
+  auto body = [&]() -> int {
+    CU(cudaMalloc(&ctx->d_st, sizeof(DevState)));
+    CU(cudaMallocHost(&ctx->h_st, sizeof(DevState)));
+    CU(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 2));
+    CU(cudaMalloc(&ctx->d_partial, sizeof(double) * (size_t)ctx->n_sm * 8));
+    CU(cudaMalloc(&ctx->d_scalar, sizeof(double) * 2));
+    CU(cudaMalloc(&ctx->d_cols, sizeof(u64) * 2 * 64 * ctx->W));
+    int rc = alloc_table(ctx, capacity);
+    if (rc) return rc;
+    rc = ensure_ops(ctx, 256);
+    if (rc) return rc;
+    init_frame(ctx);
+    return set_counts(ctx, 0);
+  };
+  const int rc = body();
+  if (rc) return bail(rc);
+  *out = ctx;
+  return OBP_OK;
+}
+
+void obp_destroy(obp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch) obp_destroy(ctx->scratch);
+  free_table(ctx);
+  free_snapshot(ctx->snap);
+  cudaFree(ctx->d_st);
+  cudaFree(ctx->d_ops);
+  cudaFree(ctx->d_partial);
+  cudaFree(ctx->d_scalar);
+  cudaFree(ctx->d_cols);
+  cudaFree(ctx->d_gens);
+  cudaFree(ctx->d_factors);
+  if (ctx->h_st) cudaFreeHost(ctx->h_st);
+  if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
+  if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
+  for (auto& ep : ctx->ev_pending) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+  for (auto& ep : ctx->ev_free) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* obp_last_error(const obp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int obp_set_stream(obp_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return OBP_ERR_BADARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return OBP_OK;
+}
+
+int obp_count(obp_ctx* ctx, uint64_t* n) {
+  if (!ctx || !n) return OBP_ERR_BADARG;
+  *n = ctx->n_live;
+  return OBP_OK;
+}
+
+int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
+             uint64_t n, double atol, obp_stats* stats) {
+  if (!ctx || (n && (!x_words || !z_words || !coeffs))) return OBP_ERR_BADARG;
+  if (n > ctx->cap) return ctx->fail(OBP_ERR_CAPACITY, "obp_load: more rows than capacity");
+  CU(cudaSetDevice(ctx->device));
+  ctx->snap.valid = false;
+  init_frame(ctx);
+  int rc = upload_cols(ctx);
+  if (rc) return rc;
+  if (n) {
+    std::vector<ulonglong2> col(n);
+    for (int w = 0; w < ctx->W; ++w) {
+      for (u64 i = 0; i < n; ++i) col[i] = make_ulonglong2(x_words[i * ctx->W + w], z_words[i * ctx->W + w]);
+      CU(cudaMemcpy(ctx->xz[w], col.data(), n * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+    }
+    // a row given with coefficient exactly 0 must stay distinguishable from a tombstone only until
+    // the zero filter runs; with atol < 0 (no filter) such rows are dropped at load
+    CU(cudaMemcpy(ctx->coef, coeffs, n * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+  rc = set_counts(ctx, n);
+  if (rc) return rc;
+  rc = ensure_ops(ctx, 4);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
+  CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  Tab t = make_tab(ctx);
+  if (n) {
+    Bracket b(ctx, OBP_K_INDEX);
+    const int g = grid_for(ctx, n);
+    k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n);
+    ctx->epoch++;
+    k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ctx->epoch, 0);
+    if (atol >= 0.0) {
+      ctx->epoch++;
+      k_trim<<<g, OBP_BS, 0, ctx->stream>>>(t, atol, ctx->epoch, 0);
+    }
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  if (rc) return rc;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    const OpStat& o = ctx->h_ops[0];
+    // rows given as exact zeros count as filtered raw rows
+    stats->n_in = n;
+    stats->raw_rows = n;
+    stats->num_unique = o.keys_present;
+    stats->num_duplicate = o.rows_surv - o.keys_present;
+    stats->num_trimmed = (n - o.rows_surv) + o.cancelled;
+    stats->sum_trimmed[0] = o.sum_re;
+    stats->sum_trimmed[1] = o.sum_im;
+    stats->n_out = ctx->n_live;
+  }
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  if (stats) stats->n_dense = ctx->n_dense;
+  return OBP_OK;
+}
+
+int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coeffs,
+                 uint64_t max_rows, uint64_t* n_out) {
+  if (!ctx || !n_out) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->n_dense != ctx->n_live) {
+    int rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  const u64 n = ctx->n_live;
+  *n_out = n;
+  if (n == 0) return OBP_OK;
+  if (n > max_rows || !x_words || !z_words || !coeffs) return ctx->fail(OBP_ERR_BADARG, "obp_download: buffer too small");
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::vector<ulonglong2> col(n);
+  for (int w = 0; w < ctx->W; ++w) {
+    CU(cudaMemcpy(col.data(), ctx->xz[w], n * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+    for (u64 i = 0; i < n; ++i) {
+      x_words[i * ctx->W + w] = col[i].x;
+      z_words[i * ctx->W + w] = col[i].y;
+    }
+  }
+  CU(cudaMemcpy(coeffs, ctx->coef, n * sizeof(double2), cudaMemcpyDeviceToHost));
+  return OBP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats) {
+  if (!ctx || (n_ops && !ops) || n_ops < 0) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_ops == 0) {
+    if (stats) { stats->n_out = ctx->n_live; stats->n_dense = ctx->n_dense; }
+    return OBP_OK;
+  }
+  // validate before enqueuing anything
+  for (int k = 0; k < n_ops; ++k) {
+    const obp_op& op = ops[k];
+    const int maxq = op.kind == OBP_OP_CLIFFORD ? 2 : 4;
+    if ((op.kind != OBP_OP_CLIFFORD && op.kind != OBP_OP_ROTATION) || op.n_qubits < 1 || op.n_qubits > maxq)
+      return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_ops: unsupported op kind or qubit count");
+    for (int j = 0; j < op.n_qubits; ++j) {
+      if (op.qubit[j] < 0 || op.qubit[j] >= ctx->nq) return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: qubit out of range");
+      for (int l = 0; l < j; ++l)
+        if (op.qubit[l] == op.qubit[j]) return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: duplicate qubit");
+    }
+    if (op.kind == OBP_OP_CLIFFORD && !lut_is_linear_bijection(op))
+      return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: Clifford table is not a linear bijection");
+    if (op.kind == OBP_OP_ROTATION && (op.gen_local & ((1u << (2 * op.n_qubits)) - 1u)) == 0)
+      return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: rotation generator is the identity");
+    if (op.kind == OBP_OP_CLIFFORD && op.group_size > 16)
+      return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: group_size > 16");
+  }
+  int rc = ensure_ops(ctx, n_ops + 1);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * (n_ops + 1), ctx->stream));
+
+  const u64 n_start = ctx->n_live;
+  u64 bound = std::max<u64>(ctx->n_dense, 1);
+  std::vector<int> slot_of_op(n_ops, -1);
+  std::vector<int> slot_gates;  // gates accounted to each slot
+  int n_slots = 0;
+  PendingBatch pb;
+  pb.reset();
+  Tab t = make_tab(ctx);
+  const size_t max_smem_slots = 32;
+
+  auto flush = [&]() -> int {
+    if (pb.b.ng == 0) return OBP_OK;
+    pb.b.atol = atol;
+    pb.b.epoch = ++ctx->epoch;
+    pb.b.slot = n_slots;
+    Bracket br(ctx, OBP_K_CLIFFORD);
+    const int g = grid_for(ctx, bound);
+    bool identity_slots = ctx->W <= 2;
+    if (identity_slots) {
+      // register variant addresses words directly: remap slots to word ids
+      for (int k = 0; k < pb.b.ng; ++k) {
+        pb.b.g[k].sa = (unsigned char)pb.b.word_of_slot[pb.b.g[k].sa];
+        pb.b.g[k].sb = (unsigned char)pb.b.word_of_slot[pb.b.g[k].sb];
+      }
+      if (ctx->W == 1) k_clifford_reg<1><<<g, OBP_BS, 0, ctx->stream>>>(t, pb.b);
+      else k_clifford_reg<2><<<g, OBP_BS, 0, ctx->stream>>>(t, pb.b);
+    } else {
+      const size_t smem = (size_t)pb.b.nslots * OBP_BS * sizeof(ulonglong2);
+      k_clifford_smem<<<g, OBP_BS, smem, ctx->stream>>>(t, pb.b);
+    }
+    CU(cudaGetLastError());
+    slot_gates.push_back(pb.n_ops);
+    n_slots++;
+    pb.reset();
+    return OBP_OK;
+  };
+
+  for (int k = 0; k < n_ops; ++k) {
+    const obp_op& op = ops[k];
+    if (op.kind == OBP_OP_CLIFFORD) {
+      const bool exact = (op.flags & OBP_FLAG_EXACT_COUNTERS) != 0;
+      // words this gate touches must fit the staging tile
+      int need_new = 0;
+      for (int j = 0; j < op.n_qubits; ++j) {
+        bool have = false;
+        for (int s = 0; s < pb.b.nslots; ++s) have |= pb.b.word_of_slot[s] == op.qubit[j] / 64;
+        need_new += !have;
+      }
+      if (pb.b.ng == OBP_CLIFF_BATCH || pb.b.nslots + need_new > (int)max_smem_slots || exact) {
+        rc = flush();
+        if (rc) return rc;
+      }
+      if (exact) {
+        // counters come from the keys before the gate acts
+        CosetP cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.nd = (int)op.group_size - 1;
+        cp.wa = op.qubit[0] / 64;
+        cp.ba = op.qubit[0] % 64;
+        cp.wb = op.n_qubits == 2 ? op.qubit[1] / 64 : -1;
+        cp.bb = op.n_qubits == 2 ? op.qubit[1] % 64 : 0;
+        for (int d = 0; d < cp.nd; ++d) {
+          const unsigned code = (unsigned)((op.group_elems >> (4 * d)) & 15ull);
+          cp.code[d] = code;
+          u64 h = 0;
+          if (code & 1u) h ^= ctx->hx[op.qubit[0]];
+          if (code & 2u) h ^= ctx->hz[op.qubit[0]];
+          if (op.n_qubits == 2) {
+            if (code & 4u) h ^= ctx->hx[op.qubit[1]];
+            if (code & 8u) h ^= ctx->hz[op.qubit[1]];
+          }
+          cp.hD[d] = h;
+        }
+        cp.scale = op.row_scale;
+        cp.atol = atol;
+        cp.slot = n_slots;  // the slot the gate's own batch will use
+        Bracket br(ctx, OBP_K_OTHER);
+        k_coset_count<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, cp);
+        CU(cudaGetLastError());
+      }
+      CliffGate& g = pb.b.g[pb.b.ng++];
+      memset(&g, 0, sizeof(g));
+      g.lut = op.lut;
+      g.sign = op.sign_mask;
+      g.nq = (unsigned char)op.n_qubits;
+      g.sa = (unsigned char)pb.slot_of_word(op.qubit[0] / 64);
+      g.ba = (unsigned char)(op.qubit[0] % 64);
+      if (op.n_qubits == 2) {
+        g.sb = (unsigned char)pb.slot_of_word(op.qubit[1] / 64);
+        g.bb = (unsigned char)(op.qubit[1] % 64);
+      } else {
+        g.sb = g.sa;
+        g.bb = g.ba;
+      }
+      pb.b.scale = std::min(pb.b.scale, op.row_scale);
+      pb.n_ops++;
+      slot_of_op[k] = n_slots;
+      frame_update(ctx, op);
+      if (exact) {
+        rc = flush();
+        if (rc) return rc;
+      }
+    } else {
+      rc = flush();
+      if (rc) return rc;
+      RotP p;
+      memset(&p, 0, sizeof(p));
+      u64 hG = 0;
+      int yG = 0;
+      for (int j = 0; j < op.n_qubits; ++j) {
+        const unsigned code = (op.gen_local >> (2 * j)) & 3u;
+        if (!code) continue;
+        const int w = op.qubit[j] / 64;
+        const u64 bit = 1ull << (op.qubit[j] % 64);
+        int sl = -1;
+        for (int s = 0; s < p.ngw; ++s)
+          if (p.gw[s] == w) sl = s;
+        if (sl < 0) {
+          sl = p.ngw++;
+          p.gw[sl] = w;
+        }
+        if (code & 1u) { p.gx[sl] |= bit; hG ^= ctx->hx[op.qubit[j]]; }
+        if (code & 2u) { p.gz[sl] |= bit; hG ^= ctx->hz[op.qubit[j]]; }
+        if (code == 3u) yG++;
+      }
+      p.hG = hG;
+      p.yG = yG;
+      p.canon_slot = 0;
+      {
+        const u64 m = p.gx[0] | p.gz[0];
+        const u64 low = m & (~m + 1);
+        p.canon_bit = low;
+        p.canon_z = (p.gx[0] & low) ? 0 : 1;
+      }
+      p.u0r = op.u0[0];
+      p.u0i = op.u0[1];
+      p.u1r = op.u1[0];
+      p.u1i = op.u1[1];
+      p.atol = atol;
+      p.epoch = ++ctx->epoch;
+      p.exact = (op.flags & OBP_FLAG_EXACT_COUNTERS) ? 1 : 0;
+      p.slot = n_slots;
+      {
+        Bracket br(ctx, OBP_K_ROTATE);
+        k_rotate<<<grid_for(ctx, bound, 4), OBP_BS, 0, ctx->stream>>>(t, p);
+        CU(cudaGetLastError());
+      }
+      slot_of_op[k] = n_slots;
+      slot_gates.push_back(1);
+      n_slots++;
+      bound = std::min<u64>(ctx->cap, bound * 2);
+    }
+  }
+  rc = flush();
+  if (rc) return rc;
+
+  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat) * n_slots, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  if (rc) return rc;
+
+  // term-gate updates: live terms at entry of every op
+  u64 updates = 0, n_in = n_start, n_in_last = n_start;
+  for (int s = 0; s < n_slots; ++s) {
+    updates += n_in * (u64)slot_gates[s];
+    n_in_last = n_in;
+    n_in = ctx->h_ops[s].n_out;
+  }
+  {
+    // per-class term counts for the roofline
+    u64 nin = n_start;
+    for (int k = 0, s_prev = -1; k < n_ops; ++k) {
+      const int s = slot_of_op[k];
+      if (s != s_prev && s_prev >= 0) nin = ctx->h_ops[s_prev].n_out;
+      ctx->prof.term_updates[ops[k].kind == OBP_OP_ROTATION ? OBP_K_ROTATE : OBP_K_CLIFFORD] += nin;
+      s_prev = s;
+    }
+  }
+  if (stats) {
+    const obp_op& last = ops[n_ops - 1];
+    const OpStat& o = ctx->h_ops[n_slots - 1];
+    const u64 k2 = (u64)last.n_components * last.n_components;
+    stats->n_in = n_in_last;
+    stats->raw_rows = n_in_last * k2;
+    stats->updates = updates;
+    if (last.flags & OBP_FLAG_EXACT_COUNTERS) {
+      if (last.kind == OBP_OP_ROTATION) {
+        stats->num_unique = o.keys_present;
+        stats->num_duplicate = o.rows_surv - o.keys_present;
+        stats->num_trimmed = (stats->raw_rows - o.rows_surv) + o.cancelled;
+        stats->sum_trimmed[0] = o.sum_re;
+        stats->sum_trimmed[1] = o.sum_im;
+      } else {
+        // cosets hit = sum_c N_c / c ; keys present = |D| * cosets
+        u64 cosets = 0;
+        for (unsigned c = 1; c <= 16; ++c) cosets += o.ncnt[c] / c;
+        const u64 rows = o.n_surv * k2;
+        const u64 uniq = (u64)last.group_size * cosets;
+        stats->num_unique = uniq;
+        stats->num_duplicate = rows - uniq;
+        stats->num_trimmed = (stats->raw_rows - rows) + (uniq - o.n_surv);
+      }
+    }
+  }
+  // keep tombstones below a quarter of the table
+  if (ctx->n_dense - ctx->n_live > std::max<u64>(1024, ctx->n_live / 4)) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  if (stats) {
+    stats->n_out = ctx->n_live;
+    stats->n_dense = ctx->n_dense;
+  }
+  return OBP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) {
+  if (!ctx || qubit < 0 || qubit >= ctx->nq) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_ops(ctx, 2);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat), ctx->stream));
+  const u64 n_in = ctx->n_live;
+  ResetP p;
+  memset(&p, 0, sizeof(p));
+  p.w = qubit / 64;
+  p.bit = 1ull << (qubit % 64);
+  p.hZ = ctx->hz[qubit];
+  p.atol = atol;
+  p.slot = 0;
+  Tab t = make_tab(ctx);
+  {
+    Bracket br(ctx, OBP_K_OTHER);
+    const int g = grid_for(ctx, std::max<u64>(ctx->n_dense, 1));
+    p.epoch = ++ctx->epoch;
+    k_reset_filter<<<g, OBP_BS, 0, ctx->stream>>>(t, p);
+    p.epoch = ++ctx->epoch;
+    k_reset_merge<<<g, OBP_BS, 0, ctx->stream>>>(t, p);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  if (rc) return rc;
+  ctx->prof.term_updates[OBP_K_OTHER] += n_in;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    const OpStat& o = ctx->h_ops[0];
+    stats->n_in = n_in;
+    stats->raw_rows = n_in;
+    stats->updates = n_in;
+    stats->num_unique = o.keys_present;
+    stats->num_duplicate = o.rows_surv - o.keys_present;
+    stats->num_trimmed = (n_in - o.rows_surv) + o.cancelled;
+    stats->sum_trimmed[0] = o.sum_re;
+    stats->sum_trimmed[1] = o.sum_im;
+  }
+  // moved rows leave stale index entries behind: compact when anything died or moved
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  if (stats) { stats->n_out = ctx->n_live; stats->n_dense = ctx->n_dense; }
+  return OBP_OK;
+}
+
+int obp_apply_damping(obp_ctx* ctx, const uint64_t* gen_x, const uint64_t* gen_z, const double* factors,
+                      int32_t n_gens, double atol, obp_stats* stats) {
+  if (!ctx || n_gens < 0 || (n_gens && (!gen_x || !gen_z || !factors))) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  const u64 n_in = ctx->n_live;
+  if (n_gens > ctx->gens_alloc) {
+    cudaFree(ctx->d_gens);
+    cudaFree(ctx->d_factors);
+    ctx->d_gens = nullptr;
+    ctx->d_factors = nullptr;
+    ctx->gens_alloc = 0;
+    CU(cudaMalloc(&ctx->d_gens, sizeof(u64) * 2 * ctx->W * n_gens));
+    CU(cudaMalloc(&ctx->d_factors, sizeof(double) * n_gens));
+    ctx->gens_alloc = n_gens;
+  }
+  if (n_gens) {
+    std::vector<u64> packed((size_t)n_gens * 2 * ctx->W);
+    for (int g = 0; g < n_gens; ++g)
+      for (int w = 0; w < ctx->W; ++w) {
+        packed[(size_t)g * 2 * ctx->W + w] = gen_x[(size_t)g * ctx->W + w];
+        packed[(size_t)g * 2 * ctx->W + ctx->W + w] = gen_z[(size_t)g * ctx->W + w];
+      }
+    CU(cudaMemcpy(ctx->d_gens, packed.data(), packed.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_factors, factors, sizeof(double) * n_gens, cudaMemcpyHostToDevice));
+  }
+  {
+    Bracket br(ctx, OBP_K_OTHER);
+    k_damp<<<grid_for(ctx, std::max<u64>(ctx->n_dense, 1)), OBP_BS, 0, ctx->stream>>>(
+        make_tab(ctx), ctx->d_gens, ctx->d_factors, n_gens, atol, ++ctx->epoch, -1);
+    CU(cudaGetLastError());
+  }
+  int rc = sync_state(ctx);
+  if (rc) return rc;
+  ctx->prof.term_updates[OBP_K_OTHER] += n_in;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_in = n_in;
+    stats->raw_rows = n_in;
+    stats->updates = n_in;
+    stats->num_unique = ctx->n_live;  // keys are already distinct: every surviving row is unique
+    stats->num_duplicate = 0;
+    stats->num_trimmed = n_in - ctx->n_live;
+    stats->n_out = ctx->n_live;
+    stats->n_dense = ctx->n_dense;
+  }
+  return OBP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double* slice_error,
+                 uint64_t* n_removed, uint64_t* n_out) {
+  if (!ctx || p_norm < 1) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  if (slice_error) *slice_error = 0.0;
+  if (n_removed) *n_removed = 0;
+  if (n_out) *n_out = ctx->n_live;
+  if (ctx->n_live == 0) return OBP_OK;
+  Tab t = make_tab(ctx);
+  double* a = (double*)ctx->spare16;
+  const int g = grid_for(ctx, ctx->n_dense);
+  const int gs = std::min(g, ctx->n_sm * 8);
+  CU(cudaMemsetAsync(&ctx->d_st->removed, 0, 2 * sizeof(u64), ctx->stream));  // removed, amax_bits
+  {
+    Bracket br(ctx, OBP_K_TRUNCATE);
+    k_absp<<<g, OBP_BS, 0, ctx->stream>>>(t, a, p_norm);
+    CU(cudaGetLastError());
+  }
+  int rc = sync_state(ctx);
+  if (rc) return rc;
+  double upper;
+  {
+    const u64 bits = ctx->h_st->amax_bits;
+    memcpy(&upper, &bits, sizeof(double));
+  }
+  // utils/truncating.py:173-196, evaluated on the host with device-side masked sums
+  double lower = 0.0, upper_error = budget, lower_error = 0.0;
+  auto isclose = [&](double x, double y) { return std::fabs(x - y) <= tol + 1e-5 * std::fabs(y); };
+  while ((upper - lower) > tol && !isclose(upper_error, lower_error)) {
+    const double mid = (upper + lower) / 2;
+    {
+      Bracket br(ctx, OBP_K_TRUNCATE);
+      k_masked_sum<<<gs, OBP_BS, 0, ctx->stream>>>(a, ctx->d_st, mid, ctx->d_partial);
+      k_final_sum<<<1, OBP_BS, 0, ctx->stream>>>(ctx->d_partial, gs, ctx->d_scalar);
+      CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const double mid_error = p_norm == 1 ? ctx->h_scalar[0] : std::pow(ctx->h_scalar[0], 1.0 / p_norm);
+    if (mid_error <= budget) {
+      lower = mid;
+      lower_error = mid_error;
+    } else {
+      upper = mid;
+      upper_error = mid_error;
+    }
+  }
+  const u64 before = ctx->n_live;
+  {
+    Bracket br(ctx, OBP_K_TRUNCATE);
+    k_trunc_kill<<<g, OBP_BS, 0, ctx->stream>>>(t, a, lower, ++ctx->epoch);
+    CU(cudaGetLastError());
+  }
+  rc = sync_state(ctx);
+  if (rc) return rc;
+  ctx->prof.term_updates[OBP_K_TRUNCATE] += before;
+  if (slice_error) *slice_error = lower_error;
+  if (n_removed) *n_removed = before - ctx->n_live;
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  if (n_out) *n_out = ctx->n_live;
+  return OBP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int obp_snapshot(obp_ctx* ctx) {
+  if (!ctx) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  Snapshot& s = ctx->snap;
+  const u64 n = ctx->n_live;
+  if (n > s.cap) {
+    free_snapshot(s);
+    const u64 nc = std::max<u64>(n + n / 2, 1024);
+    for (int w = 0; w < ctx->W; ++w) CU(cudaMalloc(&s.xz[w], nc * sizeof(ulonglong2)));
+    CU(cudaMalloc(&s.coef, nc * sizeof(double2)));
+    CU(cudaMalloc(&s.hash, nc * sizeof(u64)));
+    s.cap = nc;
+  }
+  for (int w = 0; w < ctx->W; ++w)
+    CU(cudaMemcpyAsync(s.xz[w], ctx->xz[w], n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.coef, ctx->coef, n * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.hash, ctx->hash, n * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+  s.n = n;
+  s.hx = ctx->hx;
+  s.hz = ctx->hz;
+  s.valid = true;
+  return OBP_OK;
+}
+
+int obp_restore(obp_ctx* ctx) {
+  if (!ctx) return OBP_ERR_BADARG;
+  if (!ctx->snap.valid) return ctx->fail(OBP_ERR_BADARG, "obp_restore: no snapshot");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaMemsetAsync(&ctx->d_st->error, 0, sizeof(unsigned), ctx->stream);
+  Snapshot& s = ctx->snap;
+  if (s.n > ctx->cap) return ctx->fail(OBP_ERR_CAPACITY, "obp_restore: snapshot larger than table");
+  for (int w = 0; w < ctx->W; ++w)
+    CU(cudaMemcpyAsync(ctx->xz[w], s.xz[w], s.n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->coef, s.coef, s.n * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->hash, s.hash, s.n * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->hx = s.hx;
+  ctx->hz = s.hz;
+  ctx->cols_dirty = true;
+  int rc = set_counts(ctx, s.n);
+  if (rc) return rc;
+  rc = rebuild_index(ctx);
+  if (rc) return rc;
+  return sync_state(ctx);
+}
+
+int obp_reserve(obp_ctx* ctx, uint64_t new_capacity) {
+  if (!ctx || new_capacity >= 0xffffffffull) return OBP_ERR_BADARG;
+  if (new_capacity <= ctx->cap) return OBP_OK;
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  const u64 n = ctx->n_live;
+  // move the live columns into a bigger table, one column at a time to bound the peak footprint
+  ulonglong2* old_xz[OBP_MAX_WORDS];
+  for (int w = 0; w < OBP_MAX_WORDS; ++w) old_xz[w] = ctx->xz[w];
+  double2* old_coef = ctx->coef;
+  u64* old_hash = ctx->hash;
+  cudaFree(ctx->index);
+  cudaFree(ctx->spare16);
+  cudaFree(ctx->spare8);
+  cudaFree(ctx->dest);
+  cudaFree(ctx->blk);
+  ctx->index = nullptr;
+  ctx->spare16 = nullptr;
+  ctx->spare8 = nullptr;
+  ctx->dest = nullptr;
+  ctx->blk = nullptr;
+  const u64 cap = new_capacity;
+  for (int w = 0; w < ctx->W; ++w) {
+    ulonglong2* p = nullptr;
+    CU(cudaMalloc(&p, cap * sizeof(ulonglong2)));
+    CU(cudaMemcpy(p, old_xz[w], n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice));
+    cudaFree(old_xz[w]);
+    ctx->xz[w] = p;
+  }
+  {
+    double2* p = nullptr;
+    CU(cudaMalloc(&p, cap * sizeof(double2)));
+    CU(cudaMemcpy(p, old_coef, n * sizeof(double2), cudaMemcpyDeviceToDevice));
+    cudaFree(old_coef);
+    ctx->coef = p;
+    u64* h = nullptr;
+    CU(cudaMalloc(&h, cap * sizeof(u64)));
+    CU(cudaMemcpy(h, old_hash, n * sizeof(u64), cudaMemcpyDeviceToDevice));
+    cudaFree(old_hash);
+    ctx->hash = h;
+  }
+  ctx->cap = cap;
+  ctx->T = next_pow2(std::max<u64>(2 * cap, 1024));
+  CU(cudaMalloc(&ctx->index, ctx->T * sizeof(u64)));
+  CU(cudaMalloc(&ctx->spare16, cap * sizeof(ulonglong2)));
+  CU(cudaMalloc(&ctx->spare8, cap * sizeof(u64)));
+  CU(cudaMalloc(&ctx->dest, cap * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->blk, ((cap + OBP_CHUNK - 1) / OBP_CHUNK + 1) * sizeof(unsigned)));
+  rc = rebuild_index(ctx);
+  if (rc) return rc;
+  return sync_state(ctx);
+}
+
+// -------------------------------------------------------------------------------------------------
+int obp_union_count(obp_ctx* const* ctxs, int32_t n_ctx, uint64_t* n_distinct) {
+  if (!ctxs || n_ctx < 1 || !n_distinct) return OBP_ERR_BADARG;
+  obp_ctx* ctx = ctxs[0];
+  CU(cudaSetDevice(ctx->device));
+  if (n_ctx == 1) {
+    *n_distinct = ctx->n_live;
+    return OBP_OK;
+  }
+  u64 total = 0;
+  for (int k = 0; k < n_ctx; ++k) {
+    obp_ctx* c = ctxs[k];
+    if (c->nq != ctx->nq || c->device != ctx->device) return ctx->fail(OBP_ERR_BADARG, "obp_union_count: mismatching contexts");
+    if (c->n_dense != c->n_live) {
+      int rc = compact(c);
+      if (rc) { ctx->err = c->err; return rc; }
+      rc = sync_state(c);
+      if (rc) { ctx->err = c->err; return rc; }
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    total += c->n_live;
+  }
+  if (total == 0) {
+    *n_distinct = 0;
+    return OBP_OK;
+  }
+  if (!ctx->scratch || ctx->scratch->cap < total) {
+    if (ctx->scratch) obp_destroy(ctx->scratch);
+    ctx->scratch = nullptr;
+    const int rc = obp_create(ctx->device, ctx->nq, std::max<u64>(total + total / 2, 1024), &ctx->scratch);
+    if (rc) return ctx->fail(rc, std::string("obp_union_count scratch: ") + obp_last_error(nullptr));
+  }
+  obp_ctx* sc = ctx->scratch;
+  Tab ts = make_tab(sc);
+  u64 off = 0;
+  for (int k = 0; k < n_ctx; ++k) {
+    obp_ctx* c = ctxs[k];
+    if (c->n_live == 0) continue;
+    k_copy_live_keys<<<grid_for(sc, c->n_live), OBP_BS, 0, sc->stream>>>(make_tab(c), ts, off);
+    off += c->n_live;
+  }
+  if (cudaGetLastError() != cudaSuccess) return ctx->fail(OBP_ERR_CUDA, "k_copy_live_keys launch failed");
+  int rc = set_counts(sc, total);
+  if (rc) return ctx->fail(rc, sc->err);
+  init_frame(sc);
+  rc = upload_cols(sc);
+  if (rc) return ctx->fail(rc, sc->err);
+  cudaMemsetAsync(sc->d_ops, 0, sizeof(OpStat), sc->stream);
+  cudaMemsetAsync(sc->index, 0xFF, sc->T * sizeof(u64), sc->stream);
+  ts = make_tab(sc);
+  k_hash_rows<<<grid_for(sc, total), OBP_BS, 0, sc->stream>>>(ts, sc->d_cols, total);
+  k_index_build<<<grid_for(sc, total), OBP_BS, 0, sc->stream>>>(ts, 1, -1.0, ++sc->epoch, 0);
+  if (cudaGetLastError() != cudaSuccess) return ctx->fail(OBP_ERR_CUDA, "union count launch failed");
+  cudaMemcpyAsync(sc->h_ops, sc->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, sc->stream);
+  rc = sync_state(sc);
+  if (rc) return ctx->fail(rc, sc->err);
+  *n_distinct = sc->h_ops[0].keys_present;
+  return OBP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int obp_profile_enable(obp_ctx* ctx, int32_t on) {
+  if (!ctx) return OBP_ERR_BADARG;
+  ctx->prof_on = on != 0;
+  return OBP_OK;
+}
+
+int obp_profile_get(obp_ctx* ctx, obp_profile* out, int32_t reset) {
+  if (!ctx || !out) return OBP_ERR_BADARG;
+  *out = ctx->prof;
+  if (reset) memset(&ctx->prof, 0, sizeof(ctx->prof));
+  return OBP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,891 @@
+// obp_kernels.cuh — the sm_100a kernels of the operator-backpropagation hot path.
+//
+// All table kernels are persistent grid-stride kernels (grid = a multiple of the 148 SMs) that
+// read the current row count from device memory, so a whole slice of gates is enqueued without a
+// host round trip.  Every kernel ends with finish_kernel(): the last CTA publishes the append
+// cursor as the next kernel's scan bound.
+#pragma once
+#include "obp_device.cuh"
+
+// ================================================================================================
+// k_rotate — U = u0*I + u1*G  (rx/ry/rz/rxx/ryy/rzz/t/p...), conjugation + merge + trim in one pass
+//
+// Replaces, per gate:  op.compose(U, front=True).compose(U^dag)  (utils/operations.py:103-105)
+//                      followed by simplify()                     (utils/simplify.py:115-165).
+//
+// The reference materialises 4 raw rows per term P (coefficient c):
+//   (0,0) key P      r00 = (c*u0)*conj(u0)
+//   (1,1) key P      r11 = (-1)^s (c*u1)*conj(u1)            s = symplectic product <P,G>
+//   (0,1) key P^G    r01 = ((c*u0)*conj(u1)) * (-i)^E        E = y(P)+y(G)-y(P^G)+2|zP&xG| mod 4
+//   (1,0) key P^G    r10 = ((c*u1)*conj(u0)) * (-i)^(E+2s)
+// drops every raw row with |r| <= atol, sums the rest per key, drops keys with |sum| <= atol.
+// P and Q = P^G have the same s, and E(Q) = -E(P) mod 4, so a rotation is a set of independent
+// 2x2 updates on (c_P, c_Q) pairs plus insertions of keys that were absent.  One thread per row:
+//   commuting rows (s = 0) keep their key and (up to the row filter) their coefficient;
+//   anticommuting rows look their partner up in the index.  If the partner is live the pair is
+//   updated once, by the row whose canonical generator bit is 0 ("owner"); otherwise the row
+//   updates itself and appends the partner key (warp ballot + block prefix scan, one atomicAdd
+//   per CTA on the append cursor, then an atomicCAS slot claim in the index).
+// No floating-point atomics: every coefficient is written by exactly one thread.
+// With p.exact every live row does the partner lookup, which yields the reference's
+// num_unique / num_duplicate / num_trimmed / sum_trimmed counters exactly.
+// ================================================================================================
+struct RotP {
+  int ngw;          // generator words
+  int gw[4];        // their word indices
+  u64 gx[4], gz[4];
+  u64 hG;           // hash of the generator
+  int canon_slot;   // ownership bit: generator word slot, x or z plane, bit mask
+  int canon_z;
+  u64 canon_bit;
+  int yG;           // |gx & gz|
+  double u0r, u0i, u1r, u1i;
+  double atol;
+  u64 epoch;
+  int exact;
+  int slot;
+};
+
+struct RowSet {  // surviving raw rows of one term, already summed per key
+  double2 self, cross;
+  int nself, ncross;
+};
+
+__device__ __forceinline__ RowSet rot_rows(double2 c, int E, int s, const RotP& p) {
+  const double2 u0 = make_double2(p.u0r, p.u0i), u1 = make_double2(p.u1r, p.u1i);
+  const double2 t0 = cmul(c, u0), t1 = cmul(c, u1);
+  double2 r00 = cmul(t0, cconj(u0));
+  double2 r11 = cmul(t1, cconj(u1));
+  if (s) r11 = make_double2(-r11.x, -r11.y);
+  const double2 r01 = mul_mi_pow(cmul(t0, cconj(u1)), E);
+  const double2 r10 = mul_mi_pow(cmul(t1, cconj(u0)), E + 2 * s);
+  RowSet r;
+  r.self = make_double2(0.0, 0.0);
+  r.cross = make_double2(0.0, 0.0);
+  r.nself = 0;
+  r.ncross = 0;
+  if (!is_small(r00, p.atol)) { r.self = r00; r.nself = 1; }
+  if (!is_small(r11, p.atol)) { r.self = r.nself ? cadd(r.self, r11) : r11; r.nself++; }
+  if (!is_small(r01, p.atol)) { r.cross = r01; r.ncross = 1; }
+  if (!is_small(r10, p.atol)) { r.cross = r.ncross ? cadd(r.cross, r10) : r10; r.ncross++; }
+  return r;
+}
+
+// generator words for table word w (0 if G is identity there)
+__device__ __forceinline__ void gen_word(const RotP& p, int w, u64& gx, u64& gz) {
+  gx = 0; gz = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < p.ngw && p.gw[k] == w) { gx = p.gx[k]; gz = p.gz[k]; }
+}
+
+// Find the row holding key(i) ^ G.  Returns its row id or -1.  *fresh is set when the row was
+// killed during this epoch (it was live when the kernel started).
+__device__ __forceinline__ long long find_partner(const Tab& t, const RotP& p, u64 i, u64 h2,
+                                                  u64 n_scan, double2& cq, bool& fresh) {
+  const u64 fp = h2 >> 32;
+  u64 s = h2 & t.mask;
+  fresh = false;
+  for (u64 probes = 0; probes <= t.mask; ++probes) {
+    const u64 e = ld_volatile(&t.index[s]);
+    if (e == OBP_EMPTY) return -1;
+    if ((e >> 32) == fp) {
+      const u64 j = e & 0xffffffffull;
+      if (j < n_scan && t.hash[j] == h2) {
+        bool eq = true;
+        for (int w = 0; w < t.W && eq; ++w) {
+          u64 gx, gz;
+          gen_word(p, w, gx, gz);
+          const ulonglong2 ki = t.xz[w][i], kj = t.xz[w][j];
+          eq = (kj.x == (ki.x ^ gx)) && (kj.y == (ki.y ^ gz));
+        }
+        if (eq) {
+          cq = t.coef[j];
+          if (is_live(cq)) return (long long)j;
+          if (tomb_epoch(cq) == p.epoch) { fresh = true; return (long long)j; }
+          // stale tombstone of the same key: keep probing for a live duplicate
+        }
+      }
+    }
+    s = (s + 1) & t.mask;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(OBP_BS) k_rotate(Tab t, const __grid_constant__ RotP p) {
+  __shared__ unsigned warp_tot[OBP_BS / 32];
+  __shared__ u64 s_base;
+  const u64 n = t.st->n_scan;
+  // per-thread counters
+  unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
+  int dlive = 0;
+  double sum_re = 0.0, sum_im = 0.0;
+  bool overflow = false;
+
+  for (u64 base = (u64)blockIdx.x * OBP_BS; base < n; base += (u64)gridDim.x * OBP_BS) {
+    const u64 i = base + threadIdx.x;
+    bool want_append = false;
+    double2 app_c = make_double2(0.0, 0.0);
+    if (i < n) {
+      const double2 c = t.coef[i];
+      if (is_live(c)) {
+        // commutation parity and phase exponent from the generator's words only
+        int sp = 0, E = p.yG, own_bit = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < p.ngw) {
+            const ulonglong2 key = t.xz[p.gw[k]][i];
+            const u64 m = p.gx[k] | p.gz[k];
+            sp += __popcll(key.x & p.gz[k]) + __popcll(key.y & p.gx[k]);
+            E += __popcll(key.x & key.y & m) - __popcll((key.x ^ p.gx[k]) & (key.y ^ p.gz[k]) & m) +
+                 2 * __popcll(key.y & p.gx[k]);
+            if (k == p.canon_slot) own_bit = ((p.canon_z ? key.y : key.x) & p.canon_bit) != 0;
+          }
+        }
+        const int s = sp & 1;
+        E &= 3;
+        const RowSet rp = rot_rows(c, E, s, p);
+        if (!p.exact && !s) {
+          // commuting row, fast mode: only its own key can change (row filter)
+          if (rp.nself < 2) {
+            if (rp.nself == 0 || is_small(rp.self, p.atol)) {
+              t.coef[i] = tombstone(p.epoch);
+              dlive--;
+            } else {
+              t.coef[i] = rp.self;
+            }
+          }
+        } else {
+          const u64 h2 = t.hash[i] ^ p.hG;
+          double2 cq;
+          bool fresh;
+          const long long j = find_partner(t, p, i, h2, n, cq, fresh);
+          if (j >= 0 && !fresh && !own_bit) {
+            // both rows live, this thread owns the pair
+            const RowSet rq = rot_rows(cq, (4 - E) & 3, s, p);
+            const bool pres_p = rp.nself > 0 || rq.ncross > 0;
+            const bool pres_q = rq.nself > 0 || rp.ncross > 0;
+            double2 np_ = rp.self, nq_ = rq.self;
+            if (rq.ncross) np_ = rp.nself ? cadd(np_, rq.cross) : rq.cross;
+            if (rp.ncross) nq_ = rq.nself ? cadd(nq_, rp.cross) : rp.cross;
+            rows_surv += rp.nself + rp.ncross + rq.nself + rq.ncross;
+            keys_present += (unsigned)pres_p + (unsigned)pres_q;
+            if (pres_p && !is_small(np_, p.atol)) {
+              t.coef[i] = np_;
+            } else {
+              if (pres_p) { cancelled++; sum_re += np_.x; sum_im += np_.y; }
+              t.coef[i] = tombstone(p.epoch);
+              dlive--;
+            }
+            if (pres_q && !is_small(nq_, p.atol)) {
+              t.coef[j] = nq_;
+            } else {
+              if (pres_q) { cancelled++; sum_re += nq_.x; sum_im += nq_.y; }
+              t.coef[j] = tombstone(p.epoch);
+              dlive--;
+            }
+          } else if (j < 0) {
+            // partner key absent: update this row, append the partner if it survives
+            rows_surv += rp.nself + rp.ncross;
+            keys_present += (unsigned)(rp.nself > 0) + (unsigned)(rp.ncross > 0);
+            if (rp.nself > 0 && !is_small(rp.self, p.atol)) {
+              if (rp.self.x != c.x || rp.self.y != c.y) t.coef[i] = rp.self;
+            } else {
+              if (rp.nself > 0) { cancelled++; sum_re += rp.self.x; sum_im += rp.self.y; }
+              t.coef[i] = tombstone(p.epoch);
+              dlive--;
+            }
+            if (rp.ncross > 0) {
+              if (!is_small(rp.cross, p.atol)) {
+                want_append = true;
+                app_c = rp.cross;
+              } else {
+                cancelled++; sum_re += rp.cross.x; sum_im += rp.cross.y;
+              }
+            }
+          }
+          // else: the pair is (or was) handled by its owner
+        }
+      }
+    }
+    // ---- append the new keys of this CTA iteration: ballot + block prefix scan -----------------
+    unsigned total;
+    const unsigned off = block_scan_flag(want_append, warp_tot, total);
+    if (total) {
+      if (threadIdx.x == 0) s_base = atomicAdd(&t.st->n_append, (u64)total);
+      __syncthreads();
+      if (want_append) {
+        const u64 row = s_base + off;
+        if (row < t.cap) {
+          for (int w = 0; w < t.W; ++w) {
+            u64 gx, gz;
+            gen_word(p, w, gx, gz);
+            ulonglong2 key = t.xz[w][i];
+            key.x ^= gx;
+            key.y ^= gz;
+            t.xz[w][row] = key;
+          }
+          const u64 h2 = t.hash[i] ^ p.hG;
+          t.coef[row] = app_c;
+          t.hash[row] = h2;
+          if (!index_insert(t, h2, row)) atomicOr(&t.st->error, OBP_ERR_BIT_INDEX);
+          dlive++;
+        } else {
+          overflow = true;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (overflow) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
+  // ---- counters: warp shuffle reduction, one atomic per warp ------------------------------------
+  const long long dl = warp_sum_i64((long long)dlive);
+  if (p.exact) {
+    const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present), cz = warp_sum_u64(cancelled);
+    const double sr = warp_sum_f64(sum_re), si = warp_sum_f64(sum_im);
+    if ((threadIdx.x & 31) == 0) {
+      OpStat* o = &t.ops[p.slot];
+      if (a) atomicAdd(&o->rows_surv, a);
+      if (b) atomicAdd(&o->keys_present, b);
+      if (cz) { atomicAdd(&o->cancelled, cz); atomicAdd(&o->sum_re, sr); atomicAdd(&o->sum_im, si); }
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)dl);
+  finish_kernel(t, p.slot);
+}
+
+// ================================================================================================
+// k_clifford_* — a batch of gates whose Pauli-transfer matrix is a signed permutation (h, s, x, y,
+// z, sx, cx, cz, swap, iswap, ecr, rzz(+-pi/2), ...), applied to each term in registers / shared
+// memory in one pass.  Replaces compose+simplify for those gates: the key moves to its image, the
+// coefficient picks up the sign; all k*k raw rows of a term have magnitude |c|*row_scale, so the
+// term vanishes iff that is <= atol.  Bijection on keys: no merge is needed and
+// the row's stored hash stays valid because the host re-expresses the hash frame (HashFrame).
+// ================================================================================================
+struct CliffGate {
+  u64 lut;
+  unsigned sign;
+  unsigned char sa, ba, sb, bb;  // word slot / bit of qubit a and b
+  unsigned char nq;
+  unsigned char pad[3];
+};
+
+struct CliffBatch {
+  int ng;
+  int nslots;                       // touched words
+  int word_of_slot[OBP_MAX_WORDS];
+  double scale;                     // min row_scale over the batch
+  double atol;
+  u64 epoch;
+  int slot;
+  CliffGate g[OBP_CLIFF_BATCH];
+};
+
+// one gate on local bit values; returns the flip mask d = new ^ old and updates sgn
+__device__ __forceinline__ unsigned cliff_apply_bits(const CliffGate& g, u64 xa, u64 za, u64 xb, u64 zb,
+                                                     unsigned& sgn) {
+  unsigned v = (unsigned)((xa >> g.ba) & 1ull) | ((unsigned)((za >> g.ba) & 1ull) << 1);
+  if (g.nq == 2) v |= ((unsigned)((xb >> g.bb) & 1ull) << 2) | ((unsigned)((zb >> g.bb) & 1ull) << 3);
+  const unsigned nv = (unsigned)(g.lut >> (4 * v)) & 15u;
+  sgn ^= (g.sign >> v) & 1u;
+  return nv ^ v;
+}
+
+template <int W>
+__global__ void __launch_bounds__(OBP_BS) k_clifford_reg(Tab t, const __grid_constant__ CliffBatch b) {
+  static_assert(W == 1 || W == 2, "register variant handles W <= 2");
+  const u64 n = t.st->n_scan;
+  int deaths = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c)) continue;
+    if (hypot(c.x, c.y) * b.scale <= b.atol) {
+      t.coef[i] = tombstone(b.epoch);
+      deaths++;
+      continue;
+    }
+    u64 x0, z0, x1 = 0, z1 = 0;
+    { const ulonglong2 k0 = t.xz[0][i]; x0 = k0.x; z0 = k0.y; }
+    if (W == 2) { const ulonglong2 k1 = t.xz[1][i]; x1 = k1.x; z1 = k1.y; }
+    const u64 ox0 = x0, oz0 = z0, ox1 = x1, oz1 = z1;
+    unsigned sgn = 0;
+    for (int k = 0; k < b.ng; ++k) {
+      const CliffGate g = b.g[k];
+      const u64 xa = (W == 2 && g.sa) ? x1 : x0, za = (W == 2 && g.sa) ? z1 : z0;
+      const u64 xb = (W == 2 && g.sb) ? x1 : x0, zb = (W == 2 && g.sb) ? z1 : z0;
+      const unsigned d = cliff_apply_bits(g, xa, za, xb, zb, sgn);
+      const u64 fxa = (u64)(d & 1u) << g.ba, fza = (u64)((d >> 1) & 1u) << g.ba;
+      const u64 fxb = (u64)((d >> 2) & 1u) << g.bb, fzb = (u64)((d >> 3) & 1u) << g.bb;
+      if (W == 2) {
+        x0 ^= (g.sa ? 0ull : fxa) ^ (g.sb ? 0ull : fxb);
+        z0 ^= (g.sa ? 0ull : fza) ^ (g.sb ? 0ull : fzb);
+        x1 ^= (g.sa ? fxa : 0ull) ^ (g.sb ? fxb : 0ull);
+        z1 ^= (g.sa ? fza : 0ull) ^ (g.sb ? fzb : 0ull);
+      } else {
+        x0 ^= fxa ^ fxb;
+        z0 ^= fza ^ fzb;
+      }
+    }
+    if (x0 != ox0 || z0 != oz0) t.xz[0][i] = make_ulonglong2(x0, z0);
+    if (W == 2 && (x1 != ox1 || z1 != oz1)) t.xz[1][i] = make_ulonglong2(x1, z1);
+    if (sgn) t.coef[i] = make_double2(-c.x, -c.y);
+  }
+  const long long dl = warp_sum_i64((long long)deaths);
+  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+  finish_kernel(t, b.slot);
+}
+
+// Any W: the touched word columns of OBP_BS terms are staged in shared memory ([slot][thread], so
+// every gate step is bank-conflict free), all gates of the batch are applied there, and the
+// columns are written back.  Dynamic smem: nslots * OBP_BS * 16 B.
+__global__ void __launch_bounds__(OBP_BS) k_clifford_smem(Tab t, const __grid_constant__ CliffBatch b) {
+  extern __shared__ ulonglong2 s_key[];
+  const u64 n = t.st->n_scan;
+  int deaths = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c)) continue;
+    if (hypot(c.x, c.y) * b.scale <= b.atol) {
+      t.coef[i] = tombstone(b.epoch);
+      deaths++;
+      continue;
+    }
+    for (int sl = 0; sl < b.nslots; ++sl) s_key[sl * OBP_BS + threadIdx.x] = t.xz[b.word_of_slot[sl]][i];
+    unsigned sgn = 0;
+    for (int k = 0; k < b.ng; ++k) {
+      const CliffGate g = b.g[k];
+      ulonglong2 ka = s_key[g.sa * OBP_BS + threadIdx.x];
+      if (g.nq == 2 && g.sb != g.sa) {
+        ulonglong2 kb = s_key[g.sb * OBP_BS + threadIdx.x];
+        const unsigned d = cliff_apply_bits(g, ka.x, ka.y, kb.x, kb.y, sgn);
+        ka.x ^= (u64)(d & 1u) << g.ba;
+        ka.y ^= (u64)((d >> 1) & 1u) << g.ba;
+        kb.x ^= (u64)((d >> 2) & 1u) << g.bb;
+        kb.y ^= (u64)((d >> 3) & 1u) << g.bb;
+        s_key[g.sb * OBP_BS + threadIdx.x] = kb;
+      } else {
+        const unsigned d = cliff_apply_bits(g, ka.x, ka.y, ka.x, ka.y, sgn);
+        ka.x ^= ((u64)(d & 1u) << g.ba) ^ ((u64)((d >> 2) & 1u) << g.bb);
+        ka.y ^= ((u64)((d >> 1) & 1u) << g.ba) ^ ((u64)((d >> 3) & 1u) << g.bb);
+      }
+      s_key[g.sa * OBP_BS + threadIdx.x] = ka;
+    }
+    for (int sl = 0; sl < b.nslots; ++sl) t.xz[b.word_of_slot[sl]][i] = s_key[sl * OBP_BS + threadIdx.x];
+    if (sgn) t.coef[i] = make_double2(-c.x, -c.y);
+  }
+  const long long dl = warp_sum_i64((long long)deaths);
+  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+  finish_kernel(t, b.slot);
+}
+
+// ================================================================================================
+// k_coset_count — exact simplify counters of a Clifford-class gate (run before the gate).
+// The k*k raw rows of a surviving term P carry the keys P ^ D, D in the group D of the gate's
+// Pauli differences.  num_unique = |D| * (number of cosets of D hit by the surviving terms); each
+// row counts how many live, surviving members its coset has, the host sums N_cnt / cnt.
+// ================================================================================================
+struct CosetP {
+  int nd;             // |D| - 1
+  int wa, ba, wb, bb; // word / bit of the gate's qubits (wb = -1 for one-qubit gates)
+  unsigned code[15];  // D members: x_a | z_a<<1 | x_b<<2 | z_b<<3
+  u64 hD[15];
+  double scale, atol;
+  int slot;
+};
+
+__global__ void __launch_bounds__(OBP_BS) k_coset_count(Tab t, const __grid_constant__ CosetP p) {
+  const u64 n = t.st->n_scan;
+  __shared__ unsigned s_cnt[17];
+  __shared__ unsigned s_surv;
+  if (threadIdx.x < 17) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_surv = 0;
+  __syncthreads();
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c) || hypot(c.x, c.y) * p.scale <= p.atol) continue;
+    int cnt = 1;
+    const u64 h = t.hash[i];
+    for (int d = 0; d < p.nd; ++d) {
+      const u64 mxa = (u64)(p.code[d] & 1u) << p.ba, mza = (u64)((p.code[d] >> 1) & 1u) << p.ba;
+      const u64 mxb = p.wb >= 0 ? (u64)((p.code[d] >> 2) & 1u) << p.bb : 0ull;
+      const u64 mzb = p.wb >= 0 ? (u64)((p.code[d] >> 3) & 1u) << p.bb : 0ull;
+      const u64 h2 = h ^ p.hD[d];
+      const u64 fp = h2 >> 32;
+      u64 s = h2 & t.mask;
+      for (u64 probes = 0; probes <= t.mask; ++probes) {
+        const u64 e = ld_volatile(&t.index[s]);
+        if (e == OBP_EMPTY) break;
+        if ((e >> 32) == fp) {
+          const u64 j = e & 0xffffffffull;
+          if (j < n && t.hash[j] == h2) {
+            bool eq = true;
+            for (int w = 0; w < t.W && eq; ++w) {
+              u64 mx = 0, mz = 0;
+              if (w == p.wa) { mx ^= mxa; mz ^= mza; }
+              if (w == p.wb) { mx ^= mxb; mz ^= mzb; }
+              const ulonglong2 ki = t.xz[w][i], kj = t.xz[w][j];
+              eq = (kj.x == (ki.x ^ mx)) && (kj.y == (ki.y ^ mz));
+            }
+            if (eq) {
+              const double2 cj = t.coef[j];
+              if (is_live(cj)) {
+                if (!(hypot(cj.x, cj.y) * p.scale <= p.atol)) cnt++;
+                break;
+              }
+            }
+          }
+        }
+        s = (s + 1) & t.mask;
+      }
+    }
+    atomicAdd(&s_cnt[cnt], 1u);
+    atomicAdd(&s_surv, 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 17 && s_cnt[threadIdx.x]) atomicAdd(&t.ops[p.slot].ncnt[threadIdx.x], (u64)s_cnt[threadIdx.x]);
+  if (threadIdx.x == 0 && s_surv) atomicAdd(&t.ops[p.slot].n_surv, (u64)s_surv);
+}
+
+// ================================================================================================
+// hashing and index (re)build
+// ================================================================================================
+// h = XOR of the hash-frame columns of the set key bits.  cols: [2*64*W] = x columns then z columns
+__global__ void __launch_bounds__(OBP_BS) k_hash_rows(Tab t, const u64* __restrict__ cols, u64 n) {
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    u64 h = 0;
+    for (int w = 0; w < t.W; ++w) {
+      const ulonglong2 key = t.xz[w][i];
+      u64 m = key.x;
+      while (m) { const int bpos = __ffsll((long long)m) - 1; h ^= cols[w * 64 + bpos]; m &= m - 1; }
+      m = key.y;
+      while (m) { const int bpos = __ffsll((long long)m) - 1; h ^= cols[(t.W + w) * 64 + bpos]; m &= m - 1; }
+    }
+    t.hash[i] = h;
+  }
+}
+
+// Insert every live row into the (cleared) index.  merge != 0: rows with equal keys are summed
+// into the first published one (fp64 atomicAdd; only reached for caller-supplied duplicates) and
+// rows with |c| <= atol (atol >= 0) are filtered first — the simplify() of a raw operator.
+__global__ void __launch_bounds__(OBP_BS) k_index_build(Tab t, int merge, double atol, u64 epoch, int slot) {
+  const u64 n = t.st->n_scan;
+  unsigned rows_surv = 0, published = 0;
+  int deaths = 0;
+  bool full = false;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c)) {
+      if (merge) deaths++;  // at load every uploaded row was counted live; exact zeros are not
+      continue;
+    }
+    if (merge && atol >= 0.0 && is_small(c, atol)) {
+      t.coef[i] = tombstone(epoch);
+      deaths++;
+      continue;
+    }
+    rows_surv++;
+    const u64 h = t.hash[i];
+    const u64 fp = h >> 32, entry = (fp << 32) | i;
+    u64 s = h & t.mask;
+    bool done = false;
+    for (u64 probes = 0; probes <= t.mask && !done; ++probes) {
+      u64 e = ld_volatile(&t.index[s]);
+      if (e == OBP_EMPTY) {
+        e = atomicCAS(&t.index[s], OBP_EMPTY, entry);
+        if (e == OBP_EMPTY) { published++; done = true; break; }
+      }
+      if (merge && (e >> 32) == fp) {
+        const u64 j = e & 0xffffffffull;
+        bool eq = t.hash[j] == h;
+        for (int w = 0; w < t.W && eq; ++w) {
+          const ulonglong2 ki = t.xz[w][i], kj = t.xz[w][j];
+          eq = (ki.x == kj.x) && (ki.y == kj.y);
+        }
+        if (eq) {
+          atomicAdd(&t.coef[j].x, c.x);
+          atomicAdd(&t.coef[j].y, c.y);
+          t.coef[i] = tombstone(epoch);
+          deaths++;
+          done = true;
+          break;
+        }
+      }
+      s = (s + 1) & t.mask;
+    }
+    if (!done) full = true;
+  }
+  if (full) atomicOr(&t.st->error, OBP_ERR_BIT_INDEX);
+  const long long dl = warp_sum_i64((long long)deaths);
+  const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(published);
+  if ((threadIdx.x & 31) == 0) {
+    if (dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+    if (slot >= 0) {
+      if (a) atomicAdd(&t.ops[slot].rows_surv, a);
+      if (b) atomicAdd(&t.ops[slot].keys_present, b);
+    }
+  }
+  finish_kernel(t, slot);
+}
+
+// Second zero filter of simplify(): kill merged rows with |sum| <= atol, count and sum them.
+__global__ void __launch_bounds__(OBP_BS) k_trim(Tab t, double atol, u64 epoch, int slot) {
+  const u64 n = t.st->n_scan;
+  unsigned cancelled = 0;
+  double sr = 0.0, si = 0.0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c)) continue;
+    if (is_small(c, atol)) {
+      t.coef[i] = tombstone(epoch);
+      cancelled++;
+      sr += c.x;
+      si += c.y;
+    }
+  }
+  const u64 cz = warp_sum_u64(cancelled);
+  sr = warp_sum_f64(sr);
+  si = warp_sum_f64(si);
+  if ((threadIdx.x & 31) == 0 && cz) {
+    atomicAdd(&t.st->n_live, (u64)(-(long long)cz));
+    if (slot >= 0) {
+      atomicAdd(&t.ops[slot].cancelled, cz);
+      atomicAdd(&t.ops[slot].sum_re, sr);
+      atomicAdd(&t.ops[slot].sum_im, si);
+    }
+  }
+  finish_kernel(t, slot);
+}
+
+// ================================================================================================
+// reset and Pauli-Lindblad damping
+// ================================================================================================
+// apply_reset_to (utils/operations.py:221-223) + simplify: rows with X/Y on the qubit vanish, Z
+// becomes I.  Clearing Z can collide with an existing key: the row that had Z looks the cleared key
+// up; if it is live the coefficient moves there (the partner row adds it — pair owned by the row
+// that has to move), else the row rewrites its own key/hash and is published under the new hash.
+struct ResetP {
+  int w;
+  u64 bit;
+  u64 hZ;  // hash column of z on that qubit
+  double atol;
+  u64 epoch;
+  int slot;
+};
+
+// phase 1: the raw-row zero filter — X/Y rows (coefficient set to 0) and rows with |c| <= atol die
+__global__ void __launch_bounds__(OBP_BS) k_reset_filter(Tab t, const __grid_constant__ ResetP p) {
+  const u64 n = t.st->n_scan;
+  unsigned rows_surv = 0;
+  int deaths = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c)) continue;
+    const ulonglong2 key = t.xz[p.w][i];
+    if ((key.x & p.bit) || is_small(c, p.atol)) {
+      t.coef[i] = tombstone(p.epoch);
+      deaths++;
+    } else {
+      rows_surv++;
+    }
+  }
+  const long long dl = warp_sum_i64((long long)deaths);
+  const u64 a = warp_sum_u64(rows_surv);
+  if ((threadIdx.x & 31) == 0) {
+    if (dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+    if (a) atomicAdd(&t.ops[p.slot].rows_surv, a);
+  }
+  finish_kernel(t, -1);
+}
+
+// phase 2: rows with Z on the qubit move to the cleared key.  Only those rows act: they either add
+// their coefficient to the live row that already holds the cleared key (exactly one Z row maps to
+// it, so each coefficient has one writer) or rewrite their own key/hash and publish the new hash.
+__global__ void __launch_bounds__(OBP_BS) k_reset_merge(Tab t, const __grid_constant__ ResetP p) {
+  const u64 n = t.st->n_scan;
+  unsigned keys_present = 0, cancelled = 0;
+  int deaths = 0;
+  double sr = 0.0, si = 0.0;
+  bool full = false;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    ulonglong2 key = t.xz[p.w][i];
+    if (!(key.y & p.bit)) {
+      // identity on the qubit (X/Y rows died in phase 1): key stays, counted unless it is merged away
+      const double2 ci = t.coef[i];  // live now, or cancelled by its Z partner in this phase
+      if (is_live(ci) || tomb_epoch(ci) == p.epoch) keys_present++;
+      continue;
+    }
+    const double2 c = t.coef[i];
+    if (!is_live(c)) continue;
+    const u64 h2 = t.hash[i] ^ p.hZ;
+    const u64 fp = h2 >> 32;
+    u64 s = h2 & t.mask;
+    long long j = -1;
+    for (u64 probes = 0; probes <= t.mask; ++probes) {
+      const u64 e = ld_volatile(&t.index[s]);
+      if (e == OBP_EMPTY) break;
+      if ((e >> 32) == fp) {
+        const u64 jj = e & 0xffffffffull;
+        if (jj < n && jj != i && t.hash[jj] == h2) {
+          bool eq = true;
+          for (int w = 0; w < t.W && eq; ++w) {
+            const ulonglong2 ki = t.xz[w][i], kj = t.xz[w][jj];
+            const u64 mz = (w == p.w) ? p.bit : 0ull;
+            eq = (kj.x == ki.x) && (kj.y == (ki.y ^ mz));
+          }
+          if (eq && is_live(t.coef[jj])) { j = (long long)jj; break; }
+        }
+      }
+      s = (s + 1) & t.mask;
+    }
+    if (j >= 0) {
+      const double2 sum = cadd(t.coef[j], c);
+      t.coef[i] = tombstone(p.epoch);
+      deaths++;
+      if (is_small(sum, p.atol)) {
+        // the partner row counted its key as present; it is present but cancels
+        t.coef[j] = tombstone(p.epoch);
+        deaths++;
+        cancelled++;
+        sr += sum.x;
+        si += sum.y;
+      } else {
+        t.coef[j] = sum;
+      }
+    } else {
+      key.y ^= p.bit;
+      t.xz[p.w][i] = key;
+      t.hash[i] = h2;
+      if (!index_insert(t, h2, i)) full = true;
+      keys_present++;
+    }
+  }
+  if (full) atomicOr(&t.st->error, OBP_ERR_BIT_INDEX);
+  const long long dl = warp_sum_i64((long long)deaths);
+  const u64 b = warp_sum_u64(keys_present), cz = warp_sum_u64(cancelled);
+  sr = warp_sum_f64(sr);
+  si = warp_sum_f64(si);
+  if ((threadIdx.x & 31) == 0) {
+    if (dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+    OpStat* o = &t.ops[p.slot];
+    if (b) atomicAdd(&o->keys_present, b);
+    if (cz) { atomicAdd(&o->cancelled, cz); atomicAdd(&o->sum_re, sr); atomicAdd(&o->sum_im, si); }
+  }
+  finish_kernel(t, p.slot);
+}
+
+// apply_ple_to (utils/operations.py:267-273) + simplify: c *= prod_g factor[g] over anticommuting
+// generators (applied in generator order, like the reference's loop), then the zero filter.
+// gens: [n_gens][2*W] = x words then z words.
+__global__ void __launch_bounds__(OBP_BS) k_damp(Tab t, const u64* __restrict__ gens,
+                                                  const double* __restrict__ factors, int n_gens,
+                                                  double atol, u64 epoch, int slot) {
+  const u64 n = t.st->n_scan;
+  int deaths = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    double2 c = t.coef[i];
+    if (!is_live(c)) continue;
+    bool changed = false;
+    for (int g = 0; g < n_gens; ++g) {
+      int par = 0;
+      for (int w = 0; w < t.W; ++w) {
+        const ulonglong2 key = t.xz[w][i];
+        par += __popcll(key.x & gens[(size_t)g * 2 * t.W + t.W + w]) + __popcll(key.y & gens[(size_t)g * 2 * t.W + w]);
+      }
+      if (par & 1) {
+        c.x = __dmul_rn(c.x, factors[g]);
+        c.y = __dmul_rn(c.y, factors[g]);
+        changed = true;
+      }
+    }
+    if (is_small(c, atol)) {
+      t.coef[i] = tombstone(epoch);
+      deaths++;
+    } else if (changed) {
+      t.coef[i] = c;
+    }
+  }
+  const long long dl = warp_sum_i64((long long)deaths);
+  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+  finish_kernel(t, slot);
+}
+
+// ================================================================================================
+// truncation (utils/truncating.py:171-204)
+// ================================================================================================
+// a[i] = |c_i|^p for live rows, -1 for tombstones; global max through atomicMax on the bit pattern
+__global__ void __launch_bounds__(OBP_BS) k_absp(Tab t, double* __restrict__ a, int p_norm) {
+  const u64 n = t.st->n_scan;
+  double mx = 0.0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    double v = -1.0;
+    if (is_live(c)) {
+      const double r = hypot(c.x, c.y);
+      v = p_norm == 1 ? r : (p_norm == 2 ? __dmul_rn(r, r) : pow(r, (double)p_norm));
+      mx = fmax(mx, v);
+    }
+    a[i] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(&t.st->amax_bits, (u64)__double_as_longlong(mx));
+}
+
+// partial[b] = sum of a[i] with 0 <= a[i] < mid over the rows of CTA b (fixed reduction tree)
+__global__ void __launch_bounds__(OBP_BS) k_masked_sum(const double* __restrict__ a, const DevState* st,
+                                                        double mid, double* __restrict__ partial) {
+  __shared__ double s_w[OBP_BS / 32];
+  const u64 n = st->n_scan;
+  double acc = 0.0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double v = a[i];
+    if (v >= 0.0 && v < mid) acc += v;
+  }
+  acc = warp_sum_f64(acc);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < OBP_BS / 32; ++w) tot += s_w[w];
+    partial[blockIdx.x] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(OBP_BS) k_final_sum(const double* __restrict__ partial, int nb,
+                                                       double* __restrict__ out) {
+  __shared__ double s_w[OBP_BS / 32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nb; i += OBP_BS) acc += partial[i];
+  acc = warp_sum_f64(acc);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < OBP_BS / 32; ++w) tot += s_w[w];
+    *out = tot;
+  }
+}
+
+// keep a > thr (strict), tombstone the rest
+__global__ void __launch_bounds__(OBP_BS) k_trunc_kill(Tab t, const double* __restrict__ a, double thr, u64 epoch) {
+  const u64 n = t.st->n_scan;
+  unsigned removed = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double v = a[i];
+    if (v >= 0.0 && !(v > thr)) {
+      t.coef[i] = tombstone(epoch);
+      removed++;
+    }
+  }
+  const u64 r = warp_sum_u64(removed);
+  if ((threadIdx.x & 31) == 0 && r) {
+    atomicAdd(&t.st->removed, r);
+    atomicAdd(&t.st->n_live, (u64)(-(long long)r));
+  }
+}
+
+// ================================================================================================
+// stable compaction: per-CTA live counts -> exclusive scan -> destination ids -> column scatters
+// ================================================================================================
+#define OBP_CHUNK 1024  // rows per CTA (4 rounds of OBP_BS)
+
+__global__ void __launch_bounds__(OBP_BS) k_live_count(Tab t, unsigned* __restrict__ blk_cnt) {
+  __shared__ unsigned warp_tot[OBP_BS / 32];
+  const u64 n = t.st->n_scan;
+  const u64 base = (u64)blockIdx.x * OBP_CHUNK;
+  unsigned cnt = 0;
+#pragma unroll
+  for (int r = 0; r < OBP_CHUNK / OBP_BS; ++r) {
+    const u64 i = base + (u64)r * OBP_BS + threadIdx.x;
+    if (i < n && is_live(t.coef[i])) cnt++;
+  }
+  cnt = (unsigned)warp_sum_u64(cnt);
+  if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+#pragma unroll
+    for (int w = 0; w < OBP_BS / 32; ++w) tot += warp_tot[w];
+    blk_cnt[blockIdx.x] = tot;
+  }
+}
+
+// single CTA: exclusive scan of nb counts in place, total -> st->scan_total
+__global__ void __launch_bounds__(1024) k_scan_blocks(unsigned* __restrict__ blk, u64 nb, DevState* st) {
+  __shared__ u64 s_part[1024];
+  __shared__ u64 s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (u64 base = 0; base < nb; base += 1024) {
+    const u64 i = base + threadIdx.x;
+    const u64 v = i < nb ? blk[i] : 0;
+    s_part[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+      const u64 add = threadIdx.x >= (unsigned)off ? s_part[threadIdx.x - off] : 0;
+      __syncthreads();
+      s_part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    const u64 incl = s_part[threadIdx.x];
+    if (i < nb) blk[i] = (unsigned)(s_carry + incl - v);
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st->scan_total = s_carry;
+}
+
+__global__ void __launch_bounds__(OBP_BS) k_dest(Tab t, const unsigned* __restrict__ blk_off,
+                                                  unsigned* __restrict__ dest) {
+  __shared__ unsigned warp_tot[OBP_BS / 32];
+  const u64 n = t.st->n_scan;
+  const u64 base = (u64)blockIdx.x * OBP_CHUNK;
+  unsigned run = blk_off[blockIdx.x];
+#pragma unroll 1
+  for (int r = 0; r < OBP_CHUNK / OBP_BS; ++r) {
+    const u64 i = base + (u64)r * OBP_BS + threadIdx.x;
+    const bool live = i < n && is_live(t.coef[i]);
+    unsigned total;
+    const unsigned off = block_scan_flag(live, warp_tot, total);
+    if (i < n) dest[i] = live ? run + off : 0xffffffffu;
+    run += total;
+  }
+}
+
+__global__ void __launch_bounds__(OBP_BS) k_scatter16(const ulonglong2* __restrict__ src, ulonglong2* __restrict__ dst,
+                                                       const unsigned* __restrict__ dest, const DevState* st) {
+  const u64 n = st->n_scan;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const unsigned d = dest[i];
+    if (d != 0xffffffffu) dst[d] = src[i];
+  }
+}
+__global__ void __launch_bounds__(OBP_BS) k_scatter8(const u64* __restrict__ src, u64* __restrict__ dst,
+                                                      const unsigned* __restrict__ dest, const DevState* st) {
+  const u64 n = st->n_scan;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const unsigned d = dest[i];
+    if (d != 0xffffffffu) dst[d] = src[i];
+  }
+}
+__global__ void k_set_counts(DevState* st) {
+  const u64 tot = st->scan_total;
+  st->n_scan = tot;
+  st->n_append = tot;
+  st->n_live = tot;
+}
+
+// ================================================================================================
+// union count over several tables (backpropagation.py:419-428): copy keys into one scratch table
+// ================================================================================================
+__global__ void __launch_bounds__(OBP_BS) k_copy_live_keys(Tab src, Tab dst, u64 dst_off) {
+  // src must be compact (no tombstones); copies keys and gives every row coefficient 1
+  const u64 n = src.st->n_scan;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    for (int w = 0; w < src.W; ++w) dst.xz[w][dst_off + i] = src.xz[w][i];
+    dst.coef[dst_off + i] = make_double2(1.0, 0.0);
+  }
+}

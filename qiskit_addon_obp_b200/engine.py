@@ -1,0 +1,377 @@
+"""ctypes binding of ``libobp_b200.so`` (C-ABI: ``include/obp_b200.h``) and the ``TermTable`` wrapper.
+
+There is no CPU fallback: if the shared library is missing or no sm_100a device is present, every
+entry point raises.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from contextlib import contextmanager
+
+import numpy as np
+
+from .ir import SparsePauliOp, pack_xz, unpack_xz
+from .utils.simplify import SimplifyMetadata
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libobp_b200.so")
+
+OBP_OK = 0
+OBP_ERR_CAPACITY = -4
+OBP_OP_CLIFFORD = 1
+OBP_OP_ROTATION = 2
+OBP_FLAG_EXACT_COUNTERS = 1
+OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other")
+
+#: numpy mirror of ``obp_op`` (104 bytes, natural C alignment)
+OP_DTYPE = np.dtype(
+    [
+        ("kind", "<i4"),
+        ("n_qubits", "<i4"),
+        ("qubit", "<i4", (4,)),
+        ("flags", "<u4"),
+        ("n_components", "<u4"),
+        ("lut", "<u8"),
+        ("sign_mask", "<u4"),
+        ("group_size", "<u4"),
+        ("group_elems", "<u8"),
+        ("row_scale", "<f8"),
+        ("gen_local", "<u4"),
+        ("reserved", "<u4"),
+        ("u0", "<f8", (2,)),
+        ("u1", "<f8", (2,)),
+    ],
+    align=True,
+)
+assert OP_DTYPE.itemsize == 104
+
+
+class ObpStats(C.Structure):
+    _fields_ = [
+        ("n_in", C.c_uint64),
+        ("raw_rows", C.c_uint64),
+        ("num_unique", C.c_uint64),
+        ("num_duplicate", C.c_uint64),
+        ("num_trimmed", C.c_uint64),
+        ("sum_trimmed", C.c_double * 2),
+        ("n_out", C.c_uint64),
+        ("n_dense", C.c_uint64),
+        ("updates", C.c_uint64),
+    ]
+
+
+class ObpProfile(C.Structure):
+    _fields_ = [
+        ("launches", C.c_uint64 * 6),
+        ("ms", C.c_double * 6),
+        ("term_updates", C.c_uint64 * 6),
+    ]
+
+
+class EngineError(RuntimeError):
+    """A CUDA or engine failure reported through the C-ABI."""
+
+
+class CapacityError(MemoryError):
+    """The device term table (or its index) is full; the table must be restored and grown."""
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load ``libobp_b200.so`` once; raise loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} not found: the CUDA extension is not built. There is no CPU fallback; "
+            'run `python -c "import __graft_entry__ as g; g.build()"` at the repository root.'
+        )
+    L = C.CDLL(_LIB_PATH)
+    vp, u64p, f64p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    sig = {
+        "obp_create": ([C.c_int, C.c_int, C.c_uint64, C.POINTER(vp)], C.c_int),
+        "obp_destroy": ([vp], None),
+        "obp_last_error": ([vp], C.c_char_p),
+        "obp_set_stream": ([vp, vp], C.c_int),
+        "obp_device_memory": ([C.c_int, u64p, u64p], C.c_int),
+        "obp_bytes_per_term": ([C.c_int], C.c_uint64),
+        "obp_load": ([vp, vp, vp, vp, C.c_uint64, C.c_double, C.POINTER(ObpStats)], C.c_int),
+        "obp_count": ([vp, u64p], C.c_int),
+        "obp_download": ([vp, vp, vp, vp, C.c_uint64, u64p], C.c_int),
+        "obp_apply_ops": ([vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
+        "obp_apply_reset": ([vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
+        "obp_apply_damping": ([vp, vp, vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
+        "obp_truncate": ([vp, C.c_double, C.c_int32, C.c_double, f64p, u64p, u64p], C.c_int),
+        "obp_union_count": ([C.POINTER(vp), C.c_int32, u64p], C.c_int),
+        "obp_snapshot": ([vp], C.c_int),
+        "obp_restore": ([vp], C.c_int),
+        "obp_reserve": ([vp, C.c_uint64], C.c_int),
+        "obp_profile_enable": ([vp, C.c_int32], C.c_int),
+        "obp_profile_get": ([vp, C.POINTER(ObpProfile), C.c_int32], C.c_int),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "obp_create obp_destroy obp_last_error obp_set_stream obp_device_memory obp_bytes_per_term "
+    "obp_load obp_count obp_download obp_apply_ops obp_apply_reset obp_apply_damping obp_truncate "
+    "obp_union_count obp_snapshot obp_restore obp_reserve obp_profile_enable obp_profile_get"
+).split()
+
+
+def device_memory(device: int = 0) -> tuple[int, int]:
+    free, total = C.c_uint64(), C.c_uint64()
+    rc = lib().obp_device_memory(device, C.byref(free), C.byref(total))
+    if rc != OBP_OK:
+        raise EngineError((lib().obp_last_error(None) or b"").decode())
+    return free.value, total.value
+
+
+def default_device() -> int:
+    """One process per GPU: LOCAL_RANK selects the device (``torchrun`` sets it)."""
+    return int(os.environ.get("OBP_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+class TermTable:
+    """One observable as a device-resident table of packed Pauli keys and complex128 coefficients."""
+
+    def __init__(self, num_qubits: int, capacity: int, device: int | None = None):
+        self._lib = lib()
+        self.num_qubits = int(num_qubits)
+        self.words = max(1, (self.num_qubits + 63) // 64)
+        self.capacity = int(capacity)
+        self.device = default_device() if device is None else int(device)
+        self._h = C.c_void_p()
+        rc = self._lib.obp_create(self.device, self.num_qubits, self.capacity, C.byref(self._h))
+        if rc != OBP_OK:
+            msg = (self._lib.obp_last_error(None) or b"").decode()
+            self._h = C.c_void_p()
+            raise (MemoryError if rc == -3 else EngineError)(f"obp_create failed ({rc}): {msg}")
+        self.n = 0  # live terms
+        self.n_dense = 0
+        self.zero_operator = False  # simplify.py:156-159: everything trimmed -> one identity row, coeff 0
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc == OBP_OK:
+            return
+        msg = (self._lib.obp_last_error(self._h) or b"").decode()
+        if rc == OBP_ERR_CAPACITY:
+            raise CapacityError(f"{what}: {msg}")
+        raise EngineError(f"{what} failed ({rc}): {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.obp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._lib.obp_set_stream(self._h, C.c_void_p(cuda_stream or 0)), "obp_set_stream")
+
+    def __len__(self) -> int:
+        return 1 if self.zero_operator else self.n
+
+    # -- I/O ----------------------------------------------------------------------------------
+    def load(self, op: SparsePauliOp, atol: float | None = None) -> ObpStats:
+        """Upload ``op``; ``atol=None`` merges duplicate rows only, a float runs the full simplify."""
+        if op.num_qubits != self.num_qubits:
+            raise ValueError("operator width does not match the table")
+        if len(op) > self.capacity:
+            self.reserve(2 * len(op))
+        xw, zw = pack_xz(op.x, op.z)
+        coeffs = np.ascontiguousarray(op.coeffs, dtype=np.complex128)
+        st = ObpStats()
+        rc = self._lib.obp_load(
+            self._h,
+            xw.ctypes.data_as(C.c_void_p),
+            zw.ctypes.data_as(C.c_void_p),
+            coeffs.ctypes.data_as(C.c_void_p),
+            len(op),
+            -1.0 if atol is None else float(atol),
+            C.byref(st),
+        )
+        self._check(rc, "obp_load")
+        self.n, self.n_dense = st.n_out, st.n_dense
+        self.zero_operator = atol is not None and self.n == 0
+        return st
+
+    def download(self) -> SparsePauliOp:
+        if self.zero_operator:
+            z = np.zeros((1, self.num_qubits), dtype=bool)
+            return SparsePauliOp((z.copy(), z), np.array([0j]))
+        n = self.n
+        xw = np.zeros((max(n, 1), self.words), dtype="<u8")
+        zw = np.zeros((max(n, 1), self.words), dtype="<u8")
+        co = np.zeros(max(n, 1), dtype=np.complex128)
+        got = C.c_uint64()
+        rc = self._lib.obp_download(
+            self._h,
+            xw.ctypes.data_as(C.c_void_p),
+            zw.ctypes.data_as(C.c_void_p),
+            co.ctypes.data_as(C.c_void_p),
+            max(n, 1),
+            C.byref(got),
+        )
+        self._check(rc, "obp_download")
+        n = got.value
+        self.n = self.n_dense = n
+        x, z = unpack_xz(xw[:n], zw[:n], self.num_qubits)
+        return SparsePauliOp((x, z), co[:n])
+
+    to_operator = download
+
+    # -- hot path -----------------------------------------------------------------------------
+    def apply_ops(self, ops: np.ndarray, atol: float) -> ObpStats:
+        """Run a gate program (array of ``OP_DTYPE``) on the table."""
+        st = ObpStats()
+        if self.zero_operator:
+            # the reference keeps conjugating the single zero row: every raw row is filtered
+            last = ops[-1]
+            k2 = int(last["n_components"]) ** 2
+            st.n_in, st.raw_rows, st.num_trimmed, st.n_out = 1, k2, k2, 1
+            st.updates = len(ops)
+            return st
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        rc = self._lib.obp_apply_ops(
+            self._h, ops.ctypes.data_as(C.c_void_p), len(ops), float(atol), C.byref(st)
+        )
+        self._check(rc, "obp_apply_ops")
+        self.n, self.n_dense = st.n_out, st.n_dense
+        if self.n == 0:
+            self.zero_operator = True
+        return st
+
+    def apply_reset(self, qubit: int, atol: float) -> ObpStats:
+        st = ObpStats()
+        if self.zero_operator:
+            st.n_in, st.raw_rows, st.num_trimmed, st.n_out, st.updates = 1, 1, 1, 1, 1
+            return st
+        self._check(self._lib.obp_apply_reset(self._h, int(qubit), float(atol), C.byref(st)), "obp_apply_reset")
+        self.n, self.n_dense = st.n_out, st.n_dense
+        if self.n == 0:
+            self.zero_operator = True
+        return st
+
+    def apply_damping(self, gen_x: np.ndarray, gen_z: np.ndarray, factors: np.ndarray, atol: float) -> ObpStats:
+        st = ObpStats()
+        if self.zero_operator:
+            st.n_in, st.raw_rows, st.num_trimmed, st.n_out, st.updates = 1, 1, 1, 1, 1
+            return st
+        gxw, gzw = pack_xz(gen_x, gen_z)
+        factors = np.ascontiguousarray(factors, dtype=np.float64)
+        rc = self._lib.obp_apply_damping(
+            self._h,
+            gxw.ctypes.data_as(C.c_void_p),
+            gzw.ctypes.data_as(C.c_void_p),
+            factors.ctypes.data_as(C.c_void_p),
+            len(factors),
+            float(atol),
+            C.byref(st),
+        )
+        self._check(rc, "obp_apply_damping")
+        self.n, self.n_dense = st.n_out, st.n_dense
+        if self.n == 0:
+            self.zero_operator = True
+        return st
+
+    def truncate(self, budget: float, p_norm: int, tol: float) -> tuple[float, int]:
+        """Returns ``(slice_error, n_removed)``."""
+        if self.zero_operator:
+            # |0|**p == max == 0: the search loop never runs and `0 > 0` keeps nothing; the
+            # reference then holds an empty operator
+            self.zero_operator = False
+            self.n = 0
+            return 0.0, 1
+        err, rem, out = C.c_double(), C.c_uint64(), C.c_uint64()
+        rc = self._lib.obp_truncate(
+            self._h, float(budget), int(p_norm), float(tol), C.byref(err), C.byref(rem), C.byref(out)
+        )
+        self._check(rc, "obp_truncate")
+        self.n = self.n_dense = out.value
+        return err.value, rem.value
+
+    def snapshot(self):
+        self._snap_zero = self.zero_operator
+        self._snap_n = self.n
+        self._check(self._lib.obp_snapshot(self._h), "obp_snapshot")
+        self.n_dense = self.n
+
+    def restore(self):
+        self._check(self._lib.obp_restore(self._h), "obp_restore")
+        self.zero_operator = self._snap_zero
+        self.n = self.n_dense = self._snap_n
+
+    def reserve(self, capacity: int):
+        self._check(self._lib.obp_reserve(self._h, int(capacity)), "obp_reserve")
+        self.capacity = max(self.capacity, int(capacity))
+
+    # -- measurement --------------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self._check(self._lib.obp_profile_enable(self._h, int(on)), "obp_profile_enable")
+
+    def profile(self, reset: bool = False) -> dict:
+        p = ObpProfile()
+        self._check(self._lib.obp_profile_get(self._h, C.byref(p), int(reset)), "obp_profile_get")
+        return {
+            name: {"launches": int(p.launches[k]), "ms": float(p.ms[k]), "term_updates": int(p.term_updates[k])}
+            for k, name in enumerate(OBP_K_NAMES)
+        }
+
+    # -- constructors used by the utils API ------------------------------------------------
+    @classmethod
+    @contextmanager
+    def from_operator(cls, op: SparsePauliOp, capacity: int | None = None):
+        table = cls(op.num_qubits, capacity or max(1024, 2 * len(op)))
+        try:
+            table.load(op)
+            yield table
+        finally:
+            table.close()
+
+    @classmethod
+    @contextmanager
+    def from_rows(cls, op: SparsePauliOp, atol: float):
+        """Load raw rows with the full simplify semantics; yields ``(table, SimplifyMetadata)``."""
+        table = cls(op.num_qubits, max(1024, 2 * len(op)))
+        try:
+            st = table.load(op, atol=atol)
+            s = complex(st.sum_trimmed[0], st.sum_trimmed[1])
+            md = SimplifyMetadata(
+                num_unique_paulis=int(st.num_unique),
+                num_duplicate_paulis=int(st.num_duplicate),
+                num_trimmed_paulis=int(st.num_trimmed),
+                sum_trimmed_coeffs=s if s != 0 else 0.0,
+            )
+            yield table, md
+        finally:
+            table.close()
+
+
+def union_count(tables: list[TermTable]) -> int:
+    """Distinct Pauli keys over several tables (``backpropagation.py:419-428``)."""
+    arr = (C.c_void_p * len(tables))(*[t._h for t in tables])
+    out = C.c_uint64()
+    rc = lib().obp_union_count(arr, len(tables), C.byref(out))
+    tables[0]._check(rc, "obp_union_count")
+    return int(out.value)
