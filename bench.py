@@ -1,0 +1,368 @@
+"""Benchmark of the operator-backpropagation hot path (BASELINE.json metric: Pauli term-gate updates/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--workload NAME]
+
+One *step* = one full ``backpropagate()`` of the workload (default: BASELINE config 2, the 127-qubit
+heavy-hex kicked-Ising circuit, Z_62, 20 Trotter steps, ``max_paulis=1e6``; the call runs until the
+operator budget stops it).  One *term-gate update* = one (Pauli term, applied gate) pair, counted with
+the term count at gate entry.
+
+Engine arm (default) prints one JSON line with
+  value       updates/s over the device-resident region (CUDA events from after the observable upload
+              to before the result download, max over ranks),
+  e2e         updates/s through the public ``backpropagate()`` call with host buffers (upload, host
+              gate classification, kernels, download and unpacking all inside the timed region),
+  roofline    the dominant kernel (k_rotate) against the measured HBM peak,
+  cpu_baseline  the numpy oracle port on a bounded sample of the same workload (rank 0, N=1 only).
+``--impl reference`` times the reference's CPU algorithm (the oracle port: Qiskit is not installable
+here) on the host cores, on the same workload, each step a bounded sample.
+
+N > 1 (torchrun): every rank backpropagates its own observable of the workload (independent
+observables partition the path with no data-path collective): weak scaling.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pauli_term_gate_updates_per_s"
+UNIT = "updates/s"
+L2_BYTES = 126 << 20
+
+
+def algorithmic_bytes_per_update(num_qubits: int) -> int:
+    """B_tg = 2*(16*W + 16): read the packed key + complex128 coefficient once, write them once."""
+    w = (num_qubits + 63) // 64
+    return 2 * (16 * w + 16)
+
+
+def make_workload(name: str, rank: int, args):
+    from qiskit_addon_obp_b200 import workloads as wl
+
+    if name == "config2":
+        # rank r measures Z on a different heavy-hex qubit (independent observables)
+        qubits = [62, 64, 43, 81, 24, 100, 45, 83]
+        return wl.config2_kicked_ising(
+            theta_h=args.theta, steps=20, max_paulis=args.max_paulis, observable_qubit=qubits[rank % len(qubits)]
+        )
+    if name == "config1":
+        return wl.config1_xy_chain()
+    if name == "config3":
+        return wl.config3_square_lattice(max_paulis=args.max_paulis)
+    if name == "config4":
+        return wl.config4_near_clifford(max_paulis=args.max_paulis, seed=20261019 + rank)
+    if name == "config5":
+        return wl.config5_magic_sweep(theta=args.theta, max_paulis=args.max_paulis, seed=rank)
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = (
+        "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, device: int):
+        self.device = device
+        self.samples: list[list[str]] = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) == 6:
+                self.samples.append(parts)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, s[2:]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: the oracle port on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(wl, max_updates: int) -> tuple[int, float]:
+    from oracle import obp_oracle
+
+    trace = obp_oracle.GateTrace()
+    t0 = time.perf_counter()
+    obp_oracle.backpropagate(wl.observables, wl.slices, trace=trace, max_updates=max_updates, **wl.kwargs())
+    return trace.updates, time.perf_counter() - t0
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    wl = make_workload(args.workload, 0, args)
+    cap = args.cpu_updates
+    for _ in range(args.warmup):
+        cpu_sample(wl, max(1000, cap // 20))
+    tot_u, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        u, t = cpu_sample(wl, cap)
+        tot_u += u
+        tot_t += t
+    value = tot_u / tot_t
+    sample = f"first {tot_u // max(1, args.steps)} term-gate updates of the workload per step (oracle stopped by max_updates)"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "complex128 (f64) coefficients, bool keys",
+        "data": "synthetic",
+        "config": {"workload": wl.name, "theta_h": args.theta, "max_paulis": args.max_paulis},
+        "cpu_baseline": {
+            "value": value,
+            "unit": UNIT,
+            "cores": 1,
+            "kind": "port",
+            "sample": sample,
+            "note": "numpy restatement of the reference loop (Qiskit not installable offline); single-threaded like the reference",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# engine arm
+# ---------------------------------------------------------------------------------------------
+def flush_l2(torch, device, buf):
+    buf.add_(1)  # writes 256 MiB > 126 MB L2
+    torch.cuda.synchronize(device)
+
+
+def run_engine(args, rank: int, local_rank: int, world: int) -> None:
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference)")
+    os.environ["OBP_B200_DEVICE"] = str(local_rank)
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from qiskit_addon_obp_b200 import backpropagate
+    from qiskit_addon_obp_b200 import backpropagation as bpmod
+
+    bpmod.PROFILE = True
+    wl = make_workload(args.workload, rank, args)
+    flush_buf = torch.zeros(256 << 20, dtype=torch.uint8, device=device)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    def one_step():
+        flush_l2(torch, device, flush_buf)
+        t0 = time.perf_counter()
+        out, rest, md = backpropagate(wl.observables, wl.slices, **wl.kwargs())
+        torch.cuda.synchronize(device)
+        return time.perf_counter() - t0, out, md
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e2e_s, dev_ms, updates = 0.0, 0.0, 0
+    h2d = d2h = 0
+    prof_tot: dict = {}
+    n_out = n_slices = 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        dt, out, md = one_step()
+        r = bpmod.last_run
+        e2e_s += dt
+        dev_ms += r.device_ms
+        updates += r.updates
+        h2d += r.h2d_bytes
+        d2h += r.d2h_bytes
+        for k, v in (r.profile or {}).items():
+            acc = prof_tot.setdefault(k, {"launches": 0, "ms": 0.0, "term_updates": 0})
+            for f in acc:
+                acc[f] += v[f]
+        n_out = len(out) if not isinstance(out, list) else sum(len(o) for o in out)
+        n_slices = md.num_backpropagated_slices
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks of the times, sum over ranks of the work
+    stats = torch.tensor([e2e_s, dev_ms, float(updates), float(h2d), float(d2h)], dtype=torch.float64, device=device)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_s, dev_ms = float(mx[0]), float(mx[1])
+        updates_all, h2d_all, d2h_all = float(sm[2]), float(sm[3]), float(sm[4])
+    else:
+        updates_all, h2d_all, d2h_all = float(updates), float(h2d), float(d2h)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        btg = algorithmic_bytes_per_update(wl.num_qubits)
+        rot = prof_tot.get("rotate", {"launches": 0, "ms": 0.0, "term_updates": 0})
+        achieved = (rot["term_updates"] * btg / (rot["ms"] * 1e-3) / 1e9) if rot["ms"] > 0 else None
+        kernel_ms = {k: round(v["ms"] / max(1, args.steps), 3) for k, v in prof_tot.items()}
+        launches = int(sum(v["launches"] for v in prof_tot.values()) / max(1, args.steps))
+        line = {
+            "metric": METRIC,
+            "value": updates_all / (dev_ms * 1e-3),
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": dev_ms / max(1, args.steps),
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "u64 keys + f64 complex coefficients",
+            "data": "synthetic",
+            "config": {
+                "workload": wl.name,
+                "theta_h": args.theta,
+                "max_paulis": args.max_paulis,
+                "slices_absorbed": n_slices,
+                "terms_out": n_out,
+                "updates_per_step": updates_all / max(1, args.steps),
+                "parallelism": f"{world} independent observables, one per GPU" if world > 1 else "1 GPU",
+                "l2": "256 MiB buffer rewritten before every step (L2 flush)",
+            },
+            "e2e": {
+                "value": updates_all / e2e_s,
+                "unit": UNIT,
+                "ms_per_step": 1e3 * e2e_s / max(1, args.steps),
+                "h2d_bytes_per_step": h2d_all / max(1, args.steps),
+                "d2h_bytes_per_step": d2h_all / max(1, args.steps),
+            },
+            "gpu_launches": launches,
+            "kernel_ms_per_step": kernel_ms,
+            "roofline": {
+                "kernel": "k_rotate",
+                "bound": "hbm",
+                "achieved": achieved,
+                "peak": peak,
+                "peak_source": peak_src,
+                "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None,
+                "frac_of_nominal_8000": (achieved / 8000.0) if achieved else None,
+                "bytes_per_term_gate_update": btg,
+                "launches": rot["launches"],
+                "avg_launch_ms": rot["ms"] / max(1, rot["launches"]),
+                "traffic": None,
+            },
+            "clocks": clocks,
+            "wall_s": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            u, t = cpu_sample(wl, args.cpu_updates)
+            line["cpu_baseline"] = {
+                "value": u / t,
+                "unit": UNIT,
+                "cores": 1,
+                "kind": "port",
+                "sample": f"first {u} term-gate updates of the same workload ({t:.1f} s of the numpy oracle port, 1 thread)",
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["engine", "reference"], default="engine")
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--theta", type=float, default=float(np.pi / 4))
+    ap.add_argument("--max-paulis", type=int, default=1_000_000)
+    ap.add_argument("--cpu-updates", type=int, default=600_000, help="bound of the CPU sample (term-gate updates)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_engine(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

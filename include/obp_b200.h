@@ -156,6 +156,11 @@ typedef struct {
 int obp_profile_enable(obp_ctx* ctx, int32_t on);
 int obp_profile_get(obp_ctx* ctx, obp_profile* out, int32_t reset);
 
+/* Device-side stopwatch on the context's stream (CUDA events): start records an event, stop records
+ * a second one, synchronises and returns the elapsed milliseconds between them. */
+int obp_timer_start(obp_ctx* ctx);
+int obp_timer_stop(obp_ctx* ctx, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,14 @@ class RunInfo:
 
     updates = 0  # term-gate updates: sum over applied gates of the term count at gate entry
     applied_gates = 0
-    profile: dict | None = None
+    device_ms = 0.0  # CUDA-event time from the first table load to just before the download
+    h2d_bytes = 0  # packed keys + coefficients uploaded
+    d2h_bytes = 0  # packed keys + coefficients downloaded
+    profile: dict | None = None  # per kernel class: launches, ms, term_updates (PROFILE only)
+
+
+#: set True (bench.py does) to bracket every kernel launch with CUDA events
+PROFILE = False
 
 
 last_run = RunInfo()
@@ -157,6 +164,9 @@ def backpropagate(
                     if non_trivial:
                         if not loaded[i]:
                             tables[i].load(obs_in[i])
+                            info.h2d_bytes += len(obs_in[i]) * (16 * tables[i].words + 16)
+                            tables[i].profile_enable(PROFILE)
+                            tables[i].timer_start()
                             tables[i].snapshot()
                             loaded[i] = True
                         while True:
@@ -232,13 +242,27 @@ def backpropagate(
             # after a break or a timeout the table holds an uncommitted slice: roll it back
             if len(metadata.backpropagation_history) != n_done:
                 tables[i].restore()
+            info.device_ms = max(info.device_ms, tables[i].timer_stop())
+            if PROFILE:
+                prof = tables[i].profile()
+                if info.profile is None:
+                    info.profile = prof
+                else:
+                    for k, v in prof.items():
+                        for f in v:
+                            info.profile[k][f] += v[f]
             obs_out.append(tables[i].download())
+            info.d2h_bytes += len(obs_out[-1]) * (16 * tables[i].words + 16)
     finally:
         for t in tables:
             t.close()
 
     last_run.updates = info.updates
     last_run.applied_gates = info.applied_gates
+    last_run.device_ms = info.device_ms
+    last_run.h2d_bytes = info.h2d_bytes
+    last_run.d2h_bytes = info.d2h_bytes
+    last_run.profile = info.profile
     obs_out = [restore_types(o) for o in obs_out]
     return (obs_out[0] if single else obs_out), slices_out, metadata
 

@@ -59,6 +59,7 @@ struct obp_ctx {
   std::vector<u64> hx, hz;
   bool cols_dirty = true;
   u64 epoch = 1;
+  size_t cliff_smem_optin = 48 * 1024;  // dynamic smem k_clifford_smem is opted in for
   u64 n_live = 0, n_dense = 0;
   Snapshot snap;
   obp_ctx* scratch = nullptr;  // union-count scratch table
@@ -66,6 +67,7 @@ struct obp_ctx {
   bool prof_on = false;
   obp_profile prof;
   std::vector<EventPair> ev_pending, ev_free;
+  cudaEvent_t tm_a = nullptr, tm_b = nullptr;
   std::string err;
 
   int fail(int code, const std::string& msg) {
@@ -466,6 +468,8 @@ void obp_destroy(obp_ctx* ctx) {
   if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
   for (auto& ep : ctx->ev_pending) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   for (auto& ep : ctx->ev_free) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+  if (ctx->tm_a) cudaEventDestroy(ctx->tm_a);
+  if (ctx->tm_b) cudaEventDestroy(ctx->tm_b);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -615,7 +619,7 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
   PendingBatch pb;
   pb.reset();
   Tab t = make_tab(ctx);
-  const size_t max_smem_slots = 32;
+  const size_t max_smem_slots = 32;  // 32 * 256 * 16 B = 128 KB of the 227 KB per CTA
 
   auto flush = [&]() -> int {
     if (pb.b.ng == 0) return OBP_OK;
@@ -635,6 +639,10 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
       else k_clifford_reg<2><<<g, OBP_BS, 0, ctx->stream>>>(t, pb.b);
     } else {
       const size_t smem = (size_t)pb.b.nslots * OBP_BS * sizeof(ulonglong2);
+      if (smem > ctx->cliff_smem_optin) {
+        CU(cudaFuncSetAttribute(k_clifford_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->cliff_smem_optin = smem;
+      }
       k_clifford_smem<<<g, OBP_BS, smem, ctx->stream>>>(t, pb.b);
     }
     CU(cudaGetLastError());
@@ -1178,6 +1186,28 @@ int obp_profile_get(obp_ctx* ctx, obp_profile* out, int32_t reset) {
   if (!ctx || !out) return OBP_ERR_BADARG;
   *out = ctx->prof;
   if (reset) memset(&ctx->prof, 0, sizeof(ctx->prof));
+  return OBP_OK;
+}
+
+int obp_timer_start(obp_ctx* ctx) {
+  if (!ctx) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->tm_a) {
+    CU(cudaEventCreate(&ctx->tm_a));
+    CU(cudaEventCreate(&ctx->tm_b));
+  }
+  CU(cudaEventRecord(ctx->tm_a, ctx->stream));
+  return OBP_OK;
+}
+
+int obp_timer_stop(obp_ctx* ctx, double* ms) {
+  if (!ctx || !ms || !ctx->tm_a) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->tm_b, ctx->stream));
+  CU(cudaEventSynchronize(ctx->tm_b));
+  float f = 0.f;
+  CU(cudaEventElapsedTime(&f, ctx->tm_a, ctx->tm_b));
+  *ms = (double)f;
   return OBP_OK;
 }
 

@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
         "obp_reserve": ([vp, C.c_uint64], C.c_int),
         "obp_profile_enable": ([vp, C.c_int32], C.c_int),
         "obp_profile_get": ([vp, C.POINTER(ObpProfile), C.c_int32], C.c_int),
+        "obp_timer_start": ([vp], C.c_int),
+        "obp_timer_stop": ([vp, f64p], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)
@@ -124,7 +126,8 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "obp_create obp_destroy obp_last_error obp_set_stream obp_device_memory obp_bytes_per_term "
     "obp_load obp_count obp_download obp_apply_ops obp_apply_reset obp_apply_damping obp_truncate "
-    "obp_union_count obp_snapshot obp_restore obp_reserve obp_profile_enable obp_profile_get"
+    "obp_union_count obp_snapshot obp_restore obp_reserve obp_profile_enable obp_profile_get "
+    "obp_timer_start obp_timer_stop"
 ).split()
 
 
@@ -337,6 +340,15 @@ class TermTable:
             name: {"launches": int(p.launches[k]), "ms": float(p.ms[k]), "term_updates": int(p.term_updates[k])}
             for k, name in enumerate(OBP_K_NAMES)
         }
+
+    def timer_start(self):
+        self._check(self._lib.obp_timer_start(self._h), "obp_timer_start")
+
+    def timer_stop(self) -> float:
+        """Milliseconds of device time since :meth:`timer_start` (CUDA events on the table's stream)."""
+        ms = C.c_double()
+        self._check(self._lib.obp_timer_stop(self._h, C.byref(ms)), "obp_timer_stop")
+        return ms.value
 
     # -- constructors used by the utils API ------------------------------------------------
     @classmethod

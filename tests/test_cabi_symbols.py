@@ -1,0 +1,80 @@
+"""The C-ABI library loads and exports every symbol ``include/obp_b200.h`` declares (no GPU calls)."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "obp_b200.h")
+LIB = os.path.join(ROOT, "qiskit_addon_obp_b200", "libobp_b200.so")
+
+
+def declared_functions() -> list[str]:
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(obp_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+
+        g.build()
+    return ctypes.CDLL(LIB)
+
+
+def test_header_declares_the_documented_entry_points():
+    names = declared_functions()
+    for must in ("obp_create", "obp_destroy", "obp_load", "obp_download", "obp_apply_ops", "obp_truncate", "obp_snapshot", "obp_restore"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in obp_b200.h but not exported"
+
+
+def test_python_binding_lists_the_same_symbols():
+    from qiskit_addon_obp_b200 import engine
+
+    assert sorted(engine.EXPORTED_SYMBOLS) == declared_functions()
+
+
+def test_op_record_layout_matches_header():
+    """``obp_op`` is 104 bytes with the documented field offsets (numpy mirror in engine.py)."""
+    from qiskit_addon_obp_b200.engine import OP_DTYPE, ObpProfile, ObpStats
+
+    assert OP_DTYPE.itemsize == 104
+    offs = {n: OP_DTYPE.fields[n][1] for n in OP_DTYPE.names}
+    assert offs == {
+        "kind": 0, "n_qubits": 4, "qubit": 8, "flags": 24, "n_components": 28, "lut": 32, "sign_mask": 40,
+        "group_size": 44, "group_elems": 48, "row_scale": 56, "gen_local": 64, "reserved": 68, "u0": 72, "u1": 88,
+    }  # fmt: skip
+    assert ctypes.sizeof(ObpStats) == 80
+    assert ctypes.sizeof(ObpProfile) == 6 * 8 * 3
+
+
+def test_no_cpu_fallback_without_device(lib):
+    """Without a CUDA device the engine fails loudly instead of computing on the host."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("a CUDA device is present")
+    except ImportError:
+        pass
+    from qiskit_addon_obp_b200 import backpropagate
+    from qiskit_addon_obp_b200.engine import EngineError
+    from qiskit_addon_obp_b200.ir import QuantumCircuit, SparsePauliOp
+
+    qc = QuantumCircuit(1)
+    qc.rx(0.3, 0)
+    with pytest.raises((EngineError, MemoryError)):
+        backpropagate(SparsePauliOp("Z"), [qc])
+    assert np.isfinite(1.0)

@@ -1,0 +1,327 @@
+"""GPU parity tests: the CUDA engine (through the C-ABI) against the CPU oracle.
+
+Bars (BASELINE.json north star): surviving Pauli key set bit-exact, coefficients within
+1e-10 rel / 1e-12 abs, error totals within 1e-9, integer counters exact.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import kats
+from conftest import assert_same_metadata, assert_same_operator
+from oracle import obp_oracle as oracle
+from qiskit_addon_obp_b200 import backpropagate
+from qiskit_addon_obp_b200.ir import (
+    PauliLindbladError,
+    PauliLindbladErrorInstruction,
+    QuantumCircuit,
+    SparsePauliOp,
+)
+from qiskit_addon_obp_b200.utils.simplify import OperatorBudget
+from qiskit_addon_obp_b200.utils.truncating import TruncationErrorBudget, setup_budget
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- the reference's own KATs through the engine ------------------------------------------------
+@pytest.mark.parametrize("kat", kats.ORDER_FREE, ids=lambda f: f.__name__)
+def test_reference_kat(kat):
+    kat(backpropagate)
+
+
+@pytest.mark.parametrize("kat", kats.ORDERED, ids=lambda f: f.__name__)
+def test_reference_kat_numeric(kat):
+    """Numeric KATs; row order is not part of the parity contract."""
+    kat(backpropagate, ordered=False)
+
+
+# ---- random circuits ------------------------------------------------------------------------------
+_CLIFF1 = ["h", "s", "sdg", "x", "y", "z", "sx", "sxdg"]
+_CLIFF2 = ["cx", "cz", "cy", "swap", "iswap", "ecr"]
+_ROT1 = ["rx", "ry", "rz", "p"]
+_ROT2 = ["rxx", "ryy", "rzz", "rzx"]
+_FIX_ROT = ["t", "tdg"]
+
+
+def random_slices(nq, n_slices, rng, *, p_rot=0.5, gates_per_slice=None, angles=None):
+    slices = []
+    for _ in range(n_slices):
+        qc = QuantumCircuit(nq)
+        perm = rng.permutation(nq)
+        k = 0
+        budget = gates_per_slice or nq
+        while k < nq and budget > 0:
+            budget -= 1
+            two = k + 1 < nq and rng.random() < 0.4
+            th = float(rng.uniform(-np.pi, np.pi)) if angles is None else float(rng.choice(angles))
+            if two:
+                a, b = int(perm[k]), int(perm[k + 1])
+                k += 2
+                if rng.random() < p_rot:
+                    getattr(qc, str(rng.choice(_ROT2)))(th, a, b)
+                else:
+                    getattr(qc, str(rng.choice(_CLIFF2)))(a, b)
+            else:
+                a = int(perm[k])
+                k += 1
+                r = rng.random()
+                if r < p_rot * 0.8:
+                    getattr(qc, str(rng.choice(_ROT1)))(th, a)
+                elif r < p_rot:
+                    getattr(qc, str(rng.choice(_FIX_ROT)))(a)
+                else:
+                    getattr(qc, str(rng.choice(_CLIFF1)))(a)
+        slices.append(qc)
+    return slices
+
+
+def random_observable(nq, n_terms, rng, weight=2):
+    x = np.zeros((n_terms, nq), dtype=bool)
+    z = np.zeros((n_terms, nq), dtype=bool)
+    for i in range(n_terms):
+        for q in rng.choice(nq, size=min(weight, nq), replace=False):
+            c = rng.integers(1, 4)
+            x[i, q] = bool(c & 1)
+            z[i, q] = bool(c & 2)
+    op = SparsePauliOp((x, z), rng.normal(size=n_terms) + 0j)
+    out, _ = oracle.simplify(op)
+    return out
+
+
+def _compare(obs, slices, **kw):
+    got, rest_g, md_g = backpropagate(obs, slices, **kw)
+    want, rest_w, md_w = oracle.backpropagate(obs, slices, **kw)
+    assert len(rest_g) == len(rest_w)
+    single = isinstance(obs, SparsePauliOp)
+    gl, wl = ([got], [want]) if single else (got, want)
+    tb = kw.get("truncation_error_budget")
+    for g, w in zip(gl, wl):
+        assert_same_operator(g, w)
+    assert_same_metadata(md_g, md_w)
+    del tb
+    return gl, md_g
+
+
+@pytest.mark.parametrize("nq", [3, 6, 64, 70, 130, 200])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_circuit_no_truncation(nq, seed):
+    rng = np.random.default_rng(1000 * nq + seed)
+    slices = random_slices(nq, 6, rng, gates_per_slice=8)
+    obs = random_observable(nq, 3, rng)
+    _compare(obs, slices)
+
+
+@pytest.mark.parametrize("nq,p", [(5, 1), (5, 2), (66, 1), (129, 2)])
+def test_random_circuit_truncation(nq, p):
+    rng = np.random.default_rng(77 + nq + p)
+    slices = random_slices(nq, 8, rng, gates_per_slice=6, angles=[0.1, 0.3, -0.2, 0.7])
+    obs = random_observable(nq, 2, rng)
+    _compare(obs, slices, truncation_error_budget=TruncationErrorBudget([0.02, 0.0, 0.05], 0.2, p, 1e-8))
+    _compare(obs, slices, truncation_error_budget=setup_budget(max_error_total=0.05, num_slices=8, p_norm=p))
+
+
+def test_clifford_only_counters():
+    """Clifford gates: keys move, nothing merges; counters come from the coset count kernel."""
+    rng = np.random.default_rng(5)
+    nq = 9
+    slices = random_slices(nq, 10, rng, p_rot=0.0)
+    obs = random_observable(nq, 40, rng, weight=4)
+    _compare(obs, slices)
+
+
+def test_multi_observable_and_max_paulis():
+    rng = np.random.default_rng(11)
+    nq = 8
+    slices = random_slices(nq, 10, rng, gates_per_slice=6)
+    obs = [random_observable(nq, 2, rng), random_observable(nq, 3, rng), SparsePauliOp("IIIIIIIZ")]
+    _compare(obs, slices)
+    _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=60))
+    _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=60, max_qwc_groups=1000))
+
+
+def test_small_coefficients_trim_band():
+    """Terms driven below atol by repeated small-angle branching are trimmed exactly like the reference."""
+    nq = 4
+    slices = []
+    for k in range(12):
+        qc = QuantumCircuit(nq)
+        qc.rx(1e-3, k % nq)
+        qc.rzz(2e-3, k % nq, (k + 1) % nq)
+        slices.append(qc)
+    obs = SparsePauliOp(["ZIII", "IIXY"], [1.0, 3e-6])
+    _compare(obs, slices)
+    _compare(obs, slices, operator_budget=OperatorBudget(atol=1e-5))
+
+
+def test_reset_and_noise_layers():
+    rng = np.random.default_rng(3)
+    nq = 6
+    slices = random_slices(nq, 4, rng, gates_per_slice=5)
+    ple = PauliLindbladError(["IXX", "ZYI", "IIZ"], [1e-2, 3e-3, 5e-2])
+    noisy = QuantumCircuit(nq)
+    noisy.append(PauliLindbladErrorInstruction(ple), [1, 3, 4])
+    noisy.cx(1, 3)
+    rst = QuantumCircuit(nq)
+    rst.reset(2)
+    rst.h(0)
+    obs = random_observable(nq, 6, rng, weight=3)
+    _compare(obs, slices + [noisy] + slices[:2] + [rst] + slices[2:])
+
+
+# ---- the named configurations at oracle-sized scale ----------------------------------------------
+def test_config1_full():
+    from qiskit_addon_obp_b200.workloads import config1_xy_chain
+
+    wl = config1_xy_chain()
+    gl, md = _compare(wl.observables, wl.slices, **wl.kwargs())
+    assert md.num_backpropagated_slices == 18 and len(gl[0]) == 71
+
+
+def test_config2_small():
+    from qiskit_addon_obp_b200.workloads import config2_kicked_ising
+
+    wl = config2_kicked_ising(theta_h=0.3, steps=2, max_paulis=3000)
+    _compare(wl.observables, wl.slices, **wl.kwargs())
+
+
+def test_config3_small():
+    from qiskit_addon_obp_b200.workloads import config3_square_lattice
+
+    wl = config3_square_lattice(side=10, steps=1, max_paulis=20000)
+    _compare(wl.observables, wl.slices, **wl.kwargs())
+
+
+def test_config4_small():
+    from qiskit_addon_obp_b200.workloads import config4_near_clifford
+
+    wl = config4_near_clifford(num_qubits=1000, depth=12, t_prob=0.01, max_paulis=4000)
+    _compare(wl.observables, wl.slices, **wl.kwargs())
+    wl = config4_near_clifford(num_qubits=1000, depth=12, t_prob=0.01, max_paulis=4000, per_slice=1e-4)
+    _compare(wl.observables, wl.slices, **wl.kwargs())
+
+
+def test_config5_small():
+    from qiskit_addon_obp_b200.workloads import config5_magic_sweep
+
+    wl = config5_magic_sweep(theta=np.pi / 16, depth=5, max_paulis=3000)
+    _compare(wl.observables, wl.slices, **wl.kwargs())
+
+
+# ---- utils-level entry points ----------------------------------------------------------------------
+def test_simplify_device():
+    from qiskit_addon_obp_b200.utils.simplify import simplify
+
+    coeffs = [3 + 1j, -3 - 1j, 0, 4, -5, 2.2, -1.1j]
+    labels = ["IXI", "IXI", "ZZZ", "III", "III", "XXX", "XXX"]
+    op = SparsePauliOp(labels, coeffs)
+    out, md = simplify(op)
+    assert out.sorted_by_key() == SparsePauliOp(["III", "XXX"], [-1, 2.2 - 1.1j]).sorted_by_key()
+    assert (md.num_unique_paulis, md.num_duplicate_paulis, md.num_trimmed_paulis, md.sum_trimmed_coeffs) == (3, 3, 2, 0)
+    out, md = simplify(op - op)
+    np.testing.assert_array_equal(out.coeffs, [0])
+    assert (md.num_unique_paulis, md.num_duplicate_paulis, md.num_trimmed_paulis) == (3, 9, 5)
+    op = SparsePauliOp(["IXI", "IXI", "ZZZ", "XXX", "YYY"], [1e-8, 1e-8j, 1e-8 + 1e-8j, 0.1, 0.2])
+    out, _ = simplify(op)
+    assert out.sorted_by_key() == SparsePauliOp(["ZZZ", "XXX", "YYY"], [1e-8 + 1e-8j, 0.1, 0.2]).sorted_by_key()
+    out, _ = simplify(op, atol=0.01, rtol=1e-10)
+    assert out.sorted_by_key() == SparsePauliOp(["XXX", "YYY"], [0.1, 0.2]).sorted_by_key()
+    # random duplicates, wide keys
+    rng = np.random.default_rng(0)
+    nq, n = 150, 5000
+    x = rng.random((n, nq)) < 0.02
+    z = rng.random((n, nq)) < 0.02
+    idx = rng.integers(0, n // 3, size=n)
+    big = SparsePauliOp((x[idx], z[idx]), rng.normal(size=n) * (rng.random(n) < 0.9) + 1j * rng.normal(size=n))
+    out, md = simplify(big)
+    want, md_w = oracle.simplify(big)
+    assert_same_operator(out, want)
+    assert (md.num_unique_paulis, md.num_duplicate_paulis, md.num_trimmed_paulis) == (
+        md_w.num_unique_paulis,
+        md_w.num_duplicate_paulis,
+        md_w.num_trimmed_paulis,
+    )
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_truncate_binary_search_device(p):
+    from qiskit_addon_obp_b200.utils.truncating import truncate_binary_search
+
+    rng = np.random.default_rng(p)
+    nq, n = 40, 20000
+    x = rng.random((n, nq)) < 0.2
+    z = rng.random((n, nq)) < 0.2
+    op, _ = oracle.simplify(SparsePauliOp((x, z), rng.normal(size=n) * 10.0 ** rng.uniform(-6, 0, size=n)))
+    for budget in (0.0, 1e-9, 1e-3, 0.5, 1e6):
+        got, err = truncate_binary_search(op, budget, p_norm=p, tol=1e-8)
+        want, err_w = oracle.truncate_binary_search(op, budget, p_norm=p, tol=1e-8)
+        assert abs(err - err_w) <= 1e-9 * max(1.0, abs(err_w))
+        assert_same_operator(got, want, thresholds=())
+
+
+def test_operations_device():
+    from qiskit_addon_obp_b200.ir import Instruction
+    from qiskit_addon_obp_b200.utils.operations import apply_op_to, apply_ple_to, apply_reset_to
+
+    new_op, qargs = apply_op_to(SparsePauliOp("IX"), [0, 1], Instruction("cx", (0, 1)), [0, 1], apply_as_transform=True)
+    assert np.array_equal(new_op.to_matrix(), np.fliplr(np.identity(4))) and qargs == [0, 1]
+    new_op, qargs = apply_op_to(SparsePauliOp("XX"), [2, 4], Instruction("cx", (0, 1)), [6, 8], apply_as_transform=True)
+    assert qargs == [2, 4, 6, 8] and new_op == SparsePauliOp("IIXX")
+    with pytest.raises(ValueError) as e:
+        apply_op_to(SparsePauliOp("XYZ"), [1, 2], Instruction("x", (0,)), [1], apply_as_transform=True)
+    assert e.value.args[0] == "The number of qubits in the operator (3) does not match the number of qargs (2)."
+    op = SparsePauliOp(["XYZ", "YZX", "ZXY"], [1.0, 2.0, 3.0])
+    for q, lbl, c in ((0, "XYI", 1.0), (1, "YIX", 2.0), (2, "IXY", 3.0)):
+        assert apply_reset_to(op, q) == SparsePauliOp([lbl], [c])
+    new_op, qargs = apply_ple_to(SparsePauliOp(["XZ", "YY"], [1.0, 1.0]), [1, 2], PauliLindbladError(["XX", "YY"], [1e-3, 1e-2]), [0, 1])
+    assert qargs == [0, 1, 2]
+    assert new_op.sorted_by_key() == SparsePauliOp(["XZI", "YYI"], [0.97824024, 0.998002]).sorted_by_key()
+
+
+# ---- size-independent properties at BASELINE sizes -------------------------------------------------
+def _inverse_slices(slices):
+    inv = []
+    for s in slices[::-1]:
+        qc = QuantumCircuit(s.num_qubits)
+        for ins in s.data[::-1]:
+            qc.unitary(ins.matrix.conj().T, ins.qubits, label=ins.name + "_dg")
+        inv.append(qc)
+    return inv
+
+
+def test_round_trip_config2_1e6():
+    """U then U^dag returns the observable: Z_62 with coefficient 1 (127 qubits, ~1e6 terms mid-way).
+
+    Backpropagating ``inverse + forward`` slices first absorbs ``forward`` (growing the operator to
+    the ~1e6-term regime of BASELINE config 2) and then ``inverse``, which must merge everything
+    back.  Trimming at atol=1e-8 loses at most (number of trimmed terms) * 1e-8 of weight.
+    """
+    from qiskit_addon_obp_b200.workloads import config2_kicked_ising
+
+    wl = config2_kicked_ising(theta_h=0.3, steps=4, max_paulis=None)
+    fwd = wl.slices
+    from qiskit_addon_obp_b200 import backpropagation as bpmod
+
+    out, rest, md = backpropagate(wl.observables, _inverse_slices(fwd) + fwd)
+    assert rest == []
+    peak = max(s.num_paulis[0] for s in md.backpropagation_history)
+    assert peak > 100_000, peak
+    assert bpmod.last_run.updates > 10_000_000
+    d = out.as_dict()
+    key = wl.observables.paulis.to_labels()[0]
+    assert abs(d[key] - 1.0) < 1e-5
+    rest_w = sum(abs(c) for k, c in d.items() if k != key)
+    assert rest_w < 1e-2, rest_w
+
+
+def test_norm_conservation_config5():
+    """Unitary conjugation preserves sum |c|^2 (no truncation; trimmed weight is below atol per term)."""
+    from qiskit_addon_obp_b200.workloads import config5_magic_sweep
+
+    wl = config5_magic_sweep(theta=np.pi / 8, depth=12, max_paulis=None)
+    out, rest, md = backpropagate(wl.observables, wl.slices)
+    assert rest == []
+    assert len(out) > 50_000
+    assert abs(np.sum(np.abs(out.coeffs) ** 2) - 1.0) < 1e-6
+    assert len(out.as_dict()) == len(out)
