@@ -130,7 +130,7 @@ def backpropagate(
 
     try:
         for i in range(n_obs):
-            tables.append(TermTable(num_qubits, max(capacity, 2 * len(obs_in[i])), device))
+            tables.append(TermTable.acquire(num_qubits, max(capacity, 2 * len(obs_in[i])), device))
         try:
             for slice_ in slices_ir[::-1]:
                 sm = SliceMetadata(
@@ -166,6 +166,7 @@ def backpropagate(
                             tables[i].load(obs_in[i])
                             info.h2d_bytes += len(obs_in[i]) * (16 * tables[i].words + 16)
                             tables[i].profile_enable(PROFILE)
+                            tables[i].profile(reset=True)
                             tables[i].timer_start()
                             tables[i].snapshot()
                             loaded[i] = True
@@ -255,7 +256,8 @@ def backpropagate(
             info.d2h_bytes += len(obs_out[-1]) * (16 * tables[i].words + 16)
     finally:
         for t in tables:
-            t.close()
+            t.profile_enable(False)
+            t.release()
 
     last_run.updates = info.updates
     last_run.applied_gates = info.applied_gates

@@ -23,7 +23,8 @@ struct Snapshot {
   double2* coef = nullptr;
   u64* hash = nullptr;
   u64 cap = 0;
-  u64 n = 0;
+  u64 n = 0;       // dense rows held
+  u64 n_live = 0;  // live rows among them
   bool valid = false;
   std::vector<u64> hx, hz;
 };
@@ -379,8 +380,9 @@ extern "C" {
 
 uint64_t obp_bytes_per_term(int n_qubits) {
   const u64 W = (u64)std::max(1, (n_qubits + 63) / 64);
-  // key columns + coef + hash + spare16 + spare8 + dest + index (T >= 2*cap, up to 4*cap)
-  return 16 * W + 16 + 8 + 16 + 8 + 4 + 32;
+  // key columns + coef + hash, twice (table + per-slice snapshot), + spare16 + spare8 + dest +
+  // index (T >= 2*cap, up to 4*cap)
+  return 2 * (16 * W + 16 + 8) + 16 + 8 + 4 + 32;
 }
 
 int obp_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes) {
@@ -521,10 +523,8 @@ int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, con
     k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n);
     ctx->epoch++;
     k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ctx->epoch, 0);
-    if (atol >= 0.0) {
-      ctx->epoch++;
-      k_trim<<<g, OBP_BS, 0, ctx->stream>>>(t, atol, ctx->epoch, 0);
-    }
+    ctx->epoch++;
+    k_trim<<<g, OBP_BS, 0, ctx->stream>>>(t, atol, ctx->epoch, 0);
     CU(cudaGetLastError());
   }
   CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1005,31 +1005,29 @@ int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double
 int obp_snapshot(obp_ctx* ctx) {
   if (!ctx) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
-  int rc;
-  if (ctx->n_dense != ctx->n_live) {
-    rc = compact(ctx);
-    if (rc) return rc;
-    rc = sync_state(ctx);
-    if (rc) return rc;
-  }
+  // Copies the dense rows (tombstones included) aside with stream-ordered D2D copies: no
+  // compaction, no host synchronisation.  The buffers are sized once for the whole table so the
+  // per-slice commit never allocates.
   Snapshot& s = ctx->snap;
-  const u64 n = ctx->n_live;
-  if (n > s.cap) {
+  const u64 n = ctx->n_dense;
+  if (s.cap < ctx->cap) {
+    CU(cudaStreamSynchronize(ctx->stream));
     free_snapshot(s);
-    const u64 nc = std::max<u64>(n + n / 2, 1024);
-    for (int w = 0; w < ctx->W; ++w) CU(cudaMalloc(&s.xz[w], nc * sizeof(ulonglong2)));
-    CU(cudaMalloc(&s.coef, nc * sizeof(double2)));
-    CU(cudaMalloc(&s.hash, nc * sizeof(u64)));
-    s.cap = nc;
+    for (int w = 0; w < ctx->W; ++w) CU(cudaMalloc(&s.xz[w], ctx->cap * sizeof(ulonglong2)));
+    CU(cudaMalloc(&s.coef, ctx->cap * sizeof(double2)));
+    CU(cudaMalloc(&s.hash, ctx->cap * sizeof(u64)));
+    s.cap = ctx->cap;
   }
   for (int w = 0; w < ctx->W; ++w)
     CU(cudaMemcpyAsync(s.xz[w], ctx->xz[w], n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(s.coef, ctx->coef, n * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(s.hash, ctx->hash, n * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
   s.n = n;
+  s.n_live = ctx->n_live;
   s.hx = ctx->hx;
   s.hz = ctx->hz;
   s.valid = true;
+  ctx->prof.launches[OBP_K_OTHER] += (u64)ctx->W + 2;
   return OBP_OK;
 }
 
@@ -1050,6 +1048,12 @@ int obp_restore(obp_ctx* ctx) {
   ctx->cols_dirty = true;
   int rc = set_counts(ctx, s.n);
   if (rc) return rc;
+  if (s.n_live != s.n) {
+    // the snapshot carried tombstones: n_live differs from the dense row count
+    ctx->h_st->n_live = s.n_live;
+    CU(cudaMemcpyAsync(&ctx->d_st->n_live, &ctx->h_st->n_live, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   rc = rebuild_index(ctx);
   if (rc) return rc;
   return sync_state(ctx);

@@ -475,7 +475,10 @@ __global__ void __launch_bounds__(OBP_BS) k_index_build(Tab t, int merge, double
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
     const double2 c = t.coef[i];
     if (!is_live(c)) {
-      if (merge) deaths++;  // at load every uploaded row was counted live; exact zeros are not
+      if (merge) {  // at load every uploaded row was counted live; an exact zero is a filtered raw row
+        deaths++;
+        t.coef[i] = tombstone(epoch);
+      }
       continue;
     }
     if (merge && atol >= 0.0 && is_small(c, atol)) {
@@ -528,14 +531,17 @@ __global__ void __launch_bounds__(OBP_BS) k_index_build(Tab t, int merge, double
 }
 
 // Second zero filter of simplify(): kill merged rows with |sum| <= atol, count and sum them.
+// atol < 0: only sums that cancelled to an exact zero die (keeps n_live exact after a plain merge).
 __global__ void __launch_bounds__(OBP_BS) k_trim(Tab t, double atol, u64 epoch, int slot) {
   const u64 n = t.st->n_scan;
   unsigned cancelled = 0;
   double sr = 0.0, si = 0.0;
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
     const double2 c = t.coef[i];
-    if (!is_live(c)) continue;
-    if (is_small(c, atol)) {
+    // a merged sum that cancelled to exactly +0.0 + 0.0i looks like a tombstone of epoch 0
+    const bool zero_sum = c.x == 0.0 && __double_as_longlong(c.y) == 0ll;
+    if (!is_live(c) && !zero_sum) continue;
+    if (zero_sum || is_small(c, atol)) {
       t.coef[i] = tombstone(epoch);
       cancelled++;
       sr += c.x;

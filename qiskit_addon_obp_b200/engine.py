@@ -6,13 +6,14 @@ entry point raises.  Build the library with ``python -c "import __graft_entry__ 
 
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
 from contextlib import contextmanager
 
 import numpy as np
 
-from .ir import SparsePauliOp, pack_xz, unpack_xz
+from .ir import SparsePauliOp, pack_xz
 from .utils.simplify import SimplifyMetadata
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libobp_b200.so")
@@ -144,8 +145,48 @@ def default_device() -> int:
     return int(os.environ.get("OBP_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
+#: idle tables kept for reuse, keyed by (device, num_qubits): device allocation and release cost
+#: far more than a whole 1e6-term backpropagation, so contexts are recycled across calls
+_POOL: dict[tuple[int, int], list["TermTable"]] = {}
+POOL_MAX_PER_KEY = 4
+
+
+def clear_pool() -> None:
+    """Destroy all idle pooled tables (frees their device memory)."""
+    for tabs in _POOL.values():
+        for t in tabs:
+            t.close()
+    _POOL.clear()
+
+
+atexit.register(clear_pool)
+
+
 class TermTable:
     """One observable as a device-resident table of packed Pauli keys and complex128 coefficients."""
+
+    @classmethod
+    def acquire(cls, num_qubits: int, capacity: int, device: int | None = None) -> "TermTable":
+        """A table with room for ``capacity`` terms: a recycled one when the pool has a fit."""
+        device = default_device() if device is None else int(device)
+        idle = _POOL.get((device, int(num_qubits)), [])
+        for k, t in enumerate(idle):
+            if t.capacity >= capacity:
+                idle.pop(k)
+                t.n = t.n_dense = 0
+                t.zero_operator = False
+                return t
+        return cls(num_qubits, capacity, device)
+
+    def release(self) -> None:
+        """Hand the table back to the pool (or destroy it when the pool is full)."""
+        if not self._h.value:
+            return
+        idle = _POOL.setdefault((self.device, self.num_qubits), [])
+        if len(idle) >= POOL_MAX_PER_KEY:
+            self.close()
+        else:
+            idle.append(self)
 
     def __init__(self, num_qubits: int, capacity: int, device: int | None = None):
         self._lib = lib()
@@ -202,7 +243,7 @@ class TermTable:
             raise ValueError("operator width does not match the table")
         if len(op) > self.capacity:
             self.reserve(2 * len(op))
-        xw, zw = pack_xz(op.x, op.z)
+        xw, zw = op.packed()
         coeffs = np.ascontiguousarray(op.coeffs, dtype=np.complex128)
         st = ObpStats()
         rc = self._lib.obp_load(
@@ -224,9 +265,9 @@ class TermTable:
             z = np.zeros((1, self.num_qubits), dtype=bool)
             return SparsePauliOp((z.copy(), z), np.array([0j]))
         n = self.n
-        xw = np.zeros((max(n, 1), self.words), dtype="<u8")
-        zw = np.zeros((max(n, 1), self.words), dtype="<u8")
-        co = np.zeros(max(n, 1), dtype=np.complex128)
+        xw = np.empty((max(n, 1), self.words), dtype="<u8")
+        zw = np.empty((max(n, 1), self.words), dtype="<u8")
+        co = np.empty(max(n, 1), dtype=np.complex128)
         got = C.c_uint64()
         rc = self._lib.obp_download(
             self._h,
@@ -239,8 +280,8 @@ class TermTable:
         self._check(rc, "obp_download")
         n = got.value
         self.n = self.n_dense = n
-        x, z = unpack_xz(xw[:n], zw[:n], self.num_qubits)
-        return SparsePauliOp((x, z), co[:n])
+        # the result stays in the engine's packed format; bool x/z arrays are made on first access
+        return SparsePauliOp.from_packed(xw[:n], zw[:n], co[:n], self.num_qubits)
 
     to_operator = download
 
@@ -315,15 +356,15 @@ class TermTable:
         return err.value, rem.value
 
     def snapshot(self):
+        """Commit point: stream-ordered device copy of the table (no host synchronisation)."""
         self._snap_zero = self.zero_operator
         self._snap_n = self.n
         self._check(self._lib.obp_snapshot(self._h), "obp_snapshot")
-        self.n_dense = self.n
 
     def restore(self):
         self._check(self._lib.obp_restore(self._h), "obp_restore")
         self.zero_operator = self._snap_zero
-        self.n = self.n_dense = self._snap_n
+        self.n = self._snap_n
 
     def reserve(self, capacity: int):
         self._check(self._lib.obp_reserve(self._h, int(capacity)), "obp_reserve")
@@ -354,18 +395,18 @@ class TermTable:
     @classmethod
     @contextmanager
     def from_operator(cls, op: SparsePauliOp, capacity: int | None = None):
-        table = cls(op.num_qubits, capacity or max(1024, 2 * len(op)))
+        table = cls.acquire(op.num_qubits, capacity or max(1024, 2 * len(op)))
         try:
             table.load(op)
             yield table
         finally:
-            table.close()
+            table.release()
 
     @classmethod
     @contextmanager
     def from_rows(cls, op: SparsePauliOp, atol: float):
         """Load raw rows with the full simplify semantics; yields ``(table, SimplifyMetadata)``."""
-        table = cls(op.num_qubits, max(1024, 2 * len(op)))
+        table = cls.acquire(op.num_qubits, max(1024, 2 * len(op)))
         try:
             st = table.load(op, atol=atol)
             s = complex(st.sum_trimmed[0], st.sum_trimmed[1])
@@ -377,7 +418,7 @@ class TermTable:
             )
             yield table, md
         finally:
-            table.close()
+            table.release()
 
 
 def union_count(tables: list[TermTable]) -> int:

@@ -76,9 +76,58 @@ class SparsePauliOp:
         coeffs = np.asarray(coeffs, dtype=complex).reshape(-1).copy()
         if coeffs.shape[0] != x.shape[0]:
             raise ValueError("number of coefficients does not match the number of Pauli terms")
-        self.x = x
-        self.z = z
+        self._x = x
+        self._z = z
+        self._packed = None
+        self._num_qubits = x.shape[1]
         self.coeffs = coeffs
+
+    @classmethod
+    def from_packed(cls, xw: np.ndarray, zw: np.ndarray, coeffs: np.ndarray, num_qubits: int) -> SparsePauliOp:
+        """Wrap packed symplectic words (``uint64 [n, W]``, the engine's own format) without unpacking.
+
+        The boolean ``x`` / ``z`` arrays of the Qiskit layout are materialised on first access.
+        """
+        self = cls.__new__(cls)
+        self._x = self._z = None
+        self._packed = (np.ascontiguousarray(xw, dtype="<u8"), np.ascontiguousarray(zw, dtype="<u8"))
+        self._num_qubits = int(num_qubits)
+        self.coeffs = np.asarray(coeffs, dtype=complex).reshape(-1)
+        if self._packed[0].shape != self._packed[1].shape or self._packed[0].shape[0] != self.coeffs.shape[0]:
+            raise ValueError("packed words and coefficients do not match")
+        return self
+
+    def _materialise(self) -> None:
+        if self._x is None:
+            self._x, self._z = unpack_xz(self._packed[0], self._packed[1], self._num_qubits)
+        # the boolean arrays may now be mutated in place by the caller: they become the only truth
+        self._packed = None
+
+    @property
+    def x(self) -> np.ndarray:
+        self._materialise()
+        return self._x
+
+    @x.setter
+    def x(self, value) -> None:
+        self._materialise()
+        self._x = np.ascontiguousarray(value, dtype=bool)
+
+    @property
+    def z(self) -> np.ndarray:
+        self._materialise()
+        return self._z
+
+    @z.setter
+    def z(self, value) -> None:
+        self._materialise()
+        self._z = np.ascontiguousarray(value, dtype=bool)
+
+    def packed(self) -> tuple[np.ndarray, np.ndarray]:
+        """``(x_words, z_words)`` as ``uint64 [n, W]``, qubit j -> bit j%64 of word j//64."""
+        if self._packed is not None:
+            return self._packed
+        return pack_xz(self._x, self._z)
 
     # -- construction helpers -------------------------------------------------------------
     @classmethod
@@ -105,7 +154,7 @@ class SparsePauliOp:
     # -- Qiskit-like surface --------------------------------------------------------------
     @property
     def num_qubits(self) -> int:
-        return self.x.shape[1]
+        return self._num_qubits
 
     @property
     def paulis(self) -> PauliTableView:
@@ -113,13 +162,17 @@ class SparsePauliOp:
 
     @property
     def size(self) -> int:
-        return self.x.shape[0]
+        return self.coeffs.shape[0]
 
     def __len__(self) -> int:
-        return self.x.shape[0]
+        return self.coeffs.shape[0]
 
     def copy(self) -> SparsePauliOp:
-        return SparsePauliOp((self.x.copy(), self.z.copy()), self.coeffs.copy())
+        if self._packed is not None:
+            return SparsePauliOp.from_packed(
+                self._packed[0].copy(), self._packed[1].copy(), self.coeffs.copy(), self._num_qubits
+            )
+        return SparsePauliOp((self._x.copy(), self._z.copy()), self.coeffs.copy())
 
     def to_list(self) -> list[tuple[str, complex]]:
         return list(zip(self.paulis.to_labels(), self.coeffs.tolist()))
@@ -173,7 +226,7 @@ class SparsePauliOp:
         """Rows in canonical order (ascending packed key); used to compare engine and oracle."""
         if len(self) == 0:
             return self.copy()
-        xw, zw = pack_xz(self.x, self.z)
+        xw, zw = self.packed()
         cols = [a[:, w] for w in range(xw.shape[1]) for a in (zw, xw)]
         order = np.lexsort(cols)  # last column is the primary key → highest word's x first
         return SparsePauliOp((self.x[order], self.z[order]), self.coeffs[order])
@@ -237,8 +290,9 @@ def unpack_xz(xw: np.ndarray, zw: np.ndarray, num_qubits: int) -> tuple[np.ndarr
     n = xw.shape[0]
 
     def _unpack(a):
-        b = np.ascontiguousarray(a.astype("<u8")).view(np.uint8).reshape(n, -1)
-        return np.unpackbits(b, axis=1, bitorder="little")[:, :num_qubits].astype(bool)
+        b = np.ascontiguousarray(a, dtype="<u8").view(np.uint8).reshape(n, -1)
+        bits = np.unpackbits(b, axis=1, count=num_qubits, bitorder="little")
+        return bits.view(np.bool_)  # unpackbits yields 0/1 bytes: reinterpret, do not copy
 
     return _unpack(xw), _unpack(zw)
 
