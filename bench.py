@@ -48,24 +48,38 @@ def algorithmic_bytes_per_update(num_qubits: int) -> int:
     return 2 * (16 * w + 16)
 
 
-def make_workload(name: str, rank: int, args):
+def make_workloads(name: str, rank: int, args) -> list:
+    """The workload(s) one step runs: config 2 is the named theta_h sweep, the others a single case."""
     from qiskit_addon_obp_b200 import workloads as wl
 
+    thetas = [float(t) for t in str(args.theta).split(",")]
     if name == "config2":
         # rank r measures Z on a different heavy-hex qubit (independent observables)
         qubits = [62, 64, 43, 81, 24, 100, 45, 83]
-        return wl.config2_kicked_ising(
-            theta_h=args.theta, steps=20, max_paulis=args.max_paulis, observable_qubit=qubits[rank % len(qubits)]
-        )
+        return [
+            wl.config2_kicked_ising(theta_h=t, steps=20, max_paulis=args.max_paulis, observable_qubit=qubits[rank % len(qubits)])
+            for t in thetas
+        ]
     if name == "config1":
-        return wl.config1_xy_chain()
+        return [wl.config1_xy_chain()]
     if name == "config3":
-        return wl.config3_square_lattice(max_paulis=args.max_paulis)
+        return [wl.config3_square_lattice(max_paulis=args.max_paulis)]
     if name == "config4":
-        return wl.config4_near_clifford(max_paulis=args.max_paulis, seed=20261019 + rank)
+        return [wl.config4_near_clifford(max_paulis=args.max_paulis, seed=20261019 + rank)]
     if name == "config5":
-        return wl.config5_magic_sweep(theta=args.theta, max_paulis=args.max_paulis, seed=rank)
+        return [wl.config5_magic_sweep(theta=t, max_paulis=args.max_paulis, seed=rank) for t in thetas]
     raise SystemExit(f"unknown workload {name}")
+
+
+def workload_name(wls) -> str:
+    if len(wls) == 1:
+        return wls[0].name
+    import re
+
+    angles = [re.search(r"theta_h=([0-9.]+)|RZ\(([0-9.]+)\)", w.name) for w in wls]
+    angles = [(m.group(1) or m.group(2)) if m else "?" for m in angles]
+    base = re.sub(r"theta_h=[0-9.]+, ", "", wls[0].name)
+    return f"{base}; one step = the angle sweep {{{', '.join(angles)}}}"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -133,25 +147,30 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU side: the oracle port on a bounded sample
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(wl, max_updates: int) -> tuple[int, float]:
+def cpu_sample(wls, max_updates: int) -> tuple[int, float]:
+    """The oracle port on the first ``max_updates`` term-gate updates of every workload of the step."""
     from oracle import obp_oracle
 
-    trace = obp_oracle.GateTrace()
-    t0 = time.perf_counter()
-    obp_oracle.backpropagate(wl.observables, wl.slices, trace=trace, max_updates=max_updates, **wl.kwargs())
-    return trace.updates, time.perf_counter() - t0
+    updates, t0 = 0, time.perf_counter()
+    for wl in wls:
+        trace = obp_oracle.GateTrace()
+        obp_oracle.backpropagate(
+            wl.observables, wl.slices, trace=trace, max_updates=max(1, max_updates // len(wls)), **wl.kwargs()
+        )
+        updates += trace.updates
+    return updates, time.perf_counter() - t0
 
 
 def run_reference(args, rank: int, world: int) -> None:
     if rank != 0:
         return
-    wl = make_workload(args.workload, 0, args)
+    wls = make_workloads(args.workload, 0, args)
     cap = args.cpu_updates
     for _ in range(args.warmup):
-        cpu_sample(wl, max(1000, cap // 20))
+        cpu_sample(wls, max(1000, cap // 20))
     tot_u, tot_t = 0, 0.0
     for _ in range(args.steps):
-        u, t = cpu_sample(wl, cap)
+        u, t = cpu_sample(wls, cap)
         tot_u += u
         tot_t += t
     value = tot_u / tot_t
@@ -170,7 +189,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "vs_baseline": None,
         "dtype": "complex128 (f64) coefficients, bool keys",
         "data": "synthetic",
-        "config": {"workload": wl.name, "theta_h": args.theta, "max_paulis": args.max_paulis},
+        "config": {"workload": workload_name(wls), "theta": args.theta, "max_paulis": args.max_paulis},
         "cpu_baseline": {
             "value": value,
             "unit": UNIT,
@@ -208,8 +227,8 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     from qiskit_addon_obp_b200 import backpropagate
     from qiskit_addon_obp_b200 import backpropagation as bpmod
 
-    bpmod.PROFILE = True
-    wl = make_workload(args.workload, rank, args)
+    bpmod.PROFILE = not args.no_profile
+    wls = make_workloads(args.workload, rank, args)
     flush_buf = torch.zeros(256 << 20, dtype=torch.uint8, device=device)
 
     def barrier():
@@ -219,11 +238,26 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             torch.cuda.synchronize(device)
 
     def one_step():
+        """One pass of the hot path over the step's workload(s) through the public API."""
         flush_l2(torch, device, flush_buf)
-        t0 = time.perf_counter()
-        out, rest, md = backpropagate(wl.observables, wl.slices, **wl.kwargs())
-        torch.cuda.synchronize(device)
-        return time.perf_counter() - t0, out, md
+        acc = {"dt": 0.0, "dev_ms": 0.0, "updates": 0, "h2d": 0, "d2h": 0, "n_out": 0, "slices": 0, "prof": {}}
+        for wl in wls:
+            t0 = time.perf_counter()
+            out, rest, md = backpropagate(wl.observables, wl.slices, **wl.kwargs())
+            torch.cuda.synchronize(device)
+            acc["dt"] += time.perf_counter() - t0
+            r = bpmod.last_run
+            acc["dev_ms"] += r.device_ms
+            acc["updates"] += r.updates
+            acc["h2d"] += r.h2d_bytes
+            acc["d2h"] += r.d2h_bytes
+            acc["n_out"] += len(out) if not isinstance(out, list) else sum(len(o) for o in out)
+            acc["slices"] += md.num_backpropagated_slices
+            for k, v in (r.profile or {}).items():
+                a = acc["prof"].setdefault(k, {"launches": 0, "ms": 0.0, "term_updates": 0})
+                for f in a:
+                    a[f] += v[f]
+        return acc
 
     for _ in range(args.warmup):
         one_step()
@@ -237,19 +271,17 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     n_out = n_slices = 0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
-        dt, out, md = one_step()
-        r = bpmod.last_run
-        e2e_s += dt
-        dev_ms += r.device_ms
-        updates += r.updates
-        h2d += r.h2d_bytes
-        d2h += r.d2h_bytes
-        for k, v in (r.profile or {}).items():
-            acc = prof_tot.setdefault(k, {"launches": 0, "ms": 0.0, "term_updates": 0})
-            for f in acc:
-                acc[f] += v[f]
-        n_out = len(out) if not isinstance(out, list) else sum(len(o) for o in out)
-        n_slices = md.num_backpropagated_slices
+        acc = one_step()
+        e2e_s += acc["dt"]
+        dev_ms += acc["dev_ms"]
+        updates += acc["updates"]
+        h2d += acc["h2d"]
+        d2h += acc["d2h"]
+        for k, v in acc["prof"].items():
+            a = prof_tot.setdefault(k, {"launches": 0, "ms": 0.0, "term_updates": 0})
+            for f in a:
+                a[f] += v[f]
+        n_out, n_slices = acc["n_out"], acc["slices"]
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
@@ -275,7 +307,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        btg = algorithmic_bytes_per_update(wl.num_qubits)
+        btg = algorithmic_bytes_per_update(wls[0].num_qubits)
         rot = prof_tot.get("rotate", {"launches": 0, "ms": 0.0, "term_updates": 0})
         achieved = (rot["term_updates"] * btg / (rot["ms"] * 1e-3) / 1e9) if rot["ms"] > 0 else None
         kernel_ms = {k: round(v["ms"] / max(1, args.steps), 3) for k, v in prof_tot.items()}
@@ -294,8 +326,8 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "dtype": "u64 keys + f64 complex coefficients",
             "data": "synthetic",
             "config": {
-                "workload": wl.name,
-                "theta_h": args.theta,
+                "workload": workload_name(wls),
+                "theta": args.theta,
                 "max_paulis": args.max_paulis,
                 "slices_absorbed": n_slices,
                 "terms_out": n_out,
@@ -330,7 +362,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "wall_s": wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            u, t = cpu_sample(wl, args.cpu_updates)
+            u, t = cpu_sample(wls, args.cpu_updates)
             line["cpu_baseline"] = {
                 "value": u / t,
                 "unit": UNIT,
@@ -350,7 +382,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["engine", "reference"], default="engine")
     ap.add_argument("--workload", default="config2")
-    ap.add_argument("--theta", type=float, default=float(np.pi / 4))
+    ap.add_argument("--theta", default=f"0.1,0.3,{np.pi / 4:.16f}", help="rotation angle(s), comma separated (config2: theta_h sweep)")
+    ap.add_argument("--no-profile", action="store_true", help="do not bracket kernel launches with CUDA events")
     ap.add_argument("--max-paulis", type=int, default=1_000_000)
     ap.add_argument("--cpu-updates", type=int, default=600_000, help="bound of the CPU sample (term-gate updates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -146,19 +146,17 @@ def backpropagate(
                     num_qwc_groups=None,
                 )
                 metadata.backpropagation_history.append(sm)
-                op_nodes = topological_op_order(slice_)[::-1]
+                prog = _slice_program(slice_)
                 overflowed = False
                 for i in range(n_obs):
-                    applied = []
+                    applied: list[int] = []
                     support = set(qargs[i])
-                    for node in op_nodes:
-                        if node.name == "barrier":
-                            continue
-                        if support.isdisjoint(node.qubits):
+                    for k, qs in enumerate(prog.qubit_sets):
+                        if support.isdisjoint(qs):
                             continue  # outside the light cone (backpropagation.py:183)
-                        applied.append(node)
-                        if node.name != "reset":
-                            support.update(node.qubits)
+                        applied.append(k)
+                        if prog.nodes[k].name != "reset":
+                            support |= qs
                     non_trivial = bool(applied)
                     sidx = metadata.num_backpropagated_slices
                     if non_trivial:
@@ -172,7 +170,7 @@ def backpropagate(
                             loaded[i] = True
                         while True:
                             try:
-                                _run_slice(tables[i], applied, atol, sm, i, info)
+                                _run_slice(tables[i], prog, applied, atol, sm, i, info)
                                 if trunc_active:
                                     budget = metadata.left_over_error_budget(i, sidx)
                                     err, removed = tables[i].truncate(
@@ -281,26 +279,72 @@ def _grow(table: TermTable) -> None:
     table.reserve(new_cap)
 
 
-def _run_slice(table: TermTable, applied, atol: float, sm: SliceMetadata, i: int, info: RunInfo) -> None:
+class SliceProgram:
+    """A slice compiled once: its gates in the reference's application order plus their device records.
+
+    ``nodes`` are the instructions of ``circuit_to_dag(slice).topological_op_nodes()`` reversed
+    (``backpropagation.py:170``) without barriers (:173); ``recs[k]`` is the classified ``obp_op``
+    record of ``nodes[k]`` (``kind`` 0 for reset / LayerError, which have their own entry points).
+    """
+
+    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data")
+
+    def __init__(self, slice_: QuantumCircuit):
+        self.n_data = len(slice_.data)
+        self.nodes = [n for n in topological_op_order(slice_)[::-1] if n.name != "barrier"]
+        self.qubit_sets = [frozenset(n.qubits) for n in self.nodes]
+        self.recs = np.zeros(len(self.nodes), dtype=OP_DTYPE)
+        self.special = [n.name in ("reset", "LayerError") for n in self.nodes]
+        self.errors: dict[int, Exception] = {}
+        qubit = self.recs["qubit"]
+        for k, node in enumerate(self.nodes):
+            if self.special[k]:
+                continue
+            try:
+                prog = program_for(node)
+            except (NotImplementedError, ValueError) as exc:  # only raised if the gate is applied
+                self.errors[k] = exc
+                continue
+            self.recs[k] = prog.template[0]
+            qubit[k, : prog.n_qubits] = node.qubits
+
+
+def _slice_program(slice_: QuantumCircuit) -> SliceProgram:
+    prog = getattr(slice_, "_obp_program", None)
+    if prog is None or prog.n_data != len(slice_.data):
+        prog = SliceProgram(slice_)
+        slice_._obp_program = prog
+    return prog
+
+
+def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: float, sm: SliceMetadata, i: int,
+               info: RunInfo) -> None:
     """Execute the applied gates of one slice on one observable and record the last gate's counters."""
-    seg: list[np.ndarray] = []
     stats = None
-    last_idx = len(applied) - 1
+    last = applied[-1]
+    seg: list[int] = []
 
     def flush():
         nonlocal seg, stats
         if seg:
-            stats = table.apply_ops(np.concatenate(seg), atol)
+            ops = prog.recs[seg]  # fancy index: a fresh array
+            if seg[-1] == last:
+                ops["flags"][-1] = OBP_FLAG_EXACT_COUNTERS
+            stats = table.apply_ops(ops, atol)
             info.updates += int(stats.updates)
             seg = []
 
-    for k, node in enumerate(applied):
+    for k in applied:
+        if not prog.special[k]:
+            if k in prog.errors:
+                raise prog.errors[k]
+            seg.append(k)
+            continue
+        flush()
+        node = prog.nodes[k]
         if node.name == "reset":
-            flush()
             stats = table.apply_reset(node.qubits[0], atol)
-            info.updates += int(stats.updates)
-        elif node.name == "LayerError":
-            flush()
+        else:
             ple = node.ple
             if ple is None:
                 raise RuntimeError(
@@ -313,16 +357,9 @@ def _run_slice(table: TermTable, applied, atol: float, sm: SliceMetadata, i: int
             gx[:, list(node.qubits)] = gens.x
             gz[:, list(node.qubits)] = gens.z
             stats = table.apply_damping(gx, gz, np.exp(-2 * np.asarray(ple.rates, dtype=float)), atol)
-            info.updates += int(stats.updates)
-        else:
-            prog = program_for(node)
-            rec = prog.template.copy()
-            rec["qubit"][0, : prog.n_qubits] = node.qubits
-            if k == last_idx:
-                rec["flags"] = OBP_FLAG_EXACT_COUNTERS
-            seg.append(rec)
-        info.applied_gates += 1
+        info.updates += int(stats.updates)
     flush()
+    info.applied_gates += len(applied)
     # the slice reports the counters of its last applied gate (backpropagation.py:218-237)
     sm.raw_num_paulis[i] = int(stats.raw_rows)
     sm.num_unique_paulis[i] = int(stats.num_unique)
