@@ -14,6 +14,7 @@ import logging
 import os
 import signal
 import sys
+import time
 from collections.abc import Sequence
 
 import numpy as np
@@ -46,6 +47,8 @@ class RunInfo:
 
 #: set True (bench.py does) to bracket every kernel launch with CUDA events
 PROFILE = False
+#: print one line per gate program (sizes, wall time) — debugging aid
+TRACE = bool(os.environ.get("OBP_B200_TRACE"))
 
 
 last_run = RunInfo()
@@ -330,8 +333,23 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
             ops = prog.recs[seg]  # fancy index: a fresh array
             if seg[-1] == last:
                 ops["flags"][-1] = OBP_FLAG_EXACT_COUNTERS
-            stats = table.apply_ops(ops, atol)
+            t0 = time.perf_counter() if TRACE else 0.0
+            n_before = table.n
+            try:
+                stats = table.apply_ops(ops, atol)
+            except CapacityError as exc:
+                info.updates += getattr(exc, "updates", 0)
+                raise
             info.updates += int(stats.updates)
+            if TRACE:
+                dt = time.perf_counter() - t0
+                kinds = ops["kind"]
+                print(
+                    f"[obp trace] ops {len(ops):4d} (rot {int((kinds == 2).sum()):3d}) n {n_before:>10d} -> {int(stats.n_out):>10d} "
+                    f"dense {int(stats.n_dense):>10d} updates {int(stats.updates):>12d} {dt * 1e3:9.3f} ms "
+                    f"{int(stats.updates) / max(dt, 1e-9) / 1e9:7.2f} G upd/s",
+                    flush=True,
+                )
             seg = []
 
     for k in applied:

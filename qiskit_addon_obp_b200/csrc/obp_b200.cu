@@ -60,6 +60,7 @@ struct obp_ctx {
   std::vector<u64> hx, hz;
   bool cols_dirty = true;
   u64 epoch = 1;
+  int rot_ctas_per_sm = 0;  // resident CTAs of k_rotate per SM (occupancy API)
   size_t cliff_smem_optin = 48 * 1024;  // dynamic smem k_clifford_smem is opted in for
   u64 n_live = 0, n_dense = 0;
   Snapshot snap;
@@ -68,6 +69,8 @@ struct obp_ctx {
   bool prof_on = false;
   obp_profile prof;
   std::vector<EventPair> ev_pending, ev_free;
+  EventPair run_ep{};
+  bool run_open = false;
   cudaEvent_t tm_a = nullptr, tm_b = nullptr;
   std::string err;
 
@@ -121,36 +124,43 @@ inline int grid_for(const obp_ctx* c, u64 rows, int per_sm = 8) {
   return (int)std::min(g, mx);
 }
 
-// RAII launch bracket: counts the launch and, while profiling, records an event pair.
-struct Bracket {
-  obp_ctx* c;
-  int klass;
-  EventPair ep{};
-  bool timed = false;
-  Bracket(obp_ctx* c_, int k) : c(c_), klass(k) {
-    c->prof.launches[k]++;
-    if (c->prof_on) {
-      if (!c->ev_free.empty()) {
-        ep = c->ev_free.back();
-        c->ev_free.pop_back();
-      } else {
-        cudaEventCreate(&ep.a);
-        cudaEventCreate(&ep.b);
-      }
-      ep.klass = k;
-      cudaEventRecord(ep.a, c->stream);
-      timed = true;
-    }
+// RAII launch bracket: counts the launch and, while profiling, times it with CUDA events.  Back to
+// back launches of the same class share one event pair (the run is closed when the class changes
+// or the stream is synchronised), so profiling adds two event records per run, not per launch.
+void close_run(obp_ctx* c) {
+  if (c->run_open) {
+    cudaEventRecord(c->run_ep.b, c->stream);
+    c->ev_pending.push_back(c->run_ep);
+    c->run_open = false;
   }
-  ~Bracket() {
-    if (timed) {
-      cudaEventRecord(ep.b, c->stream);
-      c->ev_pending.push_back(ep);
+}
+
+struct Bracket {
+  Bracket(obp_ctx* c, int k) {
+    c->prof.launches[k]++;
+    if (!c->prof_on) return;
+    if (c->run_open && c->run_ep.klass == k) return;
+    close_run(c);
+    EventPair ep{};
+    if (!c->ev_free.empty()) {
+      ep = c->ev_free.back();
+      c->ev_free.pop_back();
+    } else {
+      cudaEventCreate(&ep.a);
+      cudaEventCreate(&ep.b);
     }
+    ep.klass = k;
+    cudaEventRecord(ep.a, c->stream);
+    c->run_ep = ep;
+    c->run_open = true;
   }
 };
 
 void resolve_events(obp_ctx* c) {
+  if (c->run_open) {  // callers close the run before they synchronise; this is the safety net
+    close_run(c);
+    cudaEventSynchronize(c->ev_pending.back().b);
+  }
   for (auto& ep : c->ev_pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) c->prof.ms[ep.klass] += ms;
@@ -160,6 +170,7 @@ void resolve_events(obp_ctx* c) {
 }
 
 int sync_state(obp_ctx* ctx) {
+  close_run(ctx);
   CU(cudaMemcpyAsync(ctx->h_st, ctx->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   resolve_events(ctx);
@@ -442,6 +453,8 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     if (rc) return rc;
     rc = ensure_ops(ctx, 256);
     if (rc) return rc;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->rot_ctas_per_sm, k_rotate, OBP_BS, 0));
+    if (ctx->rot_ctas_per_sm < 1) ctx->rot_ctas_per_sm = 1;
     init_frame(ctx);
     return set_counts(ctx, 0);
   };
@@ -759,7 +772,7 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
       p.slot = n_slots;
       {
         Bracket br(ctx, OBP_K_ROTATE);
-        k_rotate<<<grid_for(ctx, bound, 4), OBP_BS, 0, ctx->stream>>>(t, p);
+        k_rotate<<<grid_for(ctx, bound, ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(t, p);  // one wave
         CU(cudaGetLastError());
       }
       slot_of_op[k] = n_slots;
@@ -772,10 +785,11 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
   if (rc) return rc;
 
   CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat) * n_slots, cudaMemcpyDeviceToHost, ctx->stream));
-  rc = sync_state(ctx);
-  if (rc) return rc;
+  const int sync_rc = sync_state(ctx);
+  if (sync_rc && sync_rc != OBP_ERR_CAPACITY) return sync_rc;
 
-  // term-gate updates: live terms at entry of every op
+  // term-gate updates: live terms at entry of every op (also accounted when the table overflowed:
+  // the kernels ran, the caller rolls the slice back)
   u64 updates = 0, n_in = n_start, n_in_last = n_start;
   for (int s = 0; s < n_slots; ++s) {
     updates += n_in * (u64)slot_gates[s];
@@ -791,6 +805,10 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
       ctx->prof.term_updates[ops[k].kind == OBP_OP_ROTATION ? OBP_K_ROTATE : OBP_K_CLIFFORD] += nin;
       s_prev = s;
     }
+  }
+  if (sync_rc) {
+    if (stats) stats->updates = updates;
+    return sync_rc;
   }
   if (stats) {
     const obp_op& last = ops[n_ops - 1];
@@ -969,6 +987,7 @@ int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double
       k_final_sum<<<1, OBP_BS, 0, ctx->stream>>>(ctx->d_partial, gs, ctx->d_scalar);
       CU(cudaGetLastError());
     }
+    close_run(ctx);
     CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const double mid_error = p_norm == 1 ? ctx->h_scalar[0] : std::pow(ctx->h_scalar[0], 1.0 / p_norm);

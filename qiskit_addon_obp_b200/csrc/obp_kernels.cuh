@@ -91,7 +91,10 @@ __device__ __forceinline__ long long find_partner(const Tab& t, const RotP& p, u
     if (e == OBP_EMPTY) return -1;
     if ((e >> 32) == fp) {
       const u64 j = e & 0xffffffffull;
-      if (j < n_scan && t.hash[j] == h2) {
+      if (j < n_scan) {
+        // the 32-bit fingerprint already matched: compare the full key (all words are independent
+        // loads, issued together with the coefficient) instead of chasing hash[j] first
+        const double2 cj = t.coef[j];
         bool eq = true;
         for (int w = 0; w < t.W && eq; ++w) {
           u64 gx, gz;
@@ -100,7 +103,7 @@ __device__ __forceinline__ long long find_partner(const Tab& t, const RotP& p, u
           eq = (kj.x == (ki.x ^ gx)) && (kj.y == (ki.y ^ gz));
         }
         if (eq) {
-          cq = t.coef[j];
+          cq = cj;
           if (is_live(cq)) return (long long)j;
           if (tomb_epoch(cq) == p.epoch) { fresh = true; return (long long)j; }
           // stale tombstone of the same key: keep probing for a live duplicate
@@ -112,18 +115,22 @@ __device__ __forceinline__ long long find_partner(const Tab& t, const RotP& p, u
   return -1;
 }
 
-__global__ void __launch_bounds__(OBP_BS) k_rotate(Tab t, const __grid_constant__ RotP p) {
-  __shared__ unsigned warp_tot[OBP_BS / 32];
-  __shared__ u64 s_base;
+#ifndef OBP_ROT_MINB
+#define OBP_ROT_MINB 4  // resident CTAs per SM the register allocation is held to
+#endif
+__global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate(Tab t, const __grid_constant__ RotP p) {
   const u64 n = t.st->n_scan;
+  const unsigned lane = threadIdx.x & 31u;
   // per-thread counters
   unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
   int dlive = 0;
   double sum_re = 0.0, sum_im = 0.0;
   bool overflow = false;
 
-  for (u64 base = (u64)blockIdx.x * OBP_BS; base < n; base += (u64)gridDim.x * OBP_BS) {
-    const u64 i = base + threadIdx.x;
+  // Warps run independently (no CTA barrier): a warp whose rows need long partner probes does not
+  // hold back the others.  Rows are taken in warp-sized, fully coalesced chunks.
+  for (u64 base = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)); base < n; base += (u64)gridDim.x * OBP_BS) {
+    const u64 i = base + lane;
     bool want_append = false;
     double2 app_c = make_double2(0.0, 0.0);
     if (i < n) {
@@ -208,14 +215,14 @@ __global__ void __launch_bounds__(OBP_BS) k_rotate(Tab t, const __grid_constant_
         }
       }
     }
-    // ---- append the new keys of this CTA iteration: ballot + block prefix scan -----------------
-    unsigned total;
-    const unsigned off = block_scan_flag(want_append, warp_tot, total);
-    if (total) {
-      if (threadIdx.x == 0) s_base = atomicAdd(&t.st->n_append, (u64)total);
-      __syncthreads();
+    // ---- append the new keys of this warp: ballot, one atomicAdd on the cursor per warp ---------
+    const unsigned bal = __ballot_sync(0xffffffffu, want_append);
+    if (bal) {
+      u64 wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&t.st->n_append, (u64)__popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
       if (want_append) {
-        const u64 row = s_base + off;
+        const u64 row = wbase + __popc(bal & ((1u << lane) - 1u));
         if (row < t.cap) {
           for (int w = 0; w < t.W; ++w) {
             u64 gx, gz;
@@ -234,7 +241,6 @@ __global__ void __launch_bounds__(OBP_BS) k_rotate(Tab t, const __grid_constant_
           overflow = true;
         }
       }
-      __syncthreads();
     }
   }
   if (overflow) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
@@ -243,14 +249,14 @@ __global__ void __launch_bounds__(OBP_BS) k_rotate(Tab t, const __grid_constant_
   if (p.exact) {
     const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present), cz = warp_sum_u64(cancelled);
     const double sr = warp_sum_f64(sum_re), si = warp_sum_f64(sum_im);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
       OpStat* o = &t.ops[p.slot];
       if (a) atomicAdd(&o->rows_surv, a);
       if (b) atomicAdd(&o->keys_present, b);
       if (cz) { atomicAdd(&o->cancelled, cz); atomicAdd(&o->sum_re, sr); atomicAdd(&o->sum_im, si); }
     }
   }
-  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)dl);
+  if (lane == 0 && dl) atomicAdd(&t.st->n_live, (u64)dl);
   finish_kernel(t, p.slot);
 }
 

@@ -16,7 +16,9 @@ import numpy as np
 from .ir import SparsePauliOp, pack_xz
 from .utils.simplify import SimplifyMetadata
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libobp_b200.so")
+_LIB_PATH = os.environ.get(
+    "OBP_B200_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), "libobp_b200.so")
+)  # the override selects another build of the same CUDA library (kernel A/B runs)
 
 OBP_OK = 0
 OBP_ERR_CAPACITY = -4
@@ -300,7 +302,11 @@ class TermTable:
         rc = self._lib.obp_apply_ops(
             self._h, ops.ctypes.data_as(C.c_void_p), len(ops), float(atol), C.byref(st)
         )
-        self._check(rc, "obp_apply_ops")
+        try:
+            self._check(rc, "obp_apply_ops")
+        except CapacityError as exc:
+            exc.updates = int(st.updates)  # the kernels ran before the overflow was detected
+            raise
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0:
             self.zero_operator = True
