@@ -423,7 +423,8 @@ __global__ void __launch_bounds__(OBP_BS) k_coset_count(Tab t, const __grid_cons
         if (e == OBP_EMPTY) break;
         if ((e >> 32) == fp) {
           const u64 j = e & 0xffffffffull;
-          if (j < n && t.hash[j] == h2) {
+          if (j < n) {
+            const double2 cj = t.coef[j];  // independent of the key words: issued together
             bool eq = true;
             for (int w = 0; w < t.W && eq; ++w) {
               u64 mx = 0, mz = 0;
@@ -433,7 +434,6 @@ __global__ void __launch_bounds__(OBP_BS) k_coset_count(Tab t, const __grid_cons
               eq = (kj.x == (ki.x ^ mx)) && (kj.y == (ki.y ^ mz));
             }
             if (eq) {
-              const double2 cj = t.coef[j];
               if (is_live(cj)) {
                 if (!(hypot(cj.x, cj.y) * p.scale <= p.atol)) cnt++;
                 break;
