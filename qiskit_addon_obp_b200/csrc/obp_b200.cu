@@ -769,6 +769,7 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
       p.atol = atol;
       p.epoch = ++ctx->epoch;
       p.exact = (op.flags & OBP_FLAG_EXACT_COUNTERS) ? 1 : 0;
+      p.simple = (op.u0[1] == 0.0 && op.u1[0] == 0.0) ? 1 : 0;
       p.slot = n_slots;
       {
         Bracket br(ctx, OBP_K_ROTATE);

@@ -83,8 +83,26 @@ __device__ __forceinline__ double2 mul_mi_pow(double2 a, int e) {
     default: return make_double2(-a.y, a.x);
   }
 }
-// np.isclose(c, 0, atol, rtol) == (|c| <= atol); NaN compares false, i.e. the row is kept
-__device__ __forceinline__ bool is_small(double2 a, double atol) { return hypot(a.x, a.y) <= atol; }
+// np.isclose(c, 0, atol, rtol) == (|c| <= atol) with |c| = hypot(re, im); NaN compares false, i.e.
+// the row is kept.  hypot() is ~60 instructions in fp64, so the squared magnitude decides unless it
+// lies within 1e-9 (relative) of atol^2; only then the exact expression is evaluated.  The result is
+// bit-identical to the plain hypot test.
+__device__ __forceinline__ bool is_small(double2 a, double atol) {
+  if (atol < 0.0) return false;
+  const double m2 = fma(a.x, a.x, a.y * a.y);
+  const double t2 = atol * atol;
+  if (m2 > t2 * (1.0 + 1e-9)) return false;
+  if (m2 < t2 * (1.0 - 1e-9)) return true;
+  return hypot(a.x, a.y) <= atol;
+}
+// |c| * scale <= atol (raw-row filter of a Clifford-class gate), same two-stage evaluation
+__device__ __forceinline__ bool is_small_scaled(double2 a, double scale, double atol) {
+  const double m2 = fma(a.x, a.x, a.y * a.y) * (scale * scale);
+  const double t2 = atol * atol;
+  if (m2 > t2 * (1.0 + 1e-9)) return false;
+  if (m2 < t2 * (1.0 - 1e-9)) return true;
+  return hypot(a.x, a.y) * scale <= atol;
+}
 
 __device__ __forceinline__ u64 ld_volatile(const u64* p) { return *(const volatile u64*)p; }
 
