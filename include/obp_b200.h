@@ -142,6 +142,44 @@ int obp_restore(obp_ctx* ctx);
 /* Grow the table to hold new_capacity terms (contents preserved). */
 int obp_reserve(obp_ctx* ctx, uint64_t new_capacity);
 
+/* ---- sharded table (multi-GPU) ---------------------------------------------------------------
+ * One process per GPU; rank r of R (a power of two) holds the terms whose Clifford-invariant hash
+ * has its top log2(R) bits equal to r, so duplicate keys co-locate and Clifford gates, damping and
+ * truncation kills stay rank-local.  The reference has no counterpart (single process): these entry
+ * points split the per-gate body of backpropagation.py:210-237 around the one exchange step a
+ * branching gate needs.  All ranks must issue the same calls in the same order. */
+typedef struct {
+  uint64_t n_in, n_out, n_dense;
+  uint64_t rows_surv;     /* raw rows that passed the zero filter (counted where they are produced)   */
+  uint64_t keys_present;  /* distinct keys among them (counted where the key lives)                   */
+  uint64_t cancelled;     /* merged keys with |sum| <= atol                                           */
+  uint64_t n_records;     /* records emitted for the peer                                             */
+  double sum_trimmed[2];
+} obp_shard_counters;
+
+int obp_set_shard(obp_ctx* ctx, int32_t n_ranks, int32_t rank);
+/* Bytes of one exchange record: W x/z word pairs, the hash, the complex128 coefficient. */
+uint64_t obp_record_bytes(int n_qubits);
+/* obp_apply_ops on a sharded table: stops before the first rotation whose partner keys live on
+ * another rank.  *n_done = ops executed; *peer_xor = 0 if the program is finished, else the peer of
+ * rank r for ops[*n_done] is r ^ *peer_xor. */
+int obp_apply_ops_sharded(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,
+                          int32_t* n_done, int32_t* peer_xor);
+/* Split rotation, part 1: update the rows' own keys and write the partner-key contributions as
+ * records into the DEVICE buffer d_records (room for cap_records; out->n_records are produced). */
+int obp_rotate_emit(obp_ctx* ctx, const obp_op* op, double atol, void* d_records, uint64_t cap_records,
+                    obp_shard_counters* out);
+/* Split rotation, part 2: merge the n_records the peer sent (DEVICE buffer) and run the second
+ * zero filter.  Counters of emit and merge add up across ranks to the reference's simplify counters:
+ * num_unique = sum keys_present, num_duplicate = sum rows_surv - num_unique,
+ * num_trimmed = 4 * sum n_in(emit) - sum rows_surv + sum cancelled. */
+int obp_rotate_merge(obp_ctx* ctx, const void* d_records, uint64_t n_records, obp_shard_counters* out);
+/* Stepwise truncation: truncate_binary_search (utils/truncating.py:171-204) with the maximum
+ * (:173) and each masked sum (:187) exposed so that ranks can combine them with an allreduce. */
+int obp_trunc_begin(obp_ctx* ctx, int32_t p_norm, double* local_max);
+int obp_trunc_masked_sum(obp_ctx* ctx, double threshold, double* local_sum);
+int obp_trunc_finish(obp_ctx* ctx, double threshold, uint64_t* n_removed, uint64_t* n_out);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 
 enum { OBP_K_ROTATE = 0, OBP_K_CLIFFORD = 1, OBP_K_TRUNCATE = 2, OBP_K_COMPACT = 3,

@@ -23,6 +23,7 @@ from . import engine
 from .engine import OBP_FLAG_EXACT_COUNTERS, OP_DTYPE, CapacityError, TermTable
 from .gates import program_for
 from .ir import QuantumCircuit, SparsePauliOp, topological_op_order
+from .sharded import ShardedTable, communicator_from_env
 from .utils.metadata import OBPMetadata, SliceMetadata
 from .utils.simplify import OperatorBudget
 from .utils.truncating import TruncationErrorBudget
@@ -104,6 +105,10 @@ def backpropagate(
     qargs = [_support(o) for o in obs_in]
     device = engine.default_device()
     capacity = _default_capacity(num_qubits, operator_budget, n_obs, device)
+    comm = communicator_from_env(device)  # None: one table per observable on this GPU
+    if comm is not None:
+        if n_obs > 1 and operator_budget.is_active():
+            raise NotImplementedError("a sharded table supports operator budgets for a single observable only")
 
     metadata = OBPMetadata(
         truncation_error_budget=truncation_error_budget,
@@ -133,7 +138,11 @@ def backpropagate(
 
     try:
         for i in range(n_obs):
-            tables.append(TermTable.acquire(num_qubits, max(capacity, 2 * len(obs_in[i])), device))
+            cap_i = max(capacity, 2 * len(obs_in[i]))
+            if comm is None:
+                tables.append(TermTable.acquire(num_qubits, cap_i, device))
+            else:
+                tables.append(ShardedTable.acquire(num_qubits, cap_i, comm))
         try:
             for slice_ in slices_ir[::-1]:
                 sm = SliceMetadata(
@@ -380,11 +389,16 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
     info.applied_gates += len(applied)
     # the slice reports the counters of its last applied gate (backpropagation.py:218-237)
     sm.raw_num_paulis[i] = int(stats.raw_rows)
-    sm.num_unique_paulis[i] = int(stats.num_unique)
-    sm.num_duplicate_paulis[i] = int(stats.num_duplicate)
-    sm.num_trimmed_paulis[i] = int(stats.num_trimmed)
-    s = complex(stats.sum_trimmed[0], stats.sum_trimmed[1])
-    sm.sum_trimmed_coeffs[i] = s if s != 0 else 0.0
+    if getattr(stats, "counters_valid", True):
+        sm.num_unique_paulis[i] = int(stats.num_unique)
+        sm.num_duplicate_paulis[i] = int(stats.num_duplicate)
+        sm.num_trimmed_paulis[i] = int(stats.num_trimmed)
+        s = complex(stats.sum_trimmed[0], stats.sum_trimmed[1])
+        sm.sum_trimmed_coeffs[i] = s if s != 0 else 0.0
+    else:
+        # sharded table, last gate Clifford-class: its coset count would need a cross-rank exchange
+        sm.num_unique_paulis[i] = sm.num_duplicate_paulis[i] = sm.num_trimmed_paulis[i] = None
+        sm.sum_trimmed_coeffs[i] = None
 
 
 def _support(op: SparsePauliOp) -> list[int]:
@@ -424,7 +438,9 @@ def _observable_oversized(tables, loaded, obs_in, operator_budget, slice_id, sm)
         return union
 
     if max_paulis is not None:
-        if not host_ops and all(not t.zero_operator for t in dev_tables):
+        if not host_ops and len(dev_tables) == 1 and not dev_tables[0].zero_operator:
+            sm.sum_paulis = dev_tables[0].n  # one observable: its keys are already distinct
+        elif not host_ops and all(not t.zero_operator for t in dev_tables):
             sm.sum_paulis = engine.union_count(dev_tables)
         else:
             sm.sum_paulis = len(union_op())

@@ -60,6 +60,11 @@ struct obp_ctx {
   std::vector<u64> hx, hz;
   bool cols_dirty = true;
   u64 epoch = 1;
+  int n_ranks = 1, rank = 0, owner_shift = 64;  // sharding: owner = hash >> owner_shift
+  ShardCnt* d_cnt = nullptr;
+  ShardCnt* h_cnt = nullptr;  // pinned
+  RotP shard_rot;             // rotation being split across obp_rotate_emit / obp_rotate_merge
+  bool shard_rot_open = false;
   int rot_ctas_per_sm = 0;  // resident CTAs of k_rotate per SM (occupancy API)
   size_t cliff_smem_optin = 48 * 1024;  // dynamic smem k_clifford_smem is opted in for
   u64 n_live = 0, n_dense = 0;
@@ -382,6 +387,64 @@ struct PendingBatch {
   }
 };
 
+// kernel parameters of a rotation op under the current hash frame (epoch and slot are set by the caller)
+RotP build_rotp(const obp_ctx* ctx, const obp_op& op, double atol) {
+  RotP p;
+  memset(&p, 0, sizeof(p));
+  u64 hG = 0;
+  int yG = 0;
+  for (int j = 0; j < op.n_qubits; ++j) {
+    const unsigned code = (op.gen_local >> (2 * j)) & 3u;
+    if (!code) continue;
+    const int w = op.qubit[j] / 64;
+    const u64 bit = 1ull << (op.qubit[j] % 64);
+    int sl = -1;
+    for (int s = 0; s < p.ngw; ++s)
+      if (p.gw[s] == w) sl = s;
+    if (sl < 0) {
+      sl = p.ngw++;
+      p.gw[sl] = w;
+    }
+    if (code & 1u) { p.gx[sl] |= bit; hG ^= ctx->hx[op.qubit[j]]; }
+    if (code & 2u) { p.gz[sl] |= bit; hG ^= ctx->hz[op.qubit[j]]; }
+    if (code == 3u) yG++;
+  }
+  p.hG = hG;
+  p.yG = yG;
+  p.canon_slot = 0;
+  {
+    const u64 m = p.gx[0] | p.gz[0];
+    const u64 low = m & (~m + 1);
+    p.canon_bit = low;
+    p.canon_z = (p.gx[0] & low) ? 0 : 1;
+  }
+  p.u0r = op.u0[0];
+  p.u0i = op.u0[1];
+  p.u1r = op.u1[0];
+  p.u1i = op.u1[1];
+  p.atol = atol;
+  p.exact = (op.flags & OBP_FLAG_EXACT_COUNTERS) ? 1 : 0;
+  p.simple = (op.u0[1] == 0.0 && op.u1[0] == 0.0) ? 1 : 0;
+  return p;
+}
+
+int validate_op(obp_ctx* ctx, const obp_op& op) {
+  const int maxq = op.kind == OBP_OP_CLIFFORD ? 2 : 4;
+  if ((op.kind != OBP_OP_CLIFFORD && op.kind != OBP_OP_ROTATION) || op.n_qubits < 1 || op.n_qubits > maxq)
+    return ctx->fail(OBP_ERR_UNSUPPORTED, "unsupported op kind or qubit count");
+  for (int j = 0; j < op.n_qubits; ++j) {
+    if (op.qubit[j] < 0 || op.qubit[j] >= ctx->nq) return ctx->fail(OBP_ERR_BADARG, "qubit out of range");
+    for (int l = 0; l < j; ++l)
+      if (op.qubit[l] == op.qubit[j]) return ctx->fail(OBP_ERR_BADARG, "duplicate qubit");
+  }
+  if (op.kind == OBP_OP_CLIFFORD && !lut_is_linear_bijection(op))
+    return ctx->fail(OBP_ERR_BADARG, "Clifford table is not a linear bijection");
+  if (op.kind == OBP_OP_ROTATION && (op.gen_local & ((1u << (2 * op.n_qubits)) - 1u)) == 0)
+    return ctx->fail(OBP_ERR_BADARG, "rotation generator is the identity");
+  if (op.kind == OBP_OP_CLIFFORD && op.group_size > 16) return ctx->fail(OBP_ERR_BADARG, "group_size > 16");
+  return OBP_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -449,6 +512,8 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     CU(cudaMalloc(&ctx->d_partial, sizeof(double) * (size_t)ctx->n_sm * 8));
     CU(cudaMalloc(&ctx->d_scalar, sizeof(double) * 2));
     CU(cudaMalloc(&ctx->d_cols, sizeof(u64) * 2 * 64 * ctx->W));
+    CU(cudaMalloc(&ctx->d_cnt, sizeof(ShardCnt)));
+    CU(cudaMallocHost(&ctx->h_cnt, sizeof(ShardCnt)));
     int rc = alloc_table(ctx, capacity);
     if (rc) return rc;
     rc = ensure_ops(ctx, 256);
@@ -476,6 +541,8 @@ void obp_destroy(obp_ctx* ctx) {
   cudaFree(ctx->d_partial);
   cudaFree(ctx->d_scalar);
   cudaFree(ctx->d_cols);
+  cudaFree(ctx->d_cnt);
+  if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
   cudaFree(ctx->d_gens);
   cudaFree(ctx->d_factors);
   if (ctx->h_st) cudaFreeHost(ctx->h_st);
@@ -534,6 +601,7 @@ int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, con
     Bracket b(ctx, OBP_K_INDEX);
     const int g = grid_for(ctx, n);
     k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n);
+    if (ctx->n_ranks > 1) k_shard_filter<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->owner_shift, (u64)ctx->rank);
     ctx->epoch++;
     k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ctx->epoch, 0);
     ctx->epoch++;
@@ -546,12 +614,13 @@ int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, con
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     const OpStat& o = ctx->h_ops[0];
-    // rows given as exact zeros count as filtered raw rows
-    stats->n_in = n;
-    stats->raw_rows = n;
+    // rows given as exact zeros count as filtered raw rows; rows of other ranks do not count at all
+    const u64 n_mine = n - (ctx->n_ranks > 1 ? ctx->h_st->removed : 0);
+    stats->n_in = n_mine;
+    stats->raw_rows = n_mine;
     stats->num_unique = o.keys_present;
     stats->num_duplicate = o.rows_surv - o.keys_present;
-    stats->num_trimmed = (n - o.rows_surv) + o.cancelled;
+    stats->num_trimmed = (n_mine - o.rows_surv) + o.cancelled;
     stats->sum_trimmed[0] = o.sum_re;
     stats->sum_trimmed[1] = o.sum_im;
     stats->n_out = ctx->n_live;
@@ -594,8 +663,13 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
 }
 
 // -------------------------------------------------------------------------------------------------
-int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats) {
+// Runs ops[0, n_ops) — or, on a sharded table, up to the first rotation whose partner keys live on
+// another rank: *n_done = ops executed, *peer_xor = owner bits of that rotation's generator hash.
+static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,
+                          int32_t* n_done, int32_t* peer_xor) {
   if (!ctx || (n_ops && !ops) || n_ops < 0) return OBP_ERR_BADARG;
+  if (n_done) *n_done = n_ops;
+  if (peer_xor) *peer_xor = 0;
   CU(cudaSetDevice(ctx->device));
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n_ops == 0) {
@@ -604,21 +678,8 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
   }
   // validate before enqueuing anything
   for (int k = 0; k < n_ops; ++k) {
-    const obp_op& op = ops[k];
-    const int maxq = op.kind == OBP_OP_CLIFFORD ? 2 : 4;
-    if ((op.kind != OBP_OP_CLIFFORD && op.kind != OBP_OP_ROTATION) || op.n_qubits < 1 || op.n_qubits > maxq)
-      return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_ops: unsupported op kind or qubit count");
-    for (int j = 0; j < op.n_qubits; ++j) {
-      if (op.qubit[j] < 0 || op.qubit[j] >= ctx->nq) return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: qubit out of range");
-      for (int l = 0; l < j; ++l)
-        if (op.qubit[l] == op.qubit[j]) return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: duplicate qubit");
-    }
-    if (op.kind == OBP_OP_CLIFFORD && !lut_is_linear_bijection(op))
-      return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: Clifford table is not a linear bijection");
-    if (op.kind == OBP_OP_ROTATION && (op.gen_local & ((1u << (2 * op.n_qubits)) - 1u)) == 0)
-      return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: rotation generator is the identity");
-    if (op.kind == OBP_OP_CLIFFORD && op.group_size > 16)
-      return ctx->fail(OBP_ERR_BADARG, "obp_apply_ops: group_size > 16");
+    const int vrc = validate_op(ctx, ops[k]);
+    if (vrc) return vrc;
   }
   int rc = ensure_ops(ctx, n_ops + 1);
   if (rc) return rc;
@@ -733,43 +794,16 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
     } else {
       rc = flush();
       if (rc) return rc;
-      RotP p;
-      memset(&p, 0, sizeof(p));
-      u64 hG = 0;
-      int yG = 0;
-      for (int j = 0; j < op.n_qubits; ++j) {
-        const unsigned code = (op.gen_local >> (2 * j)) & 3u;
-        if (!code) continue;
-        const int w = op.qubit[j] / 64;
-        const u64 bit = 1ull << (op.qubit[j] % 64);
-        int sl = -1;
-        for (int s = 0; s < p.ngw; ++s)
-          if (p.gw[s] == w) sl = s;
-        if (sl < 0) {
-          sl = p.ngw++;
-          p.gw[sl] = w;
-        }
-        if (code & 1u) { p.gx[sl] |= bit; hG ^= ctx->hx[op.qubit[j]]; }
-        if (code & 2u) { p.gz[sl] |= bit; hG ^= ctx->hz[op.qubit[j]]; }
-        if (code == 3u) yG++;
+      RotP p = build_rotp(ctx, op, atol);
+      if (ctx->n_ranks > 1 && (p.hG >> ctx->owner_shift) != 0) {
+        // partner keys of this rotation belong to rank ^ d: the caller runs the split rotation
+        if (!n_done || !peer_xor) return ctx->fail(OBP_ERR_BADARG, "sharded table: use obp_apply_ops_sharded");
+        *n_done = k;
+        *peer_xor = (int32_t)(p.hG >> ctx->owner_shift);
+        n_ops = k;
+        break;
       }
-      p.hG = hG;
-      p.yG = yG;
-      p.canon_slot = 0;
-      {
-        const u64 m = p.gx[0] | p.gz[0];
-        const u64 low = m & (~m + 1);
-        p.canon_bit = low;
-        p.canon_z = (p.gx[0] & low) ? 0 : 1;
-      }
-      p.u0r = op.u0[0];
-      p.u0i = op.u0[1];
-      p.u1r = op.u1[0];
-      p.u1i = op.u1[1];
-      p.atol = atol;
       p.epoch = ++ctx->epoch;
-      p.exact = (op.flags & OBP_FLAG_EXACT_COUNTERS) ? 1 : 0;
-      p.simple = (op.u0[1] == 0.0 && op.u1[0] == 0.0) ? 1 : 0;
       p.slot = n_slots;
       {
         Bracket br(ctx, OBP_K_ROTATE);
@@ -784,6 +818,10 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
   }
   rc = flush();
   if (rc) return rc;
+  if (n_ops == 0) {  // a sharded program that starts with an exchange rotation
+    if (stats) { stats->n_in = stats->n_out = ctx->n_live; stats->n_dense = ctx->n_dense; }
+    return OBP_OK;
+  }
 
   CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat) * n_slots, cudaMemcpyDeviceToHost, ctx->stream));
   const int sync_rc = sync_state(ctx);
@@ -847,6 +885,106 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
   if (stats) {
     stats->n_out = ctx->n_live;
     stats->n_dense = ctx->n_dense;
+  }
+  return OBP_OK;
+}
+
+int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats) {
+  return apply_ops_impl(ctx, ops, n_ops, atol, stats, nullptr, nullptr);
+}
+
+int obp_apply_ops_sharded(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,
+                          int32_t* n_done, int32_t* peer_xor) {
+  if (!n_done || !peer_xor) return OBP_ERR_BADARG;
+  return apply_ops_impl(ctx, ops, n_ops, atol, stats, n_done, peer_xor);
+}
+
+// -------------------------------------------------------------------------------------------------
+// sharded table: configuration, the split rotation, stepwise truncation
+int obp_set_shard(obp_ctx* ctx, int32_t n_ranks, int32_t rank) {
+  if (!ctx || n_ranks < 1 || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks || n_ranks > 1024)
+    return OBP_ERR_BADARG;
+  int bits = 0;
+  while ((1 << bits) < n_ranks) ++bits;
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  ctx->owner_shift = 64 - bits;  // 64 for a single rank: never used as a shift then
+  return OBP_OK;
+}
+
+uint64_t obp_record_bytes(int n_qubits) {
+  const u64 W = (u64)std::max(1, (n_qubits + 63) / 64);
+  return (2 * W + 3) * sizeof(u64);
+}
+
+static void fill_shard_stats(obp_ctx* ctx, obp_shard_counters* out, u64 n_in) {
+  if (!out) return;
+  const ShardCnt& c = *ctx->h_cnt;
+  out->n_in = n_in;
+  out->n_out = ctx->n_live;
+  out->n_dense = ctx->n_dense;
+  out->rows_surv = c.rows_surv;
+  out->keys_present = c.keys_present;
+  out->cancelled = c.cancelled;
+  out->n_records = c.n_records;
+  out->sum_trimmed[0] = c.sum_re;
+  out->sum_trimmed[1] = c.sum_im;
+}
+
+int obp_rotate_emit(obp_ctx* ctx, const obp_op* op, double atol, void* d_records, uint64_t cap_records,
+                    obp_shard_counters* out) {
+  if (!ctx || !op || op->kind != OBP_OP_ROTATION || (cap_records && !d_records)) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  int rc = validate_op(ctx, *op);
+  if (rc) return rc;
+  RotP p = build_rotp(ctx, *op, atol);
+  p.epoch = ++ctx->epoch;
+  p.slot = -1;
+  ctx->shard_rot = p;
+  ctx->shard_rot_open = true;
+  const u64 n_in = ctx->n_live;
+  CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));
+  {
+    Bracket br(ctx, OBP_K_ROTATE);
+    k_rotate_emit<<<grid_for(ctx, std::max<u64>(ctx->n_dense, 1), ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(
+        make_tab(ctx), p, (u64*)d_records, cap_records, ctx->d_cnt);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  ctx->prof.term_updates[OBP_K_ROTATE] += n_in;
+  fill_shard_stats(ctx, out, n_in);
+  if (rc == OBP_OK && ctx->h_cnt->n_records > cap_records)
+    return ctx->fail(OBP_ERR_CAPACITY, "obp_rotate_emit: record buffer too small");
+  return rc;
+}
+
+int obp_rotate_merge(obp_ctx* ctx, const void* d_records, uint64_t n_records, obp_shard_counters* out) {
+  if (!ctx || (n_records && !d_records)) return OBP_ERR_BADARG;
+  if (!ctx->shard_rot_open) return ctx->fail(OBP_ERR_BADARG, "obp_rotate_merge: no rotation in flight");
+  CU(cudaSetDevice(ctx->device));
+  ctx->shard_rot_open = false;
+  const u64 n_in = ctx->n_live;
+  CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));
+  Tab t = make_tab(ctx);
+  {
+    Bracket br(ctx, OBP_K_ROTATE);
+    if (n_records)
+      k_merge_records<<<grid_for(ctx, n_records), OBP_BS, 0, ctx->stream>>>(t, (const u64*)d_records, n_records, ctx->d_cnt);
+    const u64 bound = std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense + n_records, 1));
+    k_rotate_finish<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, ctx->shard_rot, ctx->d_cnt);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = sync_state(ctx);
+  fill_shard_stats(ctx, out, n_in);
+  if (rc) return rc;
+  if (ctx->n_dense - ctx->n_live > std::max<u64>(1024, ctx->n_live / 4)) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+    if (out) out->n_dense = ctx->n_dense;
   }
   return OBP_OK;
 }
@@ -952,64 +1090,60 @@ int obp_apply_damping(obp_ctx* ctx, const uint64_t* gen_x, const uint64_t* gen_z
 }
 
 // -------------------------------------------------------------------------------------------------
-int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double* slice_error,
-                 uint64_t* n_removed, uint64_t* n_out) {
-  if (!ctx || p_norm < 1) return OBP_ERR_BADARG;
+// Stepwise truncation (utils/truncating.py:171-204): begin caches |c|^p and returns its maximum,
+// masked_sum returns sum(a[a < threshold]), finish keeps a > threshold.  obp_truncate() runs the
+// reference's bisection on one table; a sharded table runs the same loop on the host with the
+// per-rank maxima / sums combined by an allreduce between the steps.
+int obp_trunc_begin(obp_ctx* ctx, int32_t p_norm, double* local_max) {
+  if (!ctx || p_norm < 1 || !local_max) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
-  if (slice_error) *slice_error = 0.0;
-  if (n_removed) *n_removed = 0;
-  if (n_out) *n_out = ctx->n_live;
-  if (ctx->n_live == 0) return OBP_OK;
-  Tab t = make_tab(ctx);
-  double* a = (double*)ctx->spare16;
-  const int g = grid_for(ctx, ctx->n_dense);
-  const int gs = std::min(g, ctx->n_sm * 8);
+  *local_max = 0.0;
   CU(cudaMemsetAsync(&ctx->d_st->removed, 0, 2 * sizeof(u64), ctx->stream));  // removed, amax_bits
-  {
+  if (ctx->n_dense) {
     Bracket br(ctx, OBP_K_TRUNCATE);
-    k_absp<<<g, OBP_BS, 0, ctx->stream>>>(t, a, p_norm);
+    k_absp<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), (double*)ctx->spare16, p_norm);
     CU(cudaGetLastError());
   }
-  int rc = sync_state(ctx);
+  const int rc = sync_state(ctx);
   if (rc) return rc;
-  double upper;
-  {
-    const u64 bits = ctx->h_st->amax_bits;
-    memcpy(&upper, &bits, sizeof(double));
-  }
-  // utils/truncating.py:173-196, evaluated on the host with device-side masked sums
-  double lower = 0.0, upper_error = budget, lower_error = 0.0;
-  auto isclose = [&](double x, double y) { return std::fabs(x - y) <= tol + 1e-5 * std::fabs(y); };
-  while ((upper - lower) > tol && !isclose(upper_error, lower_error)) {
-    const double mid = (upper + lower) / 2;
-    {
-      Bracket br(ctx, OBP_K_TRUNCATE);
-      k_masked_sum<<<gs, OBP_BS, 0, ctx->stream>>>(a, ctx->d_st, mid, ctx->d_partial);
-      k_final_sum<<<1, OBP_BS, 0, ctx->stream>>>(ctx->d_partial, gs, ctx->d_scalar);
-      CU(cudaGetLastError());
-    }
-    close_run(ctx);
-    CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    const double mid_error = p_norm == 1 ? ctx->h_scalar[0] : std::pow(ctx->h_scalar[0], 1.0 / p_norm);
-    if (mid_error <= budget) {
-      lower = mid;
-      lower_error = mid_error;
-    } else {
-      upper = mid;
-      upper_error = mid_error;
-    }
-  }
-  const u64 before = ctx->n_live;
+  const u64 bits = ctx->h_st->amax_bits;
+  memcpy(local_max, &bits, sizeof(double));
+  return OBP_OK;
+}
+
+int obp_trunc_masked_sum(obp_ctx* ctx, double threshold, double* local_sum) {
+  if (!ctx || !local_sum) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  *local_sum = 0.0;
+  if (ctx->n_dense == 0) return OBP_OK;
+  const int gs = std::min(grid_for(ctx, ctx->n_dense), ctx->n_sm * 8);
   {
     Bracket br(ctx, OBP_K_TRUNCATE);
-    k_trunc_kill<<<g, OBP_BS, 0, ctx->stream>>>(t, a, lower, ++ctx->epoch);
+    k_masked_sum<<<gs, OBP_BS, 0, ctx->stream>>>((const double*)ctx->spare16, ctx->d_st, threshold, ctx->d_partial);
+    k_final_sum<<<1, OBP_BS, 0, ctx->stream>>>(ctx->d_partial, gs, ctx->d_scalar);
+    CU(cudaGetLastError());
+  }
+  close_run(ctx);
+  CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *local_sum = ctx->h_scalar[0];
+  return OBP_OK;
+}
+
+int obp_trunc_finish(obp_ctx* ctx, double threshold, uint64_t* n_removed, uint64_t* n_out) {
+  if (!ctx) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  const u64 before = ctx->n_live;
+  int rc;
+  if (ctx->n_dense) {
+    Bracket br(ctx, OBP_K_TRUNCATE);
+    k_trunc_kill<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), (const double*)ctx->spare16,
+                                                                         threshold, ++ctx->epoch);
     CU(cudaGetLastError());
   }
   rc = sync_state(ctx);
   if (rc) return rc;
   ctx->prof.term_updates[OBP_K_TRUNCATE] += before;
-  if (slice_error) *slice_error = lower_error;
   if (n_removed) *n_removed = before - ctx->n_live;
   if (ctx->n_dense != ctx->n_live) {
     rc = compact(ctx);
@@ -1019,6 +1153,37 @@ int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double
   }
   if (n_out) *n_out = ctx->n_live;
   return OBP_OK;
+}
+
+int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double* slice_error,
+                 uint64_t* n_removed, uint64_t* n_out) {
+  if (!ctx || p_norm < 1) return OBP_ERR_BADARG;
+  if (slice_error) *slice_error = 0.0;
+  if (n_removed) *n_removed = 0;
+  if (n_out) *n_out = ctx->n_live;
+  if (ctx->n_live == 0) return OBP_OK;
+  double upper = 0.0;
+  int rc = obp_trunc_begin(ctx, p_norm, &upper);
+  if (rc) return rc;
+  // utils/truncating.py:173-196, evaluated on the host with device-side masked sums
+  double lower = 0.0, upper_error = budget, lower_error = 0.0;
+  auto isclose = [&](double x, double y) { return std::fabs(x - y) <= tol + 1e-5 * std::fabs(y); };
+  while ((upper - lower) > tol && !isclose(upper_error, lower_error)) {
+    const double mid = (upper + lower) / 2;
+    double sum = 0.0;
+    rc = obp_trunc_masked_sum(ctx, mid, &sum);
+    if (rc) return rc;
+    const double mid_error = p_norm == 1 ? sum : std::pow(sum, 1.0 / p_norm);
+    if (mid_error <= budget) {
+      lower = mid;
+      lower_error = mid_error;
+    } else {
+      upper = mid;
+      upper_error = mid_error;
+    }
+  }
+  if (slice_error) *slice_error = lower_error;
+  return obp_trunc_finish(ctx, lower, n_removed, n_out);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -934,3 +934,260 @@ __global__ void __launch_bounds__(OBP_BS) k_copy_live_keys(Tab src, Tab dst, u64
     dst.coef[dst_off + i] = make_double2(1.0, 0.0);
   }
 }
+
+// ================================================================================================
+// Sharded table (one rank = one GPU holds the terms whose hash has owner bits == rank)
+//
+// owner(term) = top log2(R) bits of its Clifford-invariant hash.  Clifford gates, damping and
+// truncation never change a hash, so they stay rank-local.  A rotation with generator G maps key P
+// to P^G with hash h ^ h(G): when the owner bits of h(G) are zero the partner lives on the same rank
+// (plain k_rotate); otherwise ALL partners of this rank's rows live on the single peer
+// rank ^ ownerbits(h(G)).  The rotation is then split in three local passes around one pairwise
+// record exchange:
+//   k_rotate_emit    every row keeps the part of the 2x2 update that stays on its own key (rows
+//                    (0,0),(1,1)) and emits the part that lands on the partner key (rows (0,1),(1,0))
+//                    as a record {key^G words, hash^h(G), coefficient};
+//   k_merge_records  the receiver adds each record to the row holding that key or appends a new row;
+//   k_rotate_finish  the second zero filter of simplify() on the rows the gate touched.
+// A record is 2W+3 u64: x0,z0,...,x(W-1),z(W-1), hash, re, im.
+// ================================================================================================
+#define OBP_PENDING_IM 0x8000000000000000ull  // {+0.0, -0.0}: key has no surviving raw row of its own (yet)
+
+__device__ __forceinline__ bool is_pending(double2 c) {
+  return __double_as_longlong(c.x) == 0ll && (u64)__double_as_longlong(c.y) == OBP_PENDING_IM;
+}
+
+struct ShardCnt {  // per-call counters (device), summed over ranks by the host
+  u64 rows_surv, keys_present, cancelled, n_records;
+  double sum_re, sum_im;
+};
+
+__global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, const __grid_constant__ RotP p,
+                                                                      u64* __restrict__ rec, u64 rec_cap,
+                                                                      ShardCnt* __restrict__ cnt) {
+  const u64 n = t.st->n_scan;
+  const unsigned lane = threadIdx.x & 31u;
+  const int RW = 2 * t.W + 3;
+  unsigned rows_surv = 0, keys_present = 0;
+  int dlive = 0;
+  bool overflow = false;
+  for (u64 base = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)); base < n; base += (u64)gridDim.x * OBP_BS) {
+    const u64 i = base + lane;
+    bool want_emit = false;
+    double2 out_c = make_double2(0.0, 0.0);
+    if (i < n) {
+      const double2 c = t.coef[i];
+      if (is_live(c)) {
+        int sp = 0, E = p.yG;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < p.ngw) {
+            const ulonglong2 key = t.xz[p.gw[k]][i];
+            const u64 m = p.gx[k] | p.gz[k];
+            sp += __popcll(key.x & p.gz[k]) + __popcll(key.y & p.gx[k]);
+            E += __popcll(key.x & key.y & m) - __popcll((key.x ^ p.gx[k]) & (key.y ^ p.gz[k]) & m) +
+                 2 * __popcll(key.y & p.gx[k]);
+          }
+        }
+        const int s = sp & 1;
+        E &= 3;
+        if (!p.exact && !s) {
+          const RowSet rp = rot_rows_self(c, s, p);
+          if (rp.nself < 2) {
+            if (rp.nself == 0 || is_small(rp.self, p.atol)) {
+              t.coef[i] = tombstone(p.epoch);
+              dlive--;
+            } else {
+              t.coef[i] = rp.self;
+            }
+          }
+        } else {
+          const RowSet rp = rot_rows(c, E, s, p);
+          rows_surv += rp.nself + rp.ncross;
+          keys_present += (unsigned)(rp.nself > 0);
+          // the row stays live until the finish pass even when nothing of its own survives: a
+          // record from the peer may still land on it
+          t.coef[i] = rp.nself > 0 ? rp.self : make_double2(0.0, __longlong_as_double((long long)OBP_PENDING_IM));
+          if (rp.ncross > 0) {
+            want_emit = true;
+            out_c = rp.cross;
+          }
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, want_emit);
+    if (bal) {
+      u64 wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&cnt->n_records, (u64)__popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (want_emit) {
+        const u64 r = wbase + __popc(bal & ((1u << lane) - 1u));
+        if (r < rec_cap) {
+          u64* o = rec + r * RW;
+          for (int w = 0; w < t.W; ++w) {
+            u64 gx, gz;
+            gen_word(p, w, gx, gz);
+            const ulonglong2 key = t.xz[w][i];
+            o[2 * w] = key.x ^ gx;
+            o[2 * w + 1] = key.y ^ gz;
+          }
+          o[2 * t.W] = t.hash[i] ^ p.hG;
+          o[2 * t.W + 1] = (u64)__double_as_longlong(out_c.x);
+          o[2 * t.W + 2] = (u64)__double_as_longlong(out_c.y);
+        } else {
+          overflow = true;
+        }
+      }
+    }
+  }
+  if (overflow) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
+  const long long dl = warp_sum_i64((long long)dlive);
+  const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present);
+  if (lane == 0) {
+    if (a) atomicAdd(&cnt->rows_surv, a);
+    if (b) atomicAdd(&cnt->keys_present, b);
+    if (dl) atomicAdd(&t.st->n_live, (u64)dl);
+  }
+  finish_kernel(t, -1);
+}
+
+// One thread per incoming record: add to the live row with that key, or append it.
+__global__ void __launch_bounds__(OBP_BS) k_merge_records(Tab t, const u64* __restrict__ rec, u64 n_rec,
+                                                           ShardCnt* __restrict__ cnt) {
+  const u64 n = t.st->n_scan;
+  const unsigned lane = threadIdx.x & 31u;
+  const int RW = 2 * t.W + 3;
+  unsigned keys_present = 0;
+  int dlive = 0;
+  bool overflow = false, full = false;
+  for (u64 base = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)); base < n_rec; base += (u64)gridDim.x * OBP_BS) {
+    const u64 r = base + lane;
+    bool want_append = false;
+    const u64* in = rec + r * RW;
+    u64 h = 0;
+    double2 c = make_double2(0.0, 0.0);
+    if (r < n_rec) {
+      h = in[2 * t.W];
+      c = make_double2(__longlong_as_double((long long)in[2 * t.W + 1]), __longlong_as_double((long long)in[2 * t.W + 2]));
+      const u64 fp = h >> 32;
+      u64 s = h & t.mask;
+      long long j = -1;
+      for (u64 probes = 0; probes <= t.mask; ++probes) {
+        const u64 e = ld_volatile(&t.index[s]);
+        if (e == OBP_EMPTY) break;
+        if ((e >> 32) == fp) {
+          const u64 jj = e & 0xffffffffull;
+          if (jj < n) {
+            const double2 cj = t.coef[jj];
+            bool eq = true;
+            for (int w = 0; w < t.W && eq; ++w) {
+              const ulonglong2 kj = t.xz[w][jj];
+              eq = (kj.x == in[2 * w]) && (kj.y == in[2 * w + 1]);
+            }
+            if (eq && is_live(cj)) {
+              j = (long long)jj;
+              if (is_pending(cj)) {
+                t.coef[jj] = c;
+                keys_present++;
+              } else {
+                t.coef[jj] = cadd(cj, c);
+              }
+              break;
+            }
+          }
+        }
+        s = (s + 1) & t.mask;
+      }
+      if (j < 0) want_append = true;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, want_append);
+    if (bal) {
+      u64 wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&t.st->n_append, (u64)__popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (want_append) {
+        const u64 row = wbase + __popc(bal & ((1u << lane) - 1u));
+        if (row < t.cap) {
+          for (int w = 0; w < t.W; ++w) t.xz[w][row] = make_ulonglong2(in[2 * w], in[2 * w + 1]);
+          t.coef[row] = c;
+          t.hash[row] = h;
+          if (!index_insert(t, h, row)) full = true;
+          keys_present++;
+          dlive++;
+        } else {
+          overflow = true;
+        }
+      }
+    }
+  }
+  if (overflow) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
+  if (full) atomicOr(&t.st->error, OBP_ERR_BIT_INDEX);
+  const long long dl = warp_sum_i64((long long)dlive);
+  const u64 b = warp_sum_u64(keys_present);
+  if (lane == 0) {
+    if (b) atomicAdd(&cnt->keys_present, b);
+    if (dl) atomicAdd(&t.st->n_live, (u64)dl);
+  }
+  finish_kernel(t, -1);
+}
+
+// Second zero filter on the rows the split rotation touched (anticommuting rows; all rows when
+// the reference's counters are wanted).  A row still pending holds a key without any surviving raw
+// row: it disappears without being counted.
+__global__ void __launch_bounds__(OBP_BS) k_rotate_finish(Tab t, const __grid_constant__ RotP p,
+                                                           ShardCnt* __restrict__ cnt) {
+  const u64 n = t.st->n_scan;
+  unsigned cancelled = 0;
+  int deaths = 0;
+  double sr = 0.0, si = 0.0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c)) continue;
+    if (!p.exact) {
+      int sp = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < p.ngw) {
+          const ulonglong2 key = t.xz[p.gw[k]][i];
+          sp += __popcll(key.x & p.gz[k]) + __popcll(key.y & p.gx[k]);
+        }
+      }
+      if (!(sp & 1)) continue;
+    }
+    if (is_pending(c)) {
+      t.coef[i] = tombstone(p.epoch);
+      deaths++;
+    } else if (is_small(c, p.atol)) {
+      t.coef[i] = tombstone(p.epoch);
+      deaths++;
+      cancelled++;
+      sr += c.x;
+      si += c.y;
+    }
+  }
+  const long long dl = warp_sum_i64((long long)deaths);
+  const u64 cz = warp_sum_u64(cancelled);
+  sr = warp_sum_f64(sr);
+  si = warp_sum_f64(si);
+  if ((threadIdx.x & 31) == 0) {
+    if (dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+    if (cz) { atomicAdd(&cnt->cancelled, cz); atomicAdd(&cnt->sum_re, sr); atomicAdd(&cnt->sum_im, si); }
+  }
+  finish_kernel(t, -1);
+}
+
+// At load: rows whose hash belongs to another rank are dropped (every rank is given the full operator).
+// They become exact zeros, which the index build that follows counts and buries like any other
+// filtered raw row; st->removed tells the host how many rows were not this rank's.
+__global__ void __launch_bounds__(OBP_BS) k_shard_filter(Tab t, int owner_shift, u64 rank) {
+  const u64 n = t.st->n_scan;
+  unsigned foreign = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    if ((t.hash[i] >> owner_shift) != rank) {
+      t.coef[i] = make_double2(0.0, 0.0);
+      foreign++;
+    }
+  }
+  const u64 f = warp_sum_u64(foreign);
+  if ((threadIdx.x & 31) == 0 && f) atomicAdd(&t.st->removed, f);
+}

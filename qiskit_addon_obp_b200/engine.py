@@ -72,6 +72,19 @@ class ObpProfile(C.Structure):
     ]
 
 
+class ObpShardCounters(C.Structure):
+    _fields_ = [
+        ("n_in", C.c_uint64),
+        ("n_out", C.c_uint64),
+        ("n_dense", C.c_uint64),
+        ("rows_surv", C.c_uint64),
+        ("keys_present", C.c_uint64),
+        ("cancelled", C.c_uint64),
+        ("n_records", C.c_uint64),
+        ("sum_trimmed", C.c_double * 2),
+    ]
+
+
 class EngineError(RuntimeError):
     """A CUDA or engine failure reported through the C-ABI."""
 
@@ -115,6 +128,17 @@ def lib() -> C.CDLL:
         "obp_reserve": ([vp, C.c_uint64], C.c_int),
         "obp_profile_enable": ([vp, C.c_int32], C.c_int),
         "obp_profile_get": ([vp, C.POINTER(ObpProfile), C.c_int32], C.c_int),
+        "obp_set_shard": ([vp, C.c_int32, C.c_int32], C.c_int),
+        "obp_record_bytes": ([C.c_int], C.c_uint64),
+        "obp_apply_ops_sharded": (
+            [vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+            C.c_int,
+        ),
+        "obp_rotate_emit": ([vp, vp, C.c_double, vp, C.c_uint64, C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_rotate_merge": ([vp, vp, C.c_uint64, C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_trunc_begin": ([vp, C.c_int32, f64p], C.c_int),
+        "obp_trunc_masked_sum": ([vp, C.c_double, f64p], C.c_int),
+        "obp_trunc_finish": ([vp, C.c_double, u64p, u64p], C.c_int),
         "obp_timer_start": ([vp], C.c_int),
         "obp_timer_stop": ([vp, f64p], C.c_int),
     }
@@ -130,7 +154,8 @@ EXPORTED_SYMBOLS = (
     "obp_create obp_destroy obp_last_error obp_set_stream obp_device_memory obp_bytes_per_term "
     "obp_load obp_count obp_download obp_apply_ops obp_apply_reset obp_apply_damping obp_truncate "
     "obp_union_count obp_snapshot obp_restore obp_reserve obp_profile_enable obp_profile_get "
-    "obp_timer_start obp_timer_stop"
+    "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
+    "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish"
 ).split()
 
 
@@ -177,6 +202,7 @@ class TermTable:
                 idle.pop(k)
                 t.n = t.n_dense = 0
                 t.zero_operator = False
+                t.set_shard(1, 0)
                 return t
         return cls(num_qubits, capacity, device)
 
@@ -387,6 +413,61 @@ class TermTable:
             name: {"launches": int(p.launches[k]), "ms": float(p.ms[k]), "term_updates": int(p.term_updates[k])}
             for k, name in enumerate(OBP_K_NAMES)
         }
+
+    # -- sharded table (see sharded.py) ----------------------------------------------------------
+    def set_shard(self, n_ranks: int, rank: int):
+        self._check(self._lib.obp_set_shard(self._h, int(n_ranks), int(rank)), "obp_set_shard")
+
+    def apply_ops_sharded(self, ops: np.ndarray, atol: float) -> tuple[ObpStats, int, int, bool]:
+        """Run ``ops`` up to the first rotation that needs a peer: ``(stats, n_done, peer_xor, overflowed)``.
+
+        A table overflow is reported as a flag instead of an exception: all ranks must stay in
+        lock-step through the exchange that follows, the caller raises once they have agreed.
+        """
+        st, done, peer = ObpStats(), C.c_int32(), C.c_int32()
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        rc = self._lib.obp_apply_ops_sharded(
+            self._h, ops.ctypes.data_as(C.c_void_p), len(ops), float(atol), C.byref(st), C.byref(done), C.byref(peer)
+        )
+        if rc != OBP_ERR_CAPACITY:
+            self._check(rc, "obp_apply_ops_sharded")
+            self.n, self.n_dense = st.n_out, st.n_dense
+        return st, done.value, peer.value, rc == OBP_ERR_CAPACITY
+
+    def rotate_emit(self, op: np.ndarray, atol: float, d_records: int, cap_records: int) -> tuple[ObpShardCounters, bool]:
+        out = ObpShardCounters()
+        op = np.ascontiguousarray(op, dtype=OP_DTYPE)
+        rc = self._lib.obp_rotate_emit(
+            self._h, op.ctypes.data_as(C.c_void_p), float(atol), C.c_void_p(d_records), int(cap_records), C.byref(out)
+        )
+        if rc != OBP_ERR_CAPACITY:
+            self._check(rc, "obp_rotate_emit")
+        self.n, self.n_dense = out.n_out, out.n_dense
+        return out, rc == OBP_ERR_CAPACITY
+
+    def rotate_merge(self, d_records: int, n_records: int) -> tuple[ObpShardCounters, bool]:
+        out = ObpShardCounters()
+        rc = self._lib.obp_rotate_merge(self._h, C.c_void_p(d_records), int(n_records), C.byref(out))
+        if rc != OBP_ERR_CAPACITY:
+            self._check(rc, "obp_rotate_merge")
+        self.n, self.n_dense = out.n_out, out.n_dense
+        return out, rc == OBP_ERR_CAPACITY
+
+    def trunc_begin(self, p_norm: int) -> float:
+        mx = C.c_double()
+        self._check(self._lib.obp_trunc_begin(self._h, int(p_norm), C.byref(mx)), "obp_trunc_begin")
+        return mx.value
+
+    def trunc_masked_sum(self, threshold: float) -> float:
+        sm = C.c_double()
+        self._check(self._lib.obp_trunc_masked_sum(self._h, float(threshold), C.byref(sm)), "obp_trunc_masked_sum")
+        return sm.value
+
+    def trunc_finish(self, threshold: float) -> int:
+        rem, out = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.obp_trunc_finish(self._h, float(threshold), C.byref(rem), C.byref(out)), "obp_trunc_finish")
+        self.n = self.n_dense = out.value
+        return rem.value
 
     def timer_start(self):
         self._check(self._lib.obp_timer_start(self._h), "obp_timer_start")

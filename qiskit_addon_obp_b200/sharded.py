@@ -1,0 +1,390 @@
+"""One observable sharded over several GPUs by the hash of its Pauli keys.
+
+Rank ``r`` of ``R`` (a power of two) owns the terms whose Clifford-invariant 64-bit hash has its top
+``log2 R`` bits equal to ``r`` (``include/obp_b200.h``, "sharded table").  Duplicate keys therefore
+co-locate; Clifford gates, Pauli-Lindblad damping and truncation kills are rank-local; a rotation
+whose generator hash has owner bits ``d != 0`` exchanges one batch of records between the pairs
+``r <-> r ^ d`` (the "all-to-all" of a branching gate is a pairwise permutation because the hash is
+GF(2)-linear); budgets (term counts, masked sums, maxima) are combined with small allreduces.
+
+The reference is a single process (``backpropagation.py:167`` only remarks that the loop "will
+likely need to be parallelized"), so there is no reference counterpart of this module; its results
+are checked against the same oracle as the single-table path.
+
+Two communicators implement the exchange:
+
+* :class:`DistComm` — one process per GPU over ``torch.distributed`` (NCCL send/recv on device
+  buffers, NCCL allreduce); every rank runs the same driver loop (SPMD).
+* :class:`LocalComm` — all ``R`` ranks inside one process on one GPU, records handed over as device
+  pointers.  It exercises exactly the same kernels and protocol and is what the single-GPU parity
+  tests use.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import OBP_OP_ROTATION, CapacityError, TermTable, lib
+from .ir import SparsePauliOp
+
+
+class LocalComm:
+    """``R`` virtual ranks in this process (one device)."""
+
+    def __init__(self, n_ranks: int, device: int = 0):
+        self.n_ranks = int(n_ranks)
+        self.local_ranks = list(range(self.n_ranks))
+        self.device = int(device)
+        self.backend = f"local x{self.n_ranks}"
+
+    def exchange(self, bufs: dict, counts: dict, peer_xor: int) -> dict:
+        """Rank r receives what rank r ^ peer_xor emitted: ``{r: (buffer, n_records)}``."""
+        return {r: (bufs[r ^ peer_xor], counts[r ^ peer_xor]) for r in self.local_ranks}
+
+    def allreduce_sum(self, vals: dict) -> np.ndarray:
+        return np.sum([np.asarray(vals[r], dtype=np.float64) for r in self.local_ranks], axis=0)
+
+    def allreduce_max(self, vals: dict) -> np.ndarray:
+        return np.max([np.asarray(vals[r], dtype=np.float64) for r in self.local_ranks], axis=0)
+
+    def allreduce_sum_int(self, vals: dict) -> np.ndarray:
+        return np.sum([np.asarray(vals[r], dtype=np.int64) for r in self.local_ranks], axis=0)
+
+    def gather_operators(self, ops: dict) -> SparsePauliOp:
+        return _concat([ops[r] for r in self.local_ranks])
+
+
+class DistComm:
+    """One rank per process over ``torch.distributed`` (NCCL on GPUs; gloo works for host tests)."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.n_ranks = dist.get_world_size(group)
+        self.local_ranks = [self.rank]
+        self.backend = dist.get_backend(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
+        self.tdev = device
+        self.device = device.index if device.type == "cuda" else 0
+        if self.n_ranks & (self.n_ranks - 1):
+            raise ValueError("the number of ranks must be a power of two")
+
+    def exchange(self, bufs: dict, counts: dict, peer_xor: int) -> dict:
+        torch, dist = self.torch, self.dist
+        peer = self.rank ^ peer_xor
+        send, n_send = bufs[self.rank], int(counts[self.rank])
+        rec = send.shape[1]
+        # 1. counts, 2. payload — both as one batched send/recv pair with the single peer
+        c_out = torch.tensor([n_send], dtype=torch.int64, device=self.tdev)
+        c_in = torch.zeros(1, dtype=torch.int64, device=self.tdev)
+        for w in dist.batch_isend_irecv(
+            [dist.P2POp(dist.isend, c_out, peer, self.group), dist.P2POp(dist.irecv, c_in, peer, self.group)]
+        ):
+            w.wait()
+        n_recv = int(c_in.item())
+        recv = torch.empty((max(n_recv, 1), rec), dtype=send.dtype, device=self.tdev)
+        ops = []
+        if n_send:
+            ops.append(dist.P2POp(dist.isend, send[:n_send], peer, self.group))
+        if n_recv:
+            ops.append(dist.P2POp(dist.irecv, recv[:n_recv], peer, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if self.tdev.type == "cuda":
+            torch.cuda.current_stream(self.tdev).synchronize()
+        return {self.rank: (recv, n_recv)}
+
+    def _allreduce(self, vals: dict, op, dtype):
+        torch = self.torch
+        t = torch.as_tensor(np.atleast_1d(np.asarray(vals[self.rank])), dtype=dtype).to(self.tdev)
+        self.dist.all_reduce(t, op=op, group=self.group)
+        return t.cpu().numpy()
+
+    def allreduce_sum(self, vals: dict) -> np.ndarray:
+        return self._allreduce(vals, self.dist.ReduceOp.SUM, self.torch.float64)
+
+    def allreduce_max(self, vals: dict) -> np.ndarray:
+        return self._allreduce(vals, self.dist.ReduceOp.MAX, self.torch.float64)
+
+    def allreduce_sum_int(self, vals: dict) -> np.ndarray:
+        return self._allreduce(vals, self.dist.ReduceOp.SUM, self.torch.int64)
+
+    def gather_operators(self, ops: dict) -> SparsePauliOp:
+        mine = ops[self.rank]
+        xw, zw = mine.packed()
+        parts: list = [None] * self.n_ranks
+        self.dist.all_gather_object(parts, (xw, zw, mine.coeffs, mine.num_qubits), group=self.group)
+        return _concat([SparsePauliOp.from_packed(*p) for p in parts])
+
+
+def _concat(ops: list[SparsePauliOp]) -> SparsePauliOp:
+    xs, zs = zip(*[o.packed() for o in ops])
+    return SparsePauliOp.from_packed(
+        np.concatenate(xs, axis=0), np.concatenate(zs, axis=0), np.concatenate([o.coeffs for o in ops]), ops[0].num_qubits
+    )
+
+
+class _Stats:
+    """Whole-table view of per-rank counters, field-compatible with ``ObpStats`` where it matters."""
+
+    def __init__(self):
+        self.n_in = self.raw_rows = self.n_out = self.n_dense = self.updates = 0
+        self.num_unique = self.num_duplicate = self.num_trimmed = 0
+        self.sum_trimmed = [0.0, 0.0]
+        self.counters_valid = True
+
+
+class ShardedTable:
+    """Drop-in for :class:`~qiskit_addon_obp_b200.engine.TermTable` in the driver loop."""
+
+    def __init__(self, num_qubits: int, capacity: int, comm):
+        """``capacity`` is the whole table's; every rank gets 1/R of it plus 25 % slack for imbalance."""
+        self.comm = comm
+        self.num_qubits = int(num_qubits)
+        self.words = max(1, (self.num_qubits + 63) // 64)
+        self.capacity = int(capacity)
+        self.device = comm.device
+        self.rec_u64 = int(lib().obp_record_bytes(self.num_qubits)) // 8
+        per_rank = self._per_rank(capacity)
+        self.tables = {r: TermTable.acquire(num_qubits, per_rank, comm.device) for r in comm.local_ranks}
+        for r, t in self.tables.items():
+            t.set_shard(comm.n_ranks, r)
+        self.n = 0
+        self.n_dense = 0
+        self.zero_operator = False
+        self.exchanges = 0  # rotations that needed a record exchange
+        self.exchanged_records = 0
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _per_rank(self, capacity: int) -> int:
+        return max(1 << 16, int(1.25 * capacity / self.comm.n_ranks) + 1)
+
+    @classmethod
+    def acquire(cls, num_qubits, capacity, comm):
+        return cls(num_qubits, capacity, comm)
+
+    def release(self):
+        for t in self.tables.values():
+            t.release()
+        self.tables = {}
+
+    close = release
+
+    def __len__(self) -> int:
+        return 1 if self.zero_operator else self.n
+
+    def _sync_counts(self):
+        tot = self.comm.allreduce_sum_int({r: [t.n, t.n_dense] for r, t in self.tables.items()})
+        self.n, self.n_dense = int(tot[0]), int(tot[1])
+
+    def _raise_if_any(self, failed: bool, what: str):
+        flag = self.comm.allreduce_max({r: [1.0 if failed else 0.0] for r in self.tables})
+        if flag[0] > 0:
+            raise CapacityError(f"{what}: a shard overflowed its table")
+
+    # -- I/O ----------------------------------------------------------------------------------------
+    def load(self, op: SparsePauliOp, atol: float | None = None) -> _Stats:
+        out = _Stats()
+        for t in self.tables.values():  # every rank is given the whole operator and keeps its share
+            if len(op) > t.capacity:
+                t.reserve(2 * len(op))
+            t.load(op, atol)
+        self._sync_counts()
+        self.zero_operator = atol is not None and self.n == 0
+        out.n_in, out.n_out = len(op), self.n
+        return out
+
+    def download(self) -> SparsePauliOp:
+        if self.zero_operator:
+            z = np.zeros((1, self.num_qubits), dtype=bool)
+            return SparsePauliOp((z.copy(), z), np.array([0j]))
+        return self.comm.gather_operators({r: t.download() for r, t in self.tables.items()})
+
+    to_operator = download
+
+    # -- the hot path ---------------------------------------------------------------------------------
+    def apply_ops(self, ops: np.ndarray, atol: float) -> _Stats:
+        import torch
+
+        out = _Stats()
+        if self.zero_operator:
+            k2 = int(ops[-1]["n_components"]) ** 2
+            out.n_in, out.raw_rows, out.num_trimmed, out.n_out, out.updates = 1, k2, k2, 1, len(ops)
+            return out
+        pos, failed = 0, False
+        updates = 0
+        last: dict | None = None  # per-rank counters of the last executed op
+        tdev = torch.device("cuda", self.device)
+        while pos < len(ops):
+            seg = ops[pos:]
+            done = peer = 0
+            seg_stats = {}
+            for r, t in self.tables.items():
+                st, done, peer, over = t.apply_ops_sharded(seg, atol)  # every rank stops at the same op
+                failed |= over
+                seg_stats[r] = st
+                updates += int(st.updates)
+            if done > 0:
+                last = {"kind": "local", "stats": seg_stats, "op": seg[done - 1]}
+            pos += done
+            if peer == 0:
+                break
+            # ---- split rotation: emit, pairwise exchange, merge -----------------------------------
+            op = ops[pos : pos + 1]
+            bufs, counts, emit = {}, {}, {}
+            for r, t in self.tables.items():
+                cap = max(int(t.n_dense), 1)
+                bufs[r] = torch.empty((cap, self.rec_u64), dtype=torch.int64, device=tdev)
+                emit[r], over = t.rotate_emit(op, atol, bufs[r].data_ptr(), cap)
+                failed |= over
+                counts[r] = min(int(emit[r].n_records), cap)
+                updates += int(emit[r].n_in)
+            recv = self.comm.exchange(bufs, counts, peer)
+            merge = {}
+            for r, t in self.tables.items():
+                buf, n_rec = recv[r]
+                merge[r], over = t.rotate_merge(buf.data_ptr() if n_rec else 0, n_rec)
+                failed |= over
+            self.exchanges += 1
+            self.exchanged_records += sum(counts.values())
+            last = {"kind": "split", "emit": emit, "merge": merge, "op": op[0]}
+            del bufs, recv
+            pos += 1
+        self._raise_if_any(failed, "sharded gate program")
+        self._sync_counts()
+        out.updates = int(self.comm.allreduce_sum_int({r: [updates if r == min(self.tables) else 0] for r in self.tables})[0])
+        self._fill_last(out, last, ops[-1])
+        out.n_out, out.n_dense = self.n, self.n_dense
+        if self.n == 0:
+            self.zero_operator = True
+        return out
+
+    def _fill_last(self, out: _Stats, last, last_op) -> None:
+        """Whole-table simplify counters of the program's last op from the per-rank pieces."""
+        k2 = int(last_op["n_components"]) ** 2
+        if last is None:
+            out.counters_valid = False
+            return
+        if last["kind"] == "local":
+            vals = {
+                r: [st.n_in, st.num_unique, st.num_duplicate, st.num_trimmed] for r, st in last["stats"].items()
+            }
+            tot = self.comm.allreduce_sum_int(vals)
+            sums = self.comm.allreduce_sum({r: list(st.sum_trimmed) for r, st in last["stats"].items()})
+            out.n_in, out.num_unique, out.num_duplicate, out.num_trimmed = (int(v) for v in tot)
+            out.sum_trimmed = [float(sums[0]), float(sums[1])]
+            # a Clifford-class gate's coset count sees only rank-local members of a coset
+            out.counters_valid = int(last["op"]["kind"]) == OBP_OP_ROTATION or self.comm.n_ranks == 1
+        else:
+            vals, sums = {}, {}
+            for r in self.tables:
+                e, m = last["emit"][r], last["merge"][r]
+                vals[r] = [e.n_in, e.rows_surv, e.keys_present + m.keys_present, m.cancelled]
+                sums[r] = [m.sum_trimmed[0], m.sum_trimmed[1]]
+            tot = self.comm.allreduce_sum_int(vals)
+            sm = self.comm.allreduce_sum(sums)
+            n_in, rows_surv, keys, cancelled = (int(v) for v in tot)
+            out.n_in = n_in
+            out.num_unique = keys
+            out.num_duplicate = rows_surv - keys
+            out.num_trimmed = n_in * k2 - rows_surv + cancelled
+            out.sum_trimmed = [float(sm[0]), float(sm[1])]
+        out.raw_rows = out.n_in * k2
+
+    def apply_reset(self, qubit: int, atol: float):
+        raise NotImplementedError("reset moves terms between shards; not supported on a sharded table yet")
+
+    def apply_damping(self, gen_x, gen_z, factors, atol: float) -> _Stats:
+        out = _Stats()
+        if self.zero_operator:
+            out.n_in = out.raw_rows = out.num_trimmed = out.n_out = out.updates = 1
+            return out
+        n_in = self.n
+        for t in self.tables.values():
+            t.apply_damping(gen_x, gen_z, factors, atol)
+        self._sync_counts()
+        out.n_in = out.raw_rows = out.updates = n_in
+        out.num_unique, out.num_trimmed, out.n_out = self.n, n_in - self.n, self.n
+        if self.n == 0:
+            self.zero_operator = True
+        return out
+
+    def truncate(self, budget: float, p_norm: int, tol: float) -> tuple[float, int]:
+        """``truncate_binary_search`` (``utils/truncating.py:171-204``) with allreduced maxima and sums."""
+        if self.zero_operator:
+            self.zero_operator = False
+            self.n = 0
+            return 0.0, 1
+        before = self.n
+        upper = float(self.comm.allreduce_max({r: [t.trunc_begin(p_norm)] for r, t in self.tables.items()})[0])
+        lower, upper_error, lower_error = 0.0, budget, 0.0
+        while (upper - lower) > tol and not np.isclose(upper_error, lower_error, atol=tol):
+            mid = (upper + lower) / 2
+            s = float(self.comm.allreduce_sum({r: [t.trunc_masked_sum(mid)] for r, t in self.tables.items()})[0])
+            mid_error = s if p_norm == 1 else float(np.power(s, 1.0 / p_norm))
+            if mid_error <= budget:
+                lower, lower_error = mid, mid_error
+            else:
+                upper, upper_error = mid, mid_error
+        for t in self.tables.values():
+            t.trunc_finish(lower)
+        self._sync_counts()
+        return float(lower_error), before - self.n
+
+    def snapshot(self):
+        self._snap = (self.zero_operator, self.n)
+        for t in self.tables.values():
+            t.snapshot()
+
+    def restore(self):
+        for t in self.tables.values():
+            t.restore()
+        self.zero_operator, self.n = self._snap
+
+    def reserve(self, capacity: int):
+        for t in self.tables.values():
+            t.reserve(self._per_rank(capacity))
+        self.capacity = max(self.capacity, int(capacity))
+
+    # -- measurement ------------------------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        for t in self.tables.values():
+            t.profile_enable(on)
+
+    def profile(self, reset: bool = False) -> dict:
+        tot: dict = {}
+        for t in self.tables.values():
+            for k, v in t.profile(reset).items():
+                a = tot.setdefault(k, {"launches": 0, "ms": 0.0, "term_updates": 0})
+                for f in a:
+                    a[f] += v[f]
+        return tot
+
+    def timer_start(self):
+        for t in self.tables.values():
+            t.timer_start()
+
+    def timer_stop(self) -> float:
+        return max(t.timer_stop() for t in self.tables.values())
+
+
+def communicator_from_env(device: int):
+    """``OBP_B200_SHARDS=R``: R virtual ranks on this GPU; ``OBP_B200_SHARDED=1``: torch.distributed ranks."""
+    import os
+
+    virt = int(os.environ.get("OBP_B200_SHARDS", "0") or 0)
+    if virt > 1:
+        return LocalComm(virt, device)
+    if os.environ.get("OBP_B200_SHARDED", "") not in ("", "0"):
+        import torch.distributed as dist
+
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("OBP_B200_SHARDED=1 needs an initialised torch.distributed process group")
+        if dist.get_world_size() > 1:
+            return DistComm()
+    return None

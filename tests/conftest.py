@@ -70,7 +70,7 @@ def assert_same_operator(got, want, *, thresholds=(1e-8,), what="operator"):
             )
 
 
-def assert_same_metadata(got, want, *, exact_counters=True):
+def assert_same_metadata(got, want, *, exact_counters=True, allow_missing_counters=False):
     assert got.num_backpropagated_slices == want.num_backpropagated_slices
     assert len(got.backpropagation_history) == len(want.backpropagation_history)
     for s, (g, w) in enumerate(zip(got.backpropagation_history, want.backpropagation_history)):
@@ -81,15 +81,16 @@ def assert_same_metadata(got, want, *, exact_counters=True):
         assert g.num_qwc_groups == w.num_qwc_groups, f"slice {s} qwc"
         if exact_counters:
             assert g.raw_num_paulis == w.raw_num_paulis, f"slice {s} raw_num_paulis"
-            assert g.num_unique_paulis == w.num_unique_paulis, f"slice {s} num_unique"
-            assert g.num_duplicate_paulis == w.num_duplicate_paulis, f"slice {s} num_duplicate"
-            assert g.num_trimmed_paulis == w.num_trimmed_paulis, f"slice {s} num_trimmed"
-            np.testing.assert_allclose(
-                np.asarray(g.sum_trimmed_coeffs, dtype=complex),
-                np.asarray(w.sum_trimmed_coeffs, dtype=complex),
-                rtol=0,
-                atol=1e-12,
-                err_msg=f"slice {s} sum_trimmed",
-            )
+            for i in range(len(w.num_paulis)):
+                if g.num_unique_paulis[i] is None:
+                    # sharded table, slice ended on a Clifford-class gate: counters not reported
+                    assert allow_missing_counters, f"slice {s}: simplify counters missing"
+                    continue
+                assert g.num_unique_paulis[i] == w.num_unique_paulis[i], f"slice {s} num_unique"
+                assert g.num_duplicate_paulis[i] == w.num_duplicate_paulis[i], f"slice {s} num_duplicate"
+                assert g.num_trimmed_paulis[i] == w.num_trimmed_paulis[i], f"slice {s} num_trimmed"
+                assert abs(complex(g.sum_trimmed_coeffs[i]) - complex(w.sum_trimmed_coeffs[i])) <= 1e-12, (
+                    f"slice {s} sum_trimmed"
+                )
     for i in range(len(want.backpropagation_history[0].slice_errors) if want.backpropagation_history else 0):
         assert abs(got.accumulated_error(i) - want.accumulated_error(i)) <= ERROR_TOL

@@ -1,0 +1,95 @@
+"""GPU parity tests of the hash-sharded table: R virtual ranks on one B200 (``LocalComm``) run the
+same kernels and exchange protocol as R GPUs, and must reproduce the oracle like the single table."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import assert_same_metadata, assert_same_operator
+from oracle import obp_oracle as oracle
+from qiskit_addon_obp_b200 import backpropagate
+from qiskit_addon_obp_b200.ir import SparsePauliOp
+from qiskit_addon_obp_b200.utils.simplify import OperatorBudget
+from qiskit_addon_obp_b200.utils.truncating import TruncationErrorBudget, setup_budget
+from test_engine_gpu import random_observable, random_slices
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(monkeypatch, ranks, obs, slices, **kw):
+    monkeypatch.setenv("OBP_B200_SHARDS", str(ranks))
+    got, rest_g, md_g = backpropagate(obs, slices, **kw)
+    monkeypatch.delenv("OBP_B200_SHARDS")
+    want, rest_w, md_w = oracle.backpropagate(obs, slices, **kw)
+    assert len(rest_g) == len(rest_w)
+    single = isinstance(obs, SparsePauliOp)
+    for g, w in zip([got] if single else got, [want] if single else want):
+        assert_same_operator(g, w)
+    assert_same_metadata(md_g, md_w, allow_missing_counters=True)
+    return got, md_g
+
+
+@pytest.mark.parametrize("ranks", [2, 4, 8])
+@pytest.mark.parametrize("nq", [6, 70, 130])
+def test_sharded_random_circuit(monkeypatch, ranks, nq):
+    rng = np.random.default_rng(31 * nq + ranks)
+    slices = random_slices(nq, 6, rng, gates_per_slice=8)
+    obs = random_observable(nq, 4, rng)
+    _compare(monkeypatch, ranks, obs, slices)
+
+
+@pytest.mark.parametrize("ranks,p", [(2, 1), (8, 2)])
+def test_sharded_truncation(monkeypatch, ranks, p):
+    rng = np.random.default_rng(5 + ranks)
+    nq = 10
+    slices = random_slices(nq, 8, rng, gates_per_slice=6, angles=[0.1, 0.3, -0.2, 0.7])
+    obs = random_observable(nq, 3, rng)
+    _compare(monkeypatch, ranks, obs, slices, truncation_error_budget=TruncationErrorBudget([0.02, 0.0, 0.05], 0.2, p, 1e-8))
+    _compare(monkeypatch, ranks, obs, slices, truncation_error_budget=setup_budget(max_error_total=0.05, num_slices=8, p_norm=p))
+
+
+def test_sharded_rotation_counters_exact(monkeypatch):
+    """Slices ending on a rotation report the reference's simplify counters from the per-rank pieces."""
+    rng = np.random.default_rng(9)
+    nq = 7
+    slices = random_slices(nq, 10, rng, p_rot=1.0, gates_per_slice=5)
+    obs = random_observable(nq, 5, rng, weight=3)
+    _, md = _compare(monkeypatch, 4, obs, slices)
+    assert all(s.num_unique_paulis[0] is not None for s in md.backpropagation_history)
+
+
+def test_sharded_configs(monkeypatch):
+    from qiskit_addon_obp_b200.workloads import config1_xy_chain, config2_kicked_ising, config4_near_clifford
+
+    wl = config1_xy_chain()
+    _compare(monkeypatch, 8, wl.observables, wl.slices, **wl.kwargs())
+    wl = config2_kicked_ising(theta_h=0.3, steps=2, max_paulis=3000)
+    _compare(monkeypatch, 4, wl.observables, wl.slices, **wl.kwargs())
+    wl = config4_near_clifford(num_qubits=1000, depth=10, t_prob=0.01, max_paulis=4000, per_slice=1e-4)
+    _compare(monkeypatch, 8, wl.observables, wl.slices, **wl.kwargs())
+
+
+def test_sharded_max_paulis_and_multi_observable(monkeypatch):
+    rng = np.random.default_rng(2)
+    nq = 8
+    slices = random_slices(nq, 10, rng, gates_per_slice=6)
+    obs = random_observable(nq, 3, rng)
+    _compare(monkeypatch, 2, obs, slices, operator_budget=OperatorBudget(max_paulis=40))
+    _compare(monkeypatch, 4, [obs, SparsePauliOp("IIIIIIIZ")], slices)
+
+
+def test_sharded_round_trip_large(monkeypatch):
+    """U then U^dag over 8 shards at ~5e5 terms returns Z_62 (no oracle at this size)."""
+    from qiskit_addon_obp_b200.workloads import config2_kicked_ising
+    from test_engine_gpu import _inverse_slices
+
+    wl = config2_kicked_ising(theta_h=0.3, steps=6, max_paulis=None)
+    monkeypatch.setenv("OBP_B200_SHARDS", "8")
+    out, rest, md = backpropagate(wl.observables, _inverse_slices(wl.slices) + wl.slices)
+    assert rest == []
+    assert max(s.num_paulis[0] for s in md.backpropagation_history) > 100_000
+    d = out.as_dict()
+    key = wl.observables.paulis.to_labels()[0]
+    assert abs(d[key] - 1.0) < 1e-5
+    assert sum(abs(c) for k, c in d.items() if k != key) < 1e-2
