@@ -957,6 +957,13 @@ __device__ __forceinline__ bool is_pending(double2 c) {
   return __double_as_longlong(c.x) == 0ll && (u64)__double_as_longlong(c.y) == OBP_PENDING_IM;
 }
 
+// A sum that cancelled to exactly +0.0 + 0.0i has the bit pattern of an (epoch 0) tombstone; while a
+// split rotation is in flight such a value must stay a live row until the finish pass has counted
+// it, so it is stored as -0.0 - 0.0i (live, not pending, arithmetically still zero).
+__device__ __forceinline__ double2 keep_live(double2 c) {
+  return is_live(c) && !is_pending(c) ? c : make_double2(-0.0, -0.0);
+}
+
 struct ShardCnt {  // per-call counters (device), summed over ranks by the host
   u64 rows_surv, keys_present, cancelled, n_records;
   double sum_re, sum_im;
@@ -1007,7 +1014,7 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, con
           keys_present += (unsigned)(rp.nself > 0);
           // the row stays live until the finish pass even when nothing of its own survives: a
           // record from the peer may still land on it
-          t.coef[i] = rp.nself > 0 ? rp.self : make_double2(0.0, __longlong_as_double((long long)OBP_PENDING_IM));
+          t.coef[i] = rp.nself > 0 ? keep_live(rp.self) : make_double2(0.0, __longlong_as_double((long long)OBP_PENDING_IM));
           if (rp.ncross > 0) {
             want_emit = true;
             out_c = rp.cross;
@@ -1068,7 +1075,8 @@ __global__ void __launch_bounds__(OBP_BS) k_merge_records(Tab t, const u64* __re
     double2 c = make_double2(0.0, 0.0);
     if (r < n_rec) {
       h = in[2 * t.W];
-      c = make_double2(__longlong_as_double((long long)in[2 * t.W + 1]), __longlong_as_double((long long)in[2 * t.W + 2]));
+      c = keep_live(make_double2(__longlong_as_double((long long)in[2 * t.W + 1]),
+                                 __longlong_as_double((long long)in[2 * t.W + 2])));
       const u64 fp = h >> 32;
       u64 s = h & t.mask;
       long long j = -1;
@@ -1090,7 +1098,7 @@ __global__ void __launch_bounds__(OBP_BS) k_merge_records(Tab t, const u64* __re
                 t.coef[jj] = c;
                 keys_present++;
               } else {
-                t.coef[jj] = cadd(cj, c);
+                t.coef[jj] = keep_live(cadd(cj, c));
               }
               break;
             }
