@@ -44,6 +44,9 @@ class RunInfo:
     h2d_bytes = 0  # packed keys + coefficients uploaded
     d2h_bytes = 0  # packed keys + coefficients downloaded
     profile: dict | None = None  # per kernel class: launches, ms, term_updates (PROFILE only)
+    sharded = False  # the observable was a hash-sharded table: `updates` is already the global count
+    exchanges = 0  # sharded: rotations that needed a record exchange
+    exchanged_records = 0
 
 
 #: set True (bench.py does) to bracket every kernel launch with CUDA events
@@ -266,6 +269,8 @@ def backpropagate(
             info.d2h_bytes += len(obs_out[-1]) * (16 * tables[i].words + 16)
     finally:
         for t in tables:
+            info.exchanges += getattr(t, "exchanges", 0)
+            info.exchanged_records += getattr(t, "exchanged_records", 0)
             t.profile_enable(False)
             t.release()
 
@@ -275,6 +280,9 @@ def backpropagate(
     last_run.h2d_bytes = info.h2d_bytes
     last_run.d2h_bytes = info.d2h_bytes
     last_run.profile = info.profile
+    last_run.sharded = comm is not None
+    last_run.exchanges = info.exchanges
+    last_run.exchanged_records = info.exchanged_records
     obs_out = [restore_types(o) for o in obs_out]
     return (obs_out[0] if single else obs_out), slices_out, metadata
 
