@@ -174,6 +174,23 @@ int obp_rotate_emit(obp_ctx* ctx, const obp_op* op, double atol, void* d_records
  * num_unique = sum keys_present, num_duplicate = sum rows_surv - num_unique,
  * num_trimmed = 4 * sum n_in(emit) - sum rows_surv + sum cancelled. */
 int obp_rotate_merge(obp_ctx* ctx, const void* d_records, uint64_t n_records, obp_shard_counters* out);
+/* The same split rotation with the transfer fused into the emitting kernel: every rank owns two
+ * inboxes (ping-pong) in device memory that its peers map (CUDA IPC across processes, the raw
+ * pointer inside one process); obp_rotate_emit_p2p stores the records with plain st.global into the
+ * peer's inbox over NVLink and bumps the peer's cursor with a remote atomic, so no staging buffer,
+ * no count exchange and no separate copy are needed.  The caller places one cross-rank barrier
+ * between emit and merge (all emits done and visible), nothing else. */
+int obp_inbox_create(obp_ctx* ctx, uint64_t cap_records);
+/* stage 0: unmap the peers' inboxes; stage 1: free this rank's own (every rank finishes stage 0 first). */
+int obp_inbox_release(obp_ctx* ctx, int32_t stage);
+/* handle64: 64-byte CUDA IPC handle of inbox `which` (0/1) (may be NULL); raw_ptr: its device address. */
+int obp_inbox_export(obp_ctx* ctx, int32_t which, void* handle64, uint64_t* raw_ptr);
+/* Make rank peer_rank's inbox `which` writable from this context: by IPC handle (other process) or,
+ * with handle64 == NULL, by the raw device pointer (same process). */
+int obp_inbox_attach(obp_ctx* ctx, int32_t peer_rank, int32_t which, const void* handle64, uint64_t raw_ptr);
+int obp_rotate_emit_p2p(obp_ctx* ctx, const obp_op* op, double atol, int32_t peer_rank, obp_shard_counters* out);
+int obp_rotate_merge_inbox(obp_ctx* ctx, obp_shard_counters* out);
+
 /* Stepwise truncation: truncate_binary_search (utils/truncating.py:171-204) with the maximum
  * (:173) and each masked sum (:187) exposed so that ranks can combine them with an allreduce. */
 int obp_trunc_begin(obp_ctx* ctx, int32_t p_norm, double* local_max);

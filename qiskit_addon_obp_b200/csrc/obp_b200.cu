@@ -64,6 +64,12 @@ struct obp_ctx {
   ShardCnt* d_cnt = nullptr;
   ShardCnt* h_cnt = nullptr;  // pinned
   RotP shard_rot;             // rotation being split across obp_rotate_emit / obp_rotate_merge
+  // P2P exchange: two inboxes (ping-pong) other ranks' emit kernels write into; [0] = cursor, records from +16
+  u64* inbox[2] = {nullptr, nullptr};
+  u64 inbox_cap = 0;
+  std::vector<u64*> peer_inbox[2];     // per rank: its inbox as mapped into this process (nullptr = not attached)
+  std::vector<bool> peer_is_ipc[2];
+  int xchg_parity = 0;
   bool shard_rot_open = false;
   int rot_ctas_per_sm = 0;  // resident CTAs of k_rotate per SM (occupancy API)
   size_t cliff_smem_optin = 48 * 1024;  // dynamic smem k_clifford_smem is opted in for
@@ -387,6 +393,20 @@ struct PendingBatch {
   }
 };
 
+#define OBP_INBOX_HDR 16  // u64 words before the first record (cursor + padding to 128 B)
+
+void free_inboxes(obp_ctx* ctx) {
+  for (int b = 0; b < 2; ++b) {
+    for (size_t r = 0; r < ctx->peer_inbox[b].size(); ++r)
+      if (ctx->peer_inbox[b][r] && ctx->peer_is_ipc[b][r]) cudaIpcCloseMemHandle(ctx->peer_inbox[b][r]);
+    ctx->peer_inbox[b].clear();
+    ctx->peer_is_ipc[b].clear();
+    if (ctx->inbox[b]) cudaFree(ctx->inbox[b]);
+    ctx->inbox[b] = nullptr;
+  }
+  ctx->inbox_cap = 0;
+}
+
 // kernel parameters of a rotation op under the current hash frame (epoch and slot are set by the caller)
 RotP build_rotp(const obp_ctx* ctx, const obp_op& op, double atol) {
   RotP p;
@@ -542,6 +562,7 @@ void obp_destroy(obp_ctx* ctx) {
   cudaFree(ctx->d_scalar);
   cudaFree(ctx->d_cols);
   cudaFree(ctx->d_cnt);
+  free_inboxes(ctx);
   if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
   cudaFree(ctx->d_gens);
   cudaFree(ctx->d_factors);
@@ -947,7 +968,7 @@ int obp_rotate_emit(obp_ctx* ctx, const obp_op* op, double atol, void* d_records
   {
     Bracket br(ctx, OBP_K_ROTATE);
     k_rotate_emit<<<grid_for(ctx, std::max<u64>(ctx->n_dense, 1), ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(
-        make_tab(ctx), p, (u64*)d_records, cap_records, ctx->d_cnt);
+        make_tab(ctx), p, (u64*)d_records, cap_records, &ctx->d_cnt->n_records, ctx->d_cnt);
     CU(cudaGetLastError());
   }
   CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
@@ -970,11 +991,142 @@ int obp_rotate_merge(obp_ctx* ctx, const void* d_records, uint64_t n_records, ob
   {
     Bracket br(ctx, OBP_K_ROTATE);
     if (n_records)
-      k_merge_records<<<grid_for(ctx, n_records), OBP_BS, 0, ctx->stream>>>(t, (const u64*)d_records, n_records, ctx->d_cnt);
+      k_merge_records<<<grid_for(ctx, n_records), OBP_BS, 0, ctx->stream>>>(t, (const u64*)d_records, n_records, nullptr, 0,
+                                                                          ctx->d_cnt);
     const u64 bound = std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense + n_records, 1));
     k_rotate_finish<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, ctx->shard_rot, ctx->d_cnt);
     CU(cudaGetLastError());
   }
+  CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = sync_state(ctx);
+  fill_shard_stats(ctx, out, n_in);
+  if (rc) return rc;
+  if (ctx->n_dense - ctx->n_live > std::max<u64>(1024, ctx->n_live / 4)) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+    if (out) out->n_dense = ctx->n_dense;
+  }
+  return OBP_OK;
+}
+
+// ---- P2P exchange: the emitting kernel stores its records straight into the peer's inbox -----------
+int obp_inbox_create(obp_ctx* ctx, uint64_t cap_records) {
+  if (!ctx || cap_records < 1) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_inboxes(ctx);
+  const size_t words = OBP_INBOX_HDR + (size_t)cap_records * (2 * ctx->W + 3);
+  for (int b = 0; b < 2; ++b) {
+    CU(cudaMalloc(&ctx->inbox[b], words * sizeof(u64)));
+    CU(cudaMemset(ctx->inbox[b], 0, OBP_INBOX_HDR * sizeof(u64)));
+    ctx->peer_inbox[b].assign(ctx->n_ranks, nullptr);
+    ctx->peer_is_ipc[b].assign(ctx->n_ranks, false);
+  }
+  ctx->inbox_cap = cap_records;
+  ctx->xchg_parity = 0;
+  return OBP_OK;
+}
+
+int obp_inbox_release(obp_ctx* ctx, int32_t stage) {
+  if (!ctx) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (stage == 0) {  // unmap the peers' inboxes (all ranks do this before anyone frees)
+    for (int b = 0; b < 2; ++b)
+      for (size_t r = 0; r < ctx->peer_inbox[b].size(); ++r) {
+        if (ctx->peer_inbox[b][r] && ctx->peer_is_ipc[b][r]) cudaIpcCloseMemHandle(ctx->peer_inbox[b][r]);
+        ctx->peer_inbox[b][r] = nullptr;
+      }
+  } else {
+    free_inboxes(ctx);
+  }
+  return OBP_OK;
+}
+
+int obp_inbox_export(obp_ctx* ctx, int32_t which, void* handle64, uint64_t* raw_ptr) {
+  if (!ctx || which < 0 || which > 1 || !ctx->inbox[which]) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  if (raw_ptr) *raw_ptr = (uint64_t)(uintptr_t)ctx->inbox[which];
+  if (handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->inbox[which]));
+    memcpy(handle64, &h, 64);
+  }
+  return OBP_OK;
+}
+
+int obp_inbox_attach(obp_ctx* ctx, int32_t peer_rank, int32_t which, const void* handle64, uint64_t raw_ptr) {
+  if (!ctx || which < 0 || which > 1 || peer_rank < 0 || peer_rank >= ctx->n_ranks ||
+      (size_t)peer_rank >= ctx->peer_inbox[which].size())
+    return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  if (handle64) {  // another process: map its allocation (enables peer access lazily)
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_inbox[which][peer_rank] = (u64*)p;
+    ctx->peer_is_ipc[which][peer_rank] = true;
+  } else {  // same process: the device pointer itself
+    ctx->peer_inbox[which][peer_rank] = (u64*)(uintptr_t)raw_ptr;
+    ctx->peer_is_ipc[which][peer_rank] = false;
+  }
+  return OBP_OK;
+}
+
+int obp_rotate_emit_p2p(obp_ctx* ctx, const obp_op* op, double atol, int32_t peer_rank, obp_shard_counters* out) {
+  if (!ctx || !op || op->kind != OBP_OP_ROTATION || peer_rank < 0 || peer_rank >= ctx->n_ranks) return OBP_ERR_BADARG;
+  const int b = ctx->xchg_parity;
+  if (!ctx->inbox[b] || !ctx->peer_inbox[b][peer_rank]) return ctx->fail(OBP_ERR_BADARG, "obp_rotate_emit_p2p: peer inbox not attached");
+  CU(cudaSetDevice(ctx->device));
+  int rc = validate_op(ctx, *op);
+  if (rc) return rc;
+  RotP p = build_rotp(ctx, *op, atol);
+  p.epoch = ++ctx->epoch;
+  p.slot = -1;
+  ctx->shard_rot = p;
+  ctx->shard_rot_open = true;
+  const u64 n_in = ctx->n_live;
+  u64* peer = ctx->peer_inbox[b][peer_rank];
+  CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));
+  {
+    Bracket br(ctx, OBP_K_ROTATE);
+    k_rotate_emit<<<grid_for(ctx, std::max<u64>(ctx->n_dense, 1), ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(
+        make_tab(ctx), p, peer + OBP_INBOX_HDR, ctx->inbox_cap, peer, ctx->d_cnt);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  ctx->prof.term_updates[OBP_K_ROTATE] += n_in;
+  fill_shard_stats(ctx, out, n_in);
+  return rc;
+}
+
+int obp_rotate_merge_inbox(obp_ctx* ctx, obp_shard_counters* out) {
+  if (!ctx) return OBP_ERR_BADARG;
+  if (!ctx->shard_rot_open) return ctx->fail(OBP_ERR_BADARG, "obp_rotate_merge_inbox: no rotation in flight");
+  const int b = ctx->xchg_parity;
+  if (!ctx->inbox[b]) return ctx->fail(OBP_ERR_BADARG, "obp_rotate_merge_inbox: no inbox");
+  CU(cudaSetDevice(ctx->device));
+  ctx->shard_rot_open = false;
+  ctx->xchg_parity ^= 1;
+  const u64 n_in = ctx->n_live;
+  CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));
+  Tab t = make_tab(ctx);
+  {
+    Bracket br(ctx, OBP_K_ROTATE);
+    // the peer emits at most one record per row it holds; shards are balanced, so size the grid on ours
+    const u64 guess = std::min<u64>(ctx->inbox_cap, std::max<u64>(2 * ctx->n_dense, 1 << 14));
+    k_merge_records<<<grid_for(ctx, guess), OBP_BS, 0, ctx->stream>>>(t, ctx->inbox[b] + OBP_INBOX_HDR, 0, ctx->inbox[b],
+                                                                     ctx->inbox_cap, ctx->d_cnt);
+    const u64 bound = std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense + guess, 1));
+    k_rotate_finish<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, ctx->shard_rot, ctx->d_cnt);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemsetAsync(ctx->inbox[b], 0, sizeof(u64), ctx->stream));  // cursor back to 0 for the rotation after next
   CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
   int rc = sync_state(ctx);
   fill_shard_stats(ctx, out, n_in);

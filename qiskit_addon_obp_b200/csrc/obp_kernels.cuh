@@ -969,13 +969,17 @@ struct ShardCnt {  // per-call counters (device), summed over ranks by the host
   double sum_re, sum_im;
 };
 
+// `rec` / `cursor` point either to a local staging buffer (exchange by NCCL send/recv) or straight
+// into the PEER's inbox over NVLink (P2P stores + a remote atomic on the peer's cursor): in that case
+// this one kernel is both the compute step and the transfer.
 __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, const __grid_constant__ RotP p,
                                                                       u64* __restrict__ rec, u64 rec_cap,
+                                                                      u64* __restrict__ cursor,
                                                                       ShardCnt* __restrict__ cnt) {
   const u64 n = t.st->n_scan;
   const unsigned lane = threadIdx.x & 31u;
   const int RW = 2 * t.W + 3;
-  unsigned rows_surv = 0, keys_present = 0;
+  unsigned rows_surv = 0, keys_present = 0, n_emit = 0;
   int dlive = 0;
   bool overflow = false;
   for (u64 base = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)); base < n; base += (u64)gridDim.x * OBP_BS) {
@@ -1025,9 +1029,10 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, con
     const unsigned bal = __ballot_sync(0xffffffffu, want_emit);
     if (bal) {
       u64 wbase = 0;
-      if (lane == 0) wbase = atomicAdd(&cnt->n_records, (u64)__popc(bal));
+      if (lane == 0) wbase = atomicAdd(cursor, (u64)__popc(bal));
       wbase = __shfl_sync(0xffffffffu, wbase, 0);
       if (want_emit) {
+        n_emit++;
         const u64 r = wbase + __popc(bal & ((1u << lane) - 1u));
         if (r < rec_cap) {
           u64* o = rec + r * RW;
@@ -1049,18 +1054,29 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, con
   }
   if (overflow) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
   const long long dl = warp_sum_i64((long long)dlive);
-  const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present);
+  const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present), ne = warp_sum_u64(n_emit);
   if (lane == 0) {
     if (a) atomicAdd(&cnt->rows_surv, a);
     if (b) atomicAdd(&cnt->keys_present, b);
+    if (ne && cursor != &cnt->n_records) atomicAdd(&cnt->n_records, ne);
     if (dl) atomicAdd(&t.st->n_live, (u64)dl);
   }
+  __threadfence_system();  // records written into a peer's memory must be visible before the kernel ends
   finish_kernel(t, -1);
 }
 
 // One thread per incoming record: add to the live row with that key, or append it.
 __global__ void __launch_bounds__(OBP_BS) k_merge_records(Tab t, const u64* __restrict__ rec, u64 n_rec,
+                                                           const u64* __restrict__ n_rec_ptr, u64 rec_cap,
                                                            ShardCnt* __restrict__ cnt) {
+  if (n_rec_ptr) {  // inbox filled by the peer's kernel: the count is the inbox cursor
+    n_rec = ld_volatile(n_rec_ptr);
+    if (n_rec > rec_cap) {
+      n_rec = rec_cap;
+      if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) cnt->n_records = n_rec;
+  }
   const u64 n = t.st->n_scan;
   const unsigned lane = threadIdx.x & 31u;
   const int RW = 2 * t.W + 3;

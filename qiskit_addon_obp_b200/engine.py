@@ -136,6 +136,12 @@ def lib() -> C.CDLL:
         ),
         "obp_rotate_emit": ([vp, vp, C.c_double, vp, C.c_uint64, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_rotate_merge": ([vp, vp, C.c_uint64, C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_inbox_create": ([vp, C.c_uint64], C.c_int),
+        "obp_inbox_release": ([vp, C.c_int32], C.c_int),
+        "obp_inbox_export": ([vp, C.c_int32, vp, u64p], C.c_int),
+        "obp_inbox_attach": ([vp, C.c_int32, C.c_int32, vp, C.c_uint64], C.c_int),
+        "obp_rotate_emit_p2p": ([vp, vp, C.c_double, C.c_int32, C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_rotate_merge_inbox": ([vp, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_trunc_begin": ([vp, C.c_int32, f64p], C.c_int),
         "obp_trunc_masked_sum": ([vp, C.c_double, f64p], C.c_int),
         "obp_trunc_finish": ([vp, C.c_double, u64p, u64p], C.c_int),
@@ -155,7 +161,8 @@ EXPORTED_SYMBOLS = (
     "obp_load obp_count obp_download obp_apply_ops obp_apply_reset obp_apply_damping obp_truncate "
     "obp_union_count obp_snapshot obp_restore obp_reserve obp_profile_enable obp_profile_get "
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
-    "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish"
+    "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
+    "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox"
 ).split()
 
 
@@ -450,6 +457,41 @@ class TermTable:
         rc = self._lib.obp_rotate_merge(self._h, C.c_void_p(d_records), int(n_records), C.byref(out))
         if rc != OBP_ERR_CAPACITY:
             self._check(rc, "obp_rotate_merge")
+        self.n, self.n_dense = out.n_out, out.n_dense
+        return out, rc == OBP_ERR_CAPACITY
+
+    def inbox_create(self, cap_records: int):
+        self._check(self._lib.obp_inbox_create(self._h, int(cap_records)), "obp_inbox_create")
+
+    def inbox_release(self, stage: int):
+        self._check(self._lib.obp_inbox_release(self._h, int(stage)), "obp_inbox_release")
+
+    def inbox_export(self, which: int) -> tuple[bytes, int]:
+        """``(64-byte CUDA IPC handle, raw device pointer)`` of inbox ``which``."""
+        h, ptr = C.create_string_buffer(64), C.c_uint64()
+        self._check(self._lib.obp_inbox_export(self._h, int(which), h, C.byref(ptr)), "obp_inbox_export")
+        return h.raw, ptr.value
+
+    def inbox_attach(self, peer_rank: int, which: int, handle: bytes | None, raw_ptr: int):
+        buf = C.create_string_buffer(handle, 64) if handle is not None else None
+        self._check(
+            self._lib.obp_inbox_attach(self._h, int(peer_rank), int(which), buf, int(raw_ptr)), "obp_inbox_attach"
+        )
+
+    def rotate_emit_p2p(self, op: np.ndarray, atol: float, peer_rank: int) -> tuple[ObpShardCounters, bool]:
+        out = ObpShardCounters()
+        op = np.ascontiguousarray(op, dtype=OP_DTYPE)
+        rc = self._lib.obp_rotate_emit_p2p(self._h, op.ctypes.data_as(C.c_void_p), float(atol), int(peer_rank), C.byref(out))
+        if rc != OBP_ERR_CAPACITY:
+            self._check(rc, "obp_rotate_emit_p2p")
+        self.n, self.n_dense = out.n_out, out.n_dense
+        return out, rc == OBP_ERR_CAPACITY
+
+    def rotate_merge_inbox(self) -> tuple[ObpShardCounters, bool]:
+        out = ObpShardCounters()
+        rc = self._lib.obp_rotate_merge_inbox(self._h, C.byref(out))
+        if rc != OBP_ERR_CAPACITY:
+            self._check(rc, "obp_rotate_merge_inbox")
         self.n, self.n_dense = out.n_out, out.n_dense
         return out, rc == OBP_ERR_CAPACITY
 

@@ -22,6 +22,8 @@ Two communicators implement the exchange:
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .engine import OBP_OP_ROTATION, CapacityError, TermTable, lib
@@ -52,6 +54,13 @@ class LocalComm:
 
     def gather_operators(self, ops: dict) -> SparsePauliOp:
         return _concat([ops[r] for r in self.local_ranks])
+
+    def barrier(self) -> None:
+        pass  # one thread runs all ranks: every emit has returned before the first merge starts
+
+    def share_inboxes(self, exports: dict) -> dict:
+        """``exports[r] = [(ipc handle, raw pointer)] * 2`` -> the same for every rank, IPC handle dropped."""
+        return {r: [(None, ptr) for _, ptr in exports[r]] for r in self.local_ranks}
 
 
 class DistComm:
@@ -114,6 +123,16 @@ class DistComm:
     def allreduce_sum_int(self, vals: dict) -> np.ndarray:
         return self._allreduce(vals, self.dist.ReduceOp.SUM, self.torch.int64)
 
+    def barrier(self) -> None:
+        if self.tdev.type == "cuda":
+            self.torch.cuda.synchronize(self.tdev)
+        self.dist.barrier(group=self.group)
+
+    def share_inboxes(self, exports: dict) -> dict:
+        parts: list = [None] * self.n_ranks
+        self.dist.all_gather_object(parts, exports[self.rank], group=self.group)
+        return {r: [(h, 0) for h, _ in parts[r]] for r in range(self.n_ranks)}
+
     def gather_operators(self, ops: dict) -> SparsePauliOp:
         mine = ops[self.rank]
         xw, zw = mine.packed()
@@ -154,6 +173,9 @@ class ShardedTable:
         self.tables = {r: TermTable.acquire(num_qubits, per_rank, comm.device) for r in comm.local_ranks}
         for r, t in self.tables.items():
             t.set_shard(comm.n_ranks, r)
+        self.p2p = os.environ.get("OBP_B200_P2P", "1") not in ("0", "")
+        if self.p2p:
+            self._setup_inboxes(per_rank)
         self.n = 0
         self.n_dense = 0
         self.zero_operator = False
@@ -168,7 +190,28 @@ class ShardedTable:
     def acquire(cls, num_qubits, capacity, comm):
         return cls(num_qubits, capacity, comm)
 
+    def _setup_inboxes(self, per_rank: int) -> None:
+        """Every rank allocates its two inboxes and maps those of all its peers (collective)."""
+        for t in self.tables.values():
+            t.inbox_create(per_rank)
+        shared = self.comm.share_inboxes({r: [t.inbox_export(0), t.inbox_export(1)] for r, t in self.tables.items()})
+        for r, t in self.tables.items():
+            for peer, boxes in shared.items():
+                if peer != r:
+                    for which, (handle, ptr) in enumerate(boxes):
+                        t.inbox_attach(peer, which, handle, ptr)
+        self.comm.barrier()
+
+    def _drop_inboxes(self) -> None:
+        for t in self.tables.values():
+            t.inbox_release(0)
+        self.comm.barrier()
+        for t in self.tables.values():
+            t.inbox_release(1)
+
     def release(self):
+        if self.tables and self.p2p:
+            self._drop_inboxes()
         for t in self.tables.values():
             t.release()
         self.tables = {}
@@ -236,24 +279,36 @@ class ShardedTable:
                 break
             # ---- split rotation: emit, pairwise exchange, merge -----------------------------------
             op = ops[pos : pos + 1]
-            bufs, counts, emit = {}, {}, {}
-            for r, t in self.tables.items():
-                cap = max(int(t.n_dense), 1)
-                bufs[r] = torch.empty((cap, self.rec_u64), dtype=torch.int64, device=tdev)
-                emit[r], over = t.rotate_emit(op, atol, bufs[r].data_ptr(), cap)
-                failed |= over
-                counts[r] = min(int(emit[r].n_records), cap)
-                updates += int(emit[r].n_in)
-            recv = self.comm.exchange(bufs, counts, peer)
-            merge = {}
-            for r, t in self.tables.items():
-                buf, n_rec = recv[r]
-                merge[r], over = t.rotate_merge(buf.data_ptr() if n_rec else 0, n_rec)
-                failed |= over
+            emit, merge, counts = {}, {}, {}
+            if self.p2p:
+                # the emitting kernel stores its records straight into the peer's inbox over NVLink
+                for r, t in self.tables.items():
+                    emit[r], over = t.rotate_emit_p2p(op, atol, r ^ peer)
+                    failed |= over
+                    counts[r] = int(emit[r].n_records)
+                    updates += int(emit[r].n_in)
+                self.comm.barrier()
+                for r, t in self.tables.items():
+                    merge[r], over = t.rotate_merge_inbox()
+                    failed |= over
+            else:
+                bufs = {}
+                for r, t in self.tables.items():
+                    cap = max(int(t.n_dense), 1)
+                    bufs[r] = torch.empty((cap, self.rec_u64), dtype=torch.int64, device=tdev)
+                    emit[r], over = t.rotate_emit(op, atol, bufs[r].data_ptr(), cap)
+                    failed |= over
+                    counts[r] = min(int(emit[r].n_records), cap)
+                    updates += int(emit[r].n_in)
+                recv = self.comm.exchange(bufs, counts, peer)
+                for r, t in self.tables.items():
+                    buf, n_rec = recv[r]
+                    merge[r], over = t.rotate_merge(buf.data_ptr() if n_rec else 0, n_rec)
+                    failed |= over
+                del bufs, recv
             self.exchanges += 1
             self.exchanged_records += sum(counts.values())
             last = {"kind": "split", "emit": emit, "merge": merge, "op": op[0]}
-            del bufs, recv
             pos += 1
         self._raise_if_any(failed, "sharded gate program")
         self._sync_counts()
@@ -347,9 +402,13 @@ class ShardedTable:
         self.zero_operator, self.n = self._snap
 
     def reserve(self, capacity: int):
+        if self.p2p:
+            self._drop_inboxes()
         for t in self.tables.values():
             t.reserve(self._per_rank(capacity))
         self.capacity = max(self.capacity, int(capacity))
+        if self.p2p:
+            self._setup_inboxes(self._per_rank(self.capacity))
 
     # -- measurement ------------------------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

@@ -17,8 +17,9 @@ from test_engine_gpu import random_observable, random_slices
 pytestmark = pytest.mark.gpu
 
 
-def _compare(monkeypatch, ranks, obs, slices, **kw):
+def _compare(monkeypatch, ranks, obs, slices, p2p=True, **kw):
     monkeypatch.setenv("OBP_B200_SHARDS", str(ranks))
+    monkeypatch.setenv("OBP_B200_P2P", "1" if p2p else "0")
     got, rest_g, md_g = backpropagate(obs, slices, **kw)
     monkeypatch.delenv("OBP_B200_SHARDS")
     want, rest_w, md_w = oracle.backpropagate(obs, slices, **kw)
@@ -30,13 +31,15 @@ def _compare(monkeypatch, ranks, obs, slices, **kw):
     return got, md_g
 
 
+@pytest.mark.parametrize("p2p", [True, False], ids=["inbox", "staged"])
 @pytest.mark.parametrize("ranks", [2, 4, 8])
 @pytest.mark.parametrize("nq", [6, 70, 130])
-def test_sharded_random_circuit(monkeypatch, ranks, nq):
+def test_sharded_random_circuit(monkeypatch, ranks, nq, p2p):
+    """Both exchange paths: records stored straight into the peer's inbox, or staged and handed over."""
     rng = np.random.default_rng(31 * nq + ranks)
     slices = random_slices(nq, 6, rng, gates_per_slice=8)
     obs = random_observable(nq, 4, rng)
-    _compare(monkeypatch, ranks, obs, slices)
+    _compare(monkeypatch, ranks, obs, slices, p2p=p2p)
 
 
 @pytest.mark.parametrize("ranks,p", [(2, 1), (8, 2)])

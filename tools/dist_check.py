@@ -25,6 +25,9 @@ from qiskit_addon_obp_b200 import workloads as W
 from qiskit_addon_obp_b200.utils.truncating import TruncationErrorBudget
 from test_engine_gpu import random_observable, random_slices
 
+p2p = os.environ.get("OBP_B200_P2P", "1")
+
+
 def log(*a):
     if rank == 0:
         print(*a, flush=True)
@@ -45,7 +48,7 @@ got, rest, md = backpropagate(wl.observables, wl.slices, **wl.kwargs())
 want, _, md_w = oracle.backpropagate(wl.observables, wl.slices, **wl.kwargs())
 assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
 dist.barrier()
-log(f"[dist_check] parity vs oracle OK on {world} ranks (NCCL)")
+log(f"[dist_check] parity vs oracle OK on {world} ranks (NCCL, P2P inbox exchange = {p2p})")
 
 # ---- 2. throughput -----------------------------------------------------------------------------------
 def run(wl, tag):
