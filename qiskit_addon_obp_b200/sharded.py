@@ -23,6 +23,7 @@ Two communicators implement the exchange:
 from __future__ import annotations
 
 import os
+import time
 
 import numpy as np
 
@@ -134,11 +135,23 @@ class DistComm:
         return {r: [(h, 0) for h, _ in parts[r]] for r in range(self.n_ranks)}
 
     def gather_operators(self, ops: dict) -> SparsePauliOp:
+        """Every rank gets the whole operator: one padded all_gather of the packed rows (no pickling)."""
+        torch = self.torch
         mine = ops[self.rank]
         xw, zw = mine.packed()
-        parts: list = [None] * self.n_ranks
-        self.dist.all_gather_object(parts, (xw, zw, mine.coeffs, mine.num_qubits), group=self.group)
-        return _concat([SparsePauliOp.from_packed(*p) for p in parts])
+        n, w = xw.shape[0], xw.shape[1]
+        row = np.concatenate([xw, zw, mine.coeffs.view(np.float64).reshape(n, 2).view("<u8")], axis=1)  # [n, 2W+2] u64
+        sizes = self.allreduce_sum_int({self.rank: [n if r == self.rank else 0 for r in range(self.n_ranks)]})
+        n_max = int(max(sizes.max(), 1))
+        send = torch.zeros((n_max, 2 * w + 2), dtype=torch.int64, device=self.tdev)
+        if n:
+            send[:n] = torch.from_numpy(row.view(np.int64)).to(self.tdev)
+        recv = torch.empty((self.n_ranks * n_max, 2 * w + 2), dtype=torch.int64, device=self.tdev)
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        full = recv.cpu().numpy().view("<u8").reshape(self.n_ranks, n_max, 2 * w + 2)
+        rows = np.concatenate([full[r, : int(sizes[r])] for r in range(self.n_ranks)], axis=0)
+        coeffs = np.ascontiguousarray(rows[:, 2 * w :]).view(np.float64).view(np.complex128).reshape(-1)
+        return SparsePauliOp.from_packed(rows[:, :w], rows[:, w : 2 * w], coeffs, mine.num_qubits)
 
 
 def _concat(ops: list[SparsePauliOp]) -> SparsePauliOp:
@@ -181,6 +194,7 @@ class ShardedTable:
         self.zero_operator = False
         self.exchanges = 0  # rotations that needed a record exchange
         self.exchanged_records = 0
+        self.t_phase = {"local": 0.0, "emit": 0.0, "barrier": 0.0, "merge": 0.0, "reduce": 0.0}  # host seconds
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _per_rank(self, capacity: int) -> int:
@@ -188,6 +202,15 @@ class ShardedTable:
 
     @classmethod
     def acquire(cls, num_qubits, capacity, comm):
+        """A recycled table of this communicator (device memory, inboxes and peer mappings stay alive)."""
+        pool = comm.__dict__.setdefault("_idle_tables", [])
+        for k, t in enumerate(pool):
+            if t.num_qubits == int(num_qubits) and t.capacity >= int(capacity):
+                pool.pop(k)
+                t.n = t.n_dense = t.exchanges = t.exchanged_records = 0
+                t.zero_operator = False
+                t.t_phase = dict.fromkeys(t.t_phase, 0.0)
+                return t
         return cls(num_qubits, capacity, comm)
 
     def _setup_inboxes(self, per_rank: int) -> None:
@@ -210,13 +233,22 @@ class ShardedTable:
             t.inbox_release(1)
 
     def release(self):
+        """Back to the communicator's pool (collective-free); :meth:`close` really frees everything."""
+        if self.tables and os.environ.get("OBP_B200_TRACE"):
+            print(f"[obp trace] sharded table: {self.exchanges} exchanges, {self.exchanged_records} records, host seconds "
+                  + ", ".join(f"{k} {v:.3f}" for k, v in self.t_phase.items()), flush=True)
+        pool = self.comm.__dict__.setdefault("_idle_tables", [])
+        if self.tables and len(pool) < 2:
+            pool.append(self)
+        else:
+            self.close()
+
+    def close(self):
         if self.tables and self.p2p:
             self._drop_inboxes()
         for t in self.tables.values():
             t.release()
         self.tables = {}
-
-    close = release
 
     def __len__(self) -> int:
         return 1 if self.zero_operator else self.n
@@ -267,11 +299,13 @@ class ShardedTable:
             seg = ops[pos:]
             done = peer = 0
             seg_stats = {}
+            t0 = time.perf_counter()
             for r, t in self.tables.items():
                 st, done, peer, over = t.apply_ops_sharded(seg, atol)  # every rank stops at the same op
                 failed |= over
                 seg_stats[r] = st
                 updates += int(st.updates)
+            self.t_phase["local"] += time.perf_counter() - t0
             if done > 0:
                 last = {"kind": "local", "stats": seg_stats, "op": seg[done - 1]}
             pos += done
@@ -282,15 +316,22 @@ class ShardedTable:
             emit, merge, counts = {}, {}, {}
             if self.p2p:
                 # the emitting kernel stores its records straight into the peer's inbox over NVLink
+                t0 = time.perf_counter()
                 for r, t in self.tables.items():
                     emit[r], over = t.rotate_emit_p2p(op, atol, r ^ peer)
                     failed |= over
                     counts[r] = int(emit[r].n_records)
                     updates += int(emit[r].n_in)
+                t1 = time.perf_counter()
                 self.comm.barrier()
+                t2 = time.perf_counter()
                 for r, t in self.tables.items():
                     merge[r], over = t.rotate_merge_inbox()
                     failed |= over
+                t3 = time.perf_counter()
+                self.t_phase["emit"] += t1 - t0
+                self.t_phase["barrier"] += t2 - t1
+                self.t_phase["merge"] += t3 - t2
             else:
                 bufs = {}
                 for r, t in self.tables.items():
@@ -310,10 +351,12 @@ class ShardedTable:
             self.exchanged_records += sum(counts.values())
             last = {"kind": "split", "emit": emit, "merge": merge, "op": op[0]}
             pos += 1
+        t0 = time.perf_counter()
         self._raise_if_any(failed, "sharded gate program")
         self._sync_counts()
         out.updates = int(self.comm.allreduce_sum_int({r: [updates if r == min(self.tables) else 0] for r in self.tables})[0])
         self._fill_last(out, last, ops[-1])
+        self.t_phase["reduce"] += time.perf_counter() - t0
         out.n_out, out.n_dense = self.n, self.n_dense
         if self.n == 0:
             self.zero_operator = True
@@ -438,12 +481,29 @@ def communicator_from_env(device: int):
 
     virt = int(os.environ.get("OBP_B200_SHARDS", "0") or 0)
     if virt > 1:
-        return LocalComm(virt, device)
+        key = ("local", virt, device)
+        if key not in _COMMS:
+            _COMMS[key] = LocalComm(virt, device)
+        return _COMMS[key]
     if os.environ.get("OBP_B200_SHARDED", "") not in ("", "0"):
         import torch.distributed as dist
 
         if not dist.is_available() or not dist.is_initialized():
             raise RuntimeError("OBP_B200_SHARDED=1 needs an initialised torch.distributed process group")
         if dist.get_world_size() > 1:
-            return DistComm()
+            key = ("dist", dist.get_world_size(), device)
+            if key not in _COMMS:
+                _COMMS[key] = DistComm()
+            return _COMMS[key]
     return None
+
+
+#: communicators are kept for the life of the process: they own the pool of idle sharded tables
+_COMMS: dict = {}
+
+
+def close_all() -> None:
+    """Free every pooled sharded table (collective in the distributed case: all ranks must call it)."""
+    for comm in _COMMS.values():
+        for t in comm.__dict__.pop("_idle_tables", []):
+            t.close()

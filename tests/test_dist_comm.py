@@ -55,6 +55,11 @@ def _worker(rank: int, world: int, port: int, q):
         full = comm.gather_operators({rank: op})
         assert len(full) == 5 and full.packed()[0][:, 0].tolist() == [1, 1, 2, 2, 2]
         assert full.coeffs.real.tolist() == [0.5, 0.5, 1.5, 1.5, 1.5]
+        assert full.packed()[1][:, 0].tolist() == [2, 2, 4, 4, 4] and full.num_qubits == 5
+        # one rank holds nothing
+        empty = SparsePauliOp.from_packed(xw[:0], xw[:0], np.zeros(0), 5)
+        full = comm.gather_operators({rank: op if rank == 1 else empty})
+        assert len(full) == 3 and full.coeffs.real.tolist() == [1.5, 1.5, 1.5]
         q.put((rank, "ok"))
     except Exception as exc:  # noqa: BLE001
         q.put((rank, f"{type(exc).__name__}: {exc}"))
