@@ -18,7 +18,9 @@ Engine arm (default) prints one JSON line with
 here) on the host cores, on the same workload, each step a bounded sample.
 
 N > 1 (torchrun): every rank backpropagates its own observable of the workload (independent
-observables partition the path with no data-path collective): weak scaling.
+observables partition the path with no data-path collective): weak scaling.  With
+``--sharded`` the ranks instead share ONE observable as a hash-sharded table (strong scaling; meant for
+tables far beyond one GPU's L2, e.g. ``--workload config4 --max-paulis 20000000``).
 """
 
 from __future__ import annotations
@@ -223,12 +225,15 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    sharded = bool(args.sharded) and world > 1
+    if sharded:
+        os.environ["OBP_B200_SHARDED"] = "1"  # one observable, hash-sharded over all ranks (strong scaling)
 
     from qiskit_addon_obp_b200 import backpropagate
     from qiskit_addon_obp_b200 import backpropagation as bpmod
 
     bpmod.PROFILE = not args.no_profile
-    wls = make_workloads(args.workload, rank, args)
+    wls = make_workloads(args.workload, 0 if sharded else rank, args)  # sharded: every rank drives the same job
     flush_buf = torch.zeros(256 << 20, dtype=torch.uint8, device=device)
 
     def barrier():
@@ -294,7 +299,9 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         e2e_s, dev_ms = float(mx[0]), float(mx[1])
-        updates_all, h2d_all, d2h_all = float(sm[2]), float(sm[3]), float(sm[4])
+        # a sharded run already reports the whole job's update count on every rank
+        updates_all = float(mx[2]) if sharded else float(sm[2])
+        h2d_all, d2h_all = float(sm[3]), float(sm[4])
     else:
         updates_all, h2d_all, d2h_all = float(updates), float(h2d), float(d2h)
 
@@ -321,7 +328,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "warmup": args.warmup,
             "ms_per_step": dev_ms / max(1, args.steps),
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None,
             "dtype": "u64 keys + f64 complex coefficients",
             "data": "synthetic",
@@ -332,7 +339,11 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                 "slices_absorbed": n_slices,
                 "terms_out": n_out,
                 "updates_per_step": updates_all / max(1, args.steps),
-                "parallelism": f"{world} independent observables, one per GPU" if world > 1 else "1 GPU",
+                "parallelism": (
+                    f"one observable hash-sharded over {world} GPUs (pairwise P2P record exchange per branching gate)"
+                    if sharded
+                    else (f"{world} independent observables, one per GPU" if world > 1 else "1 GPU")
+                ),
                 "l2": "256 MiB buffer rewritten before every step (L2 flush)",
             },
             "e2e": {
@@ -387,6 +398,7 @@ def main() -> None:
     ap.add_argument("--max-paulis", type=int, default=1_000_000)
     ap.add_argument("--cpu-updates", type=int, default=600_000, help="bound of the CPU sample (term-gate updates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="N>1: shard ONE observable over all ranks instead of one observable per rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

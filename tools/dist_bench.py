@@ -26,4 +26,11 @@ for rep in range(3):
     if rank == 0:
         print(f"[dist_bench] {world} ranks {wl.name} rep {rep}: slices {md.num_backpropagated_slices} terms {len(out)} updates {r.updates:.4g} "
               f"wall {dt*1e3:.1f} ms -> {r.updates/dt:.3e} upd/s; exchanges {r.exchanges} records {r.exchanged_records:.4g}", flush=True)
+if os.environ.get("OBP_PROFILE_HOST") and rank == 0:
+    import cProfile, pstats
+    pr = cProfile.Profile(); pr.enable()
+    backpropagate(wl.observables, wl.slices, **wl.kwargs())
+    pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+elif os.environ.get("OBP_PROFILE_HOST"):
+    backpropagate(wl.observables, wl.slices, **wl.kwargs())
 dist.destroy_process_group()
