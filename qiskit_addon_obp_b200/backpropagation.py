@@ -316,17 +316,22 @@ class SliceProgram:
         self.recs = np.zeros(len(self.nodes), dtype=OP_DTYPE)
         self.special = [n.name in ("reset", "LayerError") for n in self.nodes]
         self.errors: dict[int, Exception] = {}
-        qubit = self.recs["qubit"]
+        # classify each distinct gate once, then fill the records of all its occurrences in one go
+        groups: dict[tuple, list[int]] = {}
         for k, node in enumerate(self.nodes):
-            if self.special[k]:
-                continue
+            if not self.special[k]:
+                key = (node.name, node.params) if node._matrix is None else (node.name, id(node._matrix))
+                groups.setdefault(key, []).append(k)
+        qubit = self.recs["qubit"]
+        for idxs in groups.values():
             try:
-                prog = program_for(node)
+                prog = program_for(self.nodes[idxs[0]])
             except (NotImplementedError, ValueError) as exc:  # only raised if the gate is applied
-                self.errors[k] = exc
+                for k in idxs:
+                    self.errors[k] = exc
                 continue
-            self.recs[k] = prog.template[0]
-            qubit[k, : prog.n_qubits] = node.qubits
+            self.recs[idxs] = prog.template[0]
+            qubit[idxs, : prog.n_qubits] = np.array([self.nodes[k].qubits for k in idxs], dtype=np.int32)
 
 
 def _slice_program(slice_: QuantumCircuit) -> SliceProgram:

@@ -555,7 +555,8 @@ def topological_op_order(circuit: QuantumCircuit) -> list[Instruction]:
         indeg[i] = len(preds)
         for q in ins.qubits:
             last_on_qubit[q] = i
-    key = [",".join(f"{q:04d}" for q in ins.qubits) for ins in circuit.data]
+    # Qiskit's key is the zero-padded qubit indices joined by commas; tuples of ints order the same way
+    key = [ins.qubits for ins in circuit.data]
     heap = [(key[i], i) for i in range(n_ops) if indeg[i] == 0]
     heapq.heapify(heap)
     out = []
