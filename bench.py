@@ -67,9 +67,9 @@ def make_workloads(name: str, rank: int, args) -> list:
     if name == "config3":
         return [wl.config3_square_lattice(max_paulis=args.max_paulis)]
     if name == "config4":
-        return [wl.config4_near_clifford(max_paulis=args.max_paulis, seed=20261019 + rank)]
+        return [wl.config4_near_clifford(depth=args.depth or 200, max_paulis=args.max_paulis, seed=20261019 + rank)]
     if name == "config5":
-        return [wl.config5_magic_sweep(theta=t, max_paulis=args.max_paulis, seed=rank) for t in thetas]
+        return [wl.config5_magic_sweep(theta=t, depth=args.depth or 40, max_paulis=args.max_paulis, seed=rank) for t in thetas]
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -259,7 +259,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             acc["n_out"] += len(out) if not isinstance(out, list) else sum(len(o) for o in out)
             acc["slices"] += md.num_backpropagated_slices
             for k, v in (r.profile or {}).items():
-                a = acc["prof"].setdefault(k, {"launches": 0, "ms": 0.0, "term_updates": 0})
+                a = acc["prof"].setdefault(k, {"launches": 0, "passes": 0, "ms": 0.0, "term_updates": 0})
                 for f in a:
                     a[f] += v[f]
         return acc
@@ -283,7 +283,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
         h2d += acc["h2d"]
         d2h += acc["d2h"]
         for k, v in acc["prof"].items():
-            a = prof_tot.setdefault(k, {"launches": 0, "ms": 0.0, "term_updates": 0})
+            a = prof_tot.setdefault(k, {"launches": 0, "passes": 0, "ms": 0.0, "term_updates": 0})
             for f in a:
                 a[f] += v[f]
         n_out, n_slices = acc["n_out"], acc["slices"]
@@ -315,7 +315,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         btg = algorithmic_bytes_per_update(wls[0].num_qubits)
-        rot = prof_tot.get("rotate", {"launches": 0, "ms": 0.0, "term_updates": 0})
+        rot = prof_tot.get("rotate", {"launches": 0, "passes": 0, "ms": 0.0, "term_updates": 0})
         achieved = (rot["term_updates"] * btg / (rot["ms"] * 1e-3) / 1e9) if rot["ms"] > 0 else None
         kernel_ms = {k: round(v["ms"] / max(1, args.steps), 3) for k, v in prof_tot.items()}
         launches = int(sum(v["launches"] for v in prof_tot.values()) / max(1, args.steps))
@@ -365,8 +365,10 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                 "frac": (achieved / peak) if achieved else None,
                 "frac_of_nominal_8000": (achieved / 8000.0) if achieved else None,
                 "bytes_per_term_gate_update": btg,
-                "launches": rot["launches"],
-                "avg_launch_ms": rot["ms"] / max(1, rot["launches"]),
+                "passes": rot["passes"],
+                "avg_pass_ms": rot["ms"] / max(1, rot["passes"]),
+                "timing": "tables <= 128 qubits: %globaltimer stamps at the grid barriers of the persistent program "
+                "kernel; wider tables: CUDA events around the k_rotate launches",
                 "traffic": None,
             },
             "clocks": clocks,
@@ -397,6 +399,7 @@ def main() -> None:
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernel launches with CUDA events")
     ap.add_argument("--max-paulis", type=int, default=1_000_000)
     ap.add_argument("--cpu-updates", type=int, default=600_000, help="bound of the CPU sample (term-gate updates)")
+    ap.add_argument("--depth", type=int, default=0, help="circuit depth of config4/config5 (0 = 200 / 40)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharded", action="store_true", help="N>1: shard ONE observable over all ranks instead of one observable per rank")
     args = ap.parse_args()

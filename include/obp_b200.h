@@ -200,12 +200,17 @@ int obp_trunc_finish(obp_ctx* ctx, double threshold, uint64_t* n_removed, uint64
 /* ---- measurement --------------------------------------------------------------------------- */
 
 enum { OBP_K_ROTATE = 0, OBP_K_CLIFFORD = 1, OBP_K_TRUNCATE = 2, OBP_K_COMPACT = 3,
-       OBP_K_INDEX = 4, OBP_K_OTHER = 5, OBP_K_COUNT = 6 };
+       OBP_K_INDEX = 4, OBP_K_OTHER = 5, OBP_K_PROGRAM = 6, OBP_K_COUNT = 7 };
 
+/* OBP_K_PROGRAM is the persistent cooperative kernel that runs a whole gate program in one launch
+ * (tables of up to 128 qubits): it counts as ONE launch; the table passes it makes are counted per
+ * class in `passes`, and their device time (from %globaltimer stamps taken inside the kernel at
+ * each grid barrier) is attributed to the class of each pass in `ms`. */
 typedef struct {
   uint64_t launches[OBP_K_COUNT];  /* kernel launches per class since the last reset           */
-  double ms[OBP_K_COUNT];          /* CUDA-event time per class (only while profiling is on)   */
-  uint64_t term_updates[OBP_K_COUNT]; /* live terms at entry summed over launches (x gates)    */
+  uint64_t passes[OBP_K_COUNT];    /* passes over the table per class (= launches for stand-alone kernels) */
+  double ms[OBP_K_COUNT];          /* device time per class (only while profiling is on)       */
+  uint64_t term_updates[OBP_K_COUNT]; /* live terms at entry summed over passes (x gates)      */
 } obp_profile;
 
 int obp_profile_enable(obp_ctx* ctx, int32_t on);

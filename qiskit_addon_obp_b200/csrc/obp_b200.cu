@@ -72,6 +72,13 @@ struct obp_ctx {
   int xchg_parity = 0;
   bool shard_rot_open = false;
   int rot_ctas_per_sm = 0;  // resident CTAs of k_rotate per SM (occupancy API)
+  int prog_ctas_per_sm = 0; // resident CTAs of k_program per SM; 0 = cooperative launch unavailable
+  unsigned char* d_prog = nullptr;  // persistent program: entries + parameter pool (device)
+  unsigned char* h_prog = nullptr;  // pinned staging of the same
+  size_t prog_alloc = 0;
+  u64* d_tbegin = nullptr;
+  u64* h_tbegin = nullptr;  // pinned
+  bool use_program = true;
   size_t cliff_smem_optin = 48 * 1024;  // dynamic smem k_clifford_smem is opted in for
   u64 n_live = 0, n_dense = 0;
   Snapshot snap;
@@ -147,8 +154,9 @@ void close_run(obp_ctx* c) {
 }
 
 struct Bracket {
-  Bracket(obp_ctx* c, int k) {
-    c->prof.launches[k]++;
+  Bracket(obp_ctx* c, int k, int n_kernels = 1) {
+    c->prof.launches[k] += (u64)n_kernels;
+    c->prof.passes[k]++;
     if (!c->prof_on) return;
     if (c->run_open && c->run_ep.klass == k) return;
     close_run(c);
@@ -250,7 +258,7 @@ int compact(obp_ctx* ctx) {
   const u64 nb = (ctx->n_dense + OBP_CHUNK - 1) / OBP_CHUNK;
   Tab t = make_tab(ctx);
   {
-    Bracket b(ctx, OBP_K_COMPACT);
+    Bracket b(ctx, OBP_K_COMPACT, 5 + ctx->W + 2);
     k_live_count<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(t, ctx->blk);
     k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk, nb, ctx->d_st);
     k_dest<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(t, ctx->blk, ctx->dest);
@@ -390,6 +398,20 @@ struct PendingBatch {
       if (b.word_of_slot[s] == w) return s;
     b.word_of_slot[b.nslots] = w;
     return b.nslots++;
+  }
+};
+
+// a gate program recorded for the persistent kernel instead of being launched op by op
+struct ProgRec {
+  std::vector<ProgEntry> entries;
+  std::vector<unsigned char> pool;
+  std::vector<int> klass;
+  void add(int kind, int slot, const void* param, size_t bytes, int k) {
+    const size_t off = (pool.size() + 15) & ~(size_t)15, padded = (bytes + 15) & ~(size_t)15;
+    pool.resize(off + padded, 0);
+    memcpy(pool.data() + off, param, bytes);
+    entries.push_back(ProgEntry{kind, slot, (unsigned)off, (unsigned)padded});
+    klass.push_back(k);
   }
 };
 
@@ -540,6 +562,16 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     if (rc) return rc;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->rot_ctas_per_sm, k_rotate, OBP_BS, 0));
     if (ctx->rot_ctas_per_sm < 1) ctx->rot_ctas_per_sm = 1;
+    if (ctx->W <= 2 && prop.cooperativeLaunch) {
+      if (ctx->W == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prog_ctas_per_sm, k_program<1>, OBP_BS, 0));
+      else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prog_ctas_per_sm, k_program<2>, OBP_BS, 0));
+    }
+    CU(cudaMalloc(&ctx->d_tbegin, sizeof(u64)));
+    CU(cudaMallocHost(&ctx->h_tbegin, sizeof(u64)));
+    {
+      const char* env = getenv("OBP_B200_NO_PROGRAM");
+      ctx->use_program = !(env && env[0] && env[0] != '0');
+    }
     init_frame(ctx);
     return set_counts(ctx, 0);
   };
@@ -562,6 +594,10 @@ void obp_destroy(obp_ctx* ctx) {
   cudaFree(ctx->d_scalar);
   cudaFree(ctx->d_cols);
   cudaFree(ctx->d_cnt);
+  cudaFree(ctx->d_prog);
+  cudaFree(ctx->d_tbegin);
+  if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
+  if (ctx->h_tbegin) cudaFreeHost(ctx->h_tbegin);
   free_inboxes(ctx);
   if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
   cudaFree(ctx->d_gens);
@@ -702,9 +738,13 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     const int vrc = validate_op(ctx, ops[k]);
     if (vrc) return vrc;
   }
-  int rc = ensure_ops(ctx, n_ops + 1);
+  // tables of <= 128 qubits: record the program and run it with ONE persistent cooperative launch
+  const bool prog_mode = ctx->use_program && ctx->prog_ctas_per_sm > 0 && ctx->W <= 2;
+  ProgRec prog;
+  int n_rot_ops = 0;
+  int rc = ensure_ops(ctx, 3 * n_ops + 2);
   if (rc) return rc;
-  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * (n_ops + 1), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * (3 * n_ops + 2), ctx->stream));
 
   const u64 n_start = ctx->n_live;
   u64 bound = std::max<u64>(ctx->n_dense, 1);
@@ -721,8 +761,6 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     pb.b.atol = atol;
     pb.b.epoch = ++ctx->epoch;
     pb.b.slot = n_slots;
-    Bracket br(ctx, OBP_K_CLIFFORD);
-    const int g = grid_for(ctx, bound);
     bool identity_slots = ctx->W <= 2;
     if (identity_slots) {
       // register variant addresses words directly: remap slots to word ids
@@ -730,6 +768,17 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
         pb.b.g[k].sa = (unsigned char)pb.b.word_of_slot[pb.b.g[k].sa];
         pb.b.g[k].sb = (unsigned char)pb.b.word_of_slot[pb.b.g[k].sb];
       }
+    }
+    if (prog_mode) {
+      prog.add(PROG_CLIFFORD, n_slots, &pb.b, offsetof(CliffBatch, g) + (size_t)pb.b.ng * sizeof(CliffGate), OBP_K_CLIFFORD);
+      slot_gates.push_back(pb.n_ops);
+      n_slots++;
+      pb.reset();
+      return OBP_OK;
+    }
+    Bracket br(ctx, OBP_K_CLIFFORD);
+    const int g = grid_for(ctx, bound);
+    if (identity_slots) {
       if (ctx->W == 1) k_clifford_reg<1><<<g, OBP_BS, 0, ctx->stream>>>(t, pb.b);
       else k_clifford_reg<2><<<g, OBP_BS, 0, ctx->stream>>>(t, pb.b);
     } else {
@@ -786,9 +835,13 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
         cp.scale = op.row_scale;
         cp.atol = atol;
         cp.slot = n_slots;  // the slot the gate's own batch will use
-        Bracket br(ctx, OBP_K_OTHER);
-        k_coset_count<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, cp);
-        CU(cudaGetLastError());
+        if (prog_mode) {
+          prog.add(PROG_COSET, n_slots, &cp, sizeof(cp), OBP_K_OTHER);
+        } else {
+          Bracket br(ctx, OBP_K_OTHER);
+          k_coset_count<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, cp);
+          CU(cudaGetLastError());
+        }
       }
       CliffGate& g = pb.b.g[pb.b.ng++];
       memset(&g, 0, sizeof(g));
@@ -826,7 +879,10 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
       }
       p.epoch = ++ctx->epoch;
       p.slot = n_slots;
-      {
+      n_rot_ops++;
+      if (prog_mode) {
+        prog.add(PROG_ROTATE, n_slots, &p, sizeof(p), OBP_K_ROTATE);
+      } else {
         Bracket br(ctx, OBP_K_ROTATE);
         k_rotate<<<grid_for(ctx, bound, ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(t, p);  // one wave
         CU(cudaGetLastError());
@@ -844,9 +900,49 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     return OBP_OK;
   }
 
-  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat) * n_slots, cudaMemcpyDeviceToHost, ctx->stream));
+  const int n_entries = (int)prog.entries.size();
+  if (prog_mode && n_entries) {
+    // upload entries + parameter pool, then one cooperative launch sized to the rows the program can reach
+    const size_t ent_bytes = (size_t)n_entries * sizeof(ProgEntry), need = ent_bytes + prog.pool.size();
+    if (need > ctx->prog_alloc) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_prog);
+      if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
+      ctx->d_prog = ctx->h_prog = nullptr;
+      ctx->prog_alloc = 0;
+      const size_t na = std::max<size_t>(2 * need, 1 << 16);
+      CU(cudaMalloc(&ctx->d_prog, na));
+      CU(cudaMallocHost(&ctx->h_prog, na));
+      ctx->prog_alloc = na;
+    }
+    memcpy(ctx->h_prog, prog.entries.data(), ent_bytes);
+    memcpy(ctx->h_prog + ent_bytes, prog.pool.data(), prog.pool.size());
+    CU(cudaMemcpyAsync(ctx->d_prog, ctx->h_prog, need, cudaMemcpyHostToDevice, ctx->stream));
+    const u64 reach = std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense, 1) << std::min(n_rot_ops, 6));
+    const int max_g = ctx->prog_ctas_per_sm * ctx->n_sm;
+    int g = (int)std::min<u64>((reach + OBP_BS - 1) / OBP_BS, (u64)max_g);
+    g = std::max(g, std::min(ctx->n_sm, max_g));
+    const ProgEntry* d_entries = (const ProgEntry*)ctx->d_prog;
+    const unsigned char* d_pool = ctx->d_prog + ent_bytes;
+    int ne = n_entries, ns = n_slots;
+    void* args[] = {(void*)&t, (void*)&d_entries, (void*)&ne, (void*)&d_pool, (void*)&ns, (void*)&ctx->d_tbegin};
+    ctx->prof.launches[OBP_K_PROGRAM]++;
+    for (int k = 0; k < n_entries; ++k) ctx->prof.passes[prog.klass[k]]++;
+    if (ctx->W == 1) CU(cudaLaunchCooperativeKernel((void*)k_program<1>, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
+    else CU(cudaLaunchCooperativeKernel((void*)k_program<2>, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_tbegin, ctx->d_tbegin, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat) * (n_slots + n_entries), cudaMemcpyDeviceToHost, ctx->stream));
   const int sync_rc = sync_state(ctx);
   if (sync_rc && sync_rc != OBP_ERR_CAPACITY) return sync_rc;
+  if (prog_mode && ctx->prof_on) {  // per-class device time from the stamps taken at the grid barriers
+    u64 t_prev = *ctx->h_tbegin;
+    for (int k = 0; k < n_entries; ++k) {
+      const u64 t_end = ctx->h_ops[n_slots + k].t_end;
+      if (t_end >= t_prev) ctx->prof.ms[prog.klass[k]] += (double)(t_end - t_prev) * 1e-6;
+      t_prev = t_end;
+    }
+  }
 
   // term-gate updates: live terms at entry of every op (also accounted when the table overflowed:
   // the kernels ran, the caller rolls the slice back)
@@ -1364,7 +1460,6 @@ int obp_snapshot(obp_ctx* ctx) {
   s.hx = ctx->hx;
   s.hz = ctx->hz;
   s.valid = true;
-  ctx->prof.launches[OBP_K_OTHER] += (u64)ctx->W + 2;
   return OBP_OK;
 }
 

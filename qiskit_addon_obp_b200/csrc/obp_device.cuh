@@ -43,6 +43,8 @@ struct OpStat {  // one slot per launched op; zeroed at program start
   double sum_re, sum_im;  // sum of the cancelled merged coefficients
   u64 n_surv;        // Clifford: live rows that passed the row filter
   u64 ncnt[17];      // Clifford: rows whose coset {P xor D} holds cnt live members
+  u64 dlive;         // persistent program: change of the live-row count by this op (two's complement)
+  u64 t_end;         // persistent program: %globaltimer (ns) when the op's grid barrier was passed
 };
 
 struct Tab {

@@ -150,8 +150,8 @@ __device__ __forceinline__ long long find_partner(const Tab& t, const RotP& p, u
 #ifndef OBP_ROT_MINB
 #define OBP_ROT_MINB 4  // resident CTAs per SM the register allocation is held to
 #endif
-__global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate(Tab t, const __grid_constant__ RotP p) {
-  const u64 n = t.st->n_scan;
+// Body of the rotation pass over rows [0, n); `live_ctr` receives the change of the live-row count.
+__device__ __forceinline__ void rotate_body(const Tab& t, const RotP& p, const u64 n, u64* live_ctr) {
   const unsigned lane = threadIdx.x & 31u;
   // per-thread counters
   unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
@@ -289,7 +289,11 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate(Tab t, const __
       if (cz) { atomicAdd(&o->cancelled, cz); atomicAdd(&o->sum_re, sr); atomicAdd(&o->sum_im, si); }
     }
   }
-  if (lane == 0 && dl) atomicAdd(&t.st->n_live, (u64)dl);
+  if (lane == 0 && dl) atomicAdd(live_ctr, (u64)dl);
+}
+
+__global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate(Tab t, const __grid_constant__ RotP p) {
+  rotate_body(t, p, t.st->n_scan, &t.st->n_live);
   finish_kernel(t, p.slot);
 }
 
@@ -331,9 +335,8 @@ __device__ __forceinline__ unsigned cliff_apply_bits(const CliffGate& g, u64 xa,
 }
 
 template <int W>
-__global__ void __launch_bounds__(OBP_BS) k_clifford_reg(Tab t, const __grid_constant__ CliffBatch b) {
+__device__ __forceinline__ void clifford_reg_body(const Tab& t, const CliffBatch& b, const u64 n, u64* live_ctr) {
   static_assert(W == 1 || W == 2, "register variant handles W <= 2");
-  const u64 n = t.st->n_scan;
   int deaths = 0;
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
     const double2 c = t.coef[i];
@@ -370,7 +373,12 @@ __global__ void __launch_bounds__(OBP_BS) k_clifford_reg(Tab t, const __grid_con
     if (sgn) t.coef[i] = make_double2(-c.x, -c.y);
   }
   const long long dl = warp_sum_i64((long long)deaths);
-  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(live_ctr, (u64)(-dl));
+}
+
+template <int W>
+__global__ void __launch_bounds__(OBP_BS) k_clifford_reg(Tab t, const __grid_constant__ CliffBatch b) {
+  clifford_reg_body<W>(t, b, t.st->n_scan, &t.st->n_live);
   finish_kernel(t, b.slot);
 }
 
@@ -432,10 +440,10 @@ struct CosetP {
   int slot;
 };
 
-__global__ void __launch_bounds__(OBP_BS) k_coset_count(Tab t, const __grid_constant__ CosetP p) {
-  const u64 n = t.st->n_scan;
+__device__ __forceinline__ void coset_body(const Tab& t, const CosetP& p, const u64 n) {
   __shared__ unsigned s_cnt[17];
   __shared__ unsigned s_surv;
+  __syncthreads();  // the previous user of these counters (a persistent program) is done with them
   if (threadIdx.x < 17) s_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) s_surv = 0;
   __syncthreads();
@@ -483,6 +491,10 @@ __global__ void __launch_bounds__(OBP_BS) k_coset_count(Tab t, const __grid_cons
   __syncthreads();
   if (threadIdx.x < 17 && s_cnt[threadIdx.x]) atomicAdd(&t.ops[p.slot].ncnt[threadIdx.x], (u64)s_cnt[threadIdx.x]);
   if (threadIdx.x == 0 && s_surv) atomicAdd(&t.ops[p.slot].n_surv, (u64)s_surv);
+}
+
+__global__ void __launch_bounds__(OBP_BS) k_coset_count(Tab t, const __grid_constant__ CosetP p) {
+  coset_body(t, p, t.st->n_scan);
 }
 
 // ================================================================================================
@@ -1214,4 +1226,75 @@ __global__ void __launch_bounds__(OBP_BS) k_shard_filter(Tab t, int owner_shift,
   }
   const u64 f = warp_sum_u64(foreign);
   if ((threadIdx.x & 31) == 0 && f) atomicAdd(&t.st->removed, f);
+}
+
+// ================================================================================================
+// k_program — one persistent cooperative launch for a whole gate program (W <= 2)
+//
+// A slice of the 127-qubit workload is ~50-130 gates, most of them on tables of a few thousand
+// rows where a kernel launch costs more than the pass itself.  The program is therefore run by ONE
+// cooperative kernel (grid = resident CTAs, never more than the rows need): every CTA loops over
+// the ops, runs the same bodies as the stand-alone kernels and meets the others at a grid barrier
+// before the next op.  Live-count changes go to per-op counters so that no CTA has to wait for a
+// bookkeeping step; CTA 0 stamps %globaltimer after each barrier, which is how the per-class times
+// of the roofline are measured inside this kernel.
+// ================================================================================================
+#include <cooperative_groups.h>
+
+enum { PROG_ROTATE = 1, PROG_CLIFFORD = 2, PROG_COSET = 3 };
+
+struct ProgEntry {
+  int kind;
+  int slot;
+  unsigned offset;  // byte offset of the op's parameters in the parameter pool (16-byte aligned)
+  unsigned bytes;
+};
+
+__device__ __forceinline__ u64 global_timer_ns() {
+  u64 v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+
+template <int W>
+__global__ void __launch_bounds__(OBP_BS, 3) k_program(Tab t, const ProgEntry* __restrict__ entries, int n_entries,
+                                                                  const unsigned char* __restrict__ pool, int n_slots,
+                                                                  u64* __restrict__ t_begin) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ __align__(16) unsigned char s_param[sizeof(CliffBatch) > sizeof(RotP) ? sizeof(CliffBatch) : sizeof(RotP)];
+  static_assert(sizeof(CosetP) <= sizeof(CliffBatch), "parameter staging buffer too small");
+  if (blockIdx.x == 0 && threadIdx.x == 0) *t_begin = global_timer_ns();
+  for (int k = 0; k < n_entries; ++k) {
+    const ProgEntry e = entries[k];
+    __syncthreads();  // everybody is done with the previous op's parameters
+    for (unsigned b = threadIdx.x * 16u; b < e.bytes; b += OBP_BS * 16u)
+      *reinterpret_cast<uint4*>(s_param + b) = *reinterpret_cast<const uint4*>(pool + e.offset + b);
+    __syncthreads();
+    u64 n = ld_volatile(&t.st->n_append);  // stable: appends of the previous op ended at the barrier
+    if (n > t.cap) n = t.cap;
+    u64* live_ctr = &t.ops[e.slot].dlive;
+    if (e.kind == PROG_ROTATE) {
+      rotate_body(t, *reinterpret_cast<const RotP*>(s_param), n, live_ctr);
+    } else if (e.kind == PROG_CLIFFORD) {
+      clifford_reg_body<W>(t, *reinterpret_cast<const CliffBatch*>(s_param), n, live_ctr);
+    } else {
+      coset_body(t, *reinterpret_cast<const CosetP*>(s_param), n);
+    }
+    __threadfence();
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) t.ops[k + n_slots].t_end = global_timer_ns();  // stamps live behind the slots
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    u64 n = t.st->n_append;
+    if (n > t.cap) n = t.cap;
+    t.st->n_append = n;
+    t.st->n_scan = n;
+    u64 live = t.st->n_live;
+    for (int s = 0; s < n_slots; ++s) {
+      live += t.ops[s].dlive;
+      t.ops[s].n_out = live;
+    }
+    t.st->n_live = live;
+  }
 }

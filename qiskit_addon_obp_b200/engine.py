@@ -25,7 +25,7 @@ OBP_ERR_CAPACITY = -4
 OBP_OP_CLIFFORD = 1
 OBP_OP_ROTATION = 2
 OBP_FLAG_EXACT_COUNTERS = 1
-OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other")
+OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other", "program")
 
 #: numpy mirror of ``obp_op`` (104 bytes, natural C alignment)
 OP_DTYPE = np.dtype(
@@ -66,9 +66,10 @@ class ObpStats(C.Structure):
 
 class ObpProfile(C.Structure):
     _fields_ = [
-        ("launches", C.c_uint64 * 6),
-        ("ms", C.c_double * 6),
-        ("term_updates", C.c_uint64 * 6),
+        ("launches", C.c_uint64 * 7),
+        ("passes", C.c_uint64 * 7),
+        ("ms", C.c_double * 7),
+        ("term_updates", C.c_uint64 * 7),
     ]
 
 
@@ -417,7 +418,12 @@ class TermTable:
         p = ObpProfile()
         self._check(self._lib.obp_profile_get(self._h, C.byref(p), int(reset)), "obp_profile_get")
         return {
-            name: {"launches": int(p.launches[k]), "ms": float(p.ms[k]), "term_updates": int(p.term_updates[k])}
+            name: {
+                "launches": int(p.launches[k]),
+                "passes": int(p.passes[k]),
+                "ms": float(p.ms[k]),
+                "term_updates": int(p.term_updates[k]),
+            }
             for k, name in enumerate(OBP_K_NAMES)
         }
 

@@ -476,7 +476,7 @@ class ShardedTable:
         tot: dict = {}
         for t in self.tables.values():
             for k, v in t.profile(reset).items():
-                a = tot.setdefault(k, {"launches": 0, "ms": 0.0, "term_updates": 0})
+                a = tot.setdefault(k, {"launches": 0, "passes": 0, "ms": 0.0, "term_updates": 0})
                 for f in a:
                     a[f] += v[f]
         return tot

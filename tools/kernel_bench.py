@@ -32,6 +32,6 @@ for r in range(reps):
     print(f"  slices {md.num_backpropagated_slices} terms_out {len(out)} peak {max(sizes)} updates {run.updates:.4g} wall {dt*1e3:.1f} ms device {run.device_ms:.1f} ms"
           f" -> e2e {run.updates/dt:.3e} upd/s, device {run.updates/(run.device_ms*1e-3):.3e} upd/s")
     for k, v in run.profile.items():
-        if v["launches"]:
+        if v["launches"] or v["passes"]:
             gbs = v["term_updates"] * btg / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 and v["term_updates"] else 0.0
-            print(f"  {k:9s} launches {v['launches']:6d} ms {v['ms']:10.3f} term_updates {v['term_updates']:.4g} -> {gbs:8.1f} GB/s algorithmic ({btg} B/update), {v['term_updates']/max(v['ms'],1e-9)/1e6:.2f} G upd/s")
+            print(f"  {k:9s} launches {v['launches']:6d} passes {v['passes']:6d} ms {v['ms']:10.3f} term_updates {v['term_updates']:.4g} -> {gbs:8.1f} GB/s algorithmic ({btg} B/update), {v['term_updates']/max(v['ms'],1e-9)/1e6:.2f} G upd/s")
