@@ -118,6 +118,13 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
  * (backpropagation.py:210-237; utils/operations.py:100-107; utils/simplify.py:80-169). */
 int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats);
 
+/* Any other gate on 1-4 qubits (cp, crz, arbitrary unitaries): U = sum_j u_j * Pauli(codes[j]) with
+ * codes[j] = local Pauli code (bit 2q = x, bit 2q+1 = z on qubits[q]) and coeffs[j] = (re, im).  Runs
+ * the reference's literal k*k raw-row expansion (utils/operations.py:103-105) followed by simplify
+ * (utils/simplify.py:115-165).  Needs room for n*k*k extra rows (OBP_ERR_CAPACITY otherwise). */
+int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int32_t n_comp, const uint32_t* codes,
+                      const double* coeffs, double atol, obp_stats* stats);
+
 /* <0|O|0> on one qubit then simplify: apply_reset_to (utils/operations.py:194-225). */
 int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats);
 

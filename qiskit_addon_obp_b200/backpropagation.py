@@ -20,7 +20,7 @@ from collections.abc import Sequence
 import numpy as np
 
 from . import engine
-from .engine import OBP_FLAG_EXACT_COUNTERS, OP_DTYPE, CapacityError, TermTable
+from .engine import OBP_FLAG_EXACT_COUNTERS, OBP_OP_GENERIC, OP_DTYPE, CapacityError, TermTable
 from .gates import program_for
 from .ir import QuantumCircuit, SparsePauliOp, topological_op_order
 from .sharded import ShardedTable, communicator_from_env
@@ -307,7 +307,7 @@ class SliceProgram:
     record of ``nodes[k]`` (``kind`` 0 for reset / LayerError, which have their own entry points).
     """
 
-    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data")
+    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data", "generic")
 
     def __init__(self, slice_: QuantumCircuit):
         self.n_data = len(slice_.data)
@@ -316,6 +316,7 @@ class SliceProgram:
         self.recs = np.zeros(len(self.nodes), dtype=OP_DTYPE)
         self.special = [n.name in ("reset", "LayerError") for n in self.nodes]
         self.errors: dict[int, Exception] = {}
+        self.generic: dict[int, object] = {}
         # classify each distinct gate once, then fill the records of all its occurrences in one go
         groups: dict[tuple, list[int]] = {}
         for k, node in enumerate(self.nodes):
@@ -329,6 +330,11 @@ class SliceProgram:
             except (NotImplementedError, ValueError) as exc:  # only raised if the gate is applied
                 for k in idxs:
                     self.errors[k] = exc
+                continue
+            if prog.kind == OBP_OP_GENERIC:  # own entry point, like reset / LayerError
+                for k in idxs:
+                    self.special[k] = True
+                    self.generic[k] = prog
                 continue
             self.recs[idxs] = prog.template[0]
             qubit[idxs, : prog.n_qubits] = np.array([self.nodes[k].qubits for k in idxs], dtype=np.int32)
@@ -382,7 +388,10 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
             continue
         flush()
         node = prog.nodes[k]
-        if node.name == "reset":
+        if k in prog.generic:
+            g = prog.generic[k]
+            stats = table.apply_generic(node.qubits, g.codes, g.coeffs, atol)
+        elif node.name == "reset":
             stats = table.apply_reset(node.qubits[0], atol)
         else:
             ple = node.ple

@@ -1238,6 +1238,92 @@ int obp_rotate_merge_inbox(obp_ctx* ctx, obp_shard_counters* out) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// Generic gate: raw k*k expansion + the merge of a freshly loaded operator (simplify.py:115-165).
+int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int32_t n_comp, const uint32_t* codes,
+                      const double* coeffs, double atol, obp_stats* stats) {
+  if (!ctx || !qubits || !codes || !coeffs || n_qubits < 1 || n_qubits > 4 || n_comp < 1 || n_comp > OBP_GEN_MAXK)
+    return OBP_ERR_BADARG;
+  if (ctx->n_ranks > 1) return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_generic: not available on a sharded table");
+  CU(cudaSetDevice(ctx->device));
+  GenP p;
+  memset(&p, 0, sizeof(p));
+  p.m = n_qubits;
+  p.k = n_comp;
+  for (int q = 0; q < n_qubits; ++q) {
+    if (qubits[q] < 0 || qubits[q] >= ctx->nq) return ctx->fail(OBP_ERR_BADARG, "obp_apply_generic: qubit out of range");
+    for (int l = 0; l < q; ++l)
+      if (qubits[l] == qubits[q]) return ctx->fail(OBP_ERR_BADARG, "obp_apply_generic: duplicate qubit");
+    p.w[q] = qubits[q] / 64;
+    p.b[q] = qubits[q] % 64;
+  }
+  for (int j = 0; j < n_comp; ++j) {
+    if (codes[j] >> (2 * n_qubits)) return ctx->fail(OBP_ERR_BADARG, "obp_apply_generic: code outside the gate's qubits");
+    p.code[j] = codes[j];
+    p.ur[j] = coeffs[2 * j];
+    p.ui[j] = coeffs[2 * j + 1];
+  }
+  int rc;
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  const u64 n = ctx->n_live, k2 = (u64)n_comp * n_comp, raw = n * k2;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n + raw > ctx->cap) return ctx->fail(OBP_ERR_CAPACITY, "obp_apply_generic: the k*k raw rows do not fit the table");
+  rc = upload_cols(ctx);
+  if (rc) return rc;
+  rc = ensure_ops(ctx, 4);
+  if (rc) return rc;
+  Tab t = make_tab(ctx);
+  {
+    Bracket br(ctx, OBP_K_OTHER, 2);
+    if (raw) k_expand<<<grid_for(ctx, raw), OBP_BS, 0, ctx->stream>>>(t, p, n);
+    if (n) k_kill_prefix<<<grid_for(ctx, n), OBP_BS, 0, ctx->stream>>>(t, n, ++ctx->epoch);
+    CU(cudaGetLastError());
+  }
+  // the table now is: n tombstones followed by `raw` fresh rows, all counted live until filtered
+  DevState s;
+  memset(&s, 0, sizeof(s));
+  s.n_scan = s.n_append = n + raw;
+  s.n_live = raw;
+  *ctx->h_st = s;
+  CU(cudaMemcpyAsync(ctx->d_st, ctx->h_st, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
+  CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  if (raw) {
+    Bracket br(ctx, OBP_K_INDEX, 3);
+    const int g = grid_for(ctx, n + raw);
+    k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n + raw);
+    k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ++ctx->epoch, 0);
+    k_trim<<<g, OBP_BS, 0, ctx->stream>>>(t, atol, ++ctx->epoch, 0);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  if (rc) return rc;
+  ctx->prof.term_updates[OBP_K_OTHER] += n;
+  if (stats) {
+    const OpStat& o = ctx->h_ops[0];
+    stats->n_in = n;
+    stats->raw_rows = raw;
+    stats->updates = n;
+    stats->num_unique = o.keys_present;
+    stats->num_duplicate = o.rows_surv - o.keys_present;
+    stats->num_trimmed = (raw - o.rows_surv) + o.cancelled;
+    stats->sum_trimmed[0] = o.sum_re;
+    stats->sum_trimmed[1] = o.sum_im;
+  }
+  rc = compact(ctx);
+  if (rc) return rc;
+  rc = sync_state(ctx);
+  if (rc) return rc;
+  if (stats) { stats->n_out = ctx->n_live; stats->n_dense = ctx->n_dense; }
+  return OBP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) {
   if (!ctx || qubit < 0 || qubit >= ctx->nq) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));

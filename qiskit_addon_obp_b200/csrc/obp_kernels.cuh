@@ -526,7 +526,9 @@ __global__ void __launch_bounds__(OBP_BS) k_index_build(Tab t, int merge, double
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
     const double2 c = t.coef[i];
     if (!is_live(c)) {
-      if (merge) {  // at load every uploaded row was counted live; an exact zero is a filtered raw row
+      // at load every given row was counted live; an exact zero is a filtered raw row.  Real
+      // tombstones (epoch > 0: the rows a generic gate expanded) were never counted.
+      if (merge && tomb_epoch(c) == 0) {
         deaths++;
         t.coef[i] = tombstone(epoch);
       }
@@ -1297,4 +1299,71 @@ __global__ void __launch_bounds__(OBP_BS, 3) k_program(Tab t, const ProgEntry* _
     }
     t.st->n_live = live;
   }
+}
+
+// ================================================================================================
+// k_expand — the literal k*k raw-row expansion of op.compose(U, front=True).compose(U^dag)
+// (utils/operations.py:103-105) for a gate that is neither Clifford-class nor a single-generator
+// rotation (cp, crz, arbitrary 1-4 qubit unitaries).  Row (i, j, l) gets key P_i ^ U_j ^ U_l and
+// coefficient c_i * u_j * conj(u_l) * (-i)^e, written at n + i*k*k + j*k + l: the reference's raw-row
+// order.  The host then runs the same merge as for a freshly loaded operator (k_hash_rows,
+// k_index_build with the raw-row zero filter, k_trim), i.e. simplify() as the reference states it.
+// ================================================================================================
+#define OBP_GEN_MAXK 16
+
+struct GenP {
+  int m;                   // gate qubits (<= 4)
+  int k;                   // Pauli components of the gate
+  int w[4];                // word of each qubit
+  int b[4];                // bit of each qubit
+  unsigned code[OBP_GEN_MAXK];  // local code: bit 2j = x, bit 2j+1 = z on the gate's qubit j
+  double ur[OBP_GEN_MAXK], ui[OBP_GEN_MAXK];
+  u64 epoch;
+};
+
+__device__ __forceinline__ int local_y(unsigned v) { return __popc(v & (v >> 1) & 0x55u); }
+__device__ __forceinline__ unsigned local_x(unsigned v) { return v & 0x55u; }
+__device__ __forceinline__ unsigned local_z(unsigned v) { return (v >> 1) & 0x55u; }
+
+__global__ void __launch_bounds__(OBP_BS) k_expand(Tab t, const __grid_constant__ GenP p, u64 n) {
+  const int k2 = p.k * p.k;
+  for (u64 r = (u64)blockIdx.x * OBP_BS + threadIdx.x; r < n * (u64)k2; r += (u64)gridDim.x * OBP_BS) {
+    const u64 i = r / (u64)k2;
+    const int jl = (int)(r % (u64)k2), j = jl / p.k, l = jl % p.k;
+    const double2 c = t.coef[i];
+    const u64 row = n + r;
+    if (!is_live(c)) {  // cannot happen after the compaction that precedes the expansion
+      t.coef[row] = make_double2(0.0, 0.0);
+      continue;
+    }
+    unsigned v = 0;
+    for (int q = 0; q < p.m; ++q) {
+      const ulonglong2 key = t.xz[p.w[q]][i];
+      v |= (unsigned)((key.x >> p.b[q]) & 1ull) << (2 * q);
+      v |= (unsigned)((key.y >> p.b[q]) & 1ull) << (2 * q + 1);
+    }
+    const unsigned cj = p.code[j], cl = p.code[l];
+    const unsigned k1 = v ^ cj, k2c = k1 ^ cl;
+    // compose(front=True): phases add, plus 2|x_P & z_U|; back (U^dag): plus 2|z_P' & x_U|
+    int e = local_y(v) + local_y(cj) + 2 * __popc(local_x(v) & local_z(cj)) - local_y(k1);
+    e += local_y(k1) + local_y(cl) + 2 * __popc(local_z(k1) & local_x(cl)) - local_y(k2c);
+    const double2 uj = make_double2(p.ur[j], p.ui[j]), ul = make_double2(p.ur[l], -p.ui[l]);
+    const double2 out = mul_mi_pow(cmul(cmul(c, uj), ul), e);
+    const unsigned flip = v ^ k2c;
+    for (int w = 0; w < t.W; ++w) {
+      ulonglong2 key = t.xz[w][i];
+      for (int q = 0; q < p.m; ++q)
+        if (p.w[q] == w) {
+          key.x ^= (u64)((flip >> (2 * q)) & 1u) << p.b[q];
+          key.y ^= (u64)((flip >> (2 * q + 1)) & 1u) << p.b[q];
+        }
+      t.xz[w][row] = key;
+    }
+    t.coef[row] = out;
+  }
+}
+
+// the expanded rows replace the originals
+__global__ void __launch_bounds__(OBP_BS) k_kill_prefix(Tab t, u64 n, u64 epoch) {
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) t.coef[i] = tombstone(epoch);
 }

@@ -24,6 +24,7 @@ OBP_OK = 0
 OBP_ERR_CAPACITY = -4
 OBP_OP_CLIFFORD = 1
 OBP_OP_ROTATION = 2
+OBP_OP_GENERIC = 3  # host-side tag only: run through obp_apply_generic, never inside an obp_op program
 OBP_FLAG_EXACT_COUNTERS = 1
 OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other", "program")
 
@@ -120,6 +121,7 @@ def lib() -> C.CDLL:
         "obp_count": ([vp, u64p], C.c_int),
         "obp_download": ([vp, vp, vp, vp, C.c_uint64, u64p], C.c_int),
         "obp_apply_ops": ([vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
+        "obp_apply_generic": ([vp, C.c_int32, vp, C.c_int32, vp, vp, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_reset": ([vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_damping": ([vp, vp, vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_truncate": ([vp, C.c_double, C.c_int32, C.c_double, f64p, u64p, u64p], C.c_int),
@@ -159,7 +161,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "obp_create obp_destroy obp_last_error obp_set_stream obp_device_memory obp_bytes_per_term "
-    "obp_load obp_count obp_download obp_apply_ops obp_apply_reset obp_apply_damping obp_truncate "
+    "obp_load obp_count obp_download obp_apply_ops obp_apply_generic obp_apply_reset obp_apply_damping obp_truncate "
     "obp_union_count obp_snapshot obp_restore obp_reserve obp_profile_enable obp_profile_get "
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
@@ -341,6 +343,26 @@ class TermTable:
         except CapacityError as exc:
             exc.updates = int(st.updates)  # the kernels ran before the overflow was detected
             raise
+        self.n, self.n_dense = st.n_out, st.n_dense
+        if self.n == 0:
+            self.zero_operator = True
+        return st
+
+    def apply_generic(self, qubits, codes, coeffs, atol: float) -> ObpStats:
+        """A gate given as its Pauli sum (local codes + complex coefficients): raw k*k expansion + simplify."""
+        st = ObpStats()
+        k2 = len(codes) ** 2
+        if self.zero_operator:
+            st.n_in, st.raw_rows, st.num_trimmed, st.n_out, st.updates = 1, k2, k2, 1, 1
+            return st
+        q = np.ascontiguousarray(qubits, dtype=np.int32)
+        cd = np.ascontiguousarray(codes, dtype=np.uint32)
+        co = np.ascontiguousarray(np.asarray(coeffs, dtype=np.complex128))
+        rc = self._lib.obp_apply_generic(
+            self._h, len(q), q.ctypes.data_as(C.c_void_p), len(cd), cd.ctypes.data_as(C.c_void_p),
+            co.ctypes.data_as(C.c_void_p), float(atol), C.byref(st),
+        )
+        self._check(rc, "obp_apply_generic")
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0:
             self.zero_operator = True

@@ -10,8 +10,10 @@ decomposition is computed once per distinct gate (cached) and classified:
 * **rotation class** — ``U = u0*I + u1*G`` with one Pauli generator ``G`` (rx, ry, rz, rxx, ryy,
   rzz, rzx, p, t, tdg, ...).  The device runs the branch-and-merge kernel (``k_rotate``).
 
-Anything else (a non-Clifford gate with more than two Pauli components, e.g. ``cp``/``crz``) is not
-on the path of any BASELINE configuration and raises ``NotImplementedError``.
+* **generic** — anything else with up to 16 Pauli components (``cp``, ``crz``, arbitrary 1-2 qubit
+  unitaries).  The device runs the reference's literal k*k raw-row expansion followed by the merge of
+  a freshly loaded operator (``k_expand`` + ``k_index_build`` + ``k_trim``); no BASELINE configuration
+  needs it, it is there for drop-in completeness.
 
 Local Pauli code of an m-qubit Pauli: bit ``2j`` = x on the gate's qubit ``j``, bit ``2j+1`` = z.
 """
@@ -23,7 +25,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .engine import OBP_OP_CLIFFORD, OBP_OP_ROTATION, OP_DTYPE
+from .engine import OBP_OP_CLIFFORD, OBP_OP_GENERIC, OBP_OP_ROTATION, OP_DTYPE
 from .ir import Instruction
 
 #: [EXT] SparsePauliOp.atol — components of a gate with |u| <= this are dropped by from_operator
@@ -79,6 +81,8 @@ class GateProgram:
     n_qubits: int
     n_components: int
     template: np.ndarray  # one OP_DTYPE record with everything but the qubits filled in
+    codes: np.ndarray | None = None  # generic gates: local Pauli codes ...
+    coeffs: np.ndarray | None = None  # ... and their complex coefficients
 
 
 def classify(matrix: np.ndarray, name: str = "gate") -> GateProgram:
@@ -127,9 +131,13 @@ def classify(matrix: np.ndarray, name: str = "gate") -> GateProgram:
         rec["u0"] = (us[0].real, us[0].imag)
         rec["u1"] = (us[1].real, us[1].imag)
         return GateProgram(OBP_OP_ROTATION, m, k, rec)
+    if m <= 4 and k <= 16:
+        # anything else: the device runs the reference's literal k*k raw-row expansion + simplify
+        rec["kind"] = OBP_OP_GENERIC
+        return GateProgram(OBP_OP_GENERIC, m, k, rec, codes=np.array(codes, dtype=np.uint32), coeffs=np.array(us))
     raise NotImplementedError(
-        f"gate {name!r} ({m} qubits, {k} Pauli components) is neither Clifford-class nor a "
-        "single-generator rotation; the generic Pauli-transfer-matrix kernel is not part of this build"
+        f"gate {name!r} ({m} qubits, {k} Pauli components) has more than 16 Pauli components; the raw-row "
+        "expansion kernel handles up to 16"
     )
 
 

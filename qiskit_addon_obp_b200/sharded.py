@@ -408,6 +408,9 @@ class ShardedTable:
             out.sum_trimmed = [float(sm[0]), float(sm[1])]
         out.raw_rows = out.n_in * k2
 
+    def apply_generic(self, qubits, codes, coeffs, atol: float):
+        raise NotImplementedError("generic (raw-row expansion) gates move terms between shards; not supported on a sharded table yet")
+
     def apply_reset(self, qubit: int, atol: float):
         raise NotImplementedError("reset moves terms between shards; not supported on a sharded table yet")
 

@@ -42,7 +42,7 @@ def apply_op_to(op1, op1_qargs, op2, op2_qargs, *, apply_as_transform: bool = Fa
     Only ``apply_as_transform=True`` (the mode ``backpropagate`` uses, ``backpropagation.py:215``)
     is implemented on the device.
     """
-    from ..engine import OBP_FLAG_EXACT_COUNTERS, TermTable
+    from ..engine import OBP_FLAG_EXACT_COUNTERS, OBP_OP_GENERIC, TermTable
     from ..gates import classify, program_for
 
     if not apply_as_transform:
@@ -59,11 +59,16 @@ def apply_op_to(op1, op1_qargs, op2, op2_qargs, *, apply_as_transform: bool = Fa
             f"the number of qargs ({len(set(op2_qargs))})."
         )
     expanded, out_qargs, pos = _expand(op1, list(op1_qargs), list(op2_qargs))
-    rec = prog.template.copy()
-    rec["qubit"][0, :m] = pos
-    rec["flags"] = OBP_FLAG_EXACT_COUNTERS
-    with TermTable.from_operator(expanded) as table:
-        table.apply_ops(rec, SparsePauliOp.atol if atol is None else atol)
+    tol = SparsePauliOp.atol if atol is None else atol
+    k2 = prog.n_components**2
+    with TermTable.from_operator(expanded, capacity=max(1024, 2 * len(expanded) * (k2 + 1))) as table:
+        if prog.kind == OBP_OP_GENERIC:
+            table.apply_generic(pos, prog.codes, prog.coeffs, tol)
+        else:
+            rec = prog.template.copy()
+            rec["qubit"][0, :m] = pos
+            rec["flags"] = OBP_FLAG_EXACT_COUNTERS
+            table.apply_ops(rec, tol)
         return table.download(), out_qargs
 
 

@@ -170,6 +170,49 @@ def test_reset_and_noise_layers():
     _compare(obs, slices + [noisy] + slices[:2] + [rst] + slices[2:])
 
 
+def test_generic_gates():
+    """cp / crz / arbitrary unitaries: the raw k*k expansion + merge path, incl. its simplify counters."""
+    rng = np.random.default_rng(21)
+    nq = 7
+
+    def haar(dim):
+        a = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        q, r = np.linalg.qr(a)
+        return q * (np.diag(r) / np.abs(np.diag(r)))
+
+    slices = []
+    for k in range(6):
+        qc = QuantumCircuit(nq)
+        qc.cp(0.3 + 0.1 * k, k % nq, (k + 2) % nq)
+        qc.rx(0.4, (k + 1) % nq)
+        qc.crz(-0.7, (k + 3) % nq, (k + 4) % nq)
+        qc.unitary(haar(2), [(k + 5) % nq])
+        if k % 2:
+            qc.unitary(haar(4), [(k + 6) % nq, (k + 1) % nq])  # 16 Pauli components
+        qc.h(k % nq)
+        slices.append(qc)
+    obs = random_observable(nq, 3, rng)
+    _compare(obs, slices)
+    _compare(obs, slices[:3] + [slices[4][:0] if False else slices[5]], truncation_error_budget=setup_budget(max_error_per_slice=0.01))
+    # a slice ENDING on a generic gate reports the reference's counters of that gate
+    last = QuantumCircuit(nq)
+    last.h(0)
+    last.cp(0.9, 0, 1)
+    rev = QuantumCircuit(nq)
+    rev.cp(0.9, 0, 1)
+    rev.h(0)
+    _compare(obs, slices[:2] + [last, rev])
+    # 130 qubits: generic gates across word boundaries
+    wide = []
+    for k in range(3):
+        qc = QuantumCircuit(130)
+        qc.cp(0.5, 63, 64)
+        qc.crz(0.2, 127, 128)
+        qc.ry(0.3, 64)
+        wide.append(qc)
+    _compare(SparsePauliOp.from_sparse_list([("ZX", [63, 128], 1.0), ("Y", [64], 0.5)], 130), wide)
+
+
 # ---- the named configurations at oracle-sized scale ----------------------------------------------
 def test_config1_full():
     from qiskit_addon_obp_b200.workloads import config1_xy_chain

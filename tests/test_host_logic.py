@@ -120,8 +120,13 @@ def test_rotation_classification():
     # Clifford angles of a rotation family are Clifford-class (signed permutation), like rzz(-pi/2) in config 2
     assert gates.program_for(Instruction("rzz", (0, 1), (-np.pi / 2,))).kind == OBP_OP_CLIFFORD
     assert gates.program_for(Instruction("rz", (0,), (np.pi,))).kind == OBP_OP_CLIFFORD
-    with pytest.raises(NotImplementedError):
-        gates.program_for(Instruction("cp", (0, 1), (0.3,)))
+    # anything else is run as the literal k*k raw-row expansion
+    from qiskit_addon_obp_b200.engine import OBP_OP_GENERIC
+
+    prog = gates.program_for(Instruction("cp", (0, 1), (0.3,)))
+    assert prog.kind == OBP_OP_GENERIC and prog.n_components == 4 and sorted(prog.codes.tolist()) == [0, 2, 8, 10]
+    m = sum(u * gates.pauli_basis(2)[c] for c, u in zip(prog.codes, prog.coeffs))
+    assert np.allclose(m, Instruction("cp", (0, 1), (0.3,)).matrix)
 
 
 def test_decompose_matches_oracle():
