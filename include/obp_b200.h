@@ -34,6 +34,10 @@ extern "C" {
 #define OBP_ERR_UNSUPPORTED (-5)
 
 #define OBP_MAX_WORDS 32 /* up to 2048 qubits */
+/* atol values with a special meaning: merge duplicates but trim nothing / keep the rows exactly as
+ * given or produced (OperatorBudget(simplify=False), backpropagation.py:220: no merge, zeros stay) */
+#define OBP_ATOL_MERGE_ONLY (-1.0)
+#define OBP_ATOL_RAW (-2.0)
 
 typedef struct obp_ctx obp_ctx;
 
@@ -121,11 +125,13 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
 /* Any other gate on 1-4 qubits (cp, crz, arbitrary unitaries): U = sum_j u_j * Pauli(codes[j]) with
  * codes[j] = local Pauli code (bit 2q = x, bit 2q+1 = z on qubits[q]) and coeffs[j] = (re, im).  Runs
  * the reference's literal k*k raw-row expansion (utils/operations.py:103-105) followed by simplify
- * (utils/simplify.py:115-165).  Needs room for n*k*k extra rows (OBP_ERR_CAPACITY otherwise). */
+ * (utils/simplify.py:115-165); simplify = 0 keeps the raw rows unmerged (OperatorBudget(simplify=False)).
+ * Needs room for n*k*k extra rows (OBP_ERR_CAPACITY otherwise). */
 int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int32_t n_comp, const uint32_t* codes,
-                      const double* coeffs, double atol, obp_stats* stats);
+                      const double* coeffs, double atol, int32_t simplify, obp_stats* stats);
 
-/* <0|O|0> on one qubit then simplify: apply_reset_to (utils/operations.py:194-225). */
+/* <0|O|0> on one qubit then simplify: apply_reset_to (utils/operations.py:194-225).
+ * atol == OBP_ATOL_RAW: without the simplify (X/Y rows keep their place with coefficient 0). */
 int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats);
 
 /* Pauli-Lindblad damping then simplify: apply_ple_to (utils/operations.py:228-275).

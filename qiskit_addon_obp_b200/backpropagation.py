@@ -20,8 +20,8 @@ from collections.abc import Sequence
 import numpy as np
 
 from . import engine
-from .engine import OBP_FLAG_EXACT_COUNTERS, OBP_OP_GENERIC, OP_DTYPE, CapacityError, TermTable
-from .gates import program_for
+from .engine import OBP_ATOL_RAW, OBP_FLAG_EXACT_COUNTERS, OBP_OP_GENERIC, OP_DTYPE, CapacityError, TermTable
+from .gates import program_for, raw_program_for
 from .ir import QuantumCircuit, SparsePauliOp, topological_op_order
 from .sharded import ShardedTable, communicator_from_env
 from .utils.metadata import OBPMetadata, SliceMetadata
@@ -95,11 +95,7 @@ def backpropagate(
     obs_in: list[SparsePauliOp] = [observables] if single else list(observables)
 
     _validate_input_options(obs_in, slices_ir, operator_budget)
-    if not operator_budget.simplify:
-        raise NotImplementedError(
-            "OperatorBudget(simplify=False) keeps the k*k raw rows of every gate unmerged; the "
-            "device path always merges. Use the default simplify=True."
-        )
+    raw = not operator_budget.simplify  # nothing merged or trimmed: every gate is a raw k*k expansion
 
     atol = SparsePauliOp.atol if operator_budget.atol is None else float(operator_budget.atol)
     num_qubits = slices_ir[0].num_qubits
@@ -109,6 +105,8 @@ def backpropagate(
     device = engine.default_device()
     capacity = _default_capacity(num_qubits, operator_budget, n_obs, device)
     comm = communicator_from_env(device)  # None: one table per observable on this GPU
+    if comm is not None and raw:
+        raise NotImplementedError("OperatorBudget(simplify=False) is not supported on a sharded table")
     if comm is not None:
         if n_obs > 1 and operator_budget.is_active():
             raise NotImplementedError("a sharded table supports operator budgets for a single observable only")
@@ -151,17 +149,17 @@ def backpropagate(
                 sm = SliceMetadata(
                     slice_errors=[0.0] * n_obs,
                     raw_num_paulis=[0] * n_obs,
-                    num_unique_paulis=list(lengths),
-                    num_duplicate_paulis=[0] * n_obs,
-                    num_trimmed_paulis=[0] * n_obs,
-                    sum_trimmed_coeffs=[0] * n_obs,
+                    num_unique_paulis=None if raw else list(lengths),
+                    num_duplicate_paulis=None if raw else [0] * n_obs,
+                    num_trimmed_paulis=None if raw else [0] * n_obs,
+                    sum_trimmed_coeffs=None if raw else [0] * n_obs,
                     num_truncated_paulis=[0] * n_obs,
                     num_paulis=[0] * n_obs,
                     sum_paulis=None,
                     num_qwc_groups=None,
                 )
                 metadata.backpropagation_history.append(sm)
-                prog = _slice_program(slice_)
+                prog = _slice_program(slice_, raw)
                 overflowed = False
                 for i in range(n_obs):
                     applied: list[int] = []
@@ -176,7 +174,7 @@ def backpropagate(
                     sidx = metadata.num_backpropagated_slices
                     if non_trivial:
                         if not loaded[i]:
-                            tables[i].load(obs_in[i])
+                            tables[i].load(obs_in[i], OBP_ATOL_RAW if raw else None)
                             info.h2d_bytes += len(obs_in[i]) * (16 * tables[i].words + 16)
                             tables[i].profile_enable(PROFILE)
                             tables[i].profile(reset=True)
@@ -185,7 +183,7 @@ def backpropagate(
                             loaded[i] = True
                         while True:
                             try:
-                                _run_slice(tables[i], prog, applied, atol, sm, i, info)
+                                _run_slice(tables[i], prog, applied, atol, sm, i, info, raw)
                                 if trunc_active:
                                     budget = metadata.left_over_error_budget(i, sidx)
                                     err, removed = tables[i].truncate(
@@ -230,7 +228,7 @@ def backpropagate(
                     )
                     break
                 if operator_budget.is_active() and _observable_oversized(
-                    tables, loaded, obs_in, operator_budget, metadata.num_backpropagated_slices, sm
+                    tables, loaded, obs_in, operator_budget, metadata.num_backpropagated_slices, sm, raw
                 ):
                     break
                 # commit (backpropagation.py:279-285): the snapshot is the deepcopy of the reference
@@ -309,8 +307,9 @@ class SliceProgram:
 
     __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data", "generic")
 
-    def __init__(self, slice_: QuantumCircuit):
+    def __init__(self, slice_: QuantumCircuit, raw: bool = False):
         self.n_data = len(slice_.data)
+        classify = raw_program_for if raw else program_for
         self.nodes = [n for n in topological_op_order(slice_)[::-1] if n.name != "barrier"]
         self.qubit_sets = [frozenset(n.qubits) for n in self.nodes]
         self.recs = np.zeros(len(self.nodes), dtype=OP_DTYPE)
@@ -326,7 +325,7 @@ class SliceProgram:
         qubit = self.recs["qubit"]
         for idxs in groups.values():
             try:
-                prog = program_for(self.nodes[idxs[0]])
+                prog = classify(self.nodes[idxs[0]])
             except (NotImplementedError, ValueError) as exc:  # only raised if the gate is applied
                 for k in idxs:
                     self.errors[k] = exc
@@ -340,16 +339,17 @@ class SliceProgram:
             qubit[idxs, : prog.n_qubits] = np.array([self.nodes[k].qubits for k in idxs], dtype=np.int32)
 
 
-def _slice_program(slice_: QuantumCircuit) -> SliceProgram:
-    prog = getattr(slice_, "_obp_program", None)
+def _slice_program(slice_: QuantumCircuit, raw: bool = False) -> SliceProgram:
+    attr = "_obp_program_raw" if raw else "_obp_program"
+    prog = getattr(slice_, attr, None)
     if prog is None or prog.n_data != len(slice_.data):
-        prog = SliceProgram(slice_)
-        slice_._obp_program = prog
+        prog = SliceProgram(slice_, raw)
+        setattr(slice_, attr, prog)
     return prog
 
 
 def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: float, sm: SliceMetadata, i: int,
-               info: RunInfo) -> None:
+               info: RunInfo, raw: bool = False) -> None:
     """Execute the applied gates of one slice on one observable and record the last gate's counters."""
     stats = None
     last = applied[-1]
@@ -390,9 +390,9 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
         node = prog.nodes[k]
         if k in prog.generic:
             g = prog.generic[k]
-            stats = table.apply_generic(node.qubits, g.codes, g.coeffs, atol)
+            stats = table.apply_generic(node.qubits, g.codes, g.coeffs, atol, simplify=not raw)
         elif node.name == "reset":
-            stats = table.apply_reset(node.qubits[0], atol)
+            stats = table.apply_reset(node.qubits[0], OBP_ATOL_RAW if raw else atol)
         else:
             ple = node.ple
             if ple is None:
@@ -405,12 +405,14 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
             gz = np.zeros((len(gens), table.num_qubits), dtype=bool)
             gx[:, list(node.qubits)] = gens.x
             gz[:, list(node.qubits)] = gens.z
-            stats = table.apply_damping(gx, gz, np.exp(-2 * np.asarray(ple.rates, dtype=float)), atol)
+            stats = table.apply_damping(gx, gz, np.exp(-2 * np.asarray(ple.rates, dtype=float)), -1.0 if raw else atol)
         info.updates += int(stats.updates)
     flush()
     info.applied_gates += len(applied)
     # the slice reports the counters of its last applied gate (backpropagation.py:218-237)
     sm.raw_num_paulis[i] = int(stats.raw_rows)
+    if raw:
+        return  # simplify=False: the four simplify counters stay None (backpropagation.py:151-160)
     if getattr(stats, "counters_valid", True):
         sm.num_unique_paulis[i] = int(stats.num_unique)
         sm.num_duplicate_paulis[i] = int(stats.num_duplicate)
@@ -440,7 +442,7 @@ def _distinct_labels(ops: list[SparsePauliOp]) -> SparsePauliOp:
     return SparsePauliOp((x[first], z[first]), np.ones(len(first)))
 
 
-def _observable_oversized(tables, loaded, obs_in, operator_budget, slice_id, sm) -> bool:
+def _observable_oversized(tables, loaded, obs_in, operator_budget, slice_id, sm, raw=False) -> bool:
     """``backpropagation.py:409-442``: distinct keys / QWC groups over all observables."""
     from .utils.qwc import qwc_group_count
 
@@ -460,7 +462,9 @@ def _observable_oversized(tables, loaded, obs_in, operator_budget, slice_id, sm)
         return union
 
     if max_paulis is not None:
-        if not host_ops and len(dev_tables) == 1 and not dev_tables[0].zero_operator:
+        if raw:
+            sm.sum_paulis = len(union_op())  # unmerged rows: count the distinct labels on the host
+        elif not host_ops and len(dev_tables) == 1 and not dev_tables[0].zero_operator:
             sm.sum_paulis = dev_tables[0].n  # one observable: its keys are already distinct
         elif not host_ops and all(not t.zero_operator for t in dev_tables):
             sm.sum_paulis = engine.union_count(dev_tables)

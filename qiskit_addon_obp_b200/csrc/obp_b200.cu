@@ -654,7 +654,13 @@ int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, con
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
   Tab t = make_tab(ctx);
-  if (n) {
+  if (n && atol == OBP_ATOL_RAW) {  // simplify=False: rows as given, duplicates and zeros included
+    Bracket b(ctx, OBP_K_INDEX, 2);
+    const int g = grid_for(ctx, n);
+    k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n);
+    k_revive_zeros<<<g, OBP_BS, 0, ctx->stream>>>(t, 0, n);
+    CU(cudaGetLastError());
+  } else if (n) {
     Bracket b(ctx, OBP_K_INDEX);
     const int g = grid_for(ctx, n);
     k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n);
@@ -1240,7 +1246,7 @@ int obp_rotate_merge_inbox(obp_ctx* ctx, obp_shard_counters* out) {
 // -------------------------------------------------------------------------------------------------
 // Generic gate: raw k*k expansion + the merge of a freshly loaded operator (simplify.py:115-165).
 int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int32_t n_comp, const uint32_t* codes,
-                      const double* coeffs, double atol, obp_stats* stats) {
+                      const double* coeffs, double atol, int32_t simplify, obp_stats* stats) {
   if (!ctx || !qubits || !codes || !coeffs || n_qubits < 1 || n_qubits > 4 || n_comp < 1 || n_comp > OBP_GEN_MAXK)
     return OBP_ERR_BADARG;
   if (ctx->n_ranks > 1) return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_generic: not available on a sharded table");
@@ -1292,6 +1298,28 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
   CU(cudaMemcpyAsync(ctx->d_st, ctx->h_st, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  if (!simplify) {  // OperatorBudget(simplify=False): keep every raw row, zeros included
+    if (raw) {
+      Bracket br(ctx, OBP_K_OTHER);
+      k_revive_zeros<<<grid_for(ctx, raw), OBP_BS, 0, ctx->stream>>>(t, n, n + raw);
+      CU(cudaGetLastError());
+    }
+    rc = sync_state(ctx);
+    if (rc) return rc;
+    ctx->prof.term_updates[OBP_K_OTHER] += n;
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+    if (stats) {
+      stats->n_in = n;
+      stats->raw_rows = raw;
+      stats->updates = n;
+      stats->n_out = ctx->n_live;
+      stats->n_dense = ctx->n_dense;
+    }
+    return OBP_OK;
+  }
   if (raw) {
     Bracket br(ctx, OBP_K_INDEX, 3);
     const int g = grid_for(ctx, n + raw);
@@ -1327,6 +1355,24 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
 int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) {
   if (!ctx || qubit < 0 || qubit >= ctx->nq) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
+  if (atol == OBP_ATOL_RAW) {  // simplify=False: zero the X/Y rows, clear the qubit, merge nothing
+    const u64 n_rows = ctx->n_live;
+    {
+      Bracket br(ctx, OBP_K_OTHER);
+      k_reset_raw<<<grid_for(ctx, std::max<u64>(ctx->n_dense, 1)), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), qubit / 64,
+                                                                                             1ull << (qubit % 64));
+      CU(cudaGetLastError());
+    }
+    const int src = sync_state(ctx);
+    if (src) return src;
+    ctx->prof.term_updates[OBP_K_OTHER] += n_rows;
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->n_in = stats->raw_rows = stats->updates = stats->n_out = n_rows;
+      stats->n_dense = ctx->n_dense;
+    }
+    return OBP_OK;
+  }
   int rc = ensure_ops(ctx, 2);
   if (rc) return rc;
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat), ctx->stream));

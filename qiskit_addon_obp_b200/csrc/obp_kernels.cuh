@@ -1367,3 +1367,27 @@ __global__ void __launch_bounds__(OBP_BS) k_expand(Tab t, const __grid_constant_
 __global__ void __launch_bounds__(OBP_BS) k_kill_prefix(Tab t, u64 n, u64 epoch) {
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) t.coef[i] = tombstone(epoch);
 }
+
+// ---- OperatorBudget(simplify=False): nothing is merged or trimmed, rows with coefficient 0 stay ------
+// an exact zero coefficient is stored as -0.0 - 0.0i so that the row does not look like a tombstone
+__global__ void __launch_bounds__(OBP_BS) k_revive_zeros(Tab t, u64 first, u64 n) {
+  for (u64 i = first + (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c) && tomb_epoch(c) == 0) t.coef[i] = make_double2(-0.0, -0.0);
+  }
+}
+
+// apply_reset_to without the simplify that follows it in the loop (utils/operations.py:221-223)
+__global__ void __launch_bounds__(OBP_BS) k_reset_raw(Tab t, int w, u64 bit) {
+  const u64 n = t.st->n_scan;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    if (!is_live(t.coef[i])) continue;
+    ulonglong2 key = t.xz[w][i];
+    if (key.x & bit) t.coef[i] = make_double2(-0.0, -0.0);
+    if ((key.x | key.y) & bit) {
+      key.x &= ~bit;
+      key.y &= ~bit;
+      t.xz[w][i] = key;
+    }
+  }
+}

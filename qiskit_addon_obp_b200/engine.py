@@ -26,6 +26,8 @@ OBP_OP_CLIFFORD = 1
 OBP_OP_ROTATION = 2
 OBP_OP_GENERIC = 3  # host-side tag only: run through obp_apply_generic, never inside an obp_op program
 OBP_FLAG_EXACT_COUNTERS = 1
+OBP_ATOL_MERGE_ONLY = -1.0
+OBP_ATOL_RAW = -2.0  # simplify=False: no merge, exact zeros stay
 OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other", "program")
 
 #: numpy mirror of ``obp_op`` (104 bytes, natural C alignment)
@@ -121,7 +123,7 @@ def lib() -> C.CDLL:
         "obp_count": ([vp, u64p], C.c_int),
         "obp_download": ([vp, vp, vp, vp, C.c_uint64, u64p], C.c_int),
         "obp_apply_ops": ([vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
-        "obp_apply_generic": ([vp, C.c_int32, vp, C.c_int32, vp, vp, C.c_double, C.POINTER(ObpStats)], C.c_int),
+        "obp_apply_generic": ([vp, C.c_int32, vp, C.c_int32, vp, vp, C.c_double, C.c_int32, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_reset": ([vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_damping": ([vp, vp, vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_truncate": ([vp, C.c_double, C.c_int32, C.c_double, f64p, u64p, u64p], C.c_int),
@@ -276,7 +278,8 @@ class TermTable:
 
     # -- I/O ----------------------------------------------------------------------------------
     def load(self, op: SparsePauliOp, atol: float | None = None) -> ObpStats:
-        """Upload ``op``; ``atol=None`` merges duplicate rows only, a float runs the full simplify."""
+        """Upload ``op``; ``atol=None`` merges duplicate rows only, a float >= 0 runs the full simplify,
+        ``OBP_ATOL_RAW`` keeps the rows exactly as given."""
         if op.num_qubits != self.num_qubits:
             raise ValueError("operator width does not match the table")
         if len(op) > self.capacity:
@@ -295,7 +298,7 @@ class TermTable:
         )
         self._check(rc, "obp_load")
         self.n, self.n_dense = st.n_out, st.n_dense
-        self.zero_operator = atol is not None and self.n == 0
+        self.zero_operator = atol is not None and atol >= 0 and self.n == 0
         return st
 
     def download(self) -> SparsePauliOp:
@@ -348,8 +351,8 @@ class TermTable:
             self.zero_operator = True
         return st
 
-    def apply_generic(self, qubits, codes, coeffs, atol: float) -> ObpStats:
-        """A gate given as its Pauli sum (local codes + complex coefficients): raw k*k expansion + simplify."""
+    def apply_generic(self, qubits, codes, coeffs, atol: float, simplify: bool = True) -> ObpStats:
+        """A gate given as its Pauli sum (local codes + complex coefficients): raw k*k expansion (+ simplify)."""
         st = ObpStats()
         k2 = len(codes) ** 2
         if self.zero_operator:
@@ -360,11 +363,11 @@ class TermTable:
         co = np.ascontiguousarray(np.asarray(coeffs, dtype=np.complex128))
         rc = self._lib.obp_apply_generic(
             self._h, len(q), q.ctypes.data_as(C.c_void_p), len(cd), cd.ctypes.data_as(C.c_void_p),
-            co.ctypes.data_as(C.c_void_p), float(atol), C.byref(st),
+            co.ctypes.data_as(C.c_void_p), float(atol), int(bool(simplify)), C.byref(st),
         )
         self._check(rc, "obp_apply_generic")
         self.n, self.n_dense = st.n_out, st.n_dense
-        if self.n == 0:
+        if self.n == 0 and simplify:
             self.zero_operator = True
         return st
 
@@ -375,7 +378,7 @@ class TermTable:
             return st
         self._check(self._lib.obp_apply_reset(self._h, int(qubit), float(atol), C.byref(st)), "obp_apply_reset")
         self.n, self.n_dense = st.n_out, st.n_dense
-        if self.n == 0:
+        if self.n == 0 and atol >= 0:
             self.zero_operator = True
         return st
 
@@ -397,7 +400,7 @@ class TermTable:
         )
         self._check(rc, "obp_apply_damping")
         self.n, self.n_dense = st.n_out, st.n_dense
-        if self.n == 0:
+        if self.n == 0 and atol >= 0:
             self.zero_operator = True
         return st
 

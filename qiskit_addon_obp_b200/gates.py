@@ -142,6 +142,25 @@ def classify(matrix: np.ndarray, name: str = "gate") -> GateProgram:
 
 
 _CACHE: dict[tuple, GateProgram] = {}
+_RAW_CACHE: dict[tuple, GateProgram] = {}
+
+
+def raw_program_for(ins: Instruction) -> GateProgram:
+    """The gate as its plain Pauli sum, for ``OperatorBudget(simplify=False)``: every gate is expanded
+    into its k*k raw rows like the reference does (``backpropagation.py:210-220`` without simplify)."""
+    key = (ins.name, ins.params) if ins._matrix is None else (ins.name, ins._matrix.shape, ins._matrix.tobytes())
+    prog = _RAW_CACHE.get(key)
+    if prog is None:
+        codes, us = pauli_decompose(ins.matrix)
+        if len(codes) > 16:
+            raise NotImplementedError(f"gate {ins.name!r} has {len(codes)} Pauli components; at most 16 are supported")
+        rec = np.zeros(1, dtype=OP_DTYPE)
+        rec["kind"] = OBP_OP_GENERIC
+        rec["n_qubits"] = len(ins.qubits)
+        rec["n_components"] = len(codes)
+        prog = GateProgram(OBP_OP_GENERIC, len(ins.qubits), len(codes), rec, np.array(codes, dtype=np.uint32), np.array(us))
+        _RAW_CACHE[key] = prog
+    return prog
 
 
 def program_for(ins: Instruction) -> GateProgram:

@@ -26,9 +26,34 @@ pytestmark = pytest.mark.gpu
 
 
 # ---- the reference's own KATs through the engine ------------------------------------------------
-@pytest.mark.parametrize("kat", kats.ORDER_FREE, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("kat", kats.ORDER_FREE + [kats.kat_reset_no_simplify], ids=lambda f: f.__name__)
 def test_reference_kat(kat):
     kat(backpropagate)
+
+
+def test_simplify_false_matches_oracle():
+    """OperatorBudget(simplify=False): raw rows multiply by k*k per gate, nothing merges (reference :220)."""
+    qc1 = QuantumCircuit(3)
+    qc1.rx(0.3, 0)
+    qc1.cx(0, 1)
+    qc2 = QuantumCircuit(3)
+    qc2.h(1)
+    qc2.reset(2)
+    qc2.rzz(0.2, 0, 1)
+    obs = SparsePauliOp(["ZIX", "XYZ", "ZIX"], [1.0, 0.5, 0.25])  # a duplicate row stays a duplicate
+    budget = OperatorBudget(simplify=False)
+    got, rest, md = backpropagate(obs, [qc1, qc2], operator_budget=budget)
+    want, _, md_w = oracle.backpropagate(obs, [qc1, qc2], operator_budget=budget)
+    assert rest == [] and len(got) == len(want)
+    assert [s.num_paulis for s in md.backpropagation_history] == [s.num_paulis for s in md_w.backpropagation_history]
+    assert [s.raw_num_paulis for s in md.backpropagation_history] == [s.raw_num_paulis for s in md_w.backpropagation_history]
+    assert all(s.num_unique_paulis is None and s.sum_trimmed_coeffs is None for s in md.backpropagation_history)
+    a, b = got.as_dict(), want.as_dict()  # sums per label
+    assert set(a) == set(b)
+    assert max(abs(a[k] - b[k]) for k in a) < 1e-12
+    got, _, _ = backpropagate(obs, [qc1, qc2], operator_budget=budget, truncation_error_budget=setup_budget(max_error_per_slice=0.05))
+    want, _, _ = oracle.backpropagate(obs, [qc1, qc2], operator_budget=budget, truncation_error_budget=setup_budget(max_error_per_slice=0.05))
+    assert len(got) == len(want)
 
 
 @pytest.mark.parametrize("kat", kats.ORDERED, ids=lambda f: f.__name__)
