@@ -401,6 +401,67 @@ struct PendingBatch {
   }
 };
 
+// ---- host-side fusion of Clifford-class gates ------------------------------------------------------
+// A one-qubit Clifford commutes with everything that does not touch its qubit, so it is held back
+// (per qubit, composing with later one-qubit Cliffords on the same qubit) until a two-qubit Clifford
+// absorbs it or another kind of op needs the qubit.  The brickwork block [1q(a), 1q(b), 2q(a,b)]
+// becomes ONE table-lookup gate; the device does a third of the bit work.
+struct FusedGate {
+  int nq = 0;
+  int q[2] = {0, 0};
+  u64 lut = 0;        // image of local code v in bits [4v, 4v+4)
+  unsigned sign = 0;  // bit v: sign flip
+  double scale = 1e300;
+  int n_gates = 0;
+};
+
+inline unsigned lut_at(u64 lut, unsigned v) { return (unsigned)((lut >> (4 * v)) & 15ull); }
+
+// `first` then `second`, both on the same qubits in the same order
+FusedGate fuse_seq(const FusedGate& first, const FusedGate& second) {
+  FusedGate r = first;
+  r.lut = 0;
+  r.sign = 0;
+  const unsigned nv = 1u << (2 * first.nq);
+  for (unsigned v = 0; v < nv; ++v) {
+    const unsigned mid = lut_at(first.lut, v);
+    r.lut |= (u64)lut_at(second.lut, mid) << (4 * v);
+    r.sign |= (((first.sign >> v) ^ (second.sign >> mid)) & 1u) << v;
+  }
+  r.scale = std::min(first.scale, second.scale);
+  r.n_gates = first.n_gates + second.n_gates;
+  return r;
+}
+
+// a one-qubit gate as a two-qubit gate acting on position pos (0 or 1) of the pair (qa, qb)
+FusedGate embed_1q(const FusedGate& g, int pos, int qa, int qb) {
+  FusedGate r;
+  r.nq = 2;
+  r.q[0] = qa;
+  r.q[1] = qb;
+  r.scale = g.scale;
+  r.n_gates = g.n_gates;
+  for (unsigned v = 0; v < 16; ++v) {
+    const unsigned mine = pos == 0 ? (v & 3u) : (v >> 2), other = pos == 0 ? (v >> 2) : (v & 3u);
+    const unsigned img = lut_at(g.lut, mine);
+    r.lut |= (u64)(pos == 0 ? (img | (other << 2)) : (other | (img << 2))) << (4 * v);
+    r.sign |= ((g.sign >> mine) & 1u) << v;
+  }
+  return r;
+}
+
+FusedGate fused_from_op(const obp_op& op) {
+  FusedGate g;
+  g.nq = op.n_qubits;
+  g.q[0] = op.qubit[0];
+  g.q[1] = op.n_qubits == 2 ? op.qubit[1] : op.qubit[0];
+  g.lut = op.lut;
+  g.sign = op.sign_mask;
+  g.scale = op.row_scale;
+  g.n_gates = 1;
+  return g;
+}
+
 // a gate program recorded for the persistent kernel instead of being launched op by op
 struct ProgRec {
   std::vector<ProgEntry> entries;
@@ -802,22 +863,107 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     return OBP_OK;
   };
 
+  // one-qubit Cliffords held back per qubit (see FusedGate)
+  std::vector<FusedGate> pend(ctx->nq);
+  std::vector<int> pend_list;  // qubits with a pending gate, in arrival order
+
+  // put one (possibly fused) Clifford gate into the current batch
+  auto emit_gate = [&](const FusedGate& fg) -> int {
+    int need_new = 0;
+    for (int j = 0; j < fg.nq; ++j) {
+      bool have = false;
+      for (int sl = 0; sl < pb.b.nslots; ++sl) have |= pb.b.word_of_slot[sl] == fg.q[j] / 64;
+      need_new += !have;
+    }
+    if (pb.b.ng == OBP_CLIFF_BATCH || pb.b.nslots + need_new > (int)max_smem_slots) {
+      const int frc = flush();
+      if (frc) return frc;
+    }
+    CliffGate& g = pb.b.g[pb.b.ng++];
+    memset(&g, 0, sizeof(g));
+    g.lut = fg.lut;
+    g.sign = fg.sign;
+    g.nq = (unsigned char)fg.nq;
+    g.sa = (unsigned char)pb.slot_of_word(fg.q[0] / 64);
+    g.ba = (unsigned char)(fg.q[0] % 64);
+    if (fg.nq == 2) {
+      g.sb = (unsigned char)pb.slot_of_word(fg.q[1] / 64);
+      g.bb = (unsigned char)(fg.q[1] % 64);
+    } else {
+      g.sb = g.sa;
+      g.bb = g.ba;
+    }
+    pb.b.scale = std::min(pb.b.scale, fg.scale);
+    pb.n_ops += fg.n_gates;
+    // the hash frame follows the keys: re-express it when the gate is really applied
+    obp_op fop;
+    memset(&fop, 0, sizeof(fop));
+    fop.n_qubits = fg.nq;
+    fop.qubit[0] = fg.q[0];
+    fop.qubit[1] = fg.q[1];
+    fop.lut = fg.lut;
+    frame_update(ctx, fop);
+    return OBP_OK;
+  };
+  auto release_qubit = [&](int q) -> int {  // apply the held-back gate of qubit q now
+    if (pend[q].n_gates == 0) return OBP_OK;
+    const FusedGate fg = pend[q];
+    pend[q] = FusedGate();
+    pend_list.erase(std::remove(pend_list.begin(), pend_list.end(), q), pend_list.end());
+    return emit_gate(fg);
+  };
+  auto release_all = [&]() -> int {
+    const std::vector<int> qs = pend_list;
+    for (int q : qs) {
+      const int r = release_qubit(q);
+      if (r) return r;
+    }
+    return OBP_OK;
+  };
+
   for (int k = 0; k < n_ops; ++k) {
     const obp_op& op = ops[k];
     if (op.kind == OBP_OP_CLIFFORD) {
       const bool exact = (op.flags & OBP_FLAG_EXACT_COUNTERS) != 0;
-      // words this gate touches must fit the staging tile
-      int need_new = 0;
-      for (int j = 0; j < op.n_qubits; ++j) {
-        bool have = false;
-        for (int s = 0; s < pb.b.nslots; ++s) have |= pb.b.word_of_slot[s] == op.qubit[j] / 64;
-        need_new += !have;
+      slot_of_op[k] = n_slots;
+      if (!exact && op.n_qubits == 1) {
+        // hold it back: it commutes with everything that does not touch its qubit
+        const int q = op.qubit[0];
+        const FusedGate g = fused_from_op(op);
+        if (pend[q].n_gates == 0) {
+          pend[q] = g;
+          pend_list.push_back(q);
+        } else {
+          pend[q] = fuse_seq(pend[q], g);
+        }
+        continue;
       }
-      if (pb.b.ng == OBP_CLIFF_BATCH || pb.b.nslots + need_new > (int)max_smem_slots || exact) {
-        rc = flush();
+      if (!exact) {
+        // two-qubit gate: absorb what is pending on its qubits
+        const int qa = op.qubit[0], qb = op.qubit[1];
+        FusedGate g = fused_from_op(op);
+        if (pend[qb].n_gates) {
+          g = fuse_seq(embed_1q(pend[qb], 1, qa, qb), g);
+          pend[qb] = FusedGate();
+          pend_list.erase(std::remove(pend_list.begin(), pend_list.end(), qb), pend_list.end());
+        }
+        if (pend[qa].n_gates) {
+          g = fuse_seq(embed_1q(pend[qa], 0, qa, qb), g);
+          pend[qa] = FusedGate();
+          pend_list.erase(std::remove(pend_list.begin(), pend_list.end(), qa), pend_list.end());
+        }
+        rc = emit_gate(g);
         if (rc) return rc;
+        continue;
       }
-      if (exact) {
+      // the slice's last gate with the reference's counters: everything held back is applied first,
+      // so that this gate's batch is the last slot of the program
+      rc = release_all();
+      if (rc) return rc;
+      rc = flush();
+      if (rc) return rc;
+      slot_of_op[k] = n_slots;
+      {
         // counters come from the keys before the gate acts
         CosetP cp;
         memset(&cp, 0, sizeof(cp));
@@ -849,29 +995,19 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
           CU(cudaGetLastError());
         }
       }
-      CliffGate& g = pb.b.g[pb.b.ng++];
-      memset(&g, 0, sizeof(g));
-      g.lut = op.lut;
-      g.sign = op.sign_mask;
-      g.nq = (unsigned char)op.n_qubits;
-      g.sa = (unsigned char)pb.slot_of_word(op.qubit[0] / 64);
-      g.ba = (unsigned char)(op.qubit[0] % 64);
-      if (op.n_qubits == 2) {
-        g.sb = (unsigned char)pb.slot_of_word(op.qubit[1] / 64);
-        g.bb = (unsigned char)(op.qubit[1] % 64);
-      } else {
-        g.sb = g.sa;
-        g.bb = g.ba;
-      }
-      pb.b.scale = std::min(pb.b.scale, op.row_scale);
-      pb.n_ops++;
-      slot_of_op[k] = n_slots;
-      frame_update(ctx, op);
-      if (exact) {
-        rc = flush();
+      rc = emit_gate(fused_from_op(op));
+      if (rc) return rc;
+      rc = flush();
+      if (rc) return rc;
+    } else {
+      if (op.flags & OBP_FLAG_EXACT_COUNTERS) {
+        rc = release_all();  // its slot must be the program's last
         if (rc) return rc;
       }
-    } else {
+      for (int j = 0; j < op.n_qubits; ++j) {
+        rc = release_qubit(op.qubit[j]);
+        if (rc) return rc;
+      }
       rc = flush();
       if (rc) return rc;
       RotP p = build_rotp(ctx, op, atol);
@@ -881,7 +1017,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
         *n_done = k;
         *peer_xor = (int32_t)(p.hG >> ctx->owner_shift);
         n_ops = k;
-        break;
+        break;  // (gates still held back are applied by the release_all() after the loop)
       }
       p.epoch = ++ctx->epoch;
       p.slot = n_slots;
@@ -899,6 +1035,8 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
       bound = std::min<u64>(ctx->cap, bound * 2);
     }
   }
+  rc = release_all();
+  if (rc) return rc;
   rc = flush();
   if (rc) return rc;
   if (n_ops == 0) {  // a sharded program that starts with an exchange rotation
