@@ -402,9 +402,9 @@ struct PendingBatch {
 };
 
 // ---- host-side fusion of Clifford-class gates ------------------------------------------------------
-// A one-qubit Clifford commutes with everything that does not touch its qubit, so it is held back
-// (per qubit, composing with later one-qubit Cliffords on the same qubit) until a two-qubit Clifford
-// absorbs it or another kind of op needs the qubit.  The brickwork block [1q(a), 1q(b), 2q(a,b)]
+// Inside a run of Clifford-class gates a one-qubit Clifford commutes with everything that does not
+// touch its qubit, so it is held back (per qubit, composing with later one-qubit Cliffords on the same
+// qubit) until a two-qubit Clifford absorbs it or the run ends (any rotation ends it).  The brickwork block [1q(a), 1q(b), 2q(a,b)]
 // becomes ONE table-lookup gate; the device does a third of the bit work.
 struct FusedGate {
   int nq = 0;
@@ -809,6 +809,10 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   const bool prog_mode = ctx->use_program && ctx->prog_ctas_per_sm > 0 && ctx->W <= 2;
   ProgRec prog;
   int n_rot_ops = 0;
+  // wider tables: a run of Clifford-class gates becomes one stream of LOAD / gate / STORE micro-ops
+  const bool stream_mode = ctx->W > 2;
+  std::vector<CliffGate> stream;
+  static thread_local CliffStream cs;  // 32 KB: kept off the stack
   int rc = ensure_ops(ctx, 3 * n_ops + 2);
   if (rc) return rc;
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * (3 * n_ops + 2), ctx->stream));
@@ -823,7 +827,39 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   Tab t = make_tab(ctx);
   const size_t max_smem_slots = 32;  // 32 * 256 * 16 B = 128 KB of the 227 KB per CTA
 
+  int stream_word = -1;  // word currently held in registers by the stream being built
+  auto stream_switch = [&](int w) {
+    if (stream_word == w) return;
+    CliffGate m;
+    memset(&m, 0, sizeof(m));
+    m.nq = OBP_STREAM_SWITCH;
+    m.ba = (unsigned char)w;
+    stream.push_back(m);
+    stream_word = w;
+  };
+
   auto flush = [&]() -> int {
+    if (stream_mode) {
+      if (stream.empty()) return OBP_OK;
+      stream_switch(OBP_MAX_WORDS);  // write the last word back
+      stream_word = -1;
+      cs.n = (int)stream.size();
+      cs.slot = n_slots;
+      cs.scale = pb.b.scale;
+      cs.atol = atol;
+      cs.epoch = ++ctx->epoch;
+      memcpy(cs.g, stream.data(), stream.size() * sizeof(CliffGate));
+      {
+        Bracket br(ctx, OBP_K_CLIFFORD);
+        k_clifford_stream<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, cs);
+        CU(cudaGetLastError());
+      }
+      stream.clear();
+      slot_gates.push_back(pb.n_ops);
+      n_slots++;
+      pb.reset();
+      return OBP_OK;
+    }
     if (pb.b.ng == 0) return OBP_OK;
     pb.b.atol = atol;
     pb.b.epoch = ++ctx->epoch;
@@ -869,6 +905,81 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
 
   // put one (possibly fused) Clifford gate into the current batch
   auto emit_gate = [&](const FusedGate& fg) -> int {
+    if (stream_mode) {
+      if (stream.size() + 8 > OBP_STREAM_MAX) {
+        const int frc = flush();
+        if (frc) return frc;
+      }
+      CliffGate g;
+      memset(&g, 0, sizeof(g));
+      g.lut = fg.lut;
+      g.sign = (unsigned short)fg.sign;
+      g.nq = (unsigned char)fg.nq;
+      const int wa = fg.q[0] / 64, wb = fg.q[1] / 64;
+      const int ba = fg.q[0] % 64, bb = fg.q[1] % 64;
+      g.ba = (unsigned char)ba;
+      g.bb = (unsigned char)(fg.nq == 2 ? bb : ba);
+      if (fg.nq == 2 && wa != wb) {
+        // the other word is touched in place; stay on (or move to) the word that is already loaded
+        if (stream_word == wb) {  // swap the roles of the two qubits so that qubit a is in the current word
+          u64 lut = 0;
+          unsigned sign = 0;
+          for (unsigned v = 0; v < 16; ++v) {
+            const unsigned vs = ((v & 3u) << 2) | (v >> 2);  // code with a and b exchanged
+            const unsigned img = lut_at(fg.lut, vs);
+            lut |= (u64)(((img & 3u) << 2) | (img >> 2)) << (4 * v);
+            sign |= ((fg.sign >> vs) & 1u) << v;
+          }
+          g.lut = lut;
+          g.sign = (unsigned short)sign;
+          g.ba = (unsigned char)bb;
+          g.bb = (unsigned char)ba;
+          g.sb = (unsigned char)wa;
+        } else {
+          stream_switch(wa);
+          g.sb = (unsigned char)wb;
+        }
+        g.nq = OBP_STREAM_CROSS;
+      } else {
+        stream_switch(wa);
+        if (fg.nq == 2 && (bb == ba + 1 || ba == bb + 1)) {
+          // adjacent bits: pair layout, low bit first: code' = x_lo | x_hi<<1 | z_lo<<2 | z_hi<<3
+          const bool a_low = ba < bb;
+          auto to_std = [&](unsigned vp) {  // pair code -> x_a | z_a<<1 | x_b<<2 | z_b<<3
+            const unsigned xlo = vp & 1u, xhi = (vp >> 1) & 1u, zlo = (vp >> 2) & 1u, zhi = (vp >> 3) & 1u;
+            const unsigned xa = a_low ? xlo : xhi, za = a_low ? zlo : zhi, xb = a_low ? xhi : xlo, zb = a_low ? zhi : zlo;
+            return xa | (za << 1) | (xb << 2) | (zb << 3);
+          };
+          auto to_pair = [&](unsigned vs) {
+            const unsigned xa = vs & 1u, za = (vs >> 1) & 1u, xb = (vs >> 2) & 1u, zb = (vs >> 3) & 1u;
+            const unsigned xlo = a_low ? xa : xb, xhi = a_low ? xb : xa, zlo = a_low ? za : zb, zhi = a_low ? zb : za;
+            return xlo | (xhi << 1) | (zlo << 2) | (zhi << 3);
+          };
+          u64 lut = 0;
+          unsigned sign = 0;
+          for (unsigned vp = 0; vp < 16; ++vp) {
+            const unsigned vs = to_std(vp);
+            lut |= (u64)to_pair(lut_at(fg.lut, vs)) << (4 * vp);
+            sign |= ((fg.sign >> vs) & 1u) << vp;
+          }
+          g.lut = lut;
+          g.sign = (unsigned short)sign;
+          g.ba = (unsigned char)std::min(ba, bb);
+          g.nq = OBP_STREAM_PAIR;
+        }
+      }
+      stream.push_back(g);
+      pb.b.scale = std::min(pb.b.scale, fg.scale);
+      pb.n_ops += fg.n_gates;
+      obp_op fop;
+      memset(&fop, 0, sizeof(fop));
+      fop.n_qubits = fg.nq;
+      fop.qubit[0] = fg.q[0];
+      fop.qubit[1] = fg.q[1];
+      fop.lut = fg.lut;
+      frame_update(ctx, fop);
+      return OBP_OK;
+    }
     int need_new = 0;
     for (int j = 0; j < fg.nq; ++j) {
       bool have = false;
@@ -882,7 +993,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     CliffGate& g = pb.b.g[pb.b.ng++];
     memset(&g, 0, sizeof(g));
     g.lut = fg.lut;
-    g.sign = fg.sign;
+    g.sign = (unsigned short)fg.sign;
     g.nq = (unsigned char)fg.nq;
     g.sa = (unsigned char)pb.slot_of_word(fg.q[0] / 64);
     g.ba = (unsigned char)(fg.q[0] % 64);
@@ -1000,14 +1111,11 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
       rc = flush();
       if (rc) return rc;
     } else {
-      if (op.flags & OBP_FLAG_EXACT_COUNTERS) {
-        rc = release_all();  // its slot must be the program's last
-        if (rc) return rc;
-      }
-      for (int j = 0; j < op.n_qubits; ++j) {
-        rc = release_qubit(op.qubit[j]);
-        if (rc) return rc;
-      }
+      // A rotation changes coefficients, and the raw-row zero filter of a Clifford-class gate
+      // (|c| * row_scale <= atol) must see the coefficients of ITS place in the program: nothing is
+      // held back across a rotation, on whatever qubit.
+      rc = release_all();
+      if (rc) return rc;
       rc = flush();
       if (rc) return rc;
       RotP p = build_rotp(ctx, op, atol);

@@ -305,13 +305,14 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate(Tab t, const __
 // term vanishes iff that is <= atol.  Bijection on keys: no merge is needed and
 // the row's stored hash stays valid because the host re-expresses the hash frame (HashFrame).
 // ================================================================================================
-struct CliffGate {
+struct CliffGate {  // 16 bytes
   u64 lut;
-  unsigned sign;
-  unsigned char sa, ba, sb, bb;  // word slot / bit of qubit a and b
+  unsigned short sign;           // bit v: U^dag sigma_v U = -sigma_lut[v]
+  unsigned char sa, ba, sb, bb;  // word slot / bit of qubit a and b (stream LOAD/STORE: ba = word index)
   unsigned char nq;
-  unsigned char pad[3];
+  unsigned char pad;
 };
+static_assert(sizeof(CliffGate) == 16, "CliffGate must stay 16 bytes");
 
 struct CliffBatch {
   int ng;
@@ -1390,4 +1391,87 @@ __global__ void __launch_bounds__(OBP_BS) k_reset_raw(Tab t, int w, u64 bit) {
       t.xz[w][i] = key;
     }
   }
+}
+
+// ================================================================================================
+// k_clifford_stream — a whole run of Clifford-class gates on a table wider than 128 qubits in ONE
+// pass, with the key words held in registers.  The host turns the run into a stream of micro-ops:
+// LOAD word w into register slot s, gate on (slot, bit) operands, STORE slot s back to word w; it
+// allocates the two slots (LRU), so a brickwork layer over 1000 qubits reads and writes each of the
+// 16 word columns once and the coefficient once (528 B per term per layer) and no shared memory is
+// involved.  The stream is read with warp-uniform loads.
+// ================================================================================================
+#define OBP_STREAM_SWITCH 0x10  // make word `ba` the current word (write the previous one back if it changed)
+#define OBP_STREAM_PAIR 0x20    // two-qubit gate on ADJACENT bits ba, ba+1 of the current word (lut in pair layout)
+#define OBP_STREAM_CROSS 0x30   // two-qubit gate: qubit a = bit ba of the current word, qubit b = bit bb of word sb
+#define OBP_STREAM_MAX 1984     // micro-ops per launch: the stream travels as a kernel parameter (constant bank)
+
+struct CliffStream {
+  int n;
+  int slot;
+  double scale, atol;
+  u64 epoch;
+  CliffGate g[OBP_STREAM_MAX];
+};
+static_assert(sizeof(CliffStream) <= 32764, "kernel parameters are limited to 32764 bytes");
+
+// nq = 1 / 2: gate on bit(s) ba (, bb) of the current word with the usual code x_a | z_a<<1 | x_b<<2 | z_b<<3.
+// OBP_STREAM_PAIR: code = x_a | x_b<<1 | z_a<<2 | z_b<<3 (two adjacent bits of x, two of z): two
+// shifts extract it and two shifts write the flip back — the common case of a brickwork bond.
+__global__ void __launch_bounds__(OBP_BS) k_clifford_stream(Tab t, const __grid_constant__ CliffStream st) {
+  const u64 n = t.st->n_scan;
+  int deaths = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    if (!is_live(c)) continue;
+    if (is_small_scaled(c, st.scale, st.atol)) {
+      t.coef[i] = tombstone(st.epoch);
+      deaths++;
+      continue;
+    }
+    u64 x = 0, z = 0, ox = 0, oz = 0;
+    int cur = -1;
+    unsigned sgn = 0;
+    for (int k = 0; k < st.n; ++k) {
+      const CliffGate g = st.g[k];
+      if (g.nq == OBP_STREAM_PAIR) {
+        const unsigned v = (unsigned)((x >> g.ba) & 3ull) | ((unsigned)((z >> g.ba) & 3ull) << 2);
+        const unsigned nv = (unsigned)(g.lut >> (4 * v)) & 15u;
+        sgn ^= (g.sign >> v) & 1u;
+        const unsigned d = nv ^ v;
+        x ^= (u64)(d & 3u) << g.ba;
+        z ^= (u64)(d >> 2) << g.ba;
+      } else if (g.nq <= 2) {
+        const unsigned dd = cliff_apply_bits(g, x, z, x, z, sgn);
+        x ^= ((u64)(dd & 1u) << g.ba) ^ ((u64)((dd >> 2) & 1u) << g.bb);
+        z ^= ((u64)((dd >> 1) & 1u) << g.ba) ^ ((u64)((dd >> 3) & 1u) << g.bb);
+      } else if (g.nq == OBP_STREAM_SWITCH) {
+        if (cur >= 0 && (x != ox || z != oz)) t.xz[cur][i] = make_ulonglong2(x, z);
+        cur = g.ba;
+        if (cur < OBP_MAX_WORDS) {
+          const ulonglong2 key = t.xz[cur][i];
+          x = ox = key.x;
+          z = oz = key.y;
+        } else {
+          cur = -1;  // end of stream marker: only the write-back above
+        }
+      } else {  // OBP_STREAM_CROSS
+        ulonglong2 kb = t.xz[g.sb][i];
+        CliffGate h = g;
+        h.nq = 2;
+        const unsigned dd = cliff_apply_bits(h, x, z, kb.x, kb.y, sgn);
+        x ^= (u64)(dd & 1u) << g.ba;
+        z ^= (u64)((dd >> 1) & 1u) << g.ba;
+        if (dd >> 2) {
+          kb.x ^= (u64)((dd >> 2) & 1u) << g.bb;
+          kb.y ^= (u64)((dd >> 3) & 1u) << g.bb;
+          t.xz[g.sb][i] = kb;
+        }
+      }
+    }
+    if (sgn) t.coef[i] = make_double2(-c.x, -c.y);
+  }
+  const long long dl = warp_sum_i64((long long)deaths);
+  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+  finish_kernel(t, st.slot);
 }
