@@ -773,15 +773,21 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
   *n_out = n;
   if (n == 0) return OBP_OK;
   if (n > max_rows || !x_words || !z_words || !coeffs) return ctx->fail(OBP_ERR_BADARG, "obp_download: buffer too small");
-  CU(cudaStreamSynchronize(ctx->stream));
-  std::vector<ulonglong2> col(n);
-  for (int w = 0; w < ctx->W; ++w) {
-    CU(cudaMemcpy(col.data(), ctx->xz[w], n * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
-    for (u64 i = 0; i < n; ++i) {
-      x_words[i * ctx->W + w] = col[i].x;
-      z_words[i * ctx->W + w] = col[i].y;
-    }
+  // transpose to the caller's [n][W] layout on the device, then three plain copies
+  u64* stage = nullptr;
+  const size_t words = (size_t)n * ctx->W;
+  if (words * 2 * sizeof(u64) <= ctx->cap * sizeof(ulonglong2) + ctx->cap * sizeof(u64) && ctx->W == 1) {
+    stage = (u64*)ctx->spare16;  // n*2 words fit the compaction scratch
+  } else {
+    CU(cudaMalloc(&stage, words * 2 * sizeof(u64)));
   }
+  k_pack_rows<<<grid_for(ctx, n), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), stage, stage + words, n);
+  cudaError_t e1 = cudaGetLastError();
+  if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+  if (e1 == cudaSuccess) e1 = cudaMemcpy(x_words, stage, words * sizeof(u64), cudaMemcpyDeviceToHost);
+  if (e1 == cudaSuccess) e1 = cudaMemcpy(z_words, stage + words, words * sizeof(u64), cudaMemcpyDeviceToHost);
+  if (stage != (u64*)ctx->spare16) cudaFree(stage);
+  if (e1 != cudaSuccess) return ctx->fail(OBP_ERR_CUDA, std::string("obp_download: ") + cudaGetErrorString(e1));
   CU(cudaMemcpy(coeffs, ctx->coef, n * sizeof(double2), cudaMemcpyDeviceToHost));
   return OBP_OK;
 }

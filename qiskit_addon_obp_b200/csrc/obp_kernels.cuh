@@ -1475,3 +1475,14 @@ __global__ void __launch_bounds__(OBP_BS) k_clifford_stream(Tab t, const __grid_
   if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)(-dl));
   finish_kernel(t, st.slot);
 }
+
+// download: the word columns of row i as consecutive u64 (the caller's [n][W] row-major layout)
+__global__ void __launch_bounds__(OBP_BS) k_pack_rows(Tab t, u64* __restrict__ out_x, u64* __restrict__ out_z, u64 n) {
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    for (int w = 0; w < t.W; ++w) {
+      const ulonglong2 key = t.xz[w][i];
+      out_x[i * t.W + w] = key.x;
+      out_z[i * t.W + w] = key.y;
+    }
+  }
+}
