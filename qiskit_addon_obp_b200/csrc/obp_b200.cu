@@ -76,6 +76,8 @@ struct obp_ctx {
   unsigned char* d_prog = nullptr;  // persistent program: entries + parameter pool (device)
   unsigned char* h_prog = nullptr;  // pinned staging of the same
   size_t prog_alloc = 0;
+  u64* d_stage = nullptr;  // download staging for tables too wide for the compaction scratch
+  size_t stage_bytes = 0;
   u64* d_tbegin = nullptr;
   u64* h_tbegin = nullptr;  // pinned
   bool use_program = true;
@@ -657,6 +659,7 @@ void obp_destroy(obp_ctx* ctx) {
   cudaFree(ctx->d_cnt);
   cudaFree(ctx->d_prog);
   cudaFree(ctx->d_tbegin);
+  cudaFree(ctx->d_stage);
   if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
   if (ctx->h_tbegin) cudaFreeHost(ctx->h_tbegin);
   free_inboxes(ctx);
@@ -774,19 +777,29 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
   if (n == 0) return OBP_OK;
   if (n > max_rows || !x_words || !z_words || !coeffs) return ctx->fail(OBP_ERR_BADARG, "obp_download: buffer too small");
   // transpose to the caller's [n][W] layout on the device, then three plain copies
+  // staging: the compaction scratch when the packed rows fit it, else a buffer kept with the context
+  // (a cudaMalloc/cudaFree pair per download costs far more than the copy itself)
   u64* stage = nullptr;
   const size_t words = (size_t)n * ctx->W;
-  if (words * 2 * sizeof(u64) <= ctx->cap * sizeof(ulonglong2) + ctx->cap * sizeof(u64) && ctx->W == 1) {
-    stage = (u64*)ctx->spare16;  // n*2 words fit the compaction scratch
+  if (words <= ctx->cap) {
+    stage = (u64*)ctx->spare16;  // cap * 16 B = room for 2 * words u64
   } else {
-    CU(cudaMalloc(&stage, words * 2 * sizeof(u64)));
+    if (words * 2 * sizeof(u64) > ctx->stage_bytes) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_stage);
+      ctx->d_stage = nullptr;
+      ctx->stage_bytes = 0;
+      const size_t nb = words * 2 * sizeof(u64) + (words >> 2) * sizeof(u64);
+      CU(cudaMalloc(&ctx->d_stage, nb));
+      ctx->stage_bytes = nb;
+    }
+    stage = ctx->d_stage;
   }
   k_pack_rows<<<grid_for(ctx, n), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), stage, stage + words, n);
   cudaError_t e1 = cudaGetLastError();
   if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
   if (e1 == cudaSuccess) e1 = cudaMemcpy(x_words, stage, words * sizeof(u64), cudaMemcpyDeviceToHost);
   if (e1 == cudaSuccess) e1 = cudaMemcpy(z_words, stage + words, words * sizeof(u64), cudaMemcpyDeviceToHost);
-  if (stage != (u64*)ctx->spare16) cudaFree(stage);
   if (e1 != cudaSuccess) return ctx->fail(OBP_ERR_CUDA, std::string("obp_download: ") + cudaGetErrorString(e1));
   CU(cudaMemcpy(coeffs, ctx->coef, n * sizeof(double2), cudaMemcpyDeviceToHost));
   return OBP_OK;
@@ -812,7 +825,9 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     if (vrc) return vrc;
   }
   // tables of <= 128 qubits: record the program and run it with ONE persistent cooperative launch
-  const bool prog_mode = ctx->use_program && ctx->prog_ctas_per_sm > 0 && ctx->W <= 2;
+  // (large tables keep the stand-alone kernels: a launch is cheap next to a pass over >= 2^18 rows and
+  // k_rotate alone holds one more CTA per SM than the program kernel)
+  const bool prog_mode = ctx->use_program && ctx->prog_ctas_per_sm > 0 && ctx->W <= 2 && ctx->n_dense < (1ull << 18);
   ProgRec prog;
   int n_rot_ops = 0;
   // wider tables: a run of Clifford-class gates becomes one stream of LOAD / gate / STORE micro-ops

@@ -161,19 +161,33 @@ __device__ __forceinline__ void rotate_body(const Tab& t, const RotP& p, const u
 
   // Warps run independently (no CTA barrier): a warp whose rows need long partner probes does not
   // hold back the others.  Rows are taken in warp-sized, fully coalesced chunks.
-  for (u64 base = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)); base < n; base += (u64)gridDim.x * OBP_BS) {
+  // The three streaming loads of a row (coefficient, first generator word, hash) are independent and
+  // are issued together, one iteration ahead of their use (software pipelining): the dependent chain
+  // of an anticommuting row is then index slot -> partner key/coefficient only.
+  const u64 stride = (u64)gridDim.x * OBP_BS;
+  const ulonglong2* __restrict__ col0 = t.xz[p.gw[0]];
+  u64 i_next = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)) + lane;
+  double2 c_next = make_double2(0.0, 0.0);
+  ulonglong2 k_next = make_ulonglong2(0ull, 0ull);
+  u64 h_next = 0;
+  if (i_next < n) { c_next = t.coef[i_next]; k_next = col0[i_next]; h_next = t.hash[i_next]; }
+  for (u64 base = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)); base < n; base += stride) {
     const u64 i = base + lane;
+    const double2 c = c_next;
+    const ulonglong2 key0 = k_next;
+    const u64 h_own = h_next;
+    i_next = i + stride;
+    if (i_next < n) { c_next = t.coef[i_next]; k_next = col0[i_next]; h_next = t.hash[i_next]; }
     bool want_append = false;
     double2 app_c = make_double2(0.0, 0.0);
     if (i < n) {
-      const double2 c = t.coef[i];
       if (is_live(c)) {
         // commutation parity and phase exponent from the generator's words only
         int sp = 0, E = p.yG, own_bit = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k < p.ngw) {
-            const ulonglong2 key = t.xz[p.gw[k]][i];
+            const ulonglong2 key = k == 0 ? key0 : t.xz[p.gw[k]][i];
             const u64 m = p.gx[k] | p.gz[k];
             sp += __popcll(key.x & p.gz[k]) + __popcll(key.y & p.gx[k]);
             E += __popcll(key.x & key.y & m) - __popcll((key.x ^ p.gx[k]) & (key.y ^ p.gz[k]) & m) +
@@ -196,7 +210,7 @@ __device__ __forceinline__ void rotate_body(const Tab& t, const RotP& p, const u
           }
         } else {
           const RowSet rp = rot_rows(c, E, s, p);
-          const u64 h2 = t.hash[i] ^ p.hG;
+          const u64 h2 = h_own ^ p.hG;
           double2 cq;
           bool fresh;
           const long long j = find_partner(t, p, i, h2, n, cq, fresh);
@@ -265,7 +279,7 @@ __device__ __forceinline__ void rotate_body(const Tab& t, const RotP& p, const u
             key.y ^= gz;
             t.xz[w][row] = key;
           }
-          const u64 h2 = t.hash[i] ^ p.hG;
+          const u64 h2 = h_own ^ p.hG;
           t.coef[row] = app_c;
           t.hash[row] = h2;
           if (!index_insert(t, h2, row)) atomicOr(&t.st->error, OBP_ERR_BIT_INDEX);
