@@ -202,6 +202,15 @@ int obp_inbox_export(obp_ctx* ctx, int32_t which, void* handle64, uint64_t* raw_
  * with handle64 == NULL, by the raw device pointer (same process). */
 int obp_inbox_attach(obp_ctx* ctx, int32_t peer_rank, int32_t which, const void* handle64, uint64_t raw_ptr);
 int obp_rotate_emit_p2p(obp_ctx* ctx, const obp_op* op, double atol, int32_t peer_rank, obp_shard_counters* out);
+/* device_flags != 0 (one process per GPU only): obp_apply_ops_sharded no longer stops at a rotation
+ * that needs a peer; it enqueues emit -> merge -> finish itself and the kernels of the two ranks are
+ * ordered by flag words in the inbox headers (the merge kernel waits on the device until the peer's
+ * emit kernel has raised `emitted`, the emit kernel waits until the peer has raised `merged` for the
+ * inbox's previous use).  No host synchronisation or NCCL call per exchange. */
+int obp_set_shard_sync(obp_ctx* ctx, int32_t device_flags);
+/* Counters of the split rotation that ended the last obp_apply_ops_sharded program in device-flag
+ * mode (out->n_in == 0: the program did not end on one). */
+int obp_last_split_counters(obp_ctx* ctx, obp_shard_counters* out);
 int obp_rotate_merge_inbox(obp_ctx* ctx, obp_shard_counters* out);
 
 /* Stepwise truncation: truncate_binary_search (utils/truncating.py:171-204) with the maximum

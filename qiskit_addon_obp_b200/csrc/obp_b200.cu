@@ -70,6 +70,9 @@ struct obp_ctx {
   std::vector<u64*> peer_inbox[2];     // per rank: its inbox as mapped into this process (nullptr = not attached)
   std::vector<bool> peer_is_ipc[2];
   int xchg_parity = 0;
+  bool last_split_is_last_op = false;  // the program just run ended on a handshake split rotation (counters in h_cnt)
+  bool flag_sync = false;  // split rotations are ordered by device-side flags, no host barrier
+  u64 xseq = 0;            // split rotations run so far (identical on all ranks)
   bool shard_rot_open = false;
   int rot_ctas_per_sm = 0;  // resident CTAs of k_rotate per SM (occupancy API)
   int prog_ctas_per_sm = 0; // resident CTAs of k_program per SM; 0 = cooperative launch unavailable
@@ -201,6 +204,7 @@ int sync_state(obp_ctx* ctx) {
     const unsigned e = ctx->h_st->error;
     ctx->h_st->error = 0;
     cudaMemsetAsync(&ctx->d_st->error, 0, sizeof(unsigned), ctx->stream);
+    if (e & OBP_ERR_BIT_PEER) return ctx->fail(OBP_ERR_CUDA, "sharded table: a peer rank's flag did not arrive within 10 s");
     return ctx->fail(OBP_ERR_CAPACITY, (e & OBP_ERR_BIT_CAP) ? "term table capacity exceeded"
                                                               : "hash index full");
   }
@@ -827,9 +831,10 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   // tables of <= 128 qubits: record the program and run it with ONE persistent cooperative launch
   // (large tables keep the stand-alone kernels: a launch is cheap next to a pass over >= 2^18 rows and
   // k_rotate alone holds one more CTA per SM than the program kernel)
-  const bool prog_mode = ctx->use_program && ctx->prog_ctas_per_sm > 0 && ctx->W <= 2 && ctx->n_dense < (1ull << 18);
+  const bool prog_mode = ctx->use_program && ctx->prog_ctas_per_sm > 0 && ctx->W <= 2 && ctx->n_dense < (1ull << 18) && !ctx->flag_sync;
   ProgRec prog;
   int n_rot_ops = 0;
+  int last_split = -1;  // index of the last split rotation run with the device-side handshake
   // wider tables: a run of Clifford-class gates becomes one stream of LOAD / gate / STORE micro-ops
   const bool stream_mode = ctx->W > 2;
   std::vector<CliffGate> stream;
@@ -1140,6 +1145,38 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
       rc = flush();
       if (rc) return rc;
       RotP p = build_rotp(ctx, op, atol);
+      if (ctx->n_ranks > 1 && (p.hG >> ctx->owner_shift) != 0 && ctx->flag_sync) {
+        // Split rotation without leaving the device: emit into the peer's inbox, merge what the peer
+        // emitted into ours, finish — the three kernels are ordered across GPUs by flags in the inbox
+        // headers (cta_wait_flag / finish_kernel_flag), the host does not synchronise.
+        const int peer_rank = ctx->rank ^ (int)(p.hG >> ctx->owner_shift);
+        const u64 seq = ++ctx->xseq;
+        const int b = (int)(seq & 1ull);
+        if (!ctx->inbox[b] || !ctx->peer_inbox[b][peer_rank]) return ctx->fail(OBP_ERR_BADARG, "sharded table: peer inbox not attached");
+        u64* peer = ctx->peer_inbox[b][peer_rank];
+        u64* mine = ctx->inbox[b];
+        p.epoch = ++ctx->epoch;
+        p.slot = n_slots;
+        CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));
+        {
+          Bracket br(ctx, OBP_K_ROTATE, 3);
+          k_rotate_emit<<<grid_for(ctx, bound, ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(
+              t, p, peer + OBP_INBOX_HDR, ctx->inbox_cap, peer + OBP_HDR_CURSOR, ctx->d_cnt,
+              peer + OBP_HDR_MERGED, seq >= 2 ? seq - 2 : 0, peer + OBP_HDR_EMITTED, seq);
+          k_merge_records<<<grid_for(ctx, std::min<u64>(ctx->inbox_cap, std::max<u64>(2 * bound, 1 << 14))), OBP_BS, 0,
+                            ctx->stream>>>(t, mine + OBP_INBOX_HDR, 0, mine + OBP_HDR_CURSOR, ctx->inbox_cap, ctx->d_cnt,
+                                           mine + OBP_HDR_EMITTED, seq);
+          bound = std::min<u64>(ctx->cap, bound * 2);
+          k_rotate_finish<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, p, ctx->d_cnt, mine, seq);
+          CU(cudaGetLastError());
+        }
+        slot_of_op[k] = n_slots;
+        slot_gates.push_back(1);
+        n_slots++;
+        n_rot_ops++;
+        last_split = k;
+        continue;
+      }
       if (ctx->n_ranks > 1 && (p.hG >> ctx->owner_shift) != 0) {
         // partner keys of this rotation belong to rank ^ d: the caller runs the split rotation
         if (!n_done || !peer_xor) return ctx->fail(OBP_ERR_BADARG, "sharded table: use obp_apply_ops_sharded");
@@ -1205,8 +1242,10 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     else CU(cudaLaunchCooperativeKernel((void*)k_program<2>, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
     CU(cudaMemcpyAsync(ctx->h_tbegin, ctx->d_tbegin, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
   }
+  if (last_split >= 0) CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat) * (n_slots + n_entries), cudaMemcpyDeviceToHost, ctx->stream));
   const int sync_rc = sync_state(ctx);
+  ctx->last_split_is_last_op = last_split >= 0 && last_split == n_ops - 1;
   if (sync_rc && sync_rc != OBP_ERR_CAPACITY) return sync_rc;
   if (prog_mode && ctx->prof_on) {  // per-class device time from the stamps taken at the grid barriers
     u64 t_prev = *ctx->h_tbegin;
@@ -1302,6 +1341,29 @@ int obp_set_shard(obp_ctx* ctx, int32_t n_ranks, int32_t rank) {
   return OBP_OK;
 }
 
+int obp_set_shard_sync(obp_ctx* ctx, int32_t device_flags) {
+  if (!ctx) return OBP_ERR_BADARG;
+  ctx->flag_sync = device_flags != 0;
+  return OBP_OK;
+}
+
+int obp_last_split_counters(obp_ctx* ctx, obp_shard_counters* out) {
+  if (!ctx || !out) return OBP_ERR_BADARG;
+  memset(out, 0, sizeof(*out));
+  if (!ctx->last_split_is_last_op) return OBP_OK;  // n_records stays 0, n_in 0: "no split rotation ended the program"
+  const ShardCnt& c = *ctx->h_cnt;
+  out->n_out = ctx->n_live;
+  out->n_dense = ctx->n_dense;
+  out->rows_surv = c.rows_surv;
+  out->keys_present = c.keys_present;
+  out->cancelled = c.cancelled;
+  out->n_records = c.n_records;
+  out->sum_trimmed[0] = c.sum_re;
+  out->sum_trimmed[1] = c.sum_im;
+  out->n_in = 1;  // marker: valid
+  return OBP_OK;
+}
+
 uint64_t obp_record_bytes(int n_qubits) {
   const u64 W = (u64)std::max(1, (n_qubits + 63) / 64);
   return (2 * W + 3) * sizeof(u64);
@@ -1337,7 +1399,7 @@ int obp_rotate_emit(obp_ctx* ctx, const obp_op* op, double atol, void* d_records
   {
     Bracket br(ctx, OBP_K_ROTATE);
     k_rotate_emit<<<grid_for(ctx, std::max<u64>(ctx->n_dense, 1), ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(
-        make_tab(ctx), p, (u64*)d_records, cap_records, &ctx->d_cnt->n_records, ctx->d_cnt);
+        make_tab(ctx), p, (u64*)d_records, cap_records, &ctx->d_cnt->n_records, ctx->d_cnt, nullptr, 0, nullptr, 0);
     CU(cudaGetLastError());
   }
   CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1361,9 +1423,9 @@ int obp_rotate_merge(obp_ctx* ctx, const void* d_records, uint64_t n_records, ob
     Bracket br(ctx, OBP_K_ROTATE);
     if (n_records)
       k_merge_records<<<grid_for(ctx, n_records), OBP_BS, 0, ctx->stream>>>(t, (const u64*)d_records, n_records, nullptr, 0,
-                                                                          ctx->d_cnt);
+                                                                          ctx->d_cnt, nullptr, 0);
     const u64 bound = std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense + n_records, 1));
-    k_rotate_finish<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, ctx->shard_rot, ctx->d_cnt);
+    k_rotate_finish<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, ctx->shard_rot, ctx->d_cnt, nullptr, 0);
     CU(cudaGetLastError());
   }
   CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1395,6 +1457,7 @@ int obp_inbox_create(obp_ctx* ctx, uint64_t cap_records) {
   }
   ctx->inbox_cap = cap_records;
   ctx->xchg_parity = 0;
+  ctx->xseq = 0;
   return OBP_OK;
 }
 
@@ -1464,7 +1527,7 @@ int obp_rotate_emit_p2p(obp_ctx* ctx, const obp_op* op, double atol, int32_t pee
   {
     Bracket br(ctx, OBP_K_ROTATE);
     k_rotate_emit<<<grid_for(ctx, std::max<u64>(ctx->n_dense, 1), ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(
-        make_tab(ctx), p, peer + OBP_INBOX_HDR, ctx->inbox_cap, peer, ctx->d_cnt);
+        make_tab(ctx), p, peer + OBP_INBOX_HDR, ctx->inbox_cap, peer, ctx->d_cnt, nullptr, 0, nullptr, 0);
     CU(cudaGetLastError());
   }
   CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1490,9 +1553,9 @@ int obp_rotate_merge_inbox(obp_ctx* ctx, obp_shard_counters* out) {
     // the peer emits at most one record per row it holds; shards are balanced, so size the grid on ours
     const u64 guess = std::min<u64>(ctx->inbox_cap, std::max<u64>(2 * ctx->n_dense, 1 << 14));
     k_merge_records<<<grid_for(ctx, guess), OBP_BS, 0, ctx->stream>>>(t, ctx->inbox[b] + OBP_INBOX_HDR, 0, ctx->inbox[b],
-                                                                     ctx->inbox_cap, ctx->d_cnt);
+                                                                     ctx->inbox_cap, ctx->d_cnt, nullptr, 0);
     const u64 bound = std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense + guess, 1));
-    k_rotate_finish<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, ctx->shard_rot, ctx->d_cnt);
+    k_rotate_finish<<<grid_for(ctx, bound), OBP_BS, 0, ctx->stream>>>(t, ctx->shard_rot, ctx->d_cnt, nullptr, 0);
     CU(cudaGetLastError());
   }
   CU(cudaMemsetAsync(ctx->inbox[b], 0, sizeof(u64), ctx->stream));  // cursor back to 0 for the rotation after next

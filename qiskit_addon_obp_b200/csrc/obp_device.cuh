@@ -22,6 +22,7 @@ typedef unsigned long long u64;
 #define OBP_EMPTY (~0ull)     // empty index slot
 #define OBP_ERR_BIT_CAP 1u    // dense table full
 #define OBP_ERR_BIT_INDEX 2u  // index probe wrapped around
+#define OBP_ERR_BIT_PEER 4u   // a peer's flag did not arrive in time (sharded table, device-side handshake)
 #define OBP_CLIFF_BATCH 96    // Clifford gates fused into one launch
 
 struct DevState {
@@ -173,4 +174,60 @@ __device__ __forceinline__ bool index_insert(const Tab& t, u64 h, u64 row) {
     s = (s + 1) & t.mask;
   }
   return false;
+}
+
+// ---- device-side handshake between ranks (sharded table) ----------------------------------------
+// Inbox header words: [0] record cursor, [1] emitted_seq (set by the SENDER's kernel when all its
+// records are visible), [2] merged_seq (set by the OWNER when it has consumed the inbox).
+#define OBP_HDR_CURSOR 0
+#define OBP_HDR_EMITTED 1
+#define OBP_HDR_MERGED 2
+
+__device__ __forceinline__ u64 globaltimer_ns() {
+  u64 v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+
+// Thread 0 of the CTA waits until *flag >= want (the flag may live in a peer GPU's memory), then the
+// CTA proceeds.  The waited-for kernel runs on ANOTHER GPU; a 10 s timeout turns a lost peer into an
+// error flag instead of a hang.
+__device__ __forceinline__ void cta_wait_flag(const u64* flag, u64 want, unsigned* err) {
+  if (flag != nullptr) {
+    if (threadIdx.x == 0) {
+      const u64 t0 = globaltimer_ns();
+      // once a wait has timed out, later waits give up at once: the run is lost, it must not hang
+      while (ld_volatile(flag) < want && !(*(volatile unsigned*)err & OBP_ERR_BIT_PEER)) {
+        if (globaltimer_ns() - t0 > 10000000000ull) {
+          atomicOr(err, OBP_ERR_BIT_PEER);
+          break;
+        }
+        __nanosleep(100);
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
+}
+
+// finish_kernel() plus: the last CTA raises a flag word (possibly in a peer's memory) once every
+// CTA's stores are visible system-wide; `also_zero` (optional) is cleared just before.
+__device__ __forceinline__ void finish_kernel_flag(const Tab& t, int slot, u64* flag, u64 value, u64* also_zero) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&t.st->ticket, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      u64 na = atomicAdd(&t.st->n_append, 0ull);
+      if (na > t.cap) na = t.cap;
+      t.st->n_append = na;
+      t.st->n_scan = na;
+      if (slot >= 0) t.ops[slot].n_out = atomicAdd(&t.st->n_live, 0ull);
+      t.st->ticket = 0;
+      if (also_zero) *(volatile u64*)also_zero = 0ull;
+      __threadfence_system();
+      if (flag) *(volatile u64*)flag = value;
+    }
+  }
 }

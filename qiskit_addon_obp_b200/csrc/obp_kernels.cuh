@@ -1004,7 +1004,11 @@ struct ShardCnt {  // per-call counters (device), summed over ranks by the host
 __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, const __grid_constant__ RotP p,
                                                                       u64* __restrict__ rec, u64 rec_cap,
                                                                       u64* __restrict__ cursor,
-                                                                      ShardCnt* __restrict__ cnt) {
+                                                                      ShardCnt* __restrict__ cnt,
+                                                                      const u64* wait_flag, u64 wait_val,
+                                                                      u64* done_flag, u64 done_val) {
+  // device-side handshake: the peer must have consumed this inbox's previous contents
+  cta_wait_flag(wait_flag, wait_val, &t.st->error);
   const u64 n = t.st->n_scan;
   const unsigned lane = threadIdx.x & 31u;
   const int RW = 2 * t.W + 3;
@@ -1090,14 +1094,17 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, con
     if (ne && cursor != &cnt->n_records) atomicAdd(&cnt->n_records, ne);
     if (dl) atomicAdd(&t.st->n_live, (u64)dl);
   }
-  __threadfence_system();  // records written into a peer's memory must be visible before the kernel ends
-  finish_kernel(t, -1);
+  // records written into a peer's memory must be visible before the kernel ends / the flag is raised
+  finish_kernel_flag(t, p.slot, done_flag, done_val, nullptr);
 }
 
 // One thread per incoming record: add to the live row with that key, or append it.
 __global__ void __launch_bounds__(OBP_BS) k_merge_records(Tab t, const u64* __restrict__ rec, u64 n_rec,
                                                            const u64* __restrict__ n_rec_ptr, u64 rec_cap,
-                                                           ShardCnt* __restrict__ cnt) {
+                                                           ShardCnt* __restrict__ cnt,
+                                                           const u64* wait_flag, u64 wait_val) {
+  // device-side handshake: the sender's kernel (on another GPU) has finished writing this inbox
+  cta_wait_flag(wait_flag, wait_val, &t.st->error);
   if (n_rec_ptr) {  // inbox filled by the peer's kernel: the count is the inbox cursor
     n_rec = ld_volatile(n_rec_ptr);
     if (n_rec > rec_cap) {
@@ -1188,7 +1195,7 @@ __global__ void __launch_bounds__(OBP_BS) k_merge_records(Tab t, const u64* __re
 // the reference's counters are wanted).  A row still pending holds a key without any surviving raw
 // row: it disappears without being counted.
 __global__ void __launch_bounds__(OBP_BS) k_rotate_finish(Tab t, const __grid_constant__ RotP p,
-                                                           ShardCnt* __restrict__ cnt) {
+                                                           ShardCnt* __restrict__ cnt, u64* inbox_hdr, u64 merged_val) {
   const u64 n = t.st->n_scan;
   unsigned cancelled = 0;
   int deaths = 0;
@@ -1226,7 +1233,9 @@ __global__ void __launch_bounds__(OBP_BS) k_rotate_finish(Tab t, const __grid_co
     if (dl) atomicAdd(&t.st->n_live, (u64)(-dl));
     if (cz) { atomicAdd(&cnt->cancelled, cz); atomicAdd(&cnt->sum_re, sr); atomicAdd(&cnt->sum_im, si); }
   }
-  finish_kernel(t, -1);
+  // handshake mode: empty the inbox (cursor) and tell the senders that it is free again
+  finish_kernel_flag(t, p.slot, inbox_hdr ? inbox_hdr + OBP_HDR_MERGED : nullptr, merged_val,
+                     inbox_hdr ? inbox_hdr + OBP_HDR_CURSOR : nullptr);
 }
 
 // At load: rows whose hash belongs to another rank are dropped (every rank is given the full operator).

@@ -147,6 +147,8 @@ def lib() -> C.CDLL:
         "obp_inbox_attach": ([vp, C.c_int32, C.c_int32, vp, C.c_uint64], C.c_int),
         "obp_rotate_emit_p2p": ([vp, vp, C.c_double, C.c_int32, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_rotate_merge_inbox": ([vp, C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_set_shard_sync": ([vp, C.c_int32], C.c_int),
+        "obp_last_split_counters": ([vp, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_trunc_begin": ([vp, C.c_int32, f64p], C.c_int),
         "obp_trunc_masked_sum": ([vp, C.c_double, f64p], C.c_int),
         "obp_trunc_finish": ([vp, C.c_double, u64p, u64p], C.c_int),
@@ -167,7 +169,8 @@ EXPORTED_SYMBOLS = (
     "obp_union_count obp_snapshot obp_restore obp_reserve obp_profile_enable obp_profile_get "
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
-    "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox"
+    "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
+    "obp_last_split_counters"
 ).split()
 
 
@@ -215,6 +218,7 @@ class TermTable:
                 t.n = t.n_dense = 0
                 t.zero_operator = False
                 t.set_shard(1, 0)
+                t.set_shard_sync(False)
                 return t
         return cls(num_qubits, capacity, device)
 
@@ -525,6 +529,15 @@ class TermTable:
             self._check(rc, "obp_rotate_merge_inbox")
         self.n, self.n_dense = out.n_out, out.n_dense
         return out, rc == OBP_ERR_CAPACITY
+
+    def set_shard_sync(self, device_flags: bool):
+        self._check(self._lib.obp_set_shard_sync(self._h, int(bool(device_flags))), "obp_set_shard_sync")
+
+    def last_split_counters(self) -> ObpShardCounters | None:
+        """Counters of the split rotation that ended the last program (device-flag mode), else ``None``."""
+        out = ObpShardCounters()
+        self._check(self._lib.obp_last_split_counters(self._h, C.byref(out)), "obp_last_split_counters")
+        return out if out.n_in else None
 
     def trunc_begin(self, p_norm: int) -> float:
         mx = C.c_double()

@@ -201,8 +201,15 @@ class ShardedTable:
         for r, t in self.tables.items():
             t.set_shard(comm.n_ranks, r)
         self.p2p = os.environ.get("OBP_B200_P2P", "1") not in ("0", "")
+        # one process per GPU: split rotations are ordered by device-side flags, the host never waits
+        self.device_flags = (
+            self.p2p and isinstance(comm, DistComm) and comm.backend == "nccl"
+            and os.environ.get("OBP_B200_DEVICE_FLAGS", "1") not in ("0", "")
+        )
         if self.p2p:
             self._setup_inboxes(per_rank)
+        for t in self.tables.values():
+            t.set_shard_sync(self.device_flags)
         self.n = 0
         self.n_dense = 0
         self.zero_operator = False
@@ -309,6 +316,19 @@ class ShardedTable:
         updates = 0
         last: dict | None = None  # per-rank counters of the last executed op
         tdev = torch.device("cuda", self.device)
+        if self.device_flags:
+            # the whole program in one call: exchanges are ordered on the devices (inbox header flags)
+            t0 = time.perf_counter()
+            (r, t), = self.tables.items()
+            st, done, peer, failed = t.apply_ops_sharded(ops, atol)
+            if done != len(ops) or peer != 0:
+                raise RuntimeError("device-flag mode: the program did not run to its end")
+            updates = int(st.updates)
+            split = t.last_split_counters()
+            last = {"kind": "local", "stats": {r: st}, "op": ops[-1]} if split is None else {
+                "kind": "split-fused", "stats": {r: st}, "cnt": {r: split}, "op": ops[-1]}
+            pos = len(ops)
+            self.t_phase["local"] += time.perf_counter() - t0
         while pos < len(ops):
             seg = ops[pos:]
             done = peer = 0
@@ -392,6 +412,15 @@ class ShardedTable:
             out.sum_trimmed = [float(sums[0]), float(sums[1])]
             # a Clifford-class gate's coset count sees only rank-local members of a coset
             out.counters_valid = int(last["op"]["kind"]) == OBP_OP_ROTATION or self.comm.n_ranks == 1
+        elif last["kind"] == "split-fused":
+            vals = {r: [last["stats"][r].n_in, c.rows_surv, c.keys_present, c.cancelled] for r, c in last["cnt"].items()}
+            sums = {r: [c.sum_trimmed[0], c.sum_trimmed[1]] for r, c in last["cnt"].items()}
+            tot = self.comm.allreduce_sum_int(vals)
+            sm = self.comm.allreduce_sum(sums)
+            n_in, rows_surv, keys, cancelled = (int(v) for v in tot)
+            out.n_in, out.num_unique, out.num_duplicate = n_in, keys, rows_surv - keys
+            out.num_trimmed = n_in * k2 - rows_surv + cancelled
+            out.sum_trimmed = [float(sm[0]), float(sm[1])]
         else:
             vals, sums = {}, {}
             for r in self.tables:
