@@ -53,6 +53,10 @@ class LocalComm:
     def allreduce_sum_int(self, vals: dict) -> np.ndarray:
         return np.sum([np.asarray(vals[r], dtype=np.int64) for r in self.local_ranks], axis=0)
 
+    def allreduce_pair(self, ints: dict, floats: dict) -> tuple[np.ndarray, np.ndarray]:
+        """Sum an int64 vector and a float64 vector over the ranks (one round trip)."""
+        return self.allreduce_sum_int(ints), self.allreduce_sum(floats)
+
     def gather_operators(self, ops: dict) -> SparsePauliOp:
         return _concat([ops[r] for r in self.local_ranks])
 
@@ -123,6 +127,17 @@ class DistComm:
 
     def allreduce_sum_int(self, vals: dict) -> np.ndarray:
         return self._allreduce(vals, self.dist.ReduceOp.SUM, self.torch.int64)
+
+    def allreduce_pair(self, ints: dict, floats: dict) -> tuple[np.ndarray, np.ndarray]:
+        """Sum an int64 vector and a float64 vector over the ranks: both collectives in flight together."""
+        torch = self.torch
+        ti = torch.as_tensor(np.asarray(ints[self.rank], dtype=np.int64)).to(self.tdev, non_blocking=True)
+        tf = torch.as_tensor(np.asarray(floats[self.rank], dtype=np.float64)).to(self.tdev, non_blocking=True)
+        wi = self.dist.all_reduce(ti, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+        wf = self.dist.all_reduce(tf, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+        wi.wait()
+        wf.wait()
+        return ti.cpu().numpy(), tf.cpu().numpy()
 
     def barrier(self) -> None:
         if self.tdev.type == "cuda":
@@ -385,56 +400,57 @@ class ShardedTable:
             self.exchanged_records += sum(counts.values())
             last = {"kind": "split", "emit": emit, "merge": merge, "op": op[0]}
             pos += 1
+        # one combined reduction per program: overflow flag, row counts, update count, last-op counters
         t0 = time.perf_counter()
-        self._raise_if_any(failed, "sharded gate program")
-        self._sync_counts()
-        out.updates = int(self.comm.allreduce_sum_int({r: [updates if r == min(self.tables) else 0] for r in self.tables})[0])
-        self._fill_last(out, last, ops[-1])
+        first = min(self.tables)
+        ints, floats = {}, {}
+        for r, t in self.tables.items():
+            c4, f2 = self._last_local(last, r)
+            ints[r] = [1 if (failed and r == first) else 0, t.n, t.n_dense, updates if r == first else 0, *c4]
+            floats[r] = f2
+        ti, tf = self.comm.allreduce_pair(ints, floats)
+        self.n, self.n_dense = int(ti[1]), int(ti[2])
+        if ti[0] > 0:
+            raise CapacityError("sharded gate program: a shard overflowed its table")
+        out.updates = int(ti[3])
+        self._fill_last(out, last, ops[-1], [int(v) for v in ti[4:8]], [float(tf[0]), float(tf[1])])
         self.t_phase["reduce"] += time.perf_counter() - t0
         out.n_out, out.n_dense = self.n, self.n_dense
         if self.n == 0:
             self.zero_operator = True
         return out
 
-    def _fill_last(self, out: _Stats, last, last_op) -> None:
-        """Whole-table simplify counters of the program's last op from the per-rank pieces."""
+    @staticmethod
+    def _last_local(last, r) -> tuple[list[int], list[float]]:
+        """This rank's four integer counters and the trimmed sum of the program's last op."""
+        if last is None:
+            return [0, 0, 0, 0], [0.0, 0.0]
+        if last["kind"] == "local":
+            st = last["stats"][r]
+            return [int(st.n_in), int(st.num_unique), int(st.num_duplicate), int(st.num_trimmed)], list(st.sum_trimmed)
+        if last["kind"] == "split-fused":
+            c = last["cnt"][r]
+            return [int(last["stats"][r].n_in), int(c.rows_surv), int(c.keys_present), int(c.cancelled)], list(c.sum_trimmed)
+        e, m = last["emit"][r], last["merge"][r]
+        return [int(e.n_in), int(e.rows_surv), int(e.keys_present + m.keys_present), int(m.cancelled)], list(m.sum_trimmed)
+
+    def _fill_last(self, out: _Stats, last, last_op, tot: list[int], sums: list[float]) -> None:
+        """Whole-table simplify counters of the program's last op from the summed per-rank pieces."""
         k2 = int(last_op["n_components"]) ** 2
         if last is None:
             out.counters_valid = False
             return
+        out.sum_trimmed = sums
         if last["kind"] == "local":
-            vals = {
-                r: [st.n_in, st.num_unique, st.num_duplicate, st.num_trimmed] for r, st in last["stats"].items()
-            }
-            tot = self.comm.allreduce_sum_int(vals)
-            sums = self.comm.allreduce_sum({r: list(st.sum_trimmed) for r, st in last["stats"].items()})
-            out.n_in, out.num_unique, out.num_duplicate, out.num_trimmed = (int(v) for v in tot)
-            out.sum_trimmed = [float(sums[0]), float(sums[1])]
+            out.n_in, out.num_unique, out.num_duplicate, out.num_trimmed = tot
             # a Clifford-class gate's coset count sees only rank-local members of a coset
             out.counters_valid = int(last["op"]["kind"]) == OBP_OP_ROTATION or self.comm.n_ranks == 1
-        elif last["kind"] == "split-fused":
-            vals = {r: [last["stats"][r].n_in, c.rows_surv, c.keys_present, c.cancelled] for r, c in last["cnt"].items()}
-            sums = {r: [c.sum_trimmed[0], c.sum_trimmed[1]] for r, c in last["cnt"].items()}
-            tot = self.comm.allreduce_sum_int(vals)
-            sm = self.comm.allreduce_sum(sums)
-            n_in, rows_surv, keys, cancelled = (int(v) for v in tot)
-            out.n_in, out.num_unique, out.num_duplicate = n_in, keys, rows_surv - keys
-            out.num_trimmed = n_in * k2 - rows_surv + cancelled
-            out.sum_trimmed = [float(sm[0]), float(sm[1])]
-        else:
-            vals, sums = {}, {}
-            for r in self.tables:
-                e, m = last["emit"][r], last["merge"][r]
-                vals[r] = [e.n_in, e.rows_surv, e.keys_present + m.keys_present, m.cancelled]
-                sums[r] = [m.sum_trimmed[0], m.sum_trimmed[1]]
-            tot = self.comm.allreduce_sum_int(vals)
-            sm = self.comm.allreduce_sum(sums)
-            n_in, rows_surv, keys, cancelled = (int(v) for v in tot)
+        else:  # a split rotation: rows counted where produced, keys where they live
+            n_in, rows_surv, keys, cancelled = tot
             out.n_in = n_in
             out.num_unique = keys
             out.num_duplicate = rows_surv - keys
             out.num_trimmed = n_in * k2 - rows_surv + cancelled
-            out.sum_trimmed = [float(sm[0]), float(sm[1])]
         out.raw_rows = out.n_in * k2
 
     def apply_generic(self, qubits, codes, coeffs, atol: float):

@@ -49,6 +49,8 @@ def _worker(rank: int, world: int, port: int, q):
         assert comm.allreduce_sum({rank: [1.5 + rank, 2.0]}).tolist() == [4.0, 4.0]
         assert comm.allreduce_max({rank: [0.25 * (rank + 1)]}).tolist() == [0.5]
         assert comm.allreduce_sum_int({rank: [10 + rank, 7]}).tolist() == [21, 14]
+        ti, tf = comm.allreduce_pair({rank: [1, rank, 5]}, {rank: [0.5, float(rank)]})
+        assert ti.tolist() == [2, 1, 10] and tf.tolist() == [1.0, 1.0]
         # operator gather: rank order, packed words preserved
         xw = np.full((2 + rank, 1), rank + 1, dtype="<u8")
         op = SparsePauliOp.from_packed(xw, xw * 2, np.full(2 + rank, rank + 0.5), 5)
@@ -90,3 +92,5 @@ def test_local_comm_matches_protocol():
     assert got == {0: ("buf3", 13), 1: ("buf2", 12), 2: ("buf1", 11), 3: ("buf0", 10)}
     assert comm.allreduce_sum({r: [r, 1.0] for r in range(4)}).tolist() == [6.0, 4.0]
     assert comm.allreduce_max({r: [float(r)] for r in range(4)}).tolist() == [3.0]
+    ti, tf = comm.allreduce_pair({r: [1, r] for r in range(4)}, {r: [0.25] for r in range(4)})
+    assert ti.tolist() == [4, 6] and tf.tolist() == [1.0]
