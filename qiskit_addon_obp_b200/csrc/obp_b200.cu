@@ -79,6 +79,9 @@ struct obp_ctx {
   unsigned char* d_prog = nullptr;  // persistent program: entries + parameter pool (device)
   unsigned char* h_prog = nullptr;  // pinned staging of the same
   size_t prog_alloc = 0;
+  TruncState* d_ts = nullptr;
+  TruncState* h_ts = nullptr;  // pinned
+  int trunc_ctas_per_sm = 0;  // resident CTAs of k_trunc_search per SM; 0 = cooperative launch unavailable
   u64* d_stage = nullptr;  // download staging for tables too wide for the compaction scratch
   size_t stage_bytes = 0;
   u64* d_tbegin = nullptr;
@@ -633,6 +636,10 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
       if (ctx->W == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prog_ctas_per_sm, k_program<1>, OBP_BS, 0));
       else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prog_ctas_per_sm, k_program<2>, OBP_BS, 0));
     }
+    if (prop.cooperativeLaunch)
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->trunc_ctas_per_sm, k_trunc_search, OBP_BS, 0));
+    CU(cudaMalloc(&ctx->d_ts, sizeof(TruncState)));
+    CU(cudaMallocHost(&ctx->h_ts, sizeof(TruncState)));
     CU(cudaMalloc(&ctx->d_tbegin, sizeof(u64)));
     CU(cudaMallocHost(&ctx->h_tbegin, sizeof(u64)));
     {
@@ -664,6 +671,8 @@ void obp_destroy(obp_ctx* ctx) {
   cudaFree(ctx->d_prog);
   cudaFree(ctx->d_tbegin);
   cudaFree(ctx->d_stage);
+  cudaFree(ctx->d_ts);
+  if (ctx->h_ts) cudaFreeHost(ctx->h_ts);
   if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
   if (ctx->h_tbegin) cudaFreeHost(ctx->h_tbegin);
   free_inboxes(ctx);
@@ -1872,6 +1881,36 @@ int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double
   if (n_removed) *n_removed = 0;
   if (n_out) *n_out = ctx->n_live;
   if (ctx->n_live == 0) return OBP_OK;
+  if (ctx->trunc_ctas_per_sm > 0 && ctx->use_program) {
+    // the whole search in one cooperative launch
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(&ctx->d_st->removed, 0, 2 * sizeof(u64), ctx->stream));  // removed, amax_bits
+    const u64 before = ctx->n_live;
+    Tab t = make_tab(ctx);
+    double* a = (double*)ctx->spare16;
+    int g = std::min(grid_for(ctx, ctx->n_dense), std::min(ctx->trunc_ctas_per_sm, 8) * ctx->n_sm);
+    u64 ep = ++ctx->epoch;
+    void* args[] = {(void*)&t, (void*)&a, (void*)&ctx->d_partial, (void*)&ctx->d_ts, (void*)&budget, (void*)&p_norm,
+                    (void*)&tol, (void*)&ep};
+    {
+      Bracket br(ctx, OBP_K_TRUNCATE);
+      CU(cudaLaunchCooperativeKernel((void*)k_trunc_search, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->h_ts, ctx->d_ts, sizeof(TruncState), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc1 = sync_state(ctx);
+    if (rc1) return rc1;
+    ctx->prof.term_updates[OBP_K_TRUNCATE] += before;
+    if (slice_error) *slice_error = ctx->h_ts->lower_err;
+    if (n_removed) *n_removed = before - ctx->n_live;
+    if (ctx->n_dense != ctx->n_live) {
+      rc1 = compact(ctx);
+      if (rc1) return rc1;
+      rc1 = sync_state(ctx);
+      if (rc1) return rc1;
+    }
+    if (n_out) *n_out = ctx->n_live;
+    return OBP_OK;
+  }
   double upper = 0.0;
   int rc = obp_trunc_begin(ctx, p_norm, &upper);
   if (rc) return rc;

@@ -1509,3 +1509,98 @@ __global__ void __launch_bounds__(OBP_BS) k_pack_rows(Tab t, u64* __restrict__ o
     }
   }
 }
+
+// ================================================================================================
+// k_trunc_search — truncate_binary_search (utils/truncating.py:171-204) in ONE cooperative launch:
+// |c|^p and its maximum, the whole bisection (one masked sum per step, fixed reduction tree, grid
+// barrier between the steps) and the final kill pass.  The host-driven version needs two launches
+// and one synchronisation per step (~30 steps per slice).
+// ================================================================================================
+struct TruncState {
+  double upper, lower, upper_err, lower_err;
+  u64 steps;
+};
+
+__global__ void __launch_bounds__(OBP_BS) k_trunc_search(Tab t, double* __restrict__ a, double* __restrict__ partial,
+                                                          TruncState* __restrict__ ts, double budget, int p_norm,
+                                                          double tol, u64 epoch) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double s_w[OBP_BS / 32];
+  const u64 n = t.st->n_scan;
+  // ---- a = |c|^p, global maximum ----------------------------------------------------------------
+  double mx = 0.0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double2 c = t.coef[i];
+    double v = -1.0;
+    if (is_live(c)) {
+      const double r = hypot(c.x, c.y);
+      v = p_norm == 1 ? r : (p_norm == 2 ? __dmul_rn(r, r) : pow(r, (double)p_norm));
+      mx = fmax(mx, v);
+    }
+    a[i] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(&t.st->amax_bits, (u64)__double_as_longlong(mx));
+  __threadfence();
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ts->upper = __longlong_as_double((long long)ld_volatile(&t.st->amax_bits));
+    ts->lower = 0.0;
+    ts->upper_err = budget;
+    ts->lower_err = 0.0;
+    ts->steps = 0;
+  }
+  __threadfence();
+  grid.sync();
+  // ---- bisection (:179-196); every CTA evaluates the same exit test on the same state -----------
+  for (int it = 0; it < 4096; ++it) {
+    const double upper = *(volatile double*)&ts->upper, lower = *(volatile double*)&ts->lower;
+    const double ue = *(volatile double*)&ts->upper_err, le = *(volatile double*)&ts->lower_err;
+    const bool close = fabs(ue - le) <= tol + 1e-5 * fabs(le);  // np.isclose(upper_error, lower_error, atol=tol)
+    if (!((upper - lower) > tol) || close) break;
+    const double mid = (upper + lower) / 2;
+    double acc = 0.0;
+    for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+      const double v = a[i];
+      if (v >= 0.0 && v < mid) acc += v;
+    }
+    acc = warp_sum_f64(acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < OBP_BS / 32; ++w) tot += s_w[w];
+      partial[blockIdx.x] = tot;
+    }
+    __threadfence();
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      double s = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += *(volatile double*)&partial[b];
+      const double mid_err = p_norm == 1 ? s : pow(s, 1.0 / (double)p_norm);
+      if (mid_err <= budget) { ts->lower = mid; ts->lower_err = mid_err; }
+      else { ts->upper = mid; ts->upper_err = mid_err; }
+      ts->steps = (u64)it + 1;
+    }
+    __threadfence();
+    grid.sync();
+  }
+  // ---- keep a > lower (:199) -----------------------------------------------------------------------
+  const double thr = *(volatile double*)&ts->lower;
+  unsigned removed = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    const double v = a[i];
+    if (v >= 0.0 && !(v > thr)) {
+      t.coef[i] = tombstone(epoch);
+      removed++;
+    }
+  }
+  const u64 r = warp_sum_u64(removed);
+  if ((threadIdx.x & 31) == 0 && r) {
+    atomicAdd(&t.st->removed, r);
+    atomicAdd(&t.st->n_live, (u64)(-(long long)r));
+  }
+}

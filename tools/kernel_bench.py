@@ -16,6 +16,10 @@ if name == "config2":
     wl = W.config2_kicked_ising(theta_h=theta, max_paulis=max_paulis)
 elif name == "config5":
     wl = W.config5_magic_sweep(theta=theta, depth=40, max_paulis=max_paulis)
+elif name == "config3":
+    wl = W.config3_square_lattice(max_paulis=max_paulis)
+elif name == "config1":
+    wl = W.config1_xy_chain()
 elif name == "config4":
     wl = W.config4_near_clifford(depth=200, max_paulis=max_paulis)
 else:
