@@ -214,6 +214,40 @@ def flush_l2(torch, device, buf):
     torch.cuda.synchronize(device)
 
 
+def large_table_roofline(backpropagate, bpmod, peak: float) -> dict:
+    """The same k_rotate kernel where it IS bound by HBM: config 2 (theta_h = 0.3) allowed to grow to
+    2e7 terms (peak ~2.7e7 rows x 56 B + index: 20x the L2), one untimed-for-`value` pass, per-class device
+    time from CUDA events around the k_rotate launches."""
+    from qiskit_addon_obp_b200 import workloads as wl
+
+    w = wl.config2_kicked_ising(theta_h=0.3, steps=20, max_paulis=20_000_000)
+    backpropagate(w.observables, w.slices, **w.kwargs())  # warm-up: table allocation, slice programs
+    backpropagate(w.observables, w.slices, **w.kwargs())
+    rot = (bpmod.last_run.profile or {}).get("rotate", {"ms": 0.0, "term_updates": 0, "passes": 0})
+    btg = algorithmic_bytes_per_update(w.num_qubits)
+    achieved = rot["term_updates"] * btg / (rot["ms"] * 1e-3) / 1e9 if rot["ms"] > 0 else None
+    return {
+        "kernel": "k_rotate",
+        "workload": w.name,
+        "bound": "hbm",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak if achieved else None,
+        "bytes_per_term_gate_update": btg,
+        "passes": rot["passes"],
+        "term_updates": rot["term_updates"],
+        "ms": rot["ms"],
+        "updates_per_s_whole_run": bpmod.last_run.updates / (bpmod.last_run.device_ms * 1e-3),
+        "traffic": {
+            "dram_bytes_per_launch": 300.4e6,
+            "rows_per_launch": 4.5e6,
+            "algorithmic_bytes_per_launch": 4.5e6 * btg,
+            "source": "ncu --set full, profiles/r1d_k_rotate_big_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
+        },
+    }
+
+
 def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     import torch
     import torch.distributed as dist
@@ -374,6 +408,8 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "clocks": clocks,
             "wall_s": wall,
         }
+        if world == 1 and not args.no_large_table and args.workload == "config2":
+            line["roofline_large_table"] = large_table_roofline(backpropagate, bpmod, peak)
         if world == 1 and not args.no_cpu_baseline:
             u, t = cpu_sample(wls, args.cpu_updates)
             line["cpu_baseline"] = {
@@ -401,6 +437,7 @@ def main() -> None:
     ap.add_argument("--cpu-updates", type=int, default=600_000, help="bound of the CPU sample (term-gate updates)")
     ap.add_argument("--depth", type=int, default=0, help="circuit depth of config4/config5 (0 = 200 / 40)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large-table", action="store_true", help="skip the extra HBM-regime roofline pass")
     ap.add_argument("--sharded", action="store_true", help="N>1: shard ONE observable over all ranks instead of one observable per rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -393,3 +393,30 @@ def test_norm_conservation_config5():
     assert len(out) > 1_000_000
     assert abs(np.sum(np.abs(out.coeffs) ** 2) - 1.0) < 1e-6
     assert len(out.as_dict()) == len(out)
+
+
+def test_max_seconds_timeout():
+    """backpropagation.py:130-142, 288-295 (test_backpropagation.py:923-977): SIGALRM stops the loop between
+    device calls, the committed state is returned, the alarm is cleared."""
+    import signal
+    import time
+
+    from qiskit_addon_obp_b200 import slice_by_depth
+
+    qc = QuantumCircuit(2)
+    qc.rx(0.1, 0)
+    qc.ry(0.1, 0)
+    qc.rz(0.1, 0)
+    qc.cx(0, 1)
+    slices = slice_by_depth(qc, 1)
+    obs = SparsePauliOp("IX")
+    t0 = time.perf_counter()
+    new_obs, rest, md = backpropagate(obs, 100_000 * slices, max_seconds=1)
+    assert time.perf_counter() - t0 < 10
+    assert len(rest) > 0 and md.num_backpropagated_slices > 0
+    assert len(rest) == 400_000 - md.num_backpropagated_slices
+    assert len(new_obs) >= 1
+    assert signal.alarm(0) == 0  # no alarm left pending
+    new_obs, rest, _ = backpropagate(obs, slices, max_seconds=1)
+    assert len(rest) == 0
+    assert signal.alarm(0) == 0

@@ -10,6 +10,8 @@ th = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
 mp = int(float(sys.argv[3])) if len(sys.argv) > 3 else 1_000_000
 wl = {"config2": lambda: W.config2_kicked_ising(theta_h=th, max_paulis=mp),
       "config4": lambda: W.config4_near_clifford(depth=200, max_paulis=mp),
+      "config1": lambda: W.config1_xy_chain(),
+      "config3": lambda: W.config3_square_lattice(max_paulis=mp),
       "config5": lambda: W.config5_magic_sweep(theta=th, max_paulis=mp)}[name]()
 backpropagate(wl.observables, wl.slices, **wl.kwargs())
 for _ in range(2):
