@@ -95,7 +95,8 @@ class ClockSampler:
 
     def __init__(self, device: int):
         self.device = device
-        self.samples: list[list[str]] = []
+        self.samples: list = []
+        self.t_begin = 0.0
         self.proc = None
         self.thread = None
 
@@ -117,7 +118,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) == 6:
-                self.samples.append(parts)
+                self.samples.append((time.perf_counter(), parts))
+
+    def mark_begin(self):
+        """Only samples taken from now on count (nvidia-smi is started earlier: its start-up stalls CUDA calls)."""
+        self.t_begin = time.perf_counter()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -129,7 +134,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for stamp, s in self.samples:
+            if stamp < self.t_begin:
+                continue
             try:
                 sm.append(float(s[0]))
                 mx.append(float(s[1]))
@@ -298,12 +305,13 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                     a[f] += v[f]
         return acc
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: by the timed region it is in its steady 100 ms polling
     for _ in range(args.warmup):
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     e2e_s, dev_ms, updates = 0.0, 0.0, 0
     h2d = d2h = 0
     prof_tot: dict = {}

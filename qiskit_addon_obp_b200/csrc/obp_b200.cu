@@ -87,6 +87,8 @@ struct obp_ctx {
   u64* d_tbegin = nullptr;
   u64* h_tbegin = nullptr;  // pinned
   bool use_program = true;
+  int prog_min_grid = 148;  // smallest grid of the persistent program kernel (grid barriers cost more with more CTAs)
+  int prog_reach_shift = 6;  // the grid is sized for rows << min(#rotations, this)
   size_t cliff_smem_optin = 48 * 1024;  // dynamic smem k_clifford_smem is opted in for
   u64 n_live = 0, n_dense = 0;
   Snapshot snap;
@@ -645,6 +647,8 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     {
       const char* env = getenv("OBP_B200_NO_PROGRAM");
       ctx->use_program = !(env && env[0] && env[0] != '0');
+      if (const char* e2 = getenv("OBP_B200_PROG_MIN_GRID")) ctx->prog_min_grid = std::max(1, atoi(e2));
+      if (const char* e3 = getenv("OBP_B200_PROG_REACH_SHIFT")) ctx->prog_reach_shift = std::max(0, atoi(e3));
     }
     init_frame(ctx);
     return set_counts(ctx, 0);
@@ -1237,10 +1241,10 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     memcpy(ctx->h_prog, prog.entries.data(), ent_bytes);
     memcpy(ctx->h_prog + ent_bytes, prog.pool.data(), prog.pool.size());
     CU(cudaMemcpyAsync(ctx->d_prog, ctx->h_prog, need, cudaMemcpyHostToDevice, ctx->stream));
-    const u64 reach = std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense, 1) << std::min(n_rot_ops, 6));
+    const u64 reach = std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense, 1) << std::min(n_rot_ops, ctx->prog_reach_shift));
     const int max_g = ctx->prog_ctas_per_sm * ctx->n_sm;
     int g = (int)std::min<u64>((reach + OBP_BS - 1) / OBP_BS, (u64)max_g);
-    g = std::max(g, std::min(ctx->n_sm, max_g));
+    g = std::max(g, std::min(ctx->prog_min_grid, max_g));
     const ProgEntry* d_entries = (const ProgEntry*)ctx->d_prog;
     const unsigned char* d_pool = ctx->d_prog + ent_bytes;
     int ne = n_entries, ns = n_slots;
