@@ -103,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL,
                 text=True,
@@ -319,6 +319,8 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         acc = one_step()
+        if os.environ.get("OBP_BENCH_VERBOSE"):
+            print(f"[bench] rank {rank} step e2e {acc['dt'] * 1e3:.2f} ms device {acc['dev_ms']:.2f} ms", file=sys.stderr, flush=True)
         e2e_s += acc["dt"]
         dev_ms += acc["dev_ms"]
         updates += acc["updates"]
@@ -435,7 +437,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["engine", "reference"], default="engine")
     ap.add_argument("--workload", default="config2")
