@@ -89,7 +89,6 @@ struct obp_ctx {
   bool use_program = true;
   int prog_min_grid = 148;  // smallest grid of the persistent program kernel (grid barriers cost more with more CTAs)
   int prog_reach_shift = 6;  // the grid is sized for rows << min(#rotations, this)
-  size_t cliff_smem_optin = 48 * 1024;  // dynamic smem k_clifford_smem is opted in for
   u64 n_live = 0, n_dense = 0;
   Snapshot snap;
   obp_ctx* scratch = nullptr;  // union-count scratch table
@@ -864,7 +863,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   PendingBatch pb;
   pb.reset();
   Tab t = make_tab(ctx);
-  const size_t max_smem_slots = 32;  // 32 * 256 * 16 B = 128 KB of the 227 KB per CTA
+  const size_t max_smem_slots = 2;  // register variant: a batch addresses at most the table's two words
 
   int stream_word = -1;  // word currently held in registers by the stream being built
   auto stream_switch = [&](int w) {
@@ -923,13 +922,6 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     if (identity_slots) {
       if (ctx->W == 1) k_clifford_reg<1><<<g, OBP_BS, 0, ctx->stream>>>(t, pb.b);
       else k_clifford_reg<2><<<g, OBP_BS, 0, ctx->stream>>>(t, pb.b);
-    } else {
-      const size_t smem = (size_t)pb.b.nslots * OBP_BS * sizeof(ulonglong2);
-      if (smem > ctx->cliff_smem_optin) {
-        CU(cudaFuncSetAttribute(k_clifford_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->cliff_smem_optin = smem;
-      }
-      k_clifford_smem<<<g, OBP_BS, smem, ctx->stream>>>(t, pb.b);
     }
     CU(cudaGetLastError());
     slot_gates.push_back(pb.n_ops);

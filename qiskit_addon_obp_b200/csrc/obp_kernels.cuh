@@ -313,11 +313,12 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate(Tab t, const __
 
 // ================================================================================================
 // k_clifford_* — a batch of gates whose Pauli-transfer matrix is a signed permutation (h, s, x, y,
-// z, sx, cx, cz, swap, iswap, ecr, rzz(+-pi/2), ...), applied to each term in registers / shared
-// memory in one pass.  Replaces compose+simplify for those gates: the key moves to its image, the
-// coefficient picks up the sign; all k*k raw rows of a term have magnitude |c|*row_scale, so the
-// term vanishes iff that is <= atol.  Bijection on keys: no merge is needed and
-// the row's stored hash stays valid because the host re-expresses the hash frame (HashFrame).
+// z, sx, cx, cz, swap, iswap, ecr, rzz(+-pi/2), ...), applied to each term in registers in one
+// pass (k_clifford_reg: tables of <= 128 qubits; k_clifford_stream further down: wider tables).
+// Replaces compose+simplify for those gates: the key moves to its image, the coefficient picks up
+// the sign; all k*k raw rows of a term have magnitude |c|*row_scale, so the term vanishes iff that
+// is <= atol.  Bijection on keys: no merge is needed and the row's stored hash stays
+// valid because the host re-expresses the hash frame (frame_update).
 // ================================================================================================
 struct CliffGate {  // 16 bytes
   u64 lut;
@@ -394,49 +395,6 @@ __device__ __forceinline__ void clifford_reg_body(const Tab& t, const CliffBatch
 template <int W>
 __global__ void __launch_bounds__(OBP_BS) k_clifford_reg(Tab t, const __grid_constant__ CliffBatch b) {
   clifford_reg_body<W>(t, b, t.st->n_scan, &t.st->n_live);
-  finish_kernel(t, b.slot);
-}
-
-// Any W: the touched word columns of OBP_BS terms are staged in shared memory ([slot][thread], so
-// every gate step is bank-conflict free), all gates of the batch are applied there, and the
-// columns are written back.  Dynamic smem: nslots * OBP_BS * 16 B.
-__global__ void __launch_bounds__(OBP_BS) k_clifford_smem(Tab t, const __grid_constant__ CliffBatch b) {
-  extern __shared__ ulonglong2 s_key[];
-  const u64 n = t.st->n_scan;
-  int deaths = 0;
-  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
-    const double2 c = t.coef[i];
-    if (!is_live(c)) continue;
-    if (is_small_scaled(c, b.scale, b.atol)) {
-      t.coef[i] = tombstone(b.epoch);
-      deaths++;
-      continue;
-    }
-    for (int sl = 0; sl < b.nslots; ++sl) s_key[sl * OBP_BS + threadIdx.x] = t.xz[b.word_of_slot[sl]][i];
-    unsigned sgn = 0;
-    for (int k = 0; k < b.ng; ++k) {
-      const CliffGate g = b.g[k];
-      ulonglong2 ka = s_key[g.sa * OBP_BS + threadIdx.x];
-      if (g.nq == 2 && g.sb != g.sa) {
-        ulonglong2 kb = s_key[g.sb * OBP_BS + threadIdx.x];
-        const unsigned d = cliff_apply_bits(g, ka.x, ka.y, kb.x, kb.y, sgn);
-        ka.x ^= (u64)(d & 1u) << g.ba;
-        ka.y ^= (u64)((d >> 1) & 1u) << g.ba;
-        kb.x ^= (u64)((d >> 2) & 1u) << g.bb;
-        kb.y ^= (u64)((d >> 3) & 1u) << g.bb;
-        s_key[g.sb * OBP_BS + threadIdx.x] = kb;
-      } else {
-        const unsigned d = cliff_apply_bits(g, ka.x, ka.y, ka.x, ka.y, sgn);
-        ka.x ^= ((u64)(d & 1u) << g.ba) ^ ((u64)((d >> 2) & 1u) << g.bb);
-        ka.y ^= ((u64)((d >> 1) & 1u) << g.ba) ^ ((u64)((d >> 3) & 1u) << g.bb);
-      }
-      s_key[g.sa * OBP_BS + threadIdx.x] = ka;
-    }
-    for (int sl = 0; sl < b.nslots; ++sl) t.xz[b.word_of_slot[sl]][i] = s_key[sl * OBP_BS + threadIdx.x];
-    if (sgn) t.coef[i] = make_double2(-c.x, -c.y);
-  }
-  const long long dl = warp_sum_i64((long long)deaths);
-  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)(-dl));
   finish_kernel(t, b.slot);
 }
 
