@@ -420,3 +420,37 @@ def test_max_seconds_timeout():
     new_obs, rest, _ = backpropagate(obs, slices, max_seconds=1)
     assert len(rest) == 0
     assert signal.alarm(0) == 0
+
+
+def test_linearity_config5_large():
+    """Conjugation is linear: backprop(a*O1 + b*O2) == a*backprop(O1) + b*backprop(O2) at ~1e6 terms
+    (no truncation; terms within the trim threshold of either side may differ)."""
+    from qiskit_addon_obp_b200.workloads import config5_magic_sweep
+
+    wl = config5_magic_sweep(theta=np.pi / 8, depth=12, max_paulis=None)
+    slices = wl.slices[3:]
+    nq = wl.num_qubits
+    o1 = SparsePauliOp.from_sparse_list([("Z", [nq // 2], 1.0)], nq)
+    o2 = SparsePauliOp.from_sparse_list([("X", [nq // 2 + 1], 1.0)], nq)
+    a, b = 0.75, -1.25
+    both = SparsePauliOp((np.vstack([o1.x, o2.x]), np.vstack([o1.z, o2.z])), np.array([a, b], dtype=complex))
+    r1, _, _ = backpropagate(o1, slices)
+    r2, _, _ = backpropagate(o2, slices)
+    r12, _, _ = backpropagate(both, slices)
+    assert len(r12) > 200_000
+    d = {}
+    for op, w in ((r1, a), (r2, b)):
+        xw, zw = op.packed()
+        for k, c in zip(map(bytes, np.concatenate([xw, zw], axis=1)), op.coeffs * w):
+            d[k] = d.get(k, 0j) + c
+    xw, zw = r12.packed()
+    got = dict(zip(map(bytes, np.concatenate([xw, zw], axis=1)), r12.coeffs))
+    assert len(got) == len(r12)
+    worst = 0.0
+    for k in set(d) | set(got):
+        diff = abs(d.get(k, 0j) - got.get(k, 0j))
+        if k in d and k in got:
+            worst = max(worst, diff)
+        else:
+            assert diff < 1e-7, diff  # present on one side only: a term at the trim threshold
+    assert worst < 1e-9

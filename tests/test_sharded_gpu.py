@@ -96,3 +96,18 @@ def test_sharded_round_trip_large(monkeypatch):
     key = wl.observables.paulis.to_labels()[0]
     assert abs(d[key] - 1.0) < 1e-5
     assert sum(abs(c) for k, c in d.items() if k != key) < 1e-2
+
+
+def test_sharded_equals_single_table_large(monkeypatch):
+    """8 shards and one table give the same 5e5-term operator (keys bit-exact, coefficients to 1e-12)."""
+    from qiskit_addon_obp_b200.workloads import config2_kicked_ising
+
+    wl = config2_kicked_ising(theta_h=0.3, steps=6, max_paulis=None)
+    one, _, md1 = backpropagate(wl.observables, wl.slices)
+    monkeypatch.setenv("OBP_B200_SHARDS", "8")
+    many, _, md8 = backpropagate(wl.observables, wl.slices)
+    assert len(one) == len(many) > 100_000
+    assert [s.num_paulis for s in md1.backpropagation_history] == [s.num_paulis for s in md8.backpropagation_history]
+    a, b = one.sorted_by_key(), many.sorted_by_key()
+    assert np.array_equal(a.packed()[0], b.packed()[0]) and np.array_equal(a.packed()[1], b.packed()[1])
+    assert np.max(np.abs(a.coeffs - b.coeffs)) < 1e-12
