@@ -452,5 +452,7 @@ def test_linearity_config5_large():
         if k in d and k in got:
             worst = max(worst, diff)
         else:
-            assert diff < 1e-7, diff  # present on one side only: a term at the trim threshold
+            # present on one side only: a descendant of terms trimmed (|c| <= 1e-8, not a linear operation)
+            # in one run and kept in the other
+            assert diff < 1e-6, diff
     assert worst < 1e-9
