@@ -187,6 +187,15 @@ int obp_rotate_emit(obp_ctx* ctx, const obp_op* op, double atol, void* d_records
  * num_unique = sum keys_present, num_duplicate = sum rows_surv - num_unique,
  * num_trimmed = 4 * sum n_in(emit) - sum rows_surv + sum cancelled. */
 int obp_rotate_merge(obp_ctx* ctx, const void* d_records, uint64_t n_records, obp_shard_counters* out);
+/* apply_reset_to on a sharded table: rows with Z on the qubit move to the key with that Z cleared,
+ * which belongs to rank ^ *peer_xor.  *peer_xor == 0: nothing was done, call obp_apply_reset (all
+ * local).  Otherwise phase 1 ran (zero filter, moving rows written as records into d_records); exchange
+ * the records with the peer and finish with obp_reset_merge.  Counters add up across ranks like those
+ * of the split rotation (raw rows = sum n_in). */
+int obp_reset_emit(obp_ctx* ctx, int32_t qubit, double atol, void* d_records, uint64_t cap_records, int32_t* peer_xor,
+                   obp_shard_counters* out);
+int obp_reset_merge(obp_ctx* ctx, double atol, const void* d_records, uint64_t n_records, obp_shard_counters* out);
+
 /* The same split rotation with the transfer fused into the emitting kernel: every rank owns two
  * inboxes (ping-pong) in device memory that its peers map (CUDA IPC across processes, the raw
  * pointer inside one process); obp_rotate_emit_p2p stores the records with plain st.global into the

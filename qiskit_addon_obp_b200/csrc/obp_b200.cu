@@ -1447,6 +1447,86 @@ int obp_rotate_merge(obp_ctx* ctx, const void* d_records, uint64_t n_records, ob
   return OBP_OK;
 }
 
+// ---- reset on a sharded table (staged exchange) -------------------------------------------------------
+// *peer_xor = owner bits of the hash column of Z on that qubit: 0 -> obp_apply_reset does everything
+// locally; else phase 1 (filter + emit the rows that must move) here, phase 2 in obp_reset_merge.
+int obp_reset_emit(obp_ctx* ctx, int32_t qubit, double atol, void* d_records, uint64_t cap_records, int32_t* peer_xor,
+                   obp_shard_counters* out) {
+  if (!ctx || qubit < 0 || qubit >= ctx->nq || !peer_xor || (cap_records && !d_records)) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  *peer_xor = ctx->n_ranks > 1 ? (int32_t)(ctx->hz[qubit] >> ctx->owner_shift) : 0;
+  if (*peer_xor == 0) return OBP_OK;
+  int rc = ensure_ops(ctx, 2);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));
+  const u64 n_in = ctx->n_live;
+  ResetP p;
+  memset(&p, 0, sizeof(p));
+  p.w = qubit / 64;
+  p.bit = 1ull << (qubit % 64);
+  p.hZ = ctx->hz[qubit];
+  p.atol = atol;
+  p.slot = 0;
+  Tab t = make_tab(ctx);
+  {
+    Bracket br(ctx, OBP_K_OTHER, 2);
+    const int g = grid_for(ctx, std::max<u64>(ctx->n_dense, 1));
+    p.epoch = ++ctx->epoch;
+    k_reset_filter<<<g, OBP_BS, 0, ctx->stream>>>(t, p);
+    p.epoch = ++ctx->epoch;
+    k_reset_emit<<<g, OBP_BS, 0, ctx->stream>>>(t, p, (u64*)d_records, cap_records, ctx->d_cnt);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  ctx->prof.term_updates[OBP_K_OTHER] += n_in;
+  fill_shard_stats(ctx, out, n_in);
+  if (out) out->rows_surv = ctx->h_ops[0].rows_surv;  // rows that passed the raw-row filter (k_reset_filter)
+  return rc;
+}
+
+int obp_reset_merge(obp_ctx* ctx, double atol, const void* d_records, uint64_t n_records, obp_shard_counters* out) {
+  if (!ctx || (n_records && !d_records)) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  const u64 n_in = ctx->n_live;
+  int rc = ensure_ops(ctx, 2);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));
+  Tab t = make_tab(ctx);
+  {
+    Bracket br(ctx, OBP_K_OTHER, 2);
+    if (n_records)
+      k_merge_records<<<grid_for(ctx, n_records), OBP_BS, 0, ctx->stream>>>(t, (const u64*)d_records, n_records, nullptr, 0,
+                                                                          ctx->d_cnt, nullptr, 0);
+    // second zero filter of simplify(): only merged sums can have become small
+    k_trim<<<grid_for(ctx, std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense + n_records, 1))), OBP_BS, 0, ctx->stream>>>(
+        t, atol, ++ctx->epoch, 0);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  fill_shard_stats(ctx, out, n_in);
+  if (out) {
+    out->cancelled = ctx->h_ops[0].cancelled;
+    out->sum_trimmed[0] = ctx->h_ops[0].sum_re;
+    out->sum_trimmed[1] = ctx->h_ops[0].sum_im;
+  }
+  if (rc) return rc;
+  // moved rows leave stale index entries behind: compact when anything died or moved
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+    if (out) out->n_dense = ctx->n_dense;
+  }
+  return OBP_OK;
+}
+
 // ---- P2P exchange: the emitting kernel stores its records straight into the peer's inbox -----------
 int obp_inbox_create(obp_ctx* ctx, uint64_t cap_records) {
   if (!ctx || cap_records < 1) return OBP_ERR_BADARG;

@@ -1562,3 +1562,60 @@ __global__ void __launch_bounds__(OBP_BS) k_trunc_search(Tab t, double* __restri
     atomicAdd(&t.st->n_live, (u64)(-(long long)r));
   }
 }
+
+// ---- reset on a sharded table whose cleared keys belong to the peer rank ---------------------------
+// After k_reset_filter (X/Y rows and |c| <= atol rows are gone): rows with Z on the qubit move to the
+// key with that Z cleared, whose hash has other owner bits — they leave as records; rows with I stay.
+__global__ void __launch_bounds__(OBP_BS) k_reset_emit(Tab t, const __grid_constant__ ResetP p, u64* __restrict__ rec,
+                                                        u64 rec_cap, ShardCnt* __restrict__ cnt) {
+  const u64 n = t.st->n_scan;
+  const unsigned lane = threadIdx.x & 31u;
+  const int RW = 2 * t.W + 3;
+  unsigned keys_present = 0;
+  int deaths = 0;
+  bool overflow = false;
+  for (u64 base = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)); base < n; base += (u64)gridDim.x * OBP_BS) {
+    const u64 i = base + lane;
+    bool want_emit = false;
+    double2 c = make_double2(0.0, 0.0);
+    if (i < n) {
+      c = t.coef[i];
+      if (is_live(c)) {
+        if (t.xz[p.w][i].y & p.bit) want_emit = true;
+        else keys_present++;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, want_emit);
+    if (bal) {
+      u64 wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&cnt->n_records, (u64)__popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (want_emit) {
+        const u64 r = wbase + __popc(bal & ((1u << lane) - 1u));
+        if (r < rec_cap) {
+          u64* o = rec + r * RW;
+          for (int w = 0; w < t.W; ++w) {
+            const ulonglong2 key = t.xz[w][i];
+            o[2 * w] = key.x;
+            o[2 * w + 1] = w == p.w ? (key.y & ~p.bit) : key.y;
+          }
+          o[2 * t.W] = t.hash[i] ^ p.hZ;
+          o[2 * t.W + 1] = (u64)__double_as_longlong(c.x);
+          o[2 * t.W + 2] = (u64)__double_as_longlong(c.y);
+          t.coef[i] = tombstone(p.epoch);
+          deaths++;
+        } else {
+          overflow = true;
+        }
+      }
+    }
+  }
+  if (overflow) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
+  const long long dl = warp_sum_i64((long long)deaths);
+  const u64 b = warp_sum_u64(keys_present);
+  if (lane == 0) {
+    if (b) atomicAdd(&cnt->keys_present, b);
+    if (dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+  }
+  finish_kernel(t, -1);
+}

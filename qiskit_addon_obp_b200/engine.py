@@ -147,8 +147,10 @@ def lib() -> C.CDLL:
         "obp_inbox_attach": ([vp, C.c_int32, C.c_int32, vp, C.c_uint64], C.c_int),
         "obp_rotate_emit_p2p": ([vp, vp, C.c_double, C.c_int32, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_rotate_merge_inbox": ([vp, C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_reset_emit": ([vp, C.c_int32, C.c_double, vp, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_reset_merge": ([vp, C.c_double, vp, C.c_uint64, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_set_shard_sync": ([vp, C.c_int32], C.c_int),
-        "obp_last_split_counters": ([vp, C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_last_split_counters obp_reset_emit obp_reset_merge": ([vp, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_trunc_begin": ([vp, C.c_int32, f64p], C.c_int),
         "obp_trunc_masked_sum": ([vp, C.c_double, f64p], C.c_int),
         "obp_trunc_finish": ([vp, C.c_double, u64p, u64p], C.c_int),
@@ -170,7 +172,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge"
 ).split()
 
 
@@ -527,6 +529,26 @@ class TermTable:
         rc = self._lib.obp_rotate_merge_inbox(self._h, C.byref(out))
         if rc != OBP_ERR_CAPACITY:
             self._check(rc, "obp_rotate_merge_inbox")
+        self.n, self.n_dense = out.n_out, out.n_dense
+        return out, rc == OBP_ERR_CAPACITY
+
+    def reset_emit(self, qubit: int, atol: float, d_records: int, cap_records: int) -> tuple[ObpShardCounters, int, bool]:
+        """Phase 1 of a reset whose cleared keys belong to another rank: ``(counters, peer_xor, overflowed)``."""
+        out, peer = ObpShardCounters(), C.c_int32()
+        rc = self._lib.obp_reset_emit(
+            self._h, int(qubit), float(atol), C.c_void_p(d_records), int(cap_records), C.byref(peer), C.byref(out)
+        )
+        if rc != OBP_ERR_CAPACITY:
+            self._check(rc, "obp_reset_emit")
+        if peer.value:
+            self.n, self.n_dense = out.n_out, out.n_dense
+        return out, peer.value, rc == OBP_ERR_CAPACITY
+
+    def reset_merge(self, atol: float, d_records: int, n_records: int) -> tuple[ObpShardCounters, bool]:
+        out = ObpShardCounters()
+        rc = self._lib.obp_reset_merge(self._h, float(atol), C.c_void_p(d_records), int(n_records), C.byref(out))
+        if rc != OBP_ERR_CAPACITY:
+            self._check(rc, "obp_reset_merge")
         self.n, self.n_dense = out.n_out, out.n_dense
         return out, rc == OBP_ERR_CAPACITY
 

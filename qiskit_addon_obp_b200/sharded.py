@@ -456,8 +456,56 @@ class ShardedTable:
     def apply_generic(self, qubits, codes, coeffs, atol: float):
         raise NotImplementedError("generic (raw-row expansion) gates move terms between shards; not supported on a sharded table yet")
 
-    def apply_reset(self, qubit: int, atol: float):
-        raise NotImplementedError("reset moves terms between shards; not supported on a sharded table yet")
+    def apply_reset(self, qubit: int, atol: float) -> _Stats:
+        """``apply_reset_to`` + simplify: local when the cleared keys keep their owner, else the rows with Z
+        on the qubit move to the peer rank (staged record exchange)."""
+        import torch
+
+        out = _Stats()
+        if self.zero_operator:
+            out.n_in = out.raw_rows = out.num_trimmed = out.n_out = out.updates = 1
+            return out
+        n_in = self.n
+        tdev = torch.device("cuda", self.device)
+        bufs, counts, emit, failed, peer = {}, {}, {}, False, 0
+        for r, t in self.tables.items():
+            cap = max(int(t.n_dense), 1)
+            bufs[r] = torch.empty((cap, self.rec_u64), dtype=torch.int64, device=tdev)
+            emit[r], peer, over = t.reset_emit(qubit, atol, bufs[r].data_ptr(), cap)
+            failed |= over
+            counts[r] = min(int(emit[r].n_records), cap)
+        if peer == 0:  # every rank sees the same hash frame: all local
+            stats = {r: t.apply_reset(qubit, atol) for r, t in self.tables.items()}
+            ints = {r: [0, t.n, t.n_dense, 0, int(stats[r].n_in), int(stats[r].num_unique), int(stats[r].num_duplicate),
+                        int(stats[r].num_trimmed)] for r, t in self.tables.items()}
+            floats = {r: list(stats[r].sum_trimmed) for r in self.tables}
+            ti, tf = self.comm.allreduce_pair(ints, floats)
+            out.n_in, out.num_unique, out.num_duplicate, out.num_trimmed = (int(v) for v in ti[4:8])
+        else:
+            recv = self.comm.exchange(bufs, counts, peer)
+            merge = {}
+            for r, t in self.tables.items():
+                buf, n_rec = recv[r]
+                merge[r], over = t.reset_merge(atol, buf.data_ptr() if n_rec else 0, n_rec)
+                failed |= over
+            first = min(self.tables)
+            ints = {r: [1 if (failed and r == first) else 0, t.n, t.n_dense, 0, int(emit[r].n_in), int(emit[r].rows_surv),
+                        int(emit[r].keys_present + merge[r].keys_present), int(merge[r].cancelled)]
+                    for r, t in self.tables.items()}
+            floats = {r: [merge[r].sum_trimmed[0], merge[r].sum_trimmed[1]] for r in self.tables}
+            ti, tf = self.comm.allreduce_pair(ints, floats)
+            if ti[0] > 0:
+                raise CapacityError("sharded reset: a shard overflowed its table")
+            g_in, rows_surv, keys, cancelled = (int(v) for v in ti[4:8])
+            out.n_in, out.num_unique, out.num_duplicate = g_in, keys, rows_surv - keys
+            out.num_trimmed = g_in - rows_surv + cancelled
+        self.n, self.n_dense = int(ti[1]), int(ti[2])
+        out.sum_trimmed = [float(tf[0]), float(tf[1])]
+        out.raw_rows = out.updates = n_in
+        out.n_out = self.n
+        if self.n == 0:
+            self.zero_operator = True
+        return out
 
     def apply_damping(self, gen_x, gen_z, factors, atol: float) -> _Stats:
         out = _Stats()

@@ -111,3 +111,30 @@ def test_sharded_equals_single_table_large(monkeypatch):
     a, b = one.sorted_by_key(), many.sorted_by_key()
     assert np.array_equal(a.packed()[0], b.packed()[0]) and np.array_equal(a.packed()[1], b.packed()[1])
     assert np.max(np.abs(a.coeffs - b.coeffs)) < 1e-12
+
+
+@pytest.mark.parametrize("ranks", [2, 8])
+def test_sharded_reset_and_noise(monkeypatch, ranks):
+    """reset moves the rows with Z on the qubit to the rank that owns the cleared key; damping is rank-local."""
+    from qiskit_addon_obp_b200.ir import PauliLindbladError, PauliLindbladErrorInstruction, QuantumCircuit
+
+    rng = np.random.default_rng(13 + ranks)
+    nq = 7
+    slices = random_slices(nq, 5, rng, gates_per_slice=6)
+    ple = PauliLindbladError(["IXX", "ZYI", "IIZ"], [1e-2, 3e-3, 5e-2])
+    noisy = QuantumCircuit(nq)
+    noisy.append(PauliLindbladErrorInstruction(ple), [1, 3, 4])
+    noisy.cx(1, 3)
+    mixed = []
+    for q in range(nq):  # a reset on every qubit: some keep their owner, most do not
+        rst = QuantumCircuit(nq)
+        rst.h((q + 1) % nq)
+        rst.reset(q)
+        mixed += [rst, slices[q % len(slices)]]
+    last = QuantumCircuit(nq)
+    last.rx(0.4, 2)
+    last.reset(3)  # applied first (reverse order) ...
+    first = QuantumCircuit(nq)
+    first.reset(5)  # ... and a slice whose only (hence last) gate is the reset: its counters are reported
+    obs = random_observable(nq, 6, rng, weight=3)
+    _compare(monkeypatch, ranks, obs, slices + [noisy] + mixed + [last, first] + slices[:2])
