@@ -150,7 +150,7 @@ def lib() -> C.CDLL:
         "obp_reset_emit": ([vp, C.c_int32, C.c_double, vp, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(ObpShardCounters)], C.c_int),
         "obp_reset_merge": ([vp, C.c_double, vp, C.c_uint64, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_set_shard_sync": ([vp, C.c_int32], C.c_int),
-        "obp_last_split_counters obp_reset_emit obp_reset_merge": ([vp, C.POINTER(ObpShardCounters)], C.c_int),
+        "obp_last_split_counters": ([vp, C.POINTER(ObpShardCounters)], C.c_int),
         "obp_trunc_begin": ([vp, C.c_int32, f64p], C.c_int),
         "obp_trunc_masked_sum": ([vp, C.c_double, f64p], C.c_int),
         "obp_trunc_finish": ([vp, C.c_double, u64p, u64p], C.c_int),
