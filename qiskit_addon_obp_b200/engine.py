@@ -219,6 +219,7 @@ class TermTable:
                 idle.pop(k)
                 t.n = t.n_dense = 0
                 t.zero_operator = False
+                t.track_zero = True
                 t.set_shard(1, 0)
                 t.set_shard_sync(False)
                 return t
@@ -249,6 +250,7 @@ class TermTable:
         self.n = 0  # live terms
         self.n_dense = 0
         self.zero_operator = False  # simplify.py:156-159: everything trimmed -> one identity row, coeff 0
+        self.track_zero = True  # False for the members of a sharded table: an empty shard is not a zero operator
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc: int, what: str):
@@ -304,7 +306,7 @@ class TermTable:
         )
         self._check(rc, "obp_load")
         self.n, self.n_dense = st.n_out, st.n_dense
-        self.zero_operator = atol is not None and atol >= 0 and self.n == 0
+        self.zero_operator = self.track_zero and atol is not None and atol >= 0 and self.n == 0
         return st
 
     def download(self) -> SparsePauliOp:
@@ -354,7 +356,7 @@ class TermTable:
             raise
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0:
-            self.zero_operator = True
+            self.zero_operator = self.track_zero
         return st
 
     def apply_generic(self, qubits, codes, coeffs, atol: float, simplify: bool = True) -> ObpStats:
@@ -374,7 +376,7 @@ class TermTable:
         self._check(rc, "obp_apply_generic")
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0 and simplify:
-            self.zero_operator = True
+            self.zero_operator = self.track_zero
         return st
 
     def apply_reset(self, qubit: int, atol: float) -> ObpStats:
@@ -385,7 +387,7 @@ class TermTable:
         self._check(self._lib.obp_apply_reset(self._h, int(qubit), float(atol), C.byref(st)), "obp_apply_reset")
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0 and atol >= 0:
-            self.zero_operator = True
+            self.zero_operator = self.track_zero
         return st
 
     def apply_damping(self, gen_x: np.ndarray, gen_z: np.ndarray, factors: np.ndarray, atol: float) -> ObpStats:
@@ -407,7 +409,7 @@ class TermTable:
         self._check(rc, "obp_apply_damping")
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0 and atol >= 0:
-            self.zero_operator = True
+            self.zero_operator = self.track_zero
         return st
 
     def truncate(self, budget: float, p_norm: int, tol: float) -> tuple[float, int]:

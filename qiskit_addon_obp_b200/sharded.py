@@ -215,6 +215,7 @@ class ShardedTable:
         self.tables = {r: TermTable.acquire(num_qubits, per_rank, comm.device) for r in comm.local_ranks}
         for r, t in self.tables.items():
             t.set_shard(comm.n_ranks, r)
+            t.track_zero = False  # an empty shard is normal; the zero-operator rule applies to the whole table
         self.p2p = os.environ.get("OBP_B200_P2P", "1") not in ("0", "")
         # one process per GPU: split rotations are ordered by device-side flags, the host never waits
         self.device_flags = (
