@@ -162,14 +162,17 @@ def backpropagate(
                 prog = _slice_program(slice_, raw)
                 overflowed = False
                 for i in range(n_obs):
-                    applied: list[int] = []
                     support = set(qargs[i])
-                    for k, qs in enumerate(prog.qubit_sets):
-                        if support.isdisjoint(qs):
-                            continue  # outside the light cone (backpropagation.py:183)
-                        applied.append(k)
-                        if prog.nodes[k].name != "reset":
-                            support |= qs
+                    if prog.touched <= support:
+                        applied = prog.all_idx  # the light cone already covers every qubit the slice touches
+                    else:
+                        applied = []
+                        for k, qs in enumerate(prog.qubit_sets):
+                            if support.isdisjoint(qs):
+                                continue  # outside the light cone (backpropagation.py:183)
+                            applied.append(k)
+                            if prog.nodes[k].name != "reset":
+                                support |= qs
                     non_trivial = bool(applied)
                     sidx = metadata.num_backpropagated_slices
                     if non_trivial:
@@ -305,13 +308,15 @@ class SliceProgram:
     record of ``nodes[k]`` (``kind`` 0 for reset / LayerError, which have their own entry points).
     """
 
-    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data", "generic")
+    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data", "generic", "touched", "all_idx")
 
     def __init__(self, slice_: QuantumCircuit, raw: bool = False):
         self.n_data = len(slice_.data)
         classify = raw_program_for if raw else program_for
         self.nodes = [n for n in topological_op_order(slice_)[::-1] if n.name != "barrier"]
         self.qubit_sets = [frozenset(n.qubits) for n in self.nodes]
+        self.touched = frozenset().union(*self.qubit_sets) if self.qubit_sets else frozenset()
+        self.all_idx = list(range(len(self.nodes)))
         self.recs = np.zeros(len(self.nodes), dtype=OP_DTYPE)
         self.special = [n.name in ("reset", "LayerError") for n in self.nodes]
         self.errors: dict[int, Exception] = {}

@@ -380,6 +380,10 @@ void frame_update(obp_ctx* ctx, const obp_op& op) {
 }
 
 bool lut_is_linear_bijection(const obp_op& op) {
+  // circuits repeat a handful of distinct gates: remember the tables that already passed
+  static thread_local std::vector<std::pair<u64, int>> ok_cache;
+  for (const auto& e : ok_cache)
+    if (e.first == op.lut && e.second == op.n_qubits) return true;
   const int nb = 2 * op.n_qubits;
   unsigned seen = 0;
   for (unsigned v = 0; v < (1u << nb); ++v) {
@@ -391,7 +395,9 @@ bool lut_is_linear_bijection(const obp_op& op) {
       if (v & (1u << i)) lin ^= (unsigned)((op.lut >> (4 * (1u << i))) & 15ull);
     if (lin != img) return false;
   }
-  return seen == ((nb == 4) ? 0xFFFFu : 0xFu);
+  const bool ok = seen == ((nb == 4) ? 0xFFFFu : 0xFu);
+  if (ok && ok_cache.size() < 256) ok_cache.emplace_back(op.lut, op.n_qubits);
+  return ok;
 }
 
 struct PendingBatch {
