@@ -1970,7 +1970,8 @@ int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double
     const u64 before = ctx->n_live;
     Tab t = make_tab(ctx);
     double* a = (double*)ctx->spare16;
-    int g = std::min(grid_for(ctx, ctx->n_dense), std::min(ctx->trunc_ctas_per_sm, 8) * ctx->n_sm);
+    // two CTAs per SM at most: every bisection step ends in two grid barriers, which cost more with more CTAs
+    int g = std::min(grid_for(ctx, ctx->n_dense), std::min(ctx->trunc_ctas_per_sm, 2) * ctx->n_sm);
     u64 ep = ++ctx->epoch;
     void* args[] = {(void*)&t, (void*)&a, (void*)&ctx->d_partial, (void*)&ctx->d_ts, (void*)&budget, (void*)&p_norm,
                     (void*)&tol, (void*)&ep};

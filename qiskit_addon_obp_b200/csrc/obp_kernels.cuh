@@ -1535,13 +1535,22 @@ __global__ void __launch_bounds__(OBP_BS) k_trunc_search(Tab t, double* __restri
     }
     __threadfence();
     grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0) {  // fixed-order reduction of the per-CTA partial sums by the whole CTA
       double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += *(volatile double*)&partial[b];
-      const double mid_err = p_norm == 1 ? s : pow(s, 1.0 / (double)p_norm);
-      if (mid_err <= budget) { ts->lower = mid; ts->lower_err = mid_err; }
-      else { ts->upper = mid; ts->upper_err = mid_err; }
-      ts->steps = (u64)it + 1;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += OBP_BS) s += *(volatile double*)&partial[b];
+      s = warp_sum_f64(s);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < OBP_BS / 32; ++w) tot += s_w[w];
+        const double mid_err = p_norm == 1 ? tot : pow(tot, 1.0 / (double)p_norm);
+        if (mid_err <= budget) { ts->lower = mid; ts->lower_err = mid_err; }
+        else { ts->upper = mid; ts->upper_err = mid_err; }
+        ts->steps = (u64)it + 1;
+      }
     }
     __threadfence();
     grid.sync();
