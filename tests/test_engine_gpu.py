@@ -456,3 +456,62 @@ def test_linearity_config5_large():
             # in one run and kept in the other
             assert diff < 1e-6, diff
     assert worst < 1e-6
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------
+def test_table_growth_and_rollback(monkeypatch):
+    """A table that overflows mid-slice is rolled back, grown and the slice re-run (no max_paulis)."""
+    monkeypatch.setenv("OBP_B200_CAPACITY", "4096")
+    rng = np.random.default_rng(4)
+    nq = 12
+    slices = random_slices(nq, 8, rng, p_rot=0.9, gates_per_slice=10)
+    obs = random_observable(nq, 4, rng)
+    gl, md = _compare(obs, slices)
+    assert len(gl[0]) > 4096  # it did outgrow the first table
+
+
+def test_everything_trimmed_zero_operator():
+    """simplify.py:156-159: when every term is trimmed the operator becomes one identity row with coefficient 0,
+    and the loop keeps going on it exactly like the reference."""
+    qc = QuantumCircuit(2)
+    qc.rx(0.3, 0)
+    qc2 = QuantumCircuit(2)
+    qc2.h(0)
+    qc2.cx(0, 1)
+    obs = SparsePauliOp(["ZI", "IX"], [3e-9, 5e-9])  # below atol after the first gate's row filter
+    _compare(obs, [qc2, qc, qc2])
+    _compare(obs, [qc2, qc], truncation_error_budget=setup_budget(max_error_per_slice=0.1))
+    _compare([obs, SparsePauliOp("ZZ")], [qc2, qc], operator_budget=OperatorBudget(max_paulis=10))
+
+
+def test_duplicate_and_zero_rows_in_the_input():
+    """Inputs are not simplified by the reference before the first gate touches them; untouched observables
+    come back unchanged, touched ones are merged by the first simplify."""
+    qc = QuantumCircuit(3)
+    qc.ry(0.4, 0)
+    obs = SparsePauliOp(["IIZ", "IIZ", "IXI", "IIX"], [0.5, 0.25, 0.0, 1.0])
+    _compare(obs, [qc])
+    untouched = SparsePauliOp(["ZII", "ZII"], [1.0, 2.0])
+    got, _, _ = backpropagate([obs, untouched], [qc])
+    assert got[1] == untouched
+
+
+def test_many_observables_union_count():
+    rng = np.random.default_rng(8)
+    nq = 6
+    slices = random_slices(nq, 6, rng, gates_per_slice=5)
+    obs = [random_observable(nq, 2, rng) for _ in range(5)] + [SparsePauliOp("IIIIIZ"), SparsePauliOp("IIIIIZ")]
+    _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=150))
+    _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=40))
+
+
+def test_wide_generator_rotation_across_words():
+    """rzz / rxx / ryy whose two qubits sit in different 64-bit words (generator spans two words)."""
+    nq = 200
+    qc = QuantumCircuit(nq)
+    qc.rzz(0.3, 63, 64)
+    qc.rxx(0.5, 10, 199)
+    qc.ryy(-0.7, 127, 128)
+    qc.rzx(0.2, 64, 0)
+    obs = SparsePauliOp.from_sparse_list([("XZ", [63, 64], 1.0), ("Y", [199], 0.5), ("ZX", [127, 128], -0.25)], nq)
+    _compare(obs, [qc, qc])
