@@ -125,6 +125,8 @@ def backpropagate(
     # input rows along unchanged (duplicates and zeros included)
     loaded = [False] * n_obs
     loaded_committed = [False] * n_obs
+    dirty = [_has_duplicates_or_zeros(o, atol) for o in obs_in]
+    raw_first = [False] * n_obs  # the table holds the unsimplified input: its first gate runs as a raw expansion
     trunc_active = truncation_error_budget.is_active()
 
     if max_seconds is not None:
@@ -177,7 +179,14 @@ def backpropagate(
                     sidx = metadata.num_backpropagated_slices
                     if non_trivial:
                         if not loaded[i]:
-                            tables[i].load(obs_in[i], OBP_ATOL_RAW if raw else None)
+                            # An input with duplicate or near-zero rows reaches the reference's first gate
+                            # unsimplified (raw_num_paulis counts every given row): keep the rows as given and
+                            # run that one gate as the literal k*k expansion + simplify.
+                            raw_first[i] = (
+                                dirty[i] and not raw and comm is None and not prog.special[applied[0]]
+                                and applied[0] not in prog.errors
+                            )
+                            tables[i].load(obs_in[i], OBP_ATOL_RAW if (raw or raw_first[i]) else None)
                             info.h2d_bytes += len(obs_in[i]) * (16 * tables[i].words + 16)
                             tables[i].profile_enable(PROFILE)
                             tables[i].profile(reset=True)
@@ -186,7 +195,8 @@ def backpropagate(
                             loaded[i] = True
                         while True:
                             try:
-                                _run_slice(tables[i], prog, applied, atol, sm, i, info, raw)
+                                _run_slice(tables[i], prog, applied, atol, sm, i, info, raw, raw_first[i])
+                                raw_first[i] = False
                                 if trunc_active:
                                     budget = metadata.left_over_error_budget(i, sidx)
                                     err, removed = tables[i].truncate(
@@ -354,11 +364,18 @@ def _slice_program(slice_: QuantumCircuit, raw: bool = False) -> SliceProgram:
 
 
 def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: float, sm: SliceMetadata, i: int,
-               info: RunInfo, raw: bool = False) -> None:
+               info: RunInfo, raw: bool = False, first_as_expansion: bool = False) -> None:
     """Execute the applied gates of one slice on one observable and record the last gate's counters."""
     stats = None
     last = applied[-1]
     seg: list[int] = []
+    if first_as_expansion:
+        node = prog.nodes[applied[0]]
+        g = raw_program_for(node)
+        stats = table.apply_generic(node.qubits, g.codes, g.coeffs, atol, simplify=True)
+        info.updates += int(stats.updates)
+        info.applied_gates += 1
+        applied = applied[1:]
 
     def flush():
         nonlocal seg, stats
@@ -428,6 +445,15 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
         # sharded table, last gate Clifford-class: its coset count would need a cross-rank exchange
         sm.num_unique_paulis[i] = sm.num_duplicate_paulis[i] = sm.num_trimmed_paulis[i] = None
         sm.sum_trimmed_coeffs[i] = None
+
+
+def _has_duplicates_or_zeros(op: SparsePauliOp, atol: float) -> bool:
+    if len(op) == 0:
+        return False
+    if np.any(np.abs(op.coeffs) <= atol):
+        return True
+    xw, zw = op.packed()
+    return len(np.unique(np.concatenate([xw, zw], axis=1), axis=0)) != len(op)
 
 
 def _support(op: SparsePauliOp) -> list[int]:
