@@ -288,6 +288,8 @@ def pack_xz(x: np.ndarray, z: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
 def unpack_xz(xw: np.ndarray, zw: np.ndarray, num_qubits: int) -> tuple[np.ndarray, np.ndarray]:
     """Inverse of :func:`pack_xz`."""
     n = xw.shape[0]
+    if n == 0:
+        return np.zeros((0, num_qubits), dtype=bool), np.zeros((0, num_qubits), dtype=bool)
 
     def _unpack(a):
         b = np.ascontiguousarray(a, dtype="<u8").view(np.uint8).reshape(n, -1)
