@@ -1,6 +1,6 @@
 """Multi-GPU check of the sharded table over NCCL (launch with torchrun, one rank per GPU).
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py [--parity-only]
 
 1. parity against the oracle on small circuits (every rank gets the whole result back),
 2. a large run (config 5 and config 2) for throughput with the exchange statistics.
@@ -49,6 +49,10 @@ want, _, md_w = oracle.backpropagate(wl.observables, wl.slices, **wl.kwargs())
 assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
 dist.barrier()
 log(f"[dist_check] parity vs oracle OK on {world} ranks (NCCL, P2P inbox exchange = {p2p})")
+
+if "--parity-only" in sys.argv:
+    dist.destroy_process_group()
+    sys.exit(0)
 
 # ---- 2. throughput -----------------------------------------------------------------------------------
 def run(wl, tag):
