@@ -266,6 +266,8 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    if args.no_download:
+        os.environ["OBP_B200_DOWNLOAD"] = "0"
     sharded = bool(args.sharded) and world > 1
     if sharded:
         os.environ["OBP_B200_SHARDED"] = "1"  # one observable, hash-sharded over all ranks (strong scaling)
@@ -390,7 +392,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                 ),
                 "l2": "256 MiB buffer rewritten before every step (L2 flush)",
             },
-            "e2e": {
+            "e2e": None if args.no_download else {
                 "value": updates_all / e2e_s,
                 "unit": UNIT,
                 "ms_per_step": 1e3 * e2e_s / max(1, args.steps),
@@ -446,6 +448,8 @@ def main() -> None:
     ap.add_argument("--max-paulis", type=int, default=1_000_000)
     ap.add_argument("--cpu-updates", type=int, default=600_000, help="bound of the CPU sample (term-gate updates)")
     ap.add_argument("--depth", type=int, default=0, help="circuit depth of config4/config5 (0 = 200 / 40)")
+    ap.add_argument("--no-download", action="store_true", help="leave the result on the device(s): for 1e8-term tables whose "
+                    "host copy would be tens of GB (e2e is then not an end-to-end number and is reported as null)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-table", action="store_true", help="skip the extra HBM-regime roofline pass")
     ap.add_argument("--sharded", action="store_true", help="N>1: shard ONE observable over all ranks instead of one observable per rank")

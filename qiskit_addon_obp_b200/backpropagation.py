@@ -105,6 +105,9 @@ def backpropagate(
     device = engine.default_device()
     capacity = _default_capacity(num_qubits, operator_budget, n_obs, device)
     comm = communicator_from_env(device)  # None: one table per observable on this GPU
+    if comm is not None and hasattr(comm, "rank") and operator_budget.max_paulis is not None:
+        # one GPU per rank: the whole table may be n_ranks times what a single device holds
+        capacity = max(capacity, min(8 * int(operator_budget.max_paulis), capacity * comm.n_ranks))
     if comm is not None and raw:
         raise NotImplementedError("OperatorBudget(simplify=False) is not supported on a sharded table")
     if comm is not None:
@@ -276,6 +279,10 @@ def backpropagate(
                     for k, v in prof.items():
                         for f in v:
                             info.profile[k][f] += v[f]
+            if os.environ.get("OBP_B200_DOWNLOAD", "1") == "0":
+                # benchmark aid for tables of 1e8 terms (tens of GB): leave the result on the device(s)
+                obs_out.append(SparsePauliOp([], num_qubits=num_qubits))
+                continue
             obs_out.append(tables[i].download())
             info.d2h_bytes += len(obs_out[-1]) * (16 * tables[i].words + 16)
     finally:

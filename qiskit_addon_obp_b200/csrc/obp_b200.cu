@@ -1,6 +1,7 @@
 // obp_b200.cu — host side of the C-ABI in include/obp_b200.h: context, gate programs, truncation,
 // compaction, snapshot.  Kernels live in obp_kernels.cuh.  Built for sm_100a only.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -87,6 +88,7 @@ struct obp_ctx {
   u64* d_tbegin = nullptr;
   u64* h_tbegin = nullptr;  // pinned
   bool use_program = true;
+  bool trace_host = false;  // OBP_B200_TRACE_HOST: print host enqueue / wait time per gate program
   int prog_min_grid = 148;  // smallest grid of the persistent program kernel (grid barriers cost more with more CTAs)
   int prog_reach_shift = 6;  // the grid is sized for rows << min(#rotations, this)
   u64 n_live = 0, n_dense = 0;
@@ -363,10 +365,10 @@ void frame_update(obp_ctx* ctx, const obp_op& op) {
     old_col[2 * j + 1] = ctx->hz[op.qubit[j]];
   }
   // new column j = XOR of old columns over the bits of the preimage of basis vector e_j
+  unsigned inv[16];
+  for (unsigned v = 0; v < (1u << nb); ++v) inv[(op.lut >> (4 * v)) & 15ull] = v;
   for (int j = 0; j < nb; ++j) {
-    unsigned pre = 0;
-    for (unsigned v = 0; v < (1u << nb); ++v)
-      if (((op.lut >> (4 * v)) & 15ull) == (1ull << j)) pre = v;
+    const unsigned pre = inv[1u << j];
     u64 c = 0;
     for (int i = 0; i < nb; ++i)
       if (pre & (1u << i)) c ^= old_col[i];
@@ -652,6 +654,7 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     {
       const char* env = getenv("OBP_B200_NO_PROGRAM");
       ctx->use_program = !(env && env[0] && env[0] != '0');
+      if (const char* e1 = getenv("OBP_B200_TRACE_HOST")) ctx->trace_host = e1[0] && e1[0] != '0';
       if (const char* e2 = getenv("OBP_B200_PROG_MIN_GRID")) ctx->prog_min_grid = std::max(1, atoi(e2));
       if (const char* e3 = getenv("OBP_B200_PROG_REACH_SHIFT")) ctx->prog_reach_shift = std::max(0, atoi(e3));
     }
@@ -846,6 +849,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     const int vrc = validate_op(ctx, ops[k]);
     if (vrc) return vrc;
   }
+  const auto t_host0 = std::chrono::steady_clock::now();
   // tables of <= 128 qubits: record the program and run it with ONE persistent cooperative launch
   // (large tables keep the stand-alone kernels: a launch is cheap next to a pass over >= 2^18 rows and
   // k_rotate alone holds one more CTA per SM than the program kernel)
@@ -938,7 +942,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
 
   // one-qubit Cliffords held back per qubit (see FusedGate)
   std::vector<FusedGate> pend(ctx->nq);
-  std::vector<int> pend_list;  // qubits with a pending gate, in arrival order
+  int n_pending = 0;  // qubits with a held-back gate
 
   // put one (possibly fused) Clifford gate into the current batch
   auto emit_gate = [&](const FusedGate& fg) -> int {
@@ -1057,12 +1061,11 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     if (pend[q].n_gates == 0) return OBP_OK;
     const FusedGate fg = pend[q];
     pend[q] = FusedGate();
-    pend_list.erase(std::remove(pend_list.begin(), pend_list.end(), q), pend_list.end());
+    n_pending--;
     return emit_gate(fg);
   };
-  auto release_all = [&]() -> int {
-    const std::vector<int> qs = pend_list;
-    for (int q : qs) {
+  auto release_all = [&]() -> int {  // descending qubit order: the order gates of a layer arrive in
+    for (int q = ctx->nq - 1; q >= 0 && n_pending > 0; --q) {
       const int r = release_qubit(q);
       if (r) return r;
     }
@@ -1080,7 +1083,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
         const FusedGate g = fused_from_op(op);
         if (pend[q].n_gates == 0) {
           pend[q] = g;
-          pend_list.push_back(q);
+          n_pending++;
         } else {
           pend[q] = fuse_seq(pend[q], g);
         }
@@ -1093,12 +1096,12 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
         if (pend[qb].n_gates) {
           g = fuse_seq(embed_1q(pend[qb], 1, qa, qb), g);
           pend[qb] = FusedGate();
-          pend_list.erase(std::remove(pend_list.begin(), pend_list.end(), qb), pend_list.end());
+          n_pending--;
         }
         if (pend[qa].n_gates) {
           g = fuse_seq(embed_1q(pend[qa], 0, qa, qb), g);
           pend[qa] = FusedGate();
-          pend_list.erase(std::remove(pend_list.begin(), pend_list.end(), qa), pend_list.end());
+          n_pending--;
         }
         rc = emit_gate(g);
         if (rc) return rc;
@@ -1255,7 +1258,14 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   }
   if (last_split >= 0) CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat) * (n_slots + n_entries), cudaMemcpyDeviceToHost, ctx->stream));
+  const auto t_host1 = std::chrono::steady_clock::now();
   const int sync_rc = sync_state(ctx);
+  if (ctx->trace_host) {
+    const auto t_host2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[obp host] ops %d slots %d: enqueue %.1f us, wait %.1f us\n", n_ops, n_slots,
+            std::chrono::duration<double, std::micro>(t_host1 - t_host0).count(),
+            std::chrono::duration<double, std::micro>(t_host2 - t_host1).count());
+  }
   ctx->last_split_is_last_op = last_split >= 0 && last_split == n_ops - 1;
   if (sync_rc && sync_rc != OBP_ERR_CAPACITY) return sync_rc;
   if (prog_mode && ctx->prof_on) {  // per-class device time from the stamps taken at the grid barriers
