@@ -446,7 +446,7 @@ def main() -> None:
     ap.add_argument("--theta", default=f"0.1,0.3,{np.pi / 4:.16f}", help="rotation angle(s), comma separated (config2: theta_h sweep)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernel launches with CUDA events")
     ap.add_argument("--max-paulis", type=int, default=1_000_000)
-    ap.add_argument("--cpu-updates", type=int, default=600_000, help="bound of the CPU sample (term-gate updates)")
+    ap.add_argument("--cpu-updates", type=int, default=3_000_000, help="bound of the CPU sample (term-gate updates)")
     ap.add_argument("--depth", type=int, default=0, help="circuit depth of config4/config5 (0 = 200 / 40)")
     ap.add_argument("--no-download", action="store_true", help="leave the result on the device(s): for 1e8-term tables whose "
                     "host copy would be tens of GB (e2e is then not an end-to-end number and is reported as null)")
