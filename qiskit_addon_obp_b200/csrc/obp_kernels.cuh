@@ -1246,24 +1246,31 @@ __global__ void __launch_bounds__(OBP_BS, 3) k_program(Tab t, const ProgEntry* _
                                                                   u64* __restrict__ t_begin) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
-  __shared__ __align__(16) unsigned char s_param[sizeof(CliffBatch) > sizeof(RotP) ? sizeof(CliffBatch) : sizeof(RotP)];
+  constexpr unsigned PARAM_BYTES = ((sizeof(CliffBatch) > sizeof(RotP) ? sizeof(CliffBatch) : sizeof(RotP)) + 15u) & ~15u;  // uint4 copies
+  __shared__ __align__(16) unsigned char s_param[2][PARAM_BYTES];  // double buffer: op k+1 is staged during op k
   static_assert(sizeof(CosetP) <= sizeof(CliffBatch), "parameter staging buffer too small");
   if (blockIdx.x == 0 && threadIdx.x == 0) *t_begin = global_timer_ns();
+  auto stage = [&](int k) {
+    const ProgEntry e = entries[k];
+    unsigned char* dst = s_param[k & 1];
+    for (unsigned b = threadIdx.x * 16u; b < e.bytes; b += OBP_BS * 16u)
+      *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(pool + e.offset + b);
+  };
+  if (n_entries > 0) stage(0);
   for (int k = 0; k < n_entries; ++k) {
     const ProgEntry e = entries[k];
-    __syncthreads();  // everybody is done with the previous op's parameters
-    for (unsigned b = threadIdx.x * 16u; b < e.bytes; b += OBP_BS * 16u)
-      *reinterpret_cast<uint4*>(s_param + b) = *reinterpret_cast<const uint4*>(pool + e.offset + b);
-    __syncthreads();
+    __syncthreads();  // op k's parameters are complete; everybody is done with op k-1's buffer
+    if (k + 1 < n_entries) stage(k + 1);  // these loads are in flight while op k runs
+    const unsigned char* par = s_param[k & 1];
     u64 n = ld_volatile(&t.st->n_append);  // stable: appends of the previous op ended at the barrier
     if (n > t.cap) n = t.cap;
     u64* live_ctr = &t.ops[e.slot].dlive;
     if (e.kind == PROG_ROTATE) {
-      rotate_body(t, *reinterpret_cast<const RotP*>(s_param), n, live_ctr);
+      rotate_body(t, *reinterpret_cast<const RotP*>(par), n, live_ctr);
     } else if (e.kind == PROG_CLIFFORD) {
-      clifford_reg_body<W>(t, *reinterpret_cast<const CliffBatch*>(s_param), n, live_ctr);
+      clifford_reg_body<W>(t, *reinterpret_cast<const CliffBatch*>(par), n, live_ctr);
     } else {
-      coset_body(t, *reinterpret_cast<const CosetP*>(s_param), n);
+      coset_body(t, *reinterpret_cast<const CosetP*>(par), n);
     }
     __threadfence();
     grid.sync();
