@@ -1249,16 +1249,22 @@ __global__ void __launch_bounds__(OBP_BS, 3) k_program(Tab t, const ProgEntry* _
   constexpr unsigned PARAM_BYTES = ((sizeof(CliffBatch) > sizeof(RotP) ? sizeof(CliffBatch) : sizeof(RotP)) + 15u) & ~15u;  // uint4 copies
   __shared__ __align__(16) unsigned char s_param[2][PARAM_BYTES];  // double buffer: op k+1 is staged during op k
   static_assert(sizeof(CosetP) <= sizeof(CliffBatch), "parameter staging buffer too small");
+  // the entry table of the program (16 B per op) is read once into shared memory
+  constexpr int ENTRY_CACHE = 384;
+  __shared__ ProgEntry s_entries[ENTRY_CACHE];
+  for (int k = threadIdx.x; k < n_entries && k < ENTRY_CACHE; k += OBP_BS) s_entries[k] = entries[k];
+  __syncthreads();
+  auto entry = [&](int k) -> ProgEntry { return k < ENTRY_CACHE ? s_entries[k] : entries[k]; };
   if (blockIdx.x == 0 && threadIdx.x == 0) *t_begin = global_timer_ns();
   auto stage = [&](int k) {
-    const ProgEntry e = entries[k];
+    const ProgEntry e = entry(k);
     unsigned char* dst = s_param[k & 1];
     for (unsigned b = threadIdx.x * 16u; b < e.bytes; b += OBP_BS * 16u)
       *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(pool + e.offset + b);
   };
   if (n_entries > 0) stage(0);
   for (int k = 0; k < n_entries; ++k) {
-    const ProgEntry e = entries[k];
+    const ProgEntry e = entry(k);
     __syncthreads();  // op k's parameters are complete; everybody is done with op k-1's buffer
     if (k + 1 < n_entries) stage(k + 1);  // these loads are in flight while op k runs
     const unsigned char* par = s_param[k & 1];
@@ -1272,8 +1278,7 @@ __global__ void __launch_bounds__(OBP_BS, 3) k_program(Tab t, const ProgEntry* _
     } else {
       coset_body(t, *reinterpret_cast<const CosetP*>(par), n);
     }
-    __threadfence();
-    grid.sync();
+    grid.sync();  // (includes the memory fence that makes this op's stores visible grid-wide)
     if (blockIdx.x == 0 && threadIdx.x == 0) t.ops[k + n_slots].t_end = global_timer_ns();  // stamps live behind the slots
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
