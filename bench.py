@@ -120,6 +120,12 @@ class ClockSampler:
             if len(parts) == 6:
                 self.samples.append((time.perf_counter(), parts))
 
+    def wait_ready(self, timeout: float = 8.0):
+        """Block until nvidia-smi delivered its first sample: its start-up (NVML init) stalls GPU work."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
     def mark_begin(self):
         """Only samples taken from now on count (nvidia-smi is started earlier: its start-up stalls CUDA calls)."""
         self.t_begin = time.perf_counter()
@@ -309,7 +315,8 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()  # before the warm-up: by the timed region it is in its steady 100 ms polling
+        sampler.start()  # before the warm-up: by the timed region it is in its steady polling
+        sampler.wait_ready()
     for _ in range(args.warmup):
         one_step()
     barrier()

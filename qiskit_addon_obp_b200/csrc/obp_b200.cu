@@ -836,6 +836,14 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
                          {stage + words, z_words, words * sizeof(u64)},
                          {ctx->coef, coeffs, (size_t)n * sizeof(double2)}};
   for (const Part& p : parts) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p.dst) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+      // the caller handed us page-locked memory (e.g. a torch pinned tensor): one direct copy
+      CU(cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      continue;
+    }
+    cudaGetLastError();  // a pageable pointer makes cudaPointerGetAttributes report an error on some drivers
     for (size_t off = 0; off < p.bytes; off += OBP_BOUNCE_BYTES) {
       const size_t len = std::min<size_t>(OBP_BOUNCE_BYTES, p.bytes - off);
       CU(cudaMemcpyAsync(ctx->h_bounce, (const char*)p.src + off, len, cudaMemcpyDeviceToHost, ctx->stream));

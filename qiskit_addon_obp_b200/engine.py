@@ -176,6 +176,22 @@ EXPORTED_SYMBOLS = (
 ).split()
 
 
+def _host_buffer(shape, dtype) -> np.ndarray:
+    """Result array for a download: page-locked (through torch's caching host allocator) when torch is
+    there, so the device-to-host copy lands in it directly at full PCIe rate; plain numpy otherwise."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    if nbytes >= (1 << 16):
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True).numpy().view(dtype).reshape(shape)
+        except Exception:  # noqa: BLE001 - torch missing or pinned allocation refused: pageable memory works too
+            pass
+    return np.empty(shape, dtype=dtype)
+
+
 def device_memory(device: int = 0) -> tuple[int, int]:
     free, total = C.c_uint64(), C.c_uint64()
     rc = lib().obp_device_memory(device, C.byref(free), C.byref(total))
@@ -314,9 +330,9 @@ class TermTable:
             z = np.zeros((1, self.num_qubits), dtype=bool)
             return SparsePauliOp((z.copy(), z), np.array([0j]))
         n = self.n
-        xw = np.empty((max(n, 1), self.words), dtype="<u8")
-        zw = np.empty((max(n, 1), self.words), dtype="<u8")
-        co = np.empty(max(n, 1), dtype=np.complex128)
+        xw = _host_buffer((max(n, 1), self.words), "<u8")
+        zw = _host_buffer((max(n, 1), self.words), "<u8")
+        co = _host_buffer((max(n, 1),), np.complex128)
         got = C.c_uint64()
         rc = self._lib.obp_download(
             self._h,
