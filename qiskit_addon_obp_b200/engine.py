@@ -181,7 +181,7 @@ def _host_buffer(shape, dtype) -> np.ndarray:
     there, so the device-to-host copy lands in it directly at full PCIe rate; plain numpy otherwise."""
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
-    if nbytes >= (1 << 16):
+    if nbytes >= (1 << 16) and os.environ.get("OBP_B200_PINNED_RESULT", "1") != "0":
         try:
             import torch
 
