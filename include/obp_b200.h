@@ -155,6 +155,15 @@ int obp_restore(obp_ctx* ctx);
 /* Grow the table to hold new_capacity terms (contents preserved). */
 int obp_reserve(obp_ctx* ctx, uint64_t new_capacity);
 
+/* Row-order mode (off by default).  The reference's simplify() returns rows in the order of each
+ * key's first appearance among the gate's k*k raw rows (utils/simplify.py:126,160-165 on top of the
+ * compose order of utils/operations.py:103-105); the in-place gate kernels of obp_apply_ops do not
+ * keep that order.  With the mode on, obp_load / obp_apply_generic / obp_apply_reset /
+ * obp_apply_damping / obp_truncate leave the table in exactly the reference's row order (every gate
+ * must then go through obp_apply_generic; obp_apply_ops returns OBP_ERR_UNSUPPORTED).  Costs 12
+ * bytes of scratch per term of capacity and the k*k expansion per gate.  Single-GPU tables only. */
+int obp_set_row_order(obp_ctx* ctx, int32_t enabled);
+
 /* ---- sharded table (multi-GPU) ---------------------------------------------------------------
  * One process per GPU; rank r of R (a power of two) holds the terms whose Clifford-invariant hash
  * has its top log2(R) bits equal to r, so duplicate keys co-locate and Clifford gates, damping and

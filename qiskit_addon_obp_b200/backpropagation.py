@@ -96,6 +96,10 @@ def backpropagate(
 
     _validate_input_options(obs_in, slices_ir, operator_budget)
     raw = not operator_budget.simplify  # nothing merged or trimmed: every gate is a raw k*k expansion
+    # OBP_B200_ROW_ORDER=1: rows come back in exactly the reference's order (first appearance among each
+    # gate's k*k raw rows).  A slow parity mode: every gate runs as the literal expansion + ordered merge.
+    ordered = os.environ.get("OBP_B200_ROW_ORDER", "0") == "1" and not raw
+    expand_all = raw or ordered
 
     atol = SparsePauliOp.atol if operator_budget.atol is None else float(operator_budget.atol)
     num_qubits = slices_ir[0].num_qubits
@@ -110,6 +114,8 @@ def backpropagate(
         capacity = max(capacity, min(8 * int(operator_budget.max_paulis), capacity * comm.n_ranks))
     if comm is not None and raw:
         raise NotImplementedError("OperatorBudget(simplify=False) is not supported on a sharded table")
+    if comm is not None and ordered:
+        raise NotImplementedError("OBP_B200_ROW_ORDER=1 is not supported on a sharded table")
     if comm is not None:
         if n_obs > 1 and operator_budget.is_active():
             raise NotImplementedError("a sharded table supports operator budgets for a single observable only")
@@ -147,6 +153,7 @@ def backpropagate(
             cap_i = max(capacity, 2 * len(obs_in[i]))
             if comm is None:
                 tables.append(TermTable.acquire(num_qubits, cap_i, device))
+                tables[-1].set_row_order(ordered)
             else:
                 tables.append(ShardedTable.acquire(num_qubits, cap_i, comm))
         try:
@@ -164,7 +171,7 @@ def backpropagate(
                     num_qwc_groups=None,
                 )
                 metadata.backpropagation_history.append(sm)
-                prog = _slice_program(slice_, raw)
+                prog = _slice_program(slice_, expand_all)
                 overflowed = False
                 for i in range(n_obs):
                     support = set(qargs[i])
@@ -185,10 +192,14 @@ def backpropagate(
                             # An input with duplicate or near-zero rows reaches the reference's first gate
                             # unsimplified (raw_num_paulis counts every given row): keep the rows as given and
                             # run that one gate as the literal k*k expansion + simplify.
-                            raw_first[i] = (
-                                dirty[i] and not raw and comm is None and not prog.special[applied[0]]
-                                and applied[0] not in prog.errors
-                            )
+                            first = applied[0]
+                            if ordered:  # every gate is an expansion + merge anyway; so is the ordered reset
+                                raw_first[i] = dirty[i] and prog.nodes[first].name != "LayerError"
+                            else:
+                                raw_first[i] = (
+                                    dirty[i] and not raw and comm is None and not prog.special[first]
+                                    and first not in prog.errors
+                                )
                             tables[i].load(obs_in[i], OBP_ATOL_RAW if (raw or raw_first[i]) else None)
                             info.h2d_bytes += len(obs_in[i]) * (16 * tables[i].words + 16)
                             tables[i].profile_enable(PROFILE)
@@ -198,7 +209,7 @@ def backpropagate(
                             loaded[i] = True
                         while True:
                             try:
-                                _run_slice(tables[i], prog, applied, atol, sm, i, info, raw, raw_first[i])
+                                _run_slice(tables[i], prog, applied, atol, sm, i, info, raw, raw_first[i] and not ordered)
                                 raw_first[i] = False
                                 if trunc_active:
                                     budget = metadata.left_over_error_budget(i, sidx)

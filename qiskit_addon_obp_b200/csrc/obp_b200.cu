@@ -83,6 +83,11 @@ struct obp_ctx {
   TruncState* d_ts = nullptr;
   TruncState* h_ts = nullptr;  // pinned
   int trunc_ctas_per_sm = 0;  // resident CTAs of k_trunc_search per SM; 0 = cooperative launch unavailable
+  bool row_order = false;          // rows are kept in the reference's first-appearance order
+  unsigned* ord_minidx = nullptr;  // row-order mode scratch: first raw position per key, flags, positions (cap u32 each)
+  unsigned* ord_flag = nullptr;
+  unsigned* ord_pos = nullptr;
+  u64 ord_cap = 0;
   void* h_bounce = nullptr;  // pinned bounce buffer of downloads (OBP_BOUNCE_BYTES)
   u64* d_stage = nullptr;  // download staging for tables too wide for the compaction scratch
   size_t stage_bytes = 0;
@@ -260,9 +265,31 @@ void init_frame(obp_ctx* ctx) {
 int rebuild_index(obp_ctx* ctx) {
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
   Bracket b(ctx, OBP_K_INDEX);
-  k_index_build<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), 0, -1.0, ctx->epoch, -1);
+  k_index_build<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), 0, -1.0, ctx->epoch, -1, nullptr);
   CU(cudaGetLastError());
   return OBP_OK;
+}
+
+// move every row i with dest[i] != NONE to row dest[i] (all columns), then rebuild the index;
+// st->scan_total holds the new row count
+int scatter_by_dest(obp_ctx* ctx) {
+  const int g = grid_for(ctx, ctx->n_dense);
+  for (int w = 0; w < ctx->W; ++w) {
+    k_scatter16<<<g, OBP_BS, 0, ctx->stream>>>(ctx->xz[w], ctx->spare16, ctx->dest, ctx->d_st);
+    std::swap(ctx->xz[w], ctx->spare16);
+  }
+  k_scatter16<<<g, OBP_BS, 0, ctx->stream>>>((const ulonglong2*)ctx->coef, ctx->spare16, ctx->dest, ctx->d_st);
+  {
+    ulonglong2* old = (ulonglong2*)ctx->coef;
+    ctx->coef = (double2*)ctx->spare16;
+    ctx->spare16 = old;
+  }
+  k_scatter8<<<g, OBP_BS, 0, ctx->stream>>>(ctx->hash, ctx->spare8, ctx->dest, ctx->d_st);
+  std::swap(ctx->hash, ctx->spare8);
+  k_set_counts<<<1, 1, 0, ctx->stream>>>(ctx->d_st);
+  CU(cudaGetLastError());
+  ctx->n_dense = ctx->n_live;  // n_live is exact on the host at every call site
+  return rebuild_index(ctx);
 }
 
 // stable compaction of all columns + index rebuild; leaves n_dense == n_live
@@ -270,29 +297,40 @@ int compact(obp_ctx* ctx) {
   if (ctx->n_dense == 0) return OBP_OK;
   const u64 nb = (ctx->n_dense + OBP_CHUNK - 1) / OBP_CHUNK;
   Tab t = make_tab(ctx);
-  {
-    Bracket b(ctx, OBP_K_COMPACT, 5 + ctx->W + 2);
-    k_live_count<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(t, ctx->blk);
-    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk, nb, ctx->d_st);
-    k_dest<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(t, ctx->blk, ctx->dest);
-    const int g = grid_for(ctx, ctx->n_dense);
-    for (int w = 0; w < ctx->W; ++w) {
-      k_scatter16<<<g, OBP_BS, 0, ctx->stream>>>(ctx->xz[w], ctx->spare16, ctx->dest, ctx->d_st);
-      std::swap(ctx->xz[w], ctx->spare16);
-    }
-    k_scatter16<<<g, OBP_BS, 0, ctx->stream>>>((const ulonglong2*)ctx->coef, ctx->spare16, ctx->dest, ctx->d_st);
-    {
-      ulonglong2* old = (ulonglong2*)ctx->coef;
-      ctx->coef = (double2*)ctx->spare16;
-      ctx->spare16 = old;
-    }
-    k_scatter8<<<g, OBP_BS, 0, ctx->stream>>>(ctx->hash, ctx->spare8, ctx->dest, ctx->d_st);
-    std::swap(ctx->hash, ctx->spare8);
-    k_set_counts<<<1, 1, 0, ctx->stream>>>(ctx->d_st);
-    CU(cudaGetLastError());
-  }
-  ctx->n_dense = ctx->n_live;  // n_live is exact on the host at every call site
-  return rebuild_index(ctx);
+  Bracket b(ctx, OBP_K_COMPACT, 5 + ctx->W + 2);
+  k_live_count<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(t, ctx->blk);
+  k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk, nb, ctx->d_st);
+  k_dest<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(t, ctx->blk, ctx->dest);
+  return scatter_by_dest(ctx);
+}
+
+// Row-order mode: like compact(), but the survivors land in the order of their keys' first
+// appearance among the raw rows (ord_minidx was filled by k_index_build).
+int compact_in_first_appearance_order(obp_ctx* ctx) {
+  if (ctx->n_dense == 0) return OBP_OK;
+  const u64 nb = (ctx->n_dense + OBP_CHUNK - 1) / OBP_CHUNK;
+  Tab t = make_tab(ctx);
+  Bracket b(ctx, OBP_K_COMPACT, 9 + ctx->W + 2);
+  const int g = grid_for(ctx, ctx->n_dense);
+  CU(cudaMemsetAsync(ctx->ord_flag, 0, ctx->n_dense * sizeof(unsigned), ctx->stream));
+  k_order_flags<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->ord_minidx, ctx->ord_flag);
+  k_flag_count<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(ctx->ord_flag, ctx->d_st, ctx->blk);
+  k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->blk, nb, ctx->d_st);
+  k_flag_pos<<<(unsigned)nb, OBP_BS, 0, ctx->stream>>>(ctx->ord_flag, ctx->d_st, ctx->blk, ctx->ord_pos);
+  k_order_dest<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->ord_minidx, ctx->ord_pos, ctx->dest);
+  return scatter_by_dest(ctx);
+}
+
+// compaction after a merge of raw rows: stable, or into first-appearance order (row-order mode)
+int compact_after_merge(obp_ctx* ctx) {
+  return ctx->row_order ? compact_in_first_appearance_order(ctx) : compact(ctx);
+}
+
+// row-order mode: every row starts as its own first appearance
+int reset_first_appearance(obp_ctx* ctx, u64 n_rows) {
+  if (!ctx->row_order || !n_rows) return OBP_OK;
+  CU(cudaMemsetAsync(ctx->ord_minidx, 0xFF, n_rows * sizeof(unsigned), ctx->stream));
+  return OBP_OK;
 }
 
 int set_counts(obp_ctx* ctx, u64 n) {
@@ -685,6 +723,9 @@ void obp_destroy(obp_ctx* ctx) {
   cudaFree(ctx->d_prog);
   cudaFree(ctx->d_tbegin);
   cudaFree(ctx->d_stage);
+  cudaFree(ctx->ord_minidx);
+  cudaFree(ctx->ord_flag);
+  cudaFree(ctx->ord_pos);
   if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
   cudaFree(ctx->d_ts);
   if (ctx->h_ts) cudaFreeHost(ctx->h_ts);
@@ -758,7 +799,9 @@ int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, con
     k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n);
     if (ctx->n_ranks > 1) k_shard_filter<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->owner_shift, (u64)ctx->rank);
     ctx->epoch++;
-    k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ctx->epoch, 0);
+    rc = reset_first_appearance(ctx, n);
+    if (rc) return rc;
+    k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ctx->epoch, 0, ctx->row_order ? ctx->ord_minidx : nullptr);
     ctx->epoch++;
     k_trim<<<g, OBP_BS, 0, ctx->stream>>>(t, atol, ctx->epoch, 0);
     CU(cudaGetLastError());
@@ -781,7 +824,7 @@ int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, con
     stats->n_out = ctx->n_live;
   }
   if (ctx->n_dense != ctx->n_live) {
-    rc = compact(ctx);
+    rc = atol == OBP_ATOL_RAW ? compact(ctx) : compact_after_merge(ctx);
     if (rc) return rc;
     rc = sync_state(ctx);
     if (rc) return rc;
@@ -815,6 +858,9 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
     if (words * 2 * sizeof(u64) > ctx->stage_bytes) {
       CU(cudaStreamSynchronize(ctx->stream));
       cudaFree(ctx->d_stage);
+  cudaFree(ctx->ord_minidx);
+  cudaFree(ctx->ord_flag);
+  cudaFree(ctx->ord_pos);
   if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
       ctx->d_stage = nullptr;
       ctx->stage_bytes = 0;
@@ -1364,6 +1410,9 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
 }
 
 int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats) {
+  if (ctx && ctx->row_order)
+    return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_ops: in-place gate kernels do not keep the reference's row order; "
+                                          "use obp_apply_generic in row-order mode");
   return apply_ops_impl(ctx, ops, n_ops, atol, stats, nullptr, nullptr);
 }
 
@@ -1779,7 +1828,9 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
     Bracket br(ctx, OBP_K_INDEX, 3);
     const int g = grid_for(ctx, n + raw);
     k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n + raw);
-    k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ++ctx->epoch, 0);
+    rc = reset_first_appearance(ctx, n + raw);
+    if (rc) return rc;
+    k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ++ctx->epoch, 0, ctx->row_order ? ctx->ord_minidx : nullptr);
     k_trim<<<g, OBP_BS, 0, ctx->stream>>>(t, atol, ++ctx->epoch, 0);
     CU(cudaGetLastError());
   }
@@ -1798,7 +1849,7 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
     stats->sum_trimmed[0] = o.sum_re;
     stats->sum_trimmed[1] = o.sum_im;
   }
-  rc = compact(ctx);
+  rc = compact_after_merge(ctx);
   if (rc) return rc;
   rc = sync_state(ctx);
   if (rc) return rc;
@@ -1807,6 +1858,59 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
 }
 
 // -------------------------------------------------------------------------------------------------
+// Row-order mode reset: the literal reference sequence — zero the X/Y rows and clear the qubit in
+// place (utils/operations.py:221-223), then simplify the rows where they lie (backpropagation.py:191).
+static int reset_in_row_order(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) {
+  int rc;
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  const u64 n_in = ctx->n_live;
+  rc = upload_cols(ctx);
+  if (rc) return rc;
+  rc = ensure_ops(ctx, 4);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
+  CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  Tab t = make_tab(ctx);
+  if (n_in) {
+    Bracket br(ctx, OBP_K_OTHER, 4);
+    const int g = grid_for(ctx, n_in);
+    k_reset_raw<<<g, OBP_BS, 0, ctx->stream>>>(t, qubit / 64, 1ull << (qubit % 64));
+    k_hash_rows<<<g, OBP_BS, 0, ctx->stream>>>(t, ctx->d_cols, n_in);
+    rc = reset_first_appearance(ctx, n_in);
+    if (rc) return rc;
+    k_index_build<<<g, OBP_BS, 0, ctx->stream>>>(t, 1, atol, ++ctx->epoch, 0, ctx->ord_minidx);
+    k_trim<<<g, OBP_BS, 0, ctx->stream>>>(t, atol, ++ctx->epoch, 0);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_state(ctx);
+  if (rc) return rc;
+  ctx->prof.term_updates[OBP_K_OTHER] += n_in;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    const OpStat& o = ctx->h_ops[0];
+    stats->n_in = stats->raw_rows = stats->updates = n_in;
+    stats->num_unique = o.keys_present;
+    stats->num_duplicate = o.rows_surv - o.keys_present;
+    stats->num_trimmed = (n_in - o.rows_surv) + o.cancelled;
+    stats->sum_trimmed[0] = o.sum_re;
+    stats->sum_trimmed[1] = o.sum_im;
+  }
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact_in_first_appearance_order(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  if (stats) { stats->n_out = ctx->n_live; stats->n_dense = ctx->n_dense; }
+  return OBP_OK;
+}
+
 int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) {
   if (!ctx || qubit < 0 || qubit >= ctx->nq) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
@@ -1828,6 +1932,7 @@ int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) 
     }
     return OBP_OK;
   }
+  if (ctx->row_order) return reset_in_row_order(ctx, qubit, atol, stats);
   int rc = ensure_ops(ctx, 2);
   if (rc) return rc;
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat), ctx->stream));
@@ -2109,6 +2214,20 @@ int obp_restore(obp_ctx* ctx) {
   return sync_state(ctx);
 }
 
+static int alloc_row_order_scratch(obp_ctx* ctx) {
+  if (ctx->ord_cap >= ctx->cap) return OBP_OK;
+  cudaFree(ctx->ord_minidx);
+  cudaFree(ctx->ord_flag);
+  cudaFree(ctx->ord_pos);
+  ctx->ord_minidx = ctx->ord_flag = ctx->ord_pos = nullptr;
+  ctx->ord_cap = 0;
+  CU(cudaMalloc(&ctx->ord_minidx, ctx->cap * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->ord_flag, ctx->cap * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->ord_pos, ctx->cap * sizeof(unsigned)));
+  ctx->ord_cap = ctx->cap;
+  return OBP_OK;
+}
+
 int obp_reserve(obp_ctx* ctx, uint64_t new_capacity) {
   if (!ctx || new_capacity >= 0xffffffffull) return OBP_ERR_BADARG;
   if (new_capacity <= ctx->cap) return OBP_OK;
@@ -2164,9 +2283,21 @@ int obp_reserve(obp_ctx* ctx, uint64_t new_capacity) {
   CU(cudaMalloc(&ctx->spare8, cap * sizeof(u64)));
   CU(cudaMalloc(&ctx->dest, cap * sizeof(unsigned)));
   CU(cudaMalloc(&ctx->blk, ((cap + OBP_CHUNK - 1) / OBP_CHUNK + 1) * sizeof(unsigned)));
+  if (ctx->row_order) {
+    rc = alloc_row_order_scratch(ctx);
+    if (rc) return rc;
+  }
   rc = rebuild_index(ctx);
   if (rc) return rc;
   return sync_state(ctx);
+}
+
+int obp_set_row_order(obp_ctx* ctx, int32_t enabled) {
+  if (!ctx) return OBP_ERR_BADARG;
+  if (enabled && ctx->n_ranks > 1) return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_set_row_order: not available on a sharded table");
+  CU(cudaSetDevice(ctx->device));
+  ctx->row_order = enabled != 0;
+  return ctx->row_order ? alloc_row_order_scratch(ctx) : OBP_OK;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -2220,7 +2351,7 @@ int obp_union_count(obp_ctx* const* ctxs, int32_t n_ctx, uint64_t* n_distinct) {
   cudaMemsetAsync(sc->index, 0xFF, sc->T * sizeof(u64), sc->stream);
   ts = make_tab(sc);
   k_hash_rows<<<grid_for(sc, total), OBP_BS, 0, sc->stream>>>(ts, sc->d_cols, total);
-  k_index_build<<<grid_for(sc, total), OBP_BS, 0, sc->stream>>>(ts, 1, -1.0, ++sc->epoch, 0);
+  k_index_build<<<grid_for(sc, total), OBP_BS, 0, sc->stream>>>(ts, 1, -1.0, ++sc->epoch, 0, nullptr);
   if (cudaGetLastError() != cudaSuccess) return ctx->fail(OBP_ERR_CUDA, "union count launch failed");
   cudaMemcpyAsync(sc->h_ops, sc->d_ops, sizeof(OpStat), cudaMemcpyDeviceToHost, sc->stream);
   rc = sync_state(sc);

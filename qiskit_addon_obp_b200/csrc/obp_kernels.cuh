@@ -491,7 +491,10 @@ __global__ void __launch_bounds__(OBP_BS) k_hash_rows(Tab t, const u64* __restri
 // Insert every live row into the (cleared) index.  merge != 0: rows with equal keys are summed
 // into the first published one (fp64 atomicAdd; only reached for caller-supplied duplicates) and
 // rows with |c| <= atol (atol >= 0) are filtered first — the simplify() of a raw operator.
-__global__ void __launch_bounds__(OBP_BS) k_index_build(Tab t, int merge, double atol, u64 epoch, int slot) {
+// minidx (optional, row-order mode): minidx[r] of the row r that ends up holding a key = the smallest
+// row index among all rows with that key, i.e. the key's FIRST APPEARANCE among the raw rows.
+__global__ void __launch_bounds__(OBP_BS) k_index_build(Tab t, int merge, double atol, u64 epoch, int slot,
+                                                         unsigned* __restrict__ minidx) {
   const u64 n = t.st->n_scan;
   unsigned rows_surv = 0, published = 0;
   int deaths = 0;
@@ -521,7 +524,12 @@ __global__ void __launch_bounds__(OBP_BS) k_index_build(Tab t, int merge, double
       u64 e = ld_volatile(&t.index[s]);
       if (e == OBP_EMPTY) {
         e = atomicCAS(&t.index[s], OBP_EMPTY, entry);
-        if (e == OBP_EMPTY) { published++; done = true; break; }
+        if (e == OBP_EMPTY) {
+          if (minidx) atomicMin(&minidx[i], (unsigned)i);
+          published++;
+          done = true;
+          break;
+        }
       }
       if (merge && (e >> 32) == fp) {
         const u64 j = e & 0xffffffffull;
@@ -533,6 +541,7 @@ __global__ void __launch_bounds__(OBP_BS) k_index_build(Tab t, int merge, double
         if (eq) {
           atomicAdd(&t.coef[j].x, c.x);
           atomicAdd(&t.coef[j].y, c.y);
+          if (minidx) atomicMin(&minidx[j], (unsigned)i);
           t.coef[i] = tombstone(epoch);
           deaths++;
           done = true;
@@ -1639,4 +1648,64 @@ __global__ void __launch_bounds__(OBP_BS) k_reset_emit(Tab t, const __grid_const
     if (dl) atomicAdd(&t.st->n_live, (u64)(-dl));
   }
   finish_kernel(t, -1);
+}
+
+// ================================================================================================
+// Row-order mode: put the surviving rows in the order of their keys' first appearance among the raw
+// rows — the row order of the reference's simplify() (unordered_unique keeps first-appearance
+// order, utils/simplify.py:126, 160-165).  flag[p] = 1 iff some surviving key first appeared at raw
+// position p; an exclusive scan of the flags is the new row index of that key.
+// ================================================================================================
+__global__ void __launch_bounds__(OBP_BS) k_order_flags(Tab t, const unsigned* __restrict__ minidx,
+                                                         unsigned* __restrict__ flag) {
+  const u64 n = t.st->n_scan;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS)
+    if (is_live(t.coef[i])) flag[minidx[i]] = 1u;
+}
+
+__global__ void __launch_bounds__(OBP_BS) k_flag_count(const unsigned* __restrict__ flag, const DevState* st,
+                                                        unsigned* __restrict__ blk_cnt) {
+  __shared__ unsigned warp_tot[OBP_BS / 32];
+  const u64 n = st->n_scan;
+  const u64 base = (u64)blockIdx.x * OBP_CHUNK;
+  unsigned cnt = 0;
+#pragma unroll
+  for (int r = 0; r < OBP_CHUNK / OBP_BS; ++r) {
+    const u64 i = base + (u64)r * OBP_BS + threadIdx.x;
+    if (i < n && flag[i]) cnt++;
+  }
+  cnt = (unsigned)warp_sum_u64(cnt);
+  if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+#pragma unroll
+    for (int w = 0; w < OBP_BS / 32; ++w) tot += warp_tot[w];
+    blk_cnt[blockIdx.x] = tot;
+  }
+}
+
+// pos[p] = number of flags before p (only meaningful where flag[p] is set)
+__global__ void __launch_bounds__(OBP_BS) k_flag_pos(const unsigned* __restrict__ flag, const DevState* st,
+                                                      const unsigned* __restrict__ blk_off, unsigned* __restrict__ pos) {
+  __shared__ unsigned warp_tot[OBP_BS / 32];
+  const u64 n = st->n_scan;
+  const u64 base = (u64)blockIdx.x * OBP_CHUNK;
+  unsigned run = blk_off[blockIdx.x];
+#pragma unroll 1
+  for (int r = 0; r < OBP_CHUNK / OBP_BS; ++r) {
+    const u64 i = base + (u64)r * OBP_BS + threadIdx.x;
+    const bool f = i < n && flag[i] != 0;
+    unsigned total;
+    const unsigned off = block_scan_flag(f, warp_tot, total);
+    if (i < n) pos[i] = run + off;
+    run += total;
+  }
+}
+
+__global__ void __launch_bounds__(OBP_BS) k_order_dest(Tab t, const unsigned* __restrict__ minidx,
+                                                        const unsigned* __restrict__ pos, unsigned* __restrict__ dest) {
+  const u64 n = t.st->n_scan;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS)
+    dest[i] = is_live(t.coef[i]) ? pos[minidx[i]] : 0xffffffffu;
 }

@@ -131,6 +131,7 @@ def lib() -> C.CDLL:
         "obp_snapshot": ([vp], C.c_int),
         "obp_restore": ([vp], C.c_int),
         "obp_reserve": ([vp, C.c_uint64], C.c_int),
+        "obp_set_row_order": ([vp, C.c_int32], C.c_int),
         "obp_profile_enable": ([vp, C.c_int32], C.c_int),
         "obp_profile_get": ([vp, C.POINTER(ObpProfile), C.c_int32], C.c_int),
         "obp_set_shard": ([vp, C.c_int32, C.c_int32], C.c_int),
@@ -168,7 +169,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "obp_create obp_destroy obp_last_error obp_set_stream obp_device_memory obp_bytes_per_term "
     "obp_load obp_count obp_download obp_apply_ops obp_apply_generic obp_apply_reset obp_apply_damping obp_truncate "
-    "obp_union_count obp_snapshot obp_restore obp_reserve obp_profile_enable obp_profile_get "
+    "obp_union_count obp_snapshot obp_restore obp_reserve obp_set_row_order obp_profile_enable obp_profile_get "
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
@@ -238,6 +239,7 @@ class TermTable:
                 t.track_zero = True
                 t.set_shard(1, 0)
                 t.set_shard_sync(False)
+                t.set_row_order(False)
                 return t
         return cls(num_qubits, capacity, device)
 
@@ -454,6 +456,11 @@ class TermTable:
         self._check(self._lib.obp_restore(self._h), "obp_restore")
         self.zero_operator = self._snap_zero
         self.n = self._snap_n
+
+    def set_row_order(self, on: bool):
+        """Keep rows in the reference's first-appearance order (every gate must then be `apply_generic`)."""
+        self._check(self._lib.obp_set_row_order(self._h, int(bool(on))), "obp_set_row_order")
+        self.row_order = bool(on)
 
     def reserve(self, capacity: int):
         self._check(self._lib.obp_reserve(self._h, int(capacity)), "obp_reserve")
