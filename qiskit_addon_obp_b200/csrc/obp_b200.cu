@@ -35,6 +35,11 @@ struct Snapshot {
 struct obp_ctx {
   int device = 0, nq = 0, W = 0, n_sm = 148;
   u64 cap = 0, T = 0;
+  // The index is sized to the CAPACITY (T = next_pow2(2 cap) slots), not to the rows.  Measured on B200
+  // (config 2, theta 0.1, tables of 10^3..10^4 rows): an index sized to the rows (load factor 1/8..1/2)
+  // is slower (12.2 -> 15.8 ms of device time per run) — an absent partner costs one probe in a
+  // near-empty index and ~2.5 dependent probes at load 1/2, and that chain, not the L2 residency of the
+  // index, is what a small-table pass waits for.
   cudaStream_t stream = nullptr, own_stream = nullptr;
   ulonglong2* xz[OBP_MAX_WORDS] = {nullptr};
   double2* coef = nullptr;
@@ -44,6 +49,12 @@ struct obp_ctx {
   u64* spare8 = nullptr;
   unsigned* dest = nullptr;
   unsigned* blk = nullptr;
+  // d_st, d_tbegin and d_ops live in ONE device block (and h_st, h_tbegin, h_ops in one pinned block):
+  // [DevState | pad to 64 | t_begin | pad to 128 | OpStat x ops_alloc], so that a gate program brings
+  // its state, time stamps and counters back with a single copy
+  unsigned char* d_res = nullptr;
+  unsigned char* h_res = nullptr;  // pinned and mapped: the persistent program kernel writes its results into it
+  u64* h_res_dev = nullptr;        // device address of h_res
   DevState* d_st = nullptr;
   OpStat* d_ops = nullptr;
   int ops_alloc = 0;
@@ -97,6 +108,7 @@ struct obp_ctx {
   bool trace_host = false;  // OBP_B200_TRACE_HOST: print host enqueue / wait time per gate program
   int prog_min_grid = 148;  // smallest grid of the persistent program kernel (grid barriers cost more with more CTAs)
   int prog_reach_shift = 6;  // the grid is sized for rows << min(#rotations, this)
+  int prog_debug = 0;         // OBP_B200_PROG_DEBUG: timing experiments inside k_program (2: skip the table work)
   u64 n_live = 0, n_dense = 0;
   Snapshot snap;
   obp_ctx* scratch = nullptr;  // union-count scratch table
@@ -205,9 +217,16 @@ void resolve_events(obp_ctx* c) {
   c->ev_pending.clear();
 }
 
-int sync_state(obp_ctx* ctx) {
+constexpr size_t RES_HDR = OBP_RES_HDR;
+static_assert(sizeof(DevState) <= 64, "result block header layout");
+
+// Bring the table state back and wait for the stream.  n_ops > 0: the first n_ops counter slots (and the
+// program's start stamp) come along in the same copy.
+// written_by_kernel: the persistent program kernel already put all of that into h_res (mapped).
+int sync_state(obp_ctx* ctx, int n_ops = 0, bool written_by_kernel = false) {
   close_run(ctx);
-  CU(cudaMemcpyAsync(ctx->h_st, ctx->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t bytes = n_ops > 0 ? RES_HDR + sizeof(OpStat) * (size_t)n_ops : sizeof(DevState);
+  if (!written_by_kernel) CU(cudaMemcpyAsync(ctx->h_res, ctx->d_res, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   resolve_events(ctx);
   ctx->n_live = ctx->h_st->n_live;
@@ -225,14 +244,31 @@ int sync_state(obp_ctx* ctx) {
 
 int ensure_ops(obp_ctx* ctx, int n) {
   if (n <= ctx->ops_alloc) return OBP_OK;
-  int na = std::max(n, std::max(256, ctx->ops_alloc * 2));
-  if (ctx->d_ops) cudaFree(ctx->d_ops);
-  if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
-  ctx->d_ops = nullptr;
-  ctx->h_ops = nullptr;
-  ctx->ops_alloc = 0;
-  CU(cudaMalloc(&ctx->d_ops, sizeof(OpStat) * na));
-  CU(cudaMallocHost(&ctx->h_ops, sizeof(OpStat) * na));
+  const int na = std::max(n, std::max(256, ctx->ops_alloc * 2));
+  const size_t bytes = RES_HDR + sizeof(OpStat) * (size_t)na;
+  unsigned char *d = nullptr, *h = nullptr;
+  CU(cudaMalloc(&d, bytes));
+  CU(cudaHostAlloc(&h, bytes, cudaHostAllocMapped));
+  CU(cudaMemset(d, 0, RES_HDR));
+  memset(h, 0, RES_HDR);
+  if (ctx->d_res) {  // the table state moves with the block
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(d, ctx->d_res, RES_HDR, cudaMemcpyDeviceToDevice));
+    memcpy(h, ctx->h_res, RES_HDR);
+    cudaFree(ctx->d_res);
+    cudaFreeHost(ctx->h_res);
+  }
+  ctx->d_res = d;
+  ctx->h_res = h;
+  ctx->d_st = (DevState*)d;
+  ctx->d_tbegin = (u64*)(d + 64);
+  ctx->d_ops = (OpStat*)(d + RES_HDR);
+  ctx->h_st = (DevState*)h;
+  ctx->h_tbegin = (u64*)(h + 64);
+  ctx->h_ops = (OpStat*)(h + RES_HDR);
+  void* hd = nullptr;
+  CU(cudaHostGetDevicePointer(&hd, h, 0));
+  ctx->h_res_dev = (u64*)hd;
   ctx->ops_alloc = na;
   return OBP_OK;
 }
@@ -667,17 +703,15 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   auto body = [&]() -> int {
-    CU(cudaMalloc(&ctx->d_st, sizeof(DevState)));
-    CU(cudaMallocHost(&ctx->h_st, sizeof(DevState)));
+    int rc = ensure_ops(ctx, 256);  // also allocates the table state (d_st / h_st) and the start stamp
+    if (rc) return rc;
     CU(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 2));
     CU(cudaMalloc(&ctx->d_partial, sizeof(double) * (size_t)ctx->n_sm * 8));
     CU(cudaMalloc(&ctx->d_scalar, sizeof(double) * 2));
     CU(cudaMalloc(&ctx->d_cols, sizeof(u64) * 2 * 64 * ctx->W));
     CU(cudaMalloc(&ctx->d_cnt, sizeof(ShardCnt)));
     CU(cudaMallocHost(&ctx->h_cnt, sizeof(ShardCnt)));
-    int rc = alloc_table(ctx, capacity);
-    if (rc) return rc;
-    rc = ensure_ops(ctx, 256);
+    rc = alloc_table(ctx, capacity);
     if (rc) return rc;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->rot_ctas_per_sm, k_rotate, OBP_BS, 0));
     if (ctx->rot_ctas_per_sm < 1) ctx->rot_ctas_per_sm = 1;
@@ -689,14 +723,13 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->trunc_ctas_per_sm, k_trunc_search, OBP_BS, 0));
     CU(cudaMalloc(&ctx->d_ts, sizeof(TruncState)));
     CU(cudaMallocHost(&ctx->h_ts, sizeof(TruncState)));
-    CU(cudaMalloc(&ctx->d_tbegin, sizeof(u64)));
-    CU(cudaMallocHost(&ctx->h_tbegin, sizeof(u64)));
     {
       const char* env = getenv("OBP_B200_NO_PROGRAM");
       ctx->use_program = !(env && env[0] && env[0] != '0');
       if (const char* e1 = getenv("OBP_B200_TRACE_HOST")) ctx->trace_host = e1[0] && e1[0] != '0';
       if (const char* e2 = getenv("OBP_B200_PROG_MIN_GRID")) ctx->prog_min_grid = std::max(1, atoi(e2));
       if (const char* e3 = getenv("OBP_B200_PROG_REACH_SHIFT")) ctx->prog_reach_shift = std::max(0, atoi(e3));
+      if (const char* e6 = getenv("OBP_B200_PROG_DEBUG")) ctx->prog_debug = atoi(e6) & ~1;
     }
     init_frame(ctx);
     return set_counts(ctx, 0);
@@ -714,14 +747,12 @@ void obp_destroy(obp_ctx* ctx) {
   if (ctx->scratch) obp_destroy(ctx->scratch);
   free_table(ctx);
   free_snapshot(ctx->snap);
-  cudaFree(ctx->d_st);
-  cudaFree(ctx->d_ops);
+  cudaFree(ctx->d_res);
   cudaFree(ctx->d_partial);
   cudaFree(ctx->d_scalar);
   cudaFree(ctx->d_cols);
   cudaFree(ctx->d_cnt);
   cudaFree(ctx->d_prog);
-  cudaFree(ctx->d_tbegin);
   cudaFree(ctx->d_stage);
   cudaFree(ctx->ord_minidx);
   cudaFree(ctx->ord_flag);
@@ -730,13 +761,11 @@ void obp_destroy(obp_ctx* ctx) {
   cudaFree(ctx->d_ts);
   if (ctx->h_ts) cudaFreeHost(ctx->h_ts);
   if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
-  if (ctx->h_tbegin) cudaFreeHost(ctx->h_tbegin);
   free_inboxes(ctx);
   if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
   cudaFree(ctx->d_gens);
   cudaFree(ctx->d_factors);
-  if (ctx->h_st) cudaFreeHost(ctx->h_st);
-  if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
+  if (ctx->h_res) cudaFreeHost(ctx->h_res);
   if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
   for (auto& ep : ctx->ev_pending) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   for (auto& ep : ctx->ev_free) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
@@ -933,7 +962,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   static thread_local CliffStream cs;  // 32 KB: kept off the stack
   int rc = ensure_ops(ctx, 3 * n_ops + 2);
   if (rc) return rc;
-  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * (3 * n_ops + 2), ctx->stream));
+  if (!prog_mode) CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * (3 * n_ops + 2), ctx->stream));  // (a program zeroes its own slots)
 
   const u64 n_start = ctx->n_live;
   u64 bound = std::max<u64>(ctx->n_dense, 1);
@@ -1319,17 +1348,23 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     const ProgEntry* d_entries = (const ProgEntry*)ctx->d_prog;
     const unsigned char* d_pool = ctx->d_prog + ent_bytes;
     int ne = n_entries, ns = n_slots;
-    void* args[] = {(void*)&t, (void*)&d_entries, (void*)&ne, (void*)&d_pool, (void*)&ns, (void*)&ctx->d_tbegin};
+    int pflags = (ctx->prof_on ? 1 : 0) | ctx->prog_debug;
+    u64* host_res = ctx->h_res_dev;
+    int n_res_ops = n_slots + (ctx->prof_on ? n_entries : 0);
+    void* args[] = {(void*)&t, (void*)&d_entries, (void*)&ne, (void*)&d_pool, (void*)&ns, (void*)&ctx->d_tbegin, (void*)&pflags, (void*)&host_res, (void*)&n_res_ops};
     ctx->prof.launches[OBP_K_PROGRAM]++;
     for (int k = 0; k < n_entries; ++k) ctx->prof.passes[prog.klass[k]]++;
-    if (ctx->W == 1) CU(cudaLaunchCooperativeKernel((void*)k_program<1>, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
-    else CU(cudaLaunchCooperativeKernel((void*)k_program<2>, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_tbegin, ctx->d_tbegin, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->W == 1) {
+      CU(cudaLaunchCooperativeKernel((void*)k_program<1>, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
+    } else {
+      CU(cudaLaunchCooperativeKernel((void*)k_program<2>, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
+    }
   }
   if (last_split >= 0) CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->h_ops, ctx->d_ops, sizeof(OpStat) * (n_slots + n_entries), cudaMemcpyDeviceToHost, ctx->stream));
   const auto t_host1 = std::chrono::steady_clock::now();
-  const int sync_rc = sync_state(ctx);
+  // state + start stamp + counters (+ the per-op barrier stamps while profiling) in one copy
+  const bool by_kernel = prog_mode && n_entries > 0;
+  const int sync_rc = sync_state(ctx, n_slots + (ctx->prof_on ? n_entries : 0), by_kernel);
   if (ctx->trace_host) {
     const auto t_host2 = std::chrono::steady_clock::now();
     fprintf(stderr, "[obp host] ops %d slots %d: enqueue %.1f us, wait %.1f us\n", n_ops, n_slots,
@@ -2174,10 +2209,19 @@ int obp_snapshot(obp_ctx* ctx) {
     CU(cudaMalloc(&s.hash, ctx->cap * sizeof(u64)));
     s.cap = ctx->cap;
   }
-  for (int w = 0; w < ctx->W; ++w)
-    CU(cudaMemcpyAsync(s.xz[w], ctx->xz[w], n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.coef, ctx->coef, n * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.hash, ctx->hash, n * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (n) {
+    CopyP p;
+    memset(&p, 0, sizeof(p));
+    for (int w = 0; w < ctx->W; ++w) { p.src16[w] = ctx->xz[w]; p.dst16[w] = s.xz[w]; }
+    p.src16[ctx->W] = (const ulonglong2*)ctx->coef;
+    p.dst16[ctx->W] = (ulonglong2*)s.coef;
+    p.n16 = ctx->W + 1;
+    p.src8 = ctx->hash;
+    p.dst8 = s.hash;
+    ctx->prof.launches[OBP_K_OTHER]++;  // counted, not timed: an open event run would swallow the next program
+    k_copy_table<<<grid_for(ctx, n), OBP_BS, 0, ctx->stream>>>(p, n);
+    CU(cudaGetLastError());
+  }
   s.n = n;
   s.n_live = ctx->n_live;
   s.hx = ctx->hx;
@@ -2194,10 +2238,19 @@ int obp_restore(obp_ctx* ctx) {
   cudaMemsetAsync(&ctx->d_st->error, 0, sizeof(unsigned), ctx->stream);
   Snapshot& s = ctx->snap;
   if (s.n > ctx->cap) return ctx->fail(OBP_ERR_CAPACITY, "obp_restore: snapshot larger than table");
-  for (int w = 0; w < ctx->W; ++w)
-    CU(cudaMemcpyAsync(ctx->xz[w], s.xz[w], s.n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->coef, s.coef, s.n * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->hash, s.hash, s.n * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (s.n) {
+    CopyP p;
+    memset(&p, 0, sizeof(p));
+    for (int w = 0; w < ctx->W; ++w) { p.src16[w] = s.xz[w]; p.dst16[w] = ctx->xz[w]; }
+    p.src16[ctx->W] = (const ulonglong2*)s.coef;
+    p.dst16[ctx->W] = (ulonglong2*)ctx->coef;
+    p.n16 = ctx->W + 1;
+    p.src8 = s.hash;
+    p.dst8 = ctx->hash;
+    ctx->prof.launches[OBP_K_OTHER]++;
+    k_copy_table<<<grid_for(ctx, s.n), OBP_BS, 0, ctx->stream>>>(p, s.n);
+    CU(cudaGetLastError());
+  }
   ctx->hx = s.hx;
   ctx->hz = s.hz;
   ctx->cols_dirty = true;

@@ -36,6 +36,10 @@ struct DevState {
   unsigned int error;   // OBP_ERR_BIT_*
 };
 
+// Result block: [DevState | pad to 64 | program start stamp | pad to 128 | OpStat slots...], the same layout on
+// the device and in the host's pinned mirror
+#define OBP_RES_HDR 128
+
 struct OpStat {  // one slot per launched op; zeroed at program start
   u64 n_out;         // live rows after the op
   u64 rows_surv;     // raw rows that passed the |row| <= atol filter

@@ -164,14 +164,14 @@ __device__ __forceinline__ void rotate_body(const Tab& t, const RotP& p, const u
   // The three streaming loads of a row (coefficient, first generator word, hash) are independent and
   // are issued together, one iteration ahead of their use (software pipelining): the dependent chain
   // of an anticommuting row is then index slot -> partner key/coefficient only.
-  const u64 stride = (u64)gridDim.x * OBP_BS;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
   const ulonglong2* __restrict__ col0 = t.xz[p.gw[0]];
-  u64 i_next = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)) + lane;
+  u64 i_next = ((u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) + lane;
   double2 c_next = make_double2(0.0, 0.0);
   ulonglong2 k_next = make_ulonglong2(0ull, 0ull);
   u64 h_next = 0;
   if (i_next < n) { c_next = t.coef[i_next]; k_next = col0[i_next]; h_next = t.hash[i_next]; }
-  for (u64 base = ((u64)blockIdx.x * OBP_BS + (threadIdx.x & ~31u)); base < n; base += stride) {
+  for (u64 base = ((u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); base < n; base += stride) {
     const u64 i = base + lane;
     const double2 c = c_next;
     const ulonglong2 key0 = k_next;
@@ -354,7 +354,7 @@ template <int W>
 __device__ __forceinline__ void clifford_reg_body(const Tab& t, const CliffBatch& b, const u64 n, u64* live_ctr) {
   static_assert(W == 1 || W == 2, "register variant handles W <= 2");
   int deaths = 0;
-  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     const double2 c = t.coef[i];
     if (!is_live(c)) continue;
     if (is_small_scaled(c, b.scale, b.atol)) {
@@ -420,7 +420,7 @@ __device__ __forceinline__ void coset_body(const Tab& t, const CosetP& p, const 
   if (threadIdx.x < 17) s_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) s_surv = 0;
   __syncthreads();
-  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     const double2 c = t.coef[i];
     if (!is_live(c) || is_small_scaled(c, p.scale, p.atol)) continue;
     int cnt = 1;
@@ -1250,25 +1250,37 @@ __device__ __forceinline__ u64 global_timer_ns() {
 }
 
 template <int W>
-__global__ void __launch_bounds__(OBP_BS, 3) k_program(Tab t, const ProgEntry* __restrict__ entries, int n_entries,
-                                                                  const unsigned char* __restrict__ pool, int n_slots,
-                                                                  u64* __restrict__ t_begin) {
+__global__ void __launch_bounds__(OBP_BS, 3)
+k_program(Tab t, const ProgEntry* __restrict__ entries, int n_entries, const unsigned char* __restrict__ pool,
+          int n_slots, u64* __restrict__ t_begin, int flags, u64* __restrict__ host_res, int n_res_ops) {
   namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+  const bool stamps = (flags & 1) != 0;  // per-op %globaltimer stamps (profiling only)
+  // Grid barrier (includes the release/acquire that makes an op's stores visible to every CTA).  Measured:
+  // ~0.8 us per op of a ~4 us small-table pass; running the program as ONE 16-CTA thread-block cluster
+  // with the hardware cluster barrier instead gained < 5 % on 10^3..10^4-row tables and lost on the
+  // rest (fewer threads in flight), so there is only this variant.
+  auto barrier = [&]() { cg::this_grid().sync(); };
   constexpr unsigned PARAM_BYTES = ((sizeof(CliffBatch) > sizeof(RotP) ? sizeof(CliffBatch) : sizeof(RotP)) + 15u) & ~15u;  // uint4 copies
   __shared__ __align__(16) unsigned char s_param[2][PARAM_BYTES];  // double buffer: op k+1 is staged during op k
   static_assert(sizeof(CosetP) <= sizeof(CliffBatch), "parameter staging buffer too small");
   // the entry table of the program (16 B per op) is read once into shared memory
   constexpr int ENTRY_CACHE = 384;
   __shared__ ProgEntry s_entries[ENTRY_CACHE];
-  for (int k = threadIdx.x; k < n_entries && k < ENTRY_CACHE; k += OBP_BS) s_entries[k] = entries[k];
+  for (int k = threadIdx.x; k < n_entries && k < ENTRY_CACHE; k += blockDim.x) s_entries[k] = entries[k];
   __syncthreads();
   auto entry = [&](int k) -> ProgEntry { return k < ENTRY_CACHE ? s_entries[k] : entries[k]; };
-  if (blockIdx.x == 0 && threadIdx.x == 0) *t_begin = global_timer_ns();
+  {
+    // the program zeroes its own counter slots (and stamp slots): one barrier instead of a memset in the stream
+    u64* w = reinterpret_cast<u64*>(t.ops);
+    const u64 n_words = (u64)(n_slots + n_entries) * (sizeof(OpStat) / sizeof(u64));
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n_words; k += (u64)gridDim.x * blockDim.x) w[k] = 0;
+    barrier();
+  }
+  if (stamps && blockIdx.x == 0 && threadIdx.x == 0) *t_begin = global_timer_ns();
   auto stage = [&](int k) {
     const ProgEntry e = entry(k);
     unsigned char* dst = s_param[k & 1];
-    for (unsigned b = threadIdx.x * 16u; b < e.bytes; b += OBP_BS * 16u)
+    for (unsigned b = threadIdx.x * 16u; b < e.bytes; b += blockDim.x * 16u)
       *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(pool + e.offset + b);
   };
   if (n_entries > 0) stage(0);
@@ -1280,27 +1292,55 @@ __global__ void __launch_bounds__(OBP_BS, 3) k_program(Tab t, const ProgEntry* _
     u64 n = ld_volatile(&t.st->n_append);  // stable: appends of the previous op ended at the barrier
     if (n > t.cap) n = t.cap;
     u64* live_ctr = &t.ops[e.slot].dlive;
-    if (e.kind == PROG_ROTATE) {
+    if (flags & 2) {
+      // timing experiment (OBP_B200_PROG_DEBUG=2): barrier + staging only, no table work
+    } else if (e.kind == PROG_ROTATE) {
       rotate_body(t, *reinterpret_cast<const RotP*>(par), n, live_ctr);
     } else if (e.kind == PROG_CLIFFORD) {
       clifford_reg_body<W>(t, *reinterpret_cast<const CliffBatch*>(par), n, live_ctr);
     } else {
       coset_body(t, *reinterpret_cast<const CosetP*>(par), n);
     }
-    grid.sync();  // (includes the memory fence that makes this op's stores visible grid-wide)
-    if (blockIdx.x == 0 && threadIdx.x == 0) t.ops[k + n_slots].t_end = global_timer_ns();  // stamps live behind the slots
+    barrier();
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) t.ops[k + n_slots].t_end = global_timer_ns();  // stamps live behind the slots
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    u64 n = t.st->n_append;
-    if (n > t.cap) n = t.cap;
-    t.st->n_append = n;
-    t.st->n_scan = n;
-    u64 live = t.st->n_live;
-    for (int s = 0; s < n_slots; ++s) {
-      live += t.ops[s].dlive;
-      t.ops[s].n_out = live;
+  if (blockIdx.x == 0) {
+    // Bookkeeping by CTA 0: row counts, the live-row count after every slot (a warp-wide prefix sum of
+    // the per-slot changes), then the state, the start stamp and the counter slots go straight into the
+    // host's pinned result block (mapped): the host only waits for the kernel, no copy in the stream.
+    __shared__ u64 s_live0;
+    if (threadIdx.x == 0) {
+      u64 n = t.st->n_append;
+      if (n > t.cap) n = t.cap;
+      t.st->n_append = n;
+      t.st->n_scan = n;
+      s_live0 = t.st->n_live;
     }
-    t.st->n_live = live;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x, per = (n_slots + 31) / 32;
+      const int s0 = lane * per, s1 = min(n_slots, s0 + per);
+      u64 local = 0;
+      for (int s = s0; s < s1; ++s) local += t.ops[s].dlive;
+      u64 incl = local;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u64 v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      u64 live = s_live0 + (incl - local);
+      for (int s = s0; s < s1; ++s) {
+        live += t.ops[s].dlive;
+        t.ops[s].n_out = live;
+      }
+      if (lane == 31) t.st->n_live = s_live0 + incl;
+    }
+    __syncthreads();
+    if (host_res) {
+      const u64* src = reinterpret_cast<const u64*>(t.st);  // DevState | start stamp | counter slots: one block
+      const int n_words = (int)((OBP_RES_HDR + (size_t)n_res_ops * sizeof(OpStat)) / sizeof(u64));
+      for (int k = threadIdx.x; k < n_words; k += blockDim.x) host_res[k] = src[k];
+    }
   }
 }
 
@@ -1708,4 +1748,23 @@ __global__ void __launch_bounds__(OBP_BS) k_order_dest(Tab t, const unsigned* __
   const u64 n = t.st->n_scan;
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS)
     dest[i] = is_live(t.coef[i]) ? pos[minidx[i]] : 0xffffffffu;
+}
+
+// ================================================================================================
+// k_copy_table — commit / roll back (obp_snapshot / obp_restore): all columns of the first n rows in
+// ONE launch instead of W + 2 stream copies (the per-slice commit is on the host's critical path).
+// ================================================================================================
+struct CopyP {
+  const ulonglong2* src16[OBP_MAX_WORDS + 1];  // key columns, then the coefficient column
+  ulonglong2* dst16[OBP_MAX_WORDS + 1];
+  const u64* src8;
+  u64* dst8;
+  int n16;
+};
+
+__global__ void __launch_bounds__(OBP_BS) k_copy_table(const __grid_constant__ CopyP p, u64 n) {
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    for (int c = 0; c < p.n16; ++c) p.dst16[c][i] = p.src16[c][i];
+    p.dst8[i] = p.src8[i];
+  }
 }
