@@ -122,6 +122,13 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
  * (backpropagation.py:210-237; utils/operations.py:100-107; utils/simplify.py:80-169). */
 int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats);
 
+/* The same call in two halves, so that the caller can prepare the next slice (light cone, gate records)
+ * while the device runs this one: obp_apply_ops_submit validates, copies the records and enqueues the
+ * kernels without waiting; obp_apply_ops_wait waits for them and returns what obp_apply_ops would have.
+ * Between the two no other call may touch the context (they return OBP_ERR_BADARG).  Single-GPU tables. */
+int obp_apply_ops_submit(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol);
+int obp_apply_ops_wait(obp_ctx* ctx, obp_stats* stats);
+
 /* Any other gate on 1-4 qubits (cp, crz, arbitrary unitaries): U = sum_j u_j * Pauli(codes[j]) with
  * codes[j] = local Pauli code (bit 2q = x, bit 2q+1 = z on qubits[q]) and coeffs[j] = (re, im).  Runs
  * the reference's literal k*k raw-row expansion (utils/operations.py:103-105) followed by simplify

@@ -105,7 +105,7 @@ def backpropagate(
     num_qubits = slices_ir[0].num_qubits
     n_obs = len(obs_in)
     # reduce_op (utils/operations.py:176-181): support set, error for a pure identity observable
-    qargs = [_support(o) for o in obs_in]
+    support_mask = [sum(1 << q for q in _support(o)) for o in obs_in]  # qubit sets as integer bit masks
     device = engine.default_device()
     capacity = _default_capacity(num_qubits, operator_budget, n_obs, device)
     comm = communicator_from_env(device)  # None: one table per observable on this GPU
@@ -157,7 +157,10 @@ def backpropagate(
             else:
                 tables.append(ShardedTable.acquire(num_qubits, cap_i, comm))
         try:
-            for slice_ in slices_ir[::-1]:
+            reversed_slices = slices_ir[::-1]
+            log_info = LOGGER.isEnabledFor(logging.INFO)
+            for slice_pos, slice_ in enumerate(reversed_slices):
+                next_slice = reversed_slices[slice_pos + 1] if slice_pos + 1 < len(reversed_slices) else None
                 sm = SliceMetadata(
                     slice_errors=[0.0] * n_obs,
                     raw_num_paulis=[0] * n_obs,
@@ -174,17 +177,8 @@ def backpropagate(
                 prog = _slice_program(slice_, expand_all)
                 overflowed = False
                 for i in range(n_obs):
-                    support = set(qargs[i])
-                    if prog.touched <= support:
-                        applied = prog.all_idx  # the light cone already covers every qubit the slice touches
-                    else:
-                        applied = []
-                        for k, qs in enumerate(prog.qubit_sets):
-                            if support.isdisjoint(qs):
-                                continue  # outside the light cone (backpropagation.py:183)
-                            applied.append(k)
-                            if prog.nodes[k].name != "reset":
-                                support |= qs
+                    plan = prog.plan(support_mask[i])  # gates inside the light cone (backpropagation.py:183)
+                    applied = plan.applied
                     non_trivial = bool(applied)
                     sidx = metadata.num_backpropagated_slices
                     if non_trivial:
@@ -207,9 +201,17 @@ def backpropagate(
                             tables[i].timer_start()
                             tables[i].snapshot()
                             loaded[i] = True
+                        prefetch = None
+                        if next_slice is not None and comm is None:
+                            # while the device runs this slice: compile the next one and its light cone
+                            def prefetch(ns=next_slice, after=plan.support_after):
+                                _slice_program(ns, expand_all).plan(after)
+
                         while True:
                             try:
-                                _run_slice(tables[i], prog, applied, atol, sm, i, info, raw, raw_first[i] and not ordered)
+                                _run_slice(tables[i], prog, plan, atol, sm, i, info, raw, raw_first[i] and not ordered,
+                                           prefetch)
+                                prefetch = None
                                 raw_first[i] = False
                                 if trunc_active:
                                     budget = metadata.left_over_error_budget(i, sidx)
@@ -235,19 +237,21 @@ def backpropagate(
                         if overflowed:
                             sm.sum_paulis = tables[i].capacity
                             break
-                        qargs[i] = sorted(support)
+                        support_mask[i] = plan.support_after
                         lengths[i] = len(tables[i])
                     if trunc_active and non_trivial:
                         lengths[i] = len(tables[i])
-                        LOGGER.info(
-                            f"[{sidx:3}] Accumulated error for the {i}-th observable: "
-                            f"{metadata.accumulated_error(i, sidx + 1):.10f}"
-                        )
+                        if log_info:
+                            LOGGER.info(
+                                f"[{sidx:3}] Accumulated error for the {i}-th observable: "
+                                f"{metadata.accumulated_error(i, sidx + 1):.10f}"
+                            )
                     sm.num_paulis[i] = lengths[i]
-                    LOGGER.info(
-                        f"[{metadata.num_backpropagated_slices:3}] size of the {i}-th observable: "
-                        f"{sm.num_paulis[i]}"
-                    )
+                    if log_info:
+                        LOGGER.info(
+                            f"[{metadata.num_backpropagated_slices:3}] size of the {i}-th observable: "
+                            f"{sm.num_paulis[i]}"
+                        )
                 if overflowed:
                     LOGGER.info(
                         f"[{metadata.num_backpropagated_slices:3}] Too many Pauli terms: more than "
@@ -336,7 +340,8 @@ class SliceProgram:
     record of ``nodes[k]`` (``kind`` 0 for reset / LayerError, which have their own entry points).
     """
 
-    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data", "generic", "touched", "all_idx")
+    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data", "generic", "touched", "all_idx",
+                 "masks", "touched_mask", "is_reset", "plans")
 
     def __init__(self, slice_: QuantumCircuit, raw: bool = False):
         self.n_data = len(slice_.data)
@@ -345,6 +350,12 @@ class SliceProgram:
         self.qubit_sets = [frozenset(n.qubits) for n in self.nodes]
         self.touched = frozenset().union(*self.qubit_sets) if self.qubit_sets else frozenset()
         self.all_idx = list(range(len(self.nodes)))
+        self.masks = [sum(1 << q for q in qs) for qs in self.qubit_sets]  # qubit sets as integer bit masks
+        self.touched_mask = 0
+        for m in self.masks:
+            self.touched_mask |= m
+        self.is_reset = [n.name == "reset" for n in self.nodes]
+        self.plans: dict[int, SlicePlan] = {}
         self.recs = np.zeros(len(self.nodes), dtype=OP_DTYPE)
         self.special = [n.name in ("reset", "LayerError") for n in self.nodes]
         self.errors: dict[int, Exception] = {}
@@ -372,6 +383,72 @@ class SliceProgram:
             qubit[idxs, : prog.n_qubits] = np.array([self.nodes[k].qubits for k in idxs], dtype=np.int32)
 
 
+    def plan(self, support: int) -> "SlicePlan":
+        """The gates of this slice inside the light cone of ``support`` (a qubit bit mask) and their device steps.
+
+        Purely structural (``backpropagation.py:183``: a gate acts iff it shares a qubit with the observable's
+        current support, and then widens it — except ``reset``), so it is computed once per (slice, support)
+        and can be prepared while the device is still busy with the previous slice.
+        """
+        plan = self.plans.get(support)
+        if plan is None:
+            if self.touched_mask & ~support == 0:
+                applied, after = self.all_idx, support  # the light cone already covers the whole slice
+            else:
+                applied, after = [], support
+                for k, m in enumerate(self.masks):
+                    if after & m:
+                        applied.append(k)
+                        if not self.is_reset[k]:
+                            after |= m
+            if len(self.plans) >= 64:
+                self.plans.clear()
+            plan = self.plans[support] = SlicePlan(self, applied, after)
+        return plan
+
+
+class SlicePlan:
+    """The applied gates of one slice for one light cone, cut into device steps.
+
+    ``steps`` is a list of ``("ops", records)`` — a run of Clifford-class / rotation gates for
+    ``obp_apply_ops``, the last gate of the slice flagged for exact counters — ``("node", k)`` — a gate
+    with its own entry point (generic, reset, LayerError) — and ``("error", exc)`` — a gate the engine
+    cannot express, raised when (and only when) it is reached.
+    """
+
+    __slots__ = ("applied", "support_after", "steps")
+
+    def __init__(self, prog: SliceProgram, applied: list[int], support_after: int):
+        self.applied = applied
+        self.support_after = support_after
+        self.steps: list[tuple] = []
+        if not applied:
+            return
+        last = applied[-1]
+        seg: list[int] = []
+
+        def cut():
+            nonlocal seg
+            if seg:
+                ops = prog.recs[seg]  # fancy index: a fresh array
+                if seg[-1] == last:
+                    ops["flags"][-1] = OBP_FLAG_EXACT_COUNTERS
+                self.steps.append(("ops", ops))
+                seg = []
+
+        for k in applied:
+            if not prog.special[k]:
+                if k in prog.errors:
+                    cut()
+                    self.steps.append(("error", prog.errors[k]))
+                    return
+                seg.append(k)
+            else:
+                cut()
+                self.steps.append(("node", k))
+        cut()
+
+
 def _slice_program(slice_: QuantumCircuit, raw: bool = False) -> SliceProgram:
     attr = "_obp_program_raw" if raw else "_obp_program"
     prog = getattr(slice_, attr, None)
@@ -381,12 +458,15 @@ def _slice_program(slice_: QuantumCircuit, raw: bool = False) -> SliceProgram:
     return prog
 
 
-def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: float, sm: SliceMetadata, i: int,
-               info: RunInfo, raw: bool = False, first_as_expansion: bool = False) -> None:
-    """Execute the applied gates of one slice on one observable and record the last gate's counters."""
+def _run_slice(table: TermTable, prog: SliceProgram, plan: SlicePlan, atol: float, sm: SliceMetadata, i: int,
+               info: RunInfo, raw: bool = False, first_as_expansion: bool = False, prefetch=None) -> None:
+    """Execute the applied gates of one slice on one observable and record the last gate's counters.
+
+    ``prefetch`` (optional) is host work for the NEXT slice; it runs between the submission of this slice's
+    first gate program and the wait for it, i.e. while the device is busy.
+    """
     stats = None
-    last = applied[-1]
-    seg: list[int] = []
+    applied = plan.applied
     if first_as_expansion:
         node = prog.nodes[applied[0]]
         g = raw_program_for(node)
@@ -394,17 +474,23 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
         info.updates += int(stats.updates)
         info.applied_gates += 1
         applied = applied[1:]
+        plan = SlicePlan(prog, applied, plan.support_after)
 
-    def flush():
-        nonlocal seg, stats
-        if seg:
-            ops = prog.recs[seg]  # fancy index: a fresh array
-            if seg[-1] == last:
-                ops["flags"][-1] = OBP_FLAG_EXACT_COUNTERS
+    sharded = isinstance(table, ShardedTable)
+    for kind, what in plan.steps:
+        if kind == "ops":
+            ops = what
             t0 = time.perf_counter() if TRACE else 0.0
             n_before = table.n
             try:
-                stats = table.apply_ops(ops, atol)
+                if sharded:
+                    stats = table.apply_ops(ops, atol)
+                else:
+                    table.apply_ops_submit(ops, atol)
+                    if prefetch is not None:
+                        run, prefetch = prefetch, None
+                        run()
+                    stats = table.apply_ops_wait()
             except CapacityError as exc:
                 info.updates += getattr(exc, "updates", 0)
                 raise
@@ -418,15 +504,10 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
                     f"{int(stats.updates) / max(dt, 1e-9) / 1e9:7.2f} G upd/s",
                     flush=True,
                 )
-            seg = []
-
-    for k in applied:
-        if not prog.special[k]:
-            if k in prog.errors:
-                raise prog.errors[k]
-            seg.append(k)
             continue
-        flush()
+        if kind == "error":
+            raise what
+        k = what
         node = prog.nodes[k]
         if k in prog.generic:
             g = prog.generic[k]
@@ -447,7 +528,8 @@ def _run_slice(table: TermTable, prog: SliceProgram, applied: list[int], atol: f
             gz[:, list(node.qubits)] = gens.z
             stats = table.apply_damping(gx, gz, np.exp(-2 * np.asarray(ple.rates, dtype=float)), -1.0 if raw else atol)
         info.updates += int(stats.updates)
-    flush()
+    if prefetch is not None:
+        prefetch()
     info.applied_gates += len(applied)
     # the slice reports the counters of its last applied gate (backpropagation.py:218-237)
     sm.raw_num_paulis[i] = int(stats.raw_rows)

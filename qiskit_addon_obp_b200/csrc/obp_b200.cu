@@ -52,6 +52,7 @@ struct obp_ctx {
   // d_st, d_tbegin and d_ops live in ONE device block (and h_st, h_tbegin, h_ops in one pinned block):
   // [DevState | pad to 64 | t_begin | pad to 128 | OpStat x ops_alloc], so that a gate program brings
   // its state, time stamps and counters back with a single copy
+  struct PendingOps* pending = nullptr;  // a submitted gate program nobody has waited for yet
   unsigned char* d_res = nullptr;
   unsigned char* h_res = nullptr;  // pinned and mapped: the persistent program kernel writes its results into it
   u64* h_res_dev = nullptr;        // device address of h_res
@@ -644,6 +645,21 @@ int validate_op(obp_ctx* ctx, const obp_op& op) {
 
 }  // namespace
 
+// A gate program that has been enqueued but not yet waited for (obp_apply_ops_submit / _wait).
+struct PendingOps {
+  std::vector<obp_op> ops;
+  ProgRec prog;
+  std::vector<int> slot_of_op, slot_gates;
+  int n_ops = 0, n_entries = 0, n_slots = 0, last_split = -1;
+  u64 n_start = 0;
+  bool prog_mode = false;
+  std::chrono::steady_clock::time_point t_host0;
+};
+
+#define OBP_NO_PENDING(ctx, what) \
+  if ((ctx) && (ctx)->pending) return (ctx)->fail(OBP_ERR_BADARG, what ": a submitted gate program is pending, call obp_apply_ops_wait first")
+
+
 // =================================================================================================
 // C-ABI
 // =================================================================================================
@@ -745,6 +761,7 @@ void obp_destroy(obp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) obp_destroy(ctx->scratch);
+  delete ctx->pending;
   free_table(ctx);
   free_snapshot(ctx->snap);
   cudaFree(ctx->d_res);
@@ -792,6 +809,7 @@ int obp_count(obp_ctx* ctx, uint64_t* n) {
 
 int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
              uint64_t n, double atol, obp_stats* stats) {
+  OBP_NO_PENDING(ctx, "obp_load");
   if (!ctx || (n && (!x_words || !z_words || !coeffs))) return OBP_ERR_BADARG;
   if (n > ctx->cap) return ctx->fail(OBP_ERR_CAPACITY, "obp_load: more rows than capacity");
   CU(cudaSetDevice(ctx->device));
@@ -864,6 +882,7 @@ int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, con
 
 int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coeffs,
                  uint64_t max_rows, uint64_t* n_out) {
+  OBP_NO_PENDING(ctx, "obp_download");
   if (!ctx || !n_out) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
   if (ctx->n_dense != ctx->n_live) {
@@ -932,8 +951,95 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
 // -------------------------------------------------------------------------------------------------
 // Runs ops[0, n_ops) — or, on a sharded table, up to the first rotation whose partner keys live on
 // another rank: *n_done = ops executed, *peer_xor = owner bits of that rotation's generator hash.
+// Second half of a gate program: wait for the device, account, compact if needed, fill the statistics.
+static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
+  int rc;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  const auto t_host1 = std::chrono::steady_clock::now();
+  // state + start stamp + counters (+ the per-op barrier stamps while profiling) in one copy
+  const bool by_kernel = P.prog_mode && P.n_entries > 0;
+  const int sync_rc = sync_state(ctx, P.n_slots + (ctx->prof_on ? P.n_entries : 0), by_kernel);
+  if (ctx->trace_host) {
+    const auto t_host2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[obp host] ops %d slots %d: enqueue %.1f us, wait %.1f us\n", P.n_ops, P.n_slots,
+            std::chrono::duration<double, std::micro>(t_host1 - P.t_host0).count(),
+            std::chrono::duration<double, std::micro>(t_host2 - t_host1).count());
+  }
+  ctx->last_split_is_last_op = P.last_split >= 0 && P.last_split == P.n_ops - 1;
+  if (sync_rc && sync_rc != OBP_ERR_CAPACITY) return sync_rc;
+  if (P.prog_mode && ctx->prof_on) {  // per-class device time from the stamps taken at the grid barriers
+    u64 t_prev = *ctx->h_tbegin;
+    for (int k = 0; k < P.n_entries; ++k) {
+      const u64 t_end = ctx->h_ops[P.n_slots + k].t_end;
+      if (t_end >= t_prev) ctx->prof.ms[P.prog.klass[k]] += (double)(t_end - t_prev) * 1e-6;
+      t_prev = t_end;
+    }
+  }
+
+  // term-gate updates: live terms at entry of every op (also accounted when the table overflowed:
+  // the kernels ran, the caller rolls the slice back)
+  u64 updates = 0, n_in = P.n_start, n_in_last = P.n_start;
+  for (int s = 0; s < P.n_slots; ++s) {
+    updates += n_in * (u64)P.slot_gates[s];
+    n_in_last = n_in;
+    n_in = ctx->h_ops[s].n_out;
+  }
+  {
+    // per-class term counts for the roofline
+    u64 nin = P.n_start;
+    for (int k = 0, s_prev = -1; k < P.n_ops; ++k) {
+      const int s = P.slot_of_op[k];
+      if (s != s_prev && s_prev >= 0) nin = ctx->h_ops[s_prev].n_out;
+      ctx->prof.term_updates[P.ops[k].kind == OBP_OP_ROTATION ? OBP_K_ROTATE : OBP_K_CLIFFORD] += nin;
+      s_prev = s;
+    }
+  }
+  if (sync_rc) {
+    if (stats) stats->updates = updates;
+    return sync_rc;
+  }
+  if (stats) {
+    const obp_op& last = P.ops[P.n_ops - 1];
+    const OpStat& o = ctx->h_ops[P.n_slots - 1];
+    const u64 k2 = (u64)last.n_components * last.n_components;
+    stats->n_in = n_in_last;
+    stats->raw_rows = n_in_last * k2;
+    stats->updates = updates;
+    if (last.flags & OBP_FLAG_EXACT_COUNTERS) {
+      if (last.kind == OBP_OP_ROTATION) {
+        stats->num_unique = o.keys_present;
+        stats->num_duplicate = o.rows_surv - o.keys_present;
+        stats->num_trimmed = (stats->raw_rows - o.rows_surv) + o.cancelled;
+        stats->sum_trimmed[0] = o.sum_re;
+        stats->sum_trimmed[1] = o.sum_im;
+      } else {
+        // cosets hit = sum_c N_c / c ; keys present = |D| * cosets
+        u64 cosets = 0;
+        for (unsigned c = 1; c <= 16; ++c) cosets += o.ncnt[c] / c;
+        const u64 rows = o.n_surv * k2;
+        const u64 uniq = (u64)last.group_size * cosets;
+        stats->num_unique = uniq;
+        stats->num_duplicate = rows - uniq;
+        stats->num_trimmed = (stats->raw_rows - rows) + (uniq - o.n_surv);
+      }
+    }
+  }
+  // keep tombstones below a quarter of the table
+  if (ctx->n_dense - ctx->n_live > std::max<u64>(1024, ctx->n_live / 4)) {
+    rc = compact(ctx);
+    if (rc) return rc;
+    rc = sync_state(ctx);
+    if (rc) return rc;
+  }
+  if (stats) {
+    stats->n_out = ctx->n_live;
+    stats->n_dense = ctx->n_dense;
+  }
+  return OBP_OK;
+}
+
 static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,
-                          int32_t* n_done, int32_t* peer_xor) {
+                          int32_t* n_done, int32_t* peer_xor, bool defer = false) {
   if (!ctx || (n_ops && !ops) || n_ops < 0) return OBP_ERR_BADARG;
   if (n_done) *n_done = n_ops;
   if (peer_xor) *peer_xor = 0;
@@ -1361,99 +1467,63 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     }
   }
   if (last_split >= 0) CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(ShardCnt), cudaMemcpyDeviceToHost, ctx->stream));
-  const auto t_host1 = std::chrono::steady_clock::now();
-  // state + start stamp + counters (+ the per-op barrier stamps while profiling) in one copy
-  const bool by_kernel = prog_mode && n_entries > 0;
-  const int sync_rc = sync_state(ctx, n_slots + (ctx->prof_on ? n_entries : 0), by_kernel);
-  if (ctx->trace_host) {
-    const auto t_host2 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[obp host] ops %d slots %d: enqueue %.1f us, wait %.1f us\n", n_ops, n_slots,
-            std::chrono::duration<double, std::micro>(t_host1 - t_host0).count(),
-            std::chrono::duration<double, std::micro>(t_host2 - t_host1).count());
+  PendingOps P;
+  P.ops.assign(ops, ops + n_ops);
+  P.prog = std::move(prog);
+  P.slot_of_op = std::move(slot_of_op);
+  P.slot_gates = std::move(slot_gates);
+  P.n_ops = n_ops;
+  P.n_entries = n_entries;
+  P.n_slots = n_slots;
+  P.last_split = last_split;
+  P.n_start = n_start;
+  P.prog_mode = prog_mode;
+  P.t_host0 = t_host0;
+  if (defer) {  // obp_apply_ops_submit: the caller overlaps its own work with the device, then calls obp_apply_ops_wait
+    delete ctx->pending;
+    ctx->pending = new PendingOps(std::move(P));
+    return OBP_OK;
   }
-  ctx->last_split_is_last_op = last_split >= 0 && last_split == n_ops - 1;
-  if (sync_rc && sync_rc != OBP_ERR_CAPACITY) return sync_rc;
-  if (prog_mode && ctx->prof_on) {  // per-class device time from the stamps taken at the grid barriers
-    u64 t_prev = *ctx->h_tbegin;
-    for (int k = 0; k < n_entries; ++k) {
-      const u64 t_end = ctx->h_ops[n_slots + k].t_end;
-      if (t_end >= t_prev) ctx->prof.ms[prog.klass[k]] += (double)(t_end - t_prev) * 1e-6;
-      t_prev = t_end;
-    }
-  }
-
-  // term-gate updates: live terms at entry of every op (also accounted when the table overflowed:
-  // the kernels ran, the caller rolls the slice back)
-  u64 updates = 0, n_in = n_start, n_in_last = n_start;
-  for (int s = 0; s < n_slots; ++s) {
-    updates += n_in * (u64)slot_gates[s];
-    n_in_last = n_in;
-    n_in = ctx->h_ops[s].n_out;
-  }
-  {
-    // per-class term counts for the roofline
-    u64 nin = n_start;
-    for (int k = 0, s_prev = -1; k < n_ops; ++k) {
-      const int s = slot_of_op[k];
-      if (s != s_prev && s_prev >= 0) nin = ctx->h_ops[s_prev].n_out;
-      ctx->prof.term_updates[ops[k].kind == OBP_OP_ROTATION ? OBP_K_ROTATE : OBP_K_CLIFFORD] += nin;
-      s_prev = s;
-    }
-  }
-  if (sync_rc) {
-    if (stats) stats->updates = updates;
-    return sync_rc;
-  }
-  if (stats) {
-    const obp_op& last = ops[n_ops - 1];
-    const OpStat& o = ctx->h_ops[n_slots - 1];
-    const u64 k2 = (u64)last.n_components * last.n_components;
-    stats->n_in = n_in_last;
-    stats->raw_rows = n_in_last * k2;
-    stats->updates = updates;
-    if (last.flags & OBP_FLAG_EXACT_COUNTERS) {
-      if (last.kind == OBP_OP_ROTATION) {
-        stats->num_unique = o.keys_present;
-        stats->num_duplicate = o.rows_surv - o.keys_present;
-        stats->num_trimmed = (stats->raw_rows - o.rows_surv) + o.cancelled;
-        stats->sum_trimmed[0] = o.sum_re;
-        stats->sum_trimmed[1] = o.sum_im;
-      } else {
-        // cosets hit = sum_c N_c / c ; keys present = |D| * cosets
-        u64 cosets = 0;
-        for (unsigned c = 1; c <= 16; ++c) cosets += o.ncnt[c] / c;
-        const u64 rows = o.n_surv * k2;
-        const u64 uniq = (u64)last.group_size * cosets;
-        stats->num_unique = uniq;
-        stats->num_duplicate = rows - uniq;
-        stats->num_trimmed = (stats->raw_rows - rows) + (uniq - o.n_surv);
-      }
-    }
-  }
-  // keep tombstones below a quarter of the table
-  if (ctx->n_dense - ctx->n_live > std::max<u64>(1024, ctx->n_live / 4)) {
-    rc = compact(ctx);
-    if (rc) return rc;
-    rc = sync_state(ctx);
-    if (rc) return rc;
-  }
-  if (stats) {
-    stats->n_out = ctx->n_live;
-    stats->n_dense = ctx->n_dense;
-  }
-  return OBP_OK;
+  return finish_ops(ctx, P, stats);
 }
 
+static const char* kRowOrderMsg =
+    "obp_apply_ops: in-place gate kernels do not keep the reference's row order; use obp_apply_generic in row-order mode";
 int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats) {
-  if (ctx && ctx->row_order)
-    return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_ops: in-place gate kernels do not keep the reference's row order; "
-                                          "use obp_apply_generic in row-order mode");
+  OBP_NO_PENDING(ctx, "obp_apply_ops");
+  if (ctx && ctx->row_order) return ctx->fail(OBP_ERR_UNSUPPORTED, kRowOrderMsg);
   return apply_ops_impl(ctx, ops, n_ops, atol, stats, nullptr, nullptr);
+}
+
+int obp_apply_ops_submit(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol) {
+  OBP_NO_PENDING(ctx, "obp_apply_ops_submit");
+  if (ctx && ctx->row_order) return ctx->fail(OBP_ERR_UNSUPPORTED, kRowOrderMsg);
+  if (ctx && ctx->n_ranks > 1) return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_ops_submit: not available on a sharded table");
+  return apply_ops_impl(ctx, ops, n_ops, atol, nullptr, nullptr, nullptr, true);
+}
+
+int obp_apply_ops_wait(obp_ctx* ctx, obp_stats* stats) {
+  if (!ctx) return OBP_ERR_BADARG;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->pending) {  // nothing was enqueued (an empty program)
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->n_in = stats->n_out = ctx->n_live;
+      stats->n_dense = ctx->n_dense;
+    }
+    return OBP_OK;
+  }
+  PendingOps* P = ctx->pending;
+  ctx->pending = nullptr;
+  const int rc = finish_ops(ctx, *P, stats);
+  delete P;
+  return rc;
 }
 
 int obp_apply_ops_sharded(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,
                           int32_t* n_done, int32_t* peer_xor) {
   if (!n_done || !peer_xor) return OBP_ERR_BADARG;
+  OBP_NO_PENDING(ctx, "obp_apply_ops_sharded");
   return apply_ops_impl(ctx, ops, n_ops, atol, stats, n_done, peer_xor);
 }
 
@@ -1786,6 +1856,7 @@ int obp_rotate_merge_inbox(obp_ctx* ctx, obp_shard_counters* out) {
 // Generic gate: raw k*k expansion + the merge of a freshly loaded operator (simplify.py:115-165).
 int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int32_t n_comp, const uint32_t* codes,
                       const double* coeffs, double atol, int32_t simplify, obp_stats* stats) {
+  OBP_NO_PENDING(ctx, "obp_apply_generic");
   if (!ctx || !qubits || !codes || !coeffs || n_qubits < 1 || n_qubits > 4 || n_comp < 1 || n_comp > OBP_GEN_MAXK)
     return OBP_ERR_BADARG;
   if (ctx->n_ranks > 1) return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_generic: not available on a sharded table");
@@ -1947,6 +2018,7 @@ static int reset_in_row_order(obp_ctx* ctx, int32_t qubit, double atol, obp_stat
 }
 
 int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) {
+  OBP_NO_PENDING(ctx, "obp_apply_reset");
   if (!ctx || qubit < 0 || qubit >= ctx->nq) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
   if (atol == OBP_ATOL_RAW) {  // simplify=False: zero the X/Y rows, clear the qubit, merge nothing
@@ -2018,6 +2090,7 @@ int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) 
 
 int obp_apply_damping(obp_ctx* ctx, const uint64_t* gen_x, const uint64_t* gen_z, const double* factors,
                       int32_t n_gens, double atol, obp_stats* stats) {
+  OBP_NO_PENDING(ctx, "obp_apply_damping");
   if (!ctx || n_gens < 0 || (n_gens && (!gen_x || !gen_z || !factors))) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
   const u64 n_in = ctx->n_live;
@@ -2132,6 +2205,7 @@ int obp_trunc_finish(obp_ctx* ctx, double threshold, uint64_t* n_removed, uint64
 
 int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double* slice_error,
                  uint64_t* n_removed, uint64_t* n_out) {
+  OBP_NO_PENDING(ctx, "obp_truncate");
   if (!ctx || p_norm < 1) return OBP_ERR_BADARG;
   if (slice_error) *slice_error = 0.0;
   if (n_removed) *n_removed = 0;
@@ -2194,6 +2268,7 @@ int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double
 
 // -------------------------------------------------------------------------------------------------
 int obp_snapshot(obp_ctx* ctx) {
+  OBP_NO_PENDING(ctx, "obp_snapshot");
   if (!ctx) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
   // Copies the dense rows (tombstones included) aside with stream-ordered D2D copies: no
@@ -2231,6 +2306,7 @@ int obp_snapshot(obp_ctx* ctx) {
 }
 
 int obp_restore(obp_ctx* ctx) {
+  OBP_NO_PENDING(ctx, "obp_restore");
   if (!ctx) return OBP_ERR_BADARG;
   if (!ctx->snap.valid) return ctx->fail(OBP_ERR_BADARG, "obp_restore: no snapshot");
   CU(cudaSetDevice(ctx->device));
@@ -2282,6 +2358,7 @@ static int alloc_row_order_scratch(obp_ctx* ctx) {
 }
 
 int obp_reserve(obp_ctx* ctx, uint64_t new_capacity) {
+  OBP_NO_PENDING(ctx, "obp_reserve");
   if (!ctx || new_capacity >= 0xffffffffull) return OBP_ERR_BADARG;
   if (new_capacity <= ctx->cap) return OBP_OK;
   CU(cudaSetDevice(ctx->device));

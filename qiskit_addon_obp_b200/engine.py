@@ -123,6 +123,8 @@ def lib() -> C.CDLL:
         "obp_count": ([vp, u64p], C.c_int),
         "obp_download": ([vp, vp, vp, vp, C.c_uint64, u64p], C.c_int),
         "obp_apply_ops": ([vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
+        "obp_apply_ops_submit": ([vp, vp, C.c_int32, C.c_double], C.c_int),
+        "obp_apply_ops_wait": ([vp, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_generic": ([vp, C.c_int32, vp, C.c_int32, vp, vp, C.c_double, C.c_int32, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_reset": ([vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_damping": ([vp, vp, vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
@@ -169,7 +171,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "obp_create obp_destroy obp_last_error obp_set_stream obp_device_memory obp_bytes_per_term "
     "obp_load obp_count obp_download obp_apply_ops obp_apply_generic obp_apply_reset obp_apply_damping obp_truncate "
-    "obp_union_count obp_snapshot obp_restore obp_reserve obp_set_row_order obp_profile_enable obp_profile_get "
+    "obp_union_count obp_snapshot obp_restore obp_reserve obp_set_row_order obp_apply_ops_submit obp_apply_ops_wait obp_profile_enable obp_profile_get "
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
@@ -371,6 +373,37 @@ class TermTable:
             self._check(rc, "obp_apply_ops")
         except CapacityError as exc:
             exc.updates = int(st.updates)  # the kernels ran before the overflow was detected
+            raise
+        self.n, self.n_dense = st.n_out, st.n_dense
+        if self.n == 0:
+            self.zero_operator = self.track_zero
+        return st
+
+    def apply_ops_submit(self, ops: np.ndarray, atol: float) -> None:
+        """First half of :meth:`apply_ops`: enqueue the program and return without waiting for the device."""
+        self._submitted_zero = None
+        if self.zero_operator:
+            last = ops[-1]
+            self._submitted_zero = (int(last["n_components"]) ** 2, len(ops))
+            return
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        rc = self._lib.obp_apply_ops_submit(self._h, ops.ctypes.data_as(C.c_void_p), len(ops), float(atol))
+        self._check(rc, "obp_apply_ops_submit")
+
+    def apply_ops_wait(self) -> ObpStats:
+        """Second half of :meth:`apply_ops`: wait for the submitted program, return its statistics."""
+        st = ObpStats()
+        if getattr(self, "_submitted_zero", None) is not None:
+            k2, n_ops = self._submitted_zero
+            self._submitted_zero = None
+            st.n_in, st.raw_rows, st.num_trimmed, st.n_out = 1, k2, k2, 1
+            st.updates = n_ops
+            return st
+        rc = self._lib.obp_apply_ops_wait(self._h, C.byref(st))
+        try:
+            self._check(rc, "obp_apply_ops_wait")
+        except CapacityError as exc:
+            exc.updates = int(st.updates)
             raise
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0:
