@@ -170,7 +170,10 @@ __device__ __forceinline__ void rotate_body(const Tab& t, const RotP& p, const u
   double2 c_next = make_double2(0.0, 0.0);
   ulonglong2 k_next = make_ulonglong2(0ull, 0ull);
   u64 h_next = 0;
-  if (i_next < n) { c_next = t.coef[i_next]; k_next = col0[i_next]; h_next = t.hash[i_next]; }
+  // (first chunk: guarded by the capacity, not by n — inside the program kernel n has just been loaded from
+  // device memory, and these loads then go out together with it instead of one round trip later; rows in
+  // [n, cap) are allocated memory whose content is never used)
+  if (i_next < t.cap) { c_next = t.coef[i_next]; k_next = col0[i_next]; h_next = t.hash[i_next]; }
   for (u64 base = ((u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); base < n; base += stride) {
     const u64 i = base + lane;
     const double2 c = c_next;

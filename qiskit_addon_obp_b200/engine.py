@@ -245,10 +245,19 @@ class TermTable:
                 return t
         return cls(num_qubits, capacity, device)
 
+    def _drain(self) -> None:
+        """Wait for (and discard the result of) a gate program that was submitted but never waited for —
+        an exception (``max_seconds`` alarm, KeyboardInterrupt) can arrive between the two halves."""
+        if getattr(self, "_submitted", False):
+            self._submitted = False
+            self._submitted_zero = None
+            self._lib.obp_apply_ops_wait(self._h, None)  # a device error here resurfaces in the next call
+
     def release(self) -> None:
         """Hand the table back to the pool (or destroy it when the pool is full)."""
         if not self._h.value:
             return
+        self._drain()
         idle = _POOL.setdefault((self.device, self.num_qubits), [])
         if len(idle) >= POOL_MAX_PER_KEY:
             self.close()
@@ -283,6 +292,7 @@ class TermTable:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            self._drain()
             self._lib.obp_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -330,6 +340,7 @@ class TermTable:
         return st
 
     def download(self) -> SparsePauliOp:
+        self._drain()
         if self.zero_operator:
             z = np.zeros((1, self.num_qubits), dtype=bool)
             return SparsePauliOp((z.copy(), z), np.array([0j]))
@@ -387,7 +398,10 @@ class TermTable:
             self._submitted_zero = (int(last["n_components"]) ** 2, len(ops))
             return
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        self._submitted = True  # (set first: an asynchronous exception right after the call must still find it)
         rc = self._lib.obp_apply_ops_submit(self._h, ops.ctypes.data_as(C.c_void_p), len(ops), float(atol))
+        if rc != 0:
+            self._submitted = False
         self._check(rc, "obp_apply_ops_submit")
 
     def apply_ops_wait(self) -> ObpStats:
@@ -400,6 +414,7 @@ class TermTable:
             st.updates = n_ops
             return st
         rc = self._lib.obp_apply_ops_wait(self._h, C.byref(st))
+        self._submitted = False
         try:
             self._check(rc, "obp_apply_ops_wait")
         except CapacityError as exc:
@@ -481,11 +496,13 @@ class TermTable:
 
     def snapshot(self):
         """Commit point: stream-ordered device copy of the table (no host synchronisation)."""
+        self._drain()
         self._snap_zero = self.zero_operator
         self._snap_n = self.n
         self._check(self._lib.obp_snapshot(self._h), "obp_snapshot")
 
     def restore(self):
+        self._drain()
         self._check(self._lib.obp_restore(self._h), "obp_restore")
         self.zero_operator = self._snap_zero
         self.n = self._snap_n
