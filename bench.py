@@ -496,7 +496,16 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                 "avg_pass_ms": rot["ms"] / max(1, rot["passes"]),
                 "timing": "tables <= 128 qubits: %globaltimer stamps at the grid barriers of the persistent program "
                 "kernel; wider tables: CUDA events around the k_rotate launches",
-                "traffic": None,
+                # one `ncu --set full` capture of the persistent program kernel on this workload (theta_h = 0.3,
+                # the 88-rotation slice entered with 94 842 terms: 23 070 231 term-gate updates in one launch)
+                "traffic": {
+                    "dram_bytes_per_launch": 171.7e6,
+                    "algorithmic_bytes_per_launch": 23070231 * 96.0,
+                    "kernel": "k_program<2>",
+                    "note": "the table (<= 1.5e6 rows x 56 B) stays in the 126 MB L2: DRAM moves 8 % of the algorithmic bytes; "
+                            "the pass is bound by the dependent L2 round trips between grid barriers, not by bytes",
+                    "source": "profiles/r1i_k_program_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
+                } if args.workload == "config2" and btg == 96 else None,
             },
             "clocks": clocks,
             "wall_s": wall,
