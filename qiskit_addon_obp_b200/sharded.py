@@ -454,7 +454,7 @@ class ShardedTable:
             out.num_trimmed = n_in * k2 - rows_surv + cancelled
         out.raw_rows = out.n_in * k2
 
-    def apply_generic(self, qubits, codes, coeffs, atol: float):
+    def apply_generic(self, qubits, codes, coeffs, atol: float, simplify: bool = True):
         raise NotImplementedError("generic (raw-row expansion) gates move terms between shards; not supported on a sharded table yet")
 
     def apply_reset(self, qubit: int, atol: float) -> _Stats:
