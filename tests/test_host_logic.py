@@ -239,3 +239,90 @@ def test_workload_shapes():
     assert names(a) == names(W.config4_near_clifford(depth=3))  # seeded: deterministic
     wl = W.config5_magic_sweep(depth=3)
     assert sum(1 for i in wl.slices[0].data if i.name == "rz") == 64
+
+
+# ---- slice plans: light cone + device steps (backpropagation.py:183 of the reference) ----------------
+def _reference_light_cone(slice_, support: set[int]) -> tuple[list[int], set[int]]:
+    """The reference's rule, stated with sets: walk the slice's gates in application order; a gate acts
+    iff it shares a qubit with the observable's support, and then widens it (a reset does not)."""
+    from qiskit_addon_obp_b200.ir import topological_op_order
+
+    nodes = [n for n in topological_op_order(slice_)[::-1] if n.name != "barrier"]
+    support = set(support)
+    applied = []
+    for k, node in enumerate(nodes):
+        if support.isdisjoint(node.qubits):
+            continue
+        applied.append(k)
+        if node.name != "reset":
+            support |= set(node.qubits)
+    return applied, support
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_slice_plan_matches_the_reference_light_cone(seed):
+    from qiskit_addon_obp_b200.backpropagation import SliceProgram
+
+    rng = np.random.default_rng(seed)
+    nq = 12
+    qc = QuantumCircuit(nq)
+    for _ in range(14):
+        r = rng.random()
+        a, b = (int(q) for q in rng.choice(nq, size=2, replace=False))
+        if r < 0.3:
+            qc.rx(float(rng.uniform(-1, 1)), a)
+        elif r < 0.5:
+            qc.cx(a, b)
+        elif r < 0.65:
+            qc.rzz(float(rng.uniform(-1, 1)), a, b)
+        elif r < 0.75:
+            qc.reset(a)
+        elif r < 0.85:
+            qc.cp(0.3, a, b)  # generic gate: its own device step
+        elif r < 0.9:
+            qc.barrier()
+        else:
+            qc.h(a)
+    prog = SliceProgram(qc)
+    for _ in range(5):
+        support = {int(q) for q in rng.choice(nq, size=int(rng.integers(1, 4)), replace=False)}
+        mask = sum(1 << q for q in support)
+        plan = prog.plan(mask)
+        want_applied, want_support = _reference_light_cone(qc, support)
+        assert plan.applied == want_applied
+        assert plan.support_after == sum(1 << q for q in want_support)
+        assert prog.plan(mask) is plan  # cached per (slice, support)
+        # the steps partition the applied gates in order; the slice's last gate asks for exact counters
+        seen = []
+        for kind, what in plan.steps:
+            if kind == "ops":
+                assert len(what) > 0
+                seen += [None] * len(what)
+            else:
+                assert kind == "node" and prog.special[what]
+                seen.append(what)
+        assert len(seen) == len(want_applied)
+        if plan.steps and plan.steps[-1][0] == "ops":
+            assert plan.steps[-1][1]["flags"][-1] == 1
+            assert not plan.steps[-1][1]["flags"][:-1].any()
+
+
+def test_slice_plan_full_cone_shortcut_and_unsupported_gate():
+    from qiskit_addon_obp_b200.backpropagation import SliceProgram
+
+    qc = QuantumCircuit(3)
+    qc.h(0)
+    qc.cx(0, 1)
+    qc.rz(0.2, 2)
+    prog = SliceProgram(qc)
+    full = prog.plan(0b111)
+    assert full.applied == [0, 1, 2] and full.support_after == 0b111
+    assert prog.plan(0b100).applied == [k for k, n in enumerate(prog.nodes) if n.name == "rz"]
+    # a gate the engine cannot express only raises when the light cone reaches it
+    bad = QuantumCircuit(6)
+    bad.unitary(np.linalg.qr(np.random.default_rng(0).normal(size=(32, 32)) + 0j)[0], [0, 1, 2, 3, 4])
+    bad.h(5)
+    prog = SliceProgram(bad)
+    assert [k for k, _ in prog.plan(1 << 5).steps] == ["ops"]
+    kinds = [k for k, _ in prog.plan(0b1).steps]
+    assert kinds[-1] == "error"
