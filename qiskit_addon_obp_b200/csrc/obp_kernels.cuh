@@ -1355,7 +1355,7 @@ k_program(Tab t, const ProgEntry* __restrict__ entries, int n_entries, const uns
 // order.  The host then runs the same merge as for a freshly loaded operator (k_hash_rows,
 // k_index_build with the raw-row zero filter, k_trim), i.e. simplify() as the reference states it.
 // ================================================================================================
-#define OBP_GEN_MAXK 16
+#define OBP_GEN_MAXK 256  // every gate on <= 4 qubits (4^4 Pauli components); GenP travels as a 5 KB kernel parameter
 
 struct GenP {
   int m;                   // gate qubits (<= 4)

@@ -10,8 +10,8 @@ decomposition is computed once per distinct gate (cached) and classified:
 * **rotation class** — ``U = u0*I + u1*G`` with one Pauli generator ``G`` (rx, ry, rz, rxx, ryy,
   rzz, rzx, p, t, tdg, ...).  The device runs the branch-and-merge kernel (``k_rotate``).
 
-* **generic** — anything else with up to 16 Pauli components (``cp``, ``crz``, arbitrary 1-2 qubit
-  unitaries).  The device runs the reference's literal k*k raw-row expansion followed by the merge of
+* **generic** — anything else on up to 4 qubits, i.e. at most 256 Pauli components (``cp``, ``crz``,
+  ``ccx``, arbitrary unitaries).  The device runs the reference's literal k*k raw-row expansion followed by the merge of
   a freshly loaded operator (``k_expand`` + ``k_index_build`` + ``k_trim``); no BASELINE configuration
   needs it, it is there for drop-in completeness.
 
@@ -131,13 +131,13 @@ def classify(matrix: np.ndarray, name: str = "gate") -> GateProgram:
         rec["u0"] = (us[0].real, us[0].imag)
         rec["u1"] = (us[1].real, us[1].imag)
         return GateProgram(OBP_OP_ROTATION, m, k, rec)
-    if m <= 4 and k <= 16:
+    if m <= 4:
         # anything else: the device runs the reference's literal k*k raw-row expansion + simplify
         rec["kind"] = OBP_OP_GENERIC
         return GateProgram(OBP_OP_GENERIC, m, k, rec, codes=np.array(codes, dtype=np.uint32), coeffs=np.array(us))
     raise NotImplementedError(
-        f"gate {name!r} ({m} qubits, {k} Pauli components) has more than 16 Pauli components; the raw-row "
-        "expansion kernel handles up to 16"
+        f"gate {name!r} acts on {m} qubits ({k} Pauli components); the raw-row expansion kernel handles "
+        "gates on up to 4 qubits"
     )
 
 
@@ -152,8 +152,8 @@ def raw_program_for(ins: Instruction) -> GateProgram:
     prog = _RAW_CACHE.get(key)
     if prog is None:
         codes, us = pauli_decompose(ins.matrix)
-        if len(codes) > 16:
-            raise NotImplementedError(f"gate {ins.name!r} has {len(codes)} Pauli components; at most 16 are supported")
+        if len(ins.qubits) > 4:
+            raise NotImplementedError(f"gate {ins.name!r} acts on {len(ins.qubits)} qubits; at most 4 are supported")
         rec = np.zeros(1, dtype=OP_DTYPE)
         rec["kind"] = OBP_OP_GENERIC
         rec["n_qubits"] = len(ins.qubits)

@@ -31,6 +31,30 @@ def test_reference_kat(kat):
     kat(backpropagate)
 
 
+def test_three_and_four_qubit_unitaries():
+    """Gates with 64 and 256 Pauli components run through the raw-row expansion kernel like cp / crz do
+    (the reference decomposes any `Operator`, backpropagation.py:213)."""
+    rng = np.random.default_rng(33)
+
+    def haar(dim):
+        a = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        q, r = np.linalg.qr(a)
+        return q * (np.diag(r) / np.abs(np.diag(r)))
+
+    nq = 6
+    qc1 = QuantumCircuit(nq)
+    qc1.unitary(haar(8), [4, 0, 2])  # 64 components, qubits out of order
+    qc1.rx(0.3, 1)
+    qc2 = QuantumCircuit(nq)
+    qc2.unitary(np.eye(8)[[0, 1, 2, 7, 4, 5, 6, 3]].astype(complex), [0, 1, 2], label="ccx")  # Toffoli: 8 components
+    qc2.cx(2, 3)
+    qc3 = QuantumCircuit(nq)
+    qc3.unitary(haar(16), [5, 1, 3, 0])  # 256 components
+    obs = SparsePauliOp(["ZIIIII", "IIXYII"], [1.0, 0.5])
+    _compare(obs, [qc1, qc2])
+    _compare(SparsePauliOp(["IIIIZI"], [1.0]), [qc3, qc2])
+
+
 def test_simplify_false_matches_oracle():
     """OperatorBudget(simplify=False): raw rows multiply by k*k per gate, nothing merges (reference :220)."""
     qc1 = QuantumCircuit(3)
