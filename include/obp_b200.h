@@ -109,6 +109,11 @@ uint64_t obp_bytes_per_term(int n_qubits);
  * reduce_op() hands to the loop (backpropagation.py:114) and simplify() itself. */
 int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
              uint64_t n, double atol, obp_stats* stats);
+/* Same as obp_load, but a snapshot taken before stays valid: the table's content is REPLACED in the middle of
+ * a slice (a sharded table runs a generic gate on the gathered operator and hands every rank its share back),
+ * obp_restore still returns to the last commit. */
+int obp_replace(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
+                uint64_t n, double atol, obp_stats* stats);
 /* Number of live terms (len(observable)). */
 int obp_count(obp_ctx* ctx, uint64_t* n);
 /* Compact and copy the live terms to host arrays with room for max_rows rows. */

@@ -807,13 +807,26 @@ int obp_count(obp_ctx* ctx, uint64_t* n) {
   return OBP_OK;
 }
 
+static int load_impl(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
+                     uint64_t n, double atol, obp_stats* stats, bool keep_snapshot);
+
 int obp_load(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
              uint64_t n, double atol, obp_stats* stats) {
+  return load_impl(ctx, x_words, z_words, coeffs, n, atol, stats, false);
+}
+
+int obp_replace(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
+                uint64_t n, double atol, obp_stats* stats) {
+  return load_impl(ctx, x_words, z_words, coeffs, n, atol, stats, true);
+}
+
+static int load_impl(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_words, const double* coeffs,
+                     uint64_t n, double atol, obp_stats* stats, bool keep_snapshot) {
   OBP_NO_PENDING(ctx, "obp_load");
   if (!ctx || (n && (!x_words || !z_words || !coeffs))) return OBP_ERR_BADARG;
   if (n > ctx->cap) return ctx->fail(OBP_ERR_CAPACITY, "obp_load: more rows than capacity");
   CU(cudaSetDevice(ctx->device));
-  ctx->snap.valid = false;
+  if (!keep_snapshot) ctx->snap.valid = false;  // (the snapshot carries its own hash frame: it survives a replace)
   init_frame(ctx);
   int rc = upload_cols(ctx);
   if (rc) return rc;

@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
         "obp_device_memory": ([C.c_int, u64p, u64p], C.c_int),
         "obp_bytes_per_term": ([C.c_int], C.c_uint64),
         "obp_load": ([vp, vp, vp, vp, C.c_uint64, C.c_double, C.POINTER(ObpStats)], C.c_int),
+        "obp_replace": ([vp, vp, vp, vp, C.c_uint64, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_count": ([vp, u64p], C.c_int),
         "obp_download": ([vp, vp, vp, vp, C.c_uint64, u64p], C.c_int),
         "obp_apply_ops": ([vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
@@ -171,7 +172,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "obp_create obp_destroy obp_last_error obp_set_stream obp_device_memory obp_bytes_per_term "
     "obp_load obp_count obp_download obp_apply_ops obp_apply_generic obp_apply_reset obp_apply_damping obp_truncate "
-    "obp_union_count obp_snapshot obp_restore obp_reserve obp_set_row_order obp_apply_ops_submit obp_apply_ops_wait obp_profile_enable obp_profile_get "
+    "obp_union_count obp_snapshot obp_restore obp_reserve obp_set_row_order obp_apply_ops_submit obp_apply_ops_wait obp_replace obp_profile_enable obp_profile_get "
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
@@ -315,9 +316,10 @@ class TermTable:
         return 1 if self.zero_operator else self.n
 
     # -- I/O ----------------------------------------------------------------------------------
-    def load(self, op: SparsePauliOp, atol: float | None = None) -> ObpStats:
+    def load(self, op: SparsePauliOp, atol: float | None = None, keep_snapshot: bool = False) -> ObpStats:
         """Upload ``op``; ``atol=None`` merges duplicate rows only, a float >= 0 runs the full simplify,
-        ``OBP_ATOL_RAW`` keeps the rows exactly as given."""
+        ``OBP_ATOL_RAW`` keeps the rows exactly as given.  ``keep_snapshot``: the last commit stays restorable
+        (``obp_replace``: the content is replaced in the middle of a slice)."""
         if op.num_qubits != self.num_qubits:
             raise ValueError("operator width does not match the table")
         if len(op) > self.capacity:
@@ -325,7 +327,7 @@ class TermTable:
         xw, zw = op.packed()
         coeffs = np.ascontiguousarray(op.coeffs, dtype=np.complex128)
         st = ObpStats()
-        rc = self._lib.obp_load(
+        rc = (self._lib.obp_replace if keep_snapshot else self._lib.obp_load)(
             self._h,
             xw.ctypes.data_as(C.c_void_p),
             zw.ctypes.data_as(C.c_void_p),

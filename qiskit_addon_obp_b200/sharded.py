@@ -454,8 +454,37 @@ class ShardedTable:
             out.num_trimmed = n_in * k2 - rows_surv + cancelled
         out.raw_rows = out.n_in * k2
 
-    def apply_generic(self, qubits, codes, coeffs, atol: float, simplify: bool = True):
-        raise NotImplementedError("generic (raw-row expansion) gates move terms between shards; not supported on a sharded table yet")
+    def apply_generic(self, qubits, codes, coeffs, atol: float, simplify: bool = True) -> _Stats:
+        """A generic gate (cp, crz, arbitrary unitaries): its k*k raw rows land on any shard, so the operator is
+        gathered, expanded and merged as ONE table on every rank (``k_expand`` + the merge of a fresh operator,
+        exact counters), and every rank keeps its share of the result.  Correct but not scalable — whole-table
+        host traffic per gate; no BASELINE configuration has such gates."""
+        if not simplify:
+            raise NotImplementedError("OperatorBudget(simplify=False) is not supported on a sharded table")
+        out = _Stats()
+        k2 = len(codes) ** 2
+        if self.zero_operator:
+            out.n_in, out.raw_rows, out.num_trimmed, out.n_out, out.updates = 1, k2, k2, 1, 1
+            return out
+        op = self.download()  # collective: every rank now holds the whole operator
+        scratch = TermTable.acquire(self.num_qubits, max(1024, 2 * len(op) * (k2 + 1)), self.device)
+        try:
+            scratch.track_zero = False
+            scratch.load(op, None)
+            st = scratch.apply_generic(qubits, codes, coeffs, atol, simplify=True)
+            res = scratch.download() if scratch.n else SparsePauliOp([], num_qubits=self.num_qubits)
+        finally:
+            scratch.release()
+        for t in self.tables.values():
+            t.load(res, None, keep_snapshot=True)  # (a sharded table keeps the rows this rank owns)
+        self._sync_counts()
+        for f in ("n_in", "raw_rows", "updates", "num_unique", "num_duplicate", "num_trimmed"):
+            setattr(out, f, int(getattr(st, f)))
+        out.sum_trimmed = [float(st.sum_trimmed[0]), float(st.sum_trimmed[1])]
+        out.n_out = self.n
+        if self.n == 0:
+            self.zero_operator = True
+        return out
 
     def apply_reset(self, qubit: int, atol: float) -> _Stats:
         """``apply_reset_to`` + simplify: local when the cleared keys keep their owner, else the rows with Z

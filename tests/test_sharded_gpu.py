@@ -138,3 +138,33 @@ def test_sharded_reset_and_noise(monkeypatch, ranks):
     first.reset(5)  # ... and a slice whose only (hence last) gate is the reset: its counters are reported
     obs = random_observable(nq, 6, rng, weight=3)
     _compare(monkeypatch, ranks, obs, slices + [noisy] + mixed + [last, first] + slices[:2])
+
+
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_sharded_generic_gates(monkeypatch, ranks):
+    """cp / crz / a random two-qubit unitary on a sharded table: gathered, expanded as one table, re-sharded;
+    counters exact; a slice that breaks the operator budget after such a gate still rolls back to the commit."""
+    from qiskit_addon_obp_b200.ir import QuantumCircuit
+
+    rng = np.random.default_rng(77)
+    nq = 8
+    a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    q, r = np.linalg.qr(a)
+    u = q * (np.diag(r) / np.abs(np.diag(r)))
+    slices = []
+    for k in range(5):
+        qc = QuantumCircuit(nq)
+        qc.rx(0.4 + 0.1 * k, k % nq)
+        qc.cp(0.3 + 0.2 * k, k % nq, (k + 3) % nq)
+        qc.cx((k + 1) % nq, (k + 2) % nq)
+        if k == 2:
+            qc.unitary(u, [(k + 4) % nq, (k + 6) % nq])
+        qc.crz(-0.6, (k + 5) % nq, (k + 7) % nq)
+        qc.ry(0.3, (k + 2) % nq)
+        slices.append(qc)
+    obs = random_observable(nq, 3, rng)
+    _, md = _compare(monkeypatch, ranks, obs, slices)
+    assert md.num_backpropagated_slices == 5
+    _, md = _compare(monkeypatch, ranks, obs, slices, operator_budget=OperatorBudget(max_paulis=60))
+    assert 0 < md.num_backpropagated_slices < 5
+    _compare(monkeypatch, ranks, obs, slices, truncation_error_budget=setup_budget(max_error_per_slice=0.01))
