@@ -107,11 +107,12 @@ class ClockSampler:
         self.thread = None
         self.stop_flag = False
         self.source = None
-        # Polling period of the background thread.  Measured on these boxes: at 20-50 ms the poller makes
-        # individual 26 ms end-to-end steps take 35-116 ms (GIL hand-offs and the driver lock NVML shares with
-        # kernel launches); at 200 ms the steps are flat.  The main thread adds one sample between steps
-        # (poll_once), outside the per-step timers, so short runs still get several samples.
-        self.period_s = float(os.environ.get("OBP_BENCH_SAMPLE_MS", "200")) / 1e3
+        # Polling period of the background thread: ~3 samples inside a default run.  End-to-end steps on these
+        # boxes are sometimes 10-90 ms slower for a few steps in a row whatever the period (20, 50, 100, 200 ms
+        # and polling between steps were all tried, each flat in some runs and noisy in others): host noise, not
+        # the poller; the device-timed `value` does not move.  OBP_BENCH_POLL_BETWEEN_STEPS=1 adds one sample
+        # per step from the main thread, outside the per-step timers.
+        self.period_s = float(os.environ.get("OBP_BENCH_SAMPLE_MS", "100")) / 1e3
         self._poll = None
 
     def start(self):
@@ -399,8 +400,8 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         acc = one_step()
-        if rank == 0:
-            sampler.poll_once()  # (device work of the step has just ended; not inside the step's own timers)
+        if rank == 0 and os.environ.get("OBP_BENCH_POLL_BETWEEN_STEPS") == "1":
+            sampler.poll_once()
         if os.environ.get("OBP_BENCH_VERBOSE"):
             print(f"[bench] rank {rank} step e2e {acc['dt'] * 1e3:.2f} ms device {acc['dev_ms']:.2f} ms", file=sys.stderr, flush=True)
         e2e_s += acc["dt"]
