@@ -112,8 +112,6 @@ def backpropagate(
     if comm is not None and hasattr(comm, "rank") and operator_budget.max_paulis is not None:
         # one GPU per rank: the whole table may be n_ranks times what a single device holds
         capacity = max(capacity, min(8 * int(operator_budget.max_paulis), capacity * comm.n_ranks))
-    if comm is not None and raw:
-        raise NotImplementedError("OperatorBudget(simplify=False) is not supported on a sharded table")
     if comm is not None and ordered:
         raise NotImplementedError("OBP_B200_ROW_ORDER=1 is not supported on a sharded table")
     if comm is not None:

@@ -1872,7 +1872,9 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
   OBP_NO_PENDING(ctx, "obp_apply_generic");
   if (!ctx || !qubits || !codes || !coeffs || n_qubits < 1 || n_qubits > 4 || n_comp < 1 || n_comp > OBP_GEN_MAXK)
     return OBP_ERR_BADARG;
-  if (ctx->n_ranks > 1) return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_generic: not available on a sharded table");
+  // (without simplify nothing merges, so it does not matter which rank holds a row: the expansion is local)
+  if (ctx->n_ranks > 1 && simplify)
+    return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_generic: with simplify, not available on a sharded table");
   CU(cudaSetDevice(ctx->device));
   GenP p;
   memset(&p, 0, sizeof(p));

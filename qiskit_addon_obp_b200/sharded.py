@@ -27,7 +27,7 @@ import time
 
 import numpy as np
 
-from .engine import OBP_OP_ROTATION, CapacityError, TermTable, lib
+from .engine import OBP_ATOL_RAW, OBP_OP_ROTATION, CapacityError, TermTable, lib
 from .ir import SparsePauliOp
 
 
@@ -302,6 +302,19 @@ class ShardedTable:
     # -- I/O ----------------------------------------------------------------------------------------
     def load(self, op: SparsePauliOp, atol: float | None = None) -> _Stats:
         out = _Stats()
+        if atol == OBP_ATOL_RAW:
+            # simplify=False: nothing ever merges, so ownership by key hash is moot — deal the rows out evenly
+            R = self.comm.n_ranks
+            xw, zw = op.packed()
+            for r, t in self.tables.items():
+                part = SparsePauliOp.from_packed(xw[r::R], zw[r::R], np.asarray(op.coeffs)[r::R], op.num_qubits)
+                if len(part) > t.capacity:
+                    t.reserve(2 * len(part))
+                t.load(part, atol)
+            self._sync_counts()
+            self.zero_operator = False
+            out.n_in, out.n_out = len(op), self.n
+            return out
         for t in self.tables.values():  # every rank is given the whole operator and keeps its share
             if len(op) > t.capacity:
                 t.reserve(2 * len(op))
@@ -459,10 +472,21 @@ class ShardedTable:
         gathered, expanded and merged as ONE table on every rank (``k_expand`` + the merge of a fresh operator,
         exact counters), and every rank keeps its share of the result.  Correct but not scalable — whole-table
         host traffic per gate; no BASELINE configuration has such gates."""
-        if not simplify:
-            raise NotImplementedError("OperatorBudget(simplify=False) is not supported on a sharded table")
         out = _Stats()
         k2 = len(codes) ** 2
+        if not simplify:
+            # OperatorBudget(simplify=False): every rank expands the rows it holds, nothing moves or merges
+            n_in = self.n
+            failed = False
+            for t in self.tables.values():
+                try:
+                    t.apply_generic(qubits, codes, coeffs, atol, simplify=False)
+                except CapacityError:
+                    failed = True
+            self._raise_if_any(failed, "sharded raw expansion")
+            self._sync_counts()
+            out.n_in, out.raw_rows, out.updates, out.n_out = n_in, n_in * k2, n_in, self.n
+            return out
         if self.zero_operator:
             out.n_in, out.raw_rows, out.num_trimmed, out.n_out, out.updates = 1, k2, k2, 1, 1
             return out
@@ -496,6 +520,12 @@ class ShardedTable:
             out.n_in = out.raw_rows = out.num_trimmed = out.n_out = out.updates = 1
             return out
         n_in = self.n
+        if atol == OBP_ATOL_RAW:  # simplify=False: zero / clear in place on every rank, nothing merges
+            for t in self.tables.values():
+                t.apply_reset(qubit, atol)
+            self._sync_counts()
+            out.n_in = out.raw_rows = out.updates = out.n_out = n_in
+            return out
         tdev = torch.device("cuda", self.device)
         bufs, counts, emit, failed, peer = {}, {}, {}, False, 0
         for r, t in self.tables.items():

@@ -168,3 +168,33 @@ def test_sharded_generic_gates(monkeypatch, ranks):
     _, md = _compare(monkeypatch, ranks, obs, slices, operator_budget=OperatorBudget(max_paulis=60))
     assert 0 < md.num_backpropagated_slices < 5
     _compare(monkeypatch, ranks, obs, slices, truncation_error_budget=setup_budget(max_error_per_slice=0.01))
+
+
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_sharded_simplify_false(monkeypatch, ranks):
+    """OperatorBudget(simplify=False) on a sharded table: every rank expands the rows it holds (k*k per gate),
+    nothing merges; sizes, raw counts and the per-label sums match the oracle (row order is not defined)."""
+    from qiskit_addon_obp_b200.ir import QuantumCircuit
+
+    qc1 = QuantumCircuit(3)
+    qc1.rx(0.3, 0)
+    qc1.cx(0, 1)
+    qc2 = QuantumCircuit(3)
+    qc2.h(1)
+    qc2.reset(2)
+    qc2.rzz(0.2, 0, 1)
+    obs = SparsePauliOp(["ZIX", "XYZ", "ZIX", "IYI", "XXI"], [1.0, 0.5, 0.25, -0.3, 0.7])
+    budget = OperatorBudget(simplify=False)
+    for kw in ({}, {"truncation_error_budget": setup_budget(max_error_per_slice=0.05)}):
+        monkeypatch.setenv("OBP_B200_SHARDS", str(ranks))
+        got, rest, md = backpropagate(obs, [qc1, qc2], operator_budget=budget, **kw)
+        monkeypatch.delenv("OBP_B200_SHARDS")
+        want, _, md_w = oracle.backpropagate(obs, [qc1, qc2], operator_budget=budget, **kw)
+        assert rest == [] and len(got) == len(want)
+        assert [s.num_paulis for s in md.backpropagation_history] == [s.num_paulis for s in md_w.backpropagation_history]
+        assert [s.raw_num_paulis for s in md.backpropagation_history] == [s.raw_num_paulis for s in md_w.backpropagation_history]
+        assert all(s.num_unique_paulis is None for s in md.backpropagation_history)
+        if not kw:
+            a, b = got.as_dict(), want.as_dict()  # sums per label
+            assert set(a) == set(b)
+            assert max(abs(a[k] - b[k]) for k in a) < 1e-12
