@@ -114,9 +114,6 @@ def backpropagate(
         capacity = max(capacity, min(8 * int(operator_budget.max_paulis), capacity * comm.n_ranks))
     if comm is not None and ordered:
         raise NotImplementedError("OBP_B200_ROW_ORDER=1 is not supported on a sharded table")
-    if comm is not None:
-        if n_obs > 1 and operator_budget.is_active():
-            raise NotImplementedError("a sharded table supports operator budgets for a single observable only")
 
     metadata = OBPMetadata(
         truncation_error_budget=truncation_error_budget,
@@ -595,8 +592,10 @@ def _observable_oversized(tables, loaded, obs_in, operator_budget, slice_id, sm,
             sm.sum_paulis = len(union_op())  # unmerged rows: count the distinct labels on the host
         elif not host_ops and len(dev_tables) == 1 and not dev_tables[0].zero_operator:
             sm.sum_paulis = dev_tables[0].n  # one observable: its keys are already distinct
-        elif not host_ops and all(not t.zero_operator for t in dev_tables):
+        elif not host_ops and all(not t.zero_operator and isinstance(t, TermTable) for t in dev_tables):
             sm.sum_paulis = engine.union_count(dev_tables)
+        # (several sharded observables: their hash frames differ, equal keys need not share a rank — the union
+        # is counted on the gathered operators, like the general case below)
         else:
             sm.sum_paulis = len(union_op())
         if sm.sum_paulis > max_paulis:

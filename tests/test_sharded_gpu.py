@@ -80,6 +80,9 @@ def test_sharded_max_paulis_and_multi_observable(monkeypatch):
     obs = random_observable(nq, 3, rng)
     _compare(monkeypatch, 2, obs, slices, operator_budget=OperatorBudget(max_paulis=40))
     _compare(monkeypatch, 4, [obs, SparsePauliOp("IIIIIIIZ")], slices)
+    # the operator budget over several sharded observables counts the union of their keys
+    _, md = _compare(monkeypatch, 2, [obs, SparsePauliOp("IIIIIIIZ"), obs], slices, operator_budget=OperatorBudget(max_paulis=60))
+    assert 0 < md.num_backpropagated_slices < 10
 
 
 def test_sharded_round_trip_large(monkeypatch):
