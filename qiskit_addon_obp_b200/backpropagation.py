@@ -186,8 +186,7 @@ def backpropagate(
                                 raw_first[i] = dirty[i] and prog.nodes[first].name != "LayerError"
                             else:
                                 raw_first[i] = (
-                                    dirty[i] and not raw and comm is None and not prog.special[first]
-                                    and first not in prog.errors
+                                    dirty[i] and not raw and not prog.special[first] and first not in prog.errors
                                 )
                             tables[i].load(obs_in[i], OBP_ATOL_RAW if (raw or raw_first[i]) else None)
                             info.h2d_bytes += len(obs_in[i]) * (16 * tables[i].words + 16)

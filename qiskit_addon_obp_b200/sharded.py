@@ -313,8 +313,10 @@ class ShardedTable:
                 t.load(part, atol)
             self._sync_counts()
             self.zero_operator = False
+            self._unsimplified = True  # rows as given (duplicates, zeros): a generic gate must see them as such
             out.n_in, out.n_out = len(op), self.n
             return out
+        self._unsimplified = False
         for t in self.tables.values():  # every rank is given the whole operator and keeps its share
             if len(op) > t.capacity:
                 t.reserve(2 * len(op))
@@ -494,7 +496,8 @@ class ShardedTable:
         scratch = TermTable.acquire(self.num_qubits, max(1024, 2 * len(op) * (k2 + 1)), self.device)
         try:
             scratch.track_zero = False
-            scratch.load(op, None)
+            scratch.load(op, OBP_ATOL_RAW if getattr(self, "_unsimplified", False) else None)
+            self._unsimplified = False
             st = scratch.apply_generic(qubits, codes, coeffs, atol, simplify=True)
             res = scratch.download() if scratch.n else SparsePauliOp([], num_qubits=self.num_qubits)
         finally:

@@ -201,3 +201,22 @@ def test_sharded_simplify_false(monkeypatch, ranks):
             a, b = got.as_dict(), want.as_dict()  # sums per label
             assert set(a) == set(b)
             assert max(abs(a[k] - b[k]) for k in a) < 1e-12
+
+
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_sharded_unsimplified_input(monkeypatch, ranks):
+    """Duplicate and near-zero input rows reach the first gate as given: its counters (raw_num_paulis over every
+    given row) match the oracle on a sharded table too."""
+    from qiskit_addon_obp_b200.ir import QuantumCircuit
+
+    qc = QuantumCircuit(3)
+    qc.rx(0.3, 0)
+    qc.cx(0, 1)
+    qc2 = QuantumCircuit(3)
+    qc2.rz(0.1, 1)
+    qc2.ry(0.4, 2)
+    obs = SparsePauliOp(["ZIX", "XYZ", "ZIX", "IIZ", "XYZ", "YYI"], [1.0, 0.5, 0.25, 1e-9, -0.2, 0.3])
+    _, md = _compare(monkeypatch, ranks, obs, [qc])
+    assert md.backpropagation_history[0].num_unique_paulis[0] is not None
+    _compare(monkeypatch, ranks, obs, [qc2, qc])
+    _compare(monkeypatch, ranks, obs, [qc, qc2])
