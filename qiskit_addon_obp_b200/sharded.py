@@ -336,12 +336,48 @@ class ShardedTable:
 
     # -- the hot path ---------------------------------------------------------------------------------
     def apply_ops(self, ops: np.ndarray, atol: float) -> _Stats:
+        """A gate program on the sharded table.  The slice's last gate carries OBP_FLAG_EXACT_COUNTERS; when
+        it is Clifford-class its counters need every member of a key's coset, which live on several ranks:
+        they are reported as None unless OBP_B200_SHARDED_EXACT_COUNTERS=1 asks for the (whole-table gather,
+        not scalable) exact path."""
         import torch
 
         out = _Stats()
         if self.zero_operator:
             k2 = int(ops[-1]["n_components"]) ** 2
             out.n_in, out.raw_rows, out.num_trimmed, out.n_out, out.updates = 1, k2, k2, 1, len(ops)
+            return out
+        if (
+            self.comm.n_ranks > 1 and int(ops[-1]["kind"]) != OBP_OP_ROTATION and int(ops[-1]["flags"]) & 1
+            and os.environ.get("OBP_B200_SHARDED_EXACT_COUNTERS", "0") == "1"
+        ):
+            head, last_op = ops[:-1], ops[-1:]
+            updates = 0
+            if len(head):
+                head = head.copy()
+                updates = int(self.apply_ops(head, atol).updates)
+                if self.zero_operator:
+                    rest = self.apply_ops(last_op, atol)
+                    rest.updates += updates
+                    return rest
+            # the last gate's counters from the gathered operator on one scratch table ...
+            op = self.download()
+            scratch = TermTable.acquire(self.num_qubits, max(1024, 2 * len(op)), self.device)
+            try:
+                scratch.track_zero = False
+                scratch.load(op, None)
+                exact = scratch.apply_ops(last_op, atol)
+            finally:
+                scratch.release()
+            # ... and the gate itself on the shards
+            plain = last_op.copy()
+            plain["flags"] = 0
+            out = self.apply_ops(plain, atol)
+            out.updates += updates
+            for f in ("n_in", "raw_rows", "num_unique", "num_duplicate", "num_trimmed"):
+                setattr(out, f, int(getattr(exact, f)))
+            out.sum_trimmed = [float(exact.sum_trimmed[0]), float(exact.sum_trimmed[1])]
+            out.counters_valid = True
             return out
         pos, failed = 0, False
         updates = 0

@@ -220,3 +220,19 @@ def test_sharded_unsimplified_input(monkeypatch, ranks):
     assert md.backpropagation_history[0].num_unique_paulis[0] is not None
     _compare(monkeypatch, ranks, obs, [qc2, qc])
     _compare(monkeypatch, ranks, obs, [qc, qc2])
+
+
+def test_sharded_exact_counters_for_clifford_ending_slices(monkeypatch):
+    """OBP_B200_SHARDED_EXACT_COUNTERS=1: slices that end on a Clifford-class gate report the reference's
+    simplify counters too (computed on the gathered operator)."""
+    rng = np.random.default_rng(19)
+    nq = 7
+    slices = random_slices(nq, 8, rng, p_rot=0.4, gates_per_slice=5)
+    obs = random_observable(nq, 4, rng, weight=3)
+    monkeypatch.setenv("OBP_B200_SHARDED_EXACT_COUNTERS", "1")
+    monkeypatch.setenv("OBP_B200_SHARDS", "4")
+    got, _, md_g = backpropagate(obs, slices)
+    monkeypatch.delenv("OBP_B200_SHARDS")
+    want, _, md_w = oracle.backpropagate(obs, slices)
+    assert_same_operator(got, want)
+    assert_same_metadata(md_g, md_w)  # no counter may be missing
