@@ -107,12 +107,14 @@ class ClockSampler:
         self.thread = None
         self.stop_flag = False
         self.source = None
-        # Polling period of the background thread: ~3 samples inside a default run.  End-to-end steps on these
-        # boxes are sometimes 10-90 ms slower for a few steps in a row whatever the period (20, 50, 100, 200 ms
-        # and polling between steps were all tried, each flat in some runs and noisy in others): host noise, not
-        # the poller; the device-timed `value` does not move.  OBP_BENCH_POLL_BETWEEN_STEPS=1 adds one sample
-        # per step from the main thread, outside the per-step timers.
-        self.period_s = float(os.environ.get("OBP_BENCH_SAMPLE_MS", "100")) / 1e3
+        # With NVML the clocks are sampled from the main thread BETWEEN the timed steps (inside the timed region,
+        # outside the per-step timers, the GPU having just finished a step): one sample per step and no query
+        # that can land inside a step (NVML takes a driver lock kernel launches need as well).
+        # OBP_BENCH_SAMPLE_MS > 0 brings a background poller back.  Note on end-to-end noise: on some of the
+        # shared boxes individual 26 ms end-to-end steps take 40-130 ms, with every polling scheme and with no
+        # polling at all, while on others ten steps in a row stay within 26.0 +- 0.5 ms; the device-timed
+        # `value` is unaffected.  It is host-side noise of the box, not of the sampler.
+        self.period_s = float(os.environ.get("OBP_BENCH_SAMPLE_MS", "0")) / 1e3
         self._poll = None
 
     def start(self):
@@ -123,8 +125,11 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
             self.nvml = pynvml
             self.source = "nvml"
-            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
-            self.thread.start()
+            self._poll = self._make_nvml_poll()
+            self._poll()  # (the first query initialises NVML's device state; keep it out of the timed region)
+            if self.period_s > 0:
+                self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+                self.thread.start()
             return
         except Exception:  # noqa: BLE001 - no NVML bindings / init failure: fall back to the CLI
             self.source = None
@@ -150,7 +155,7 @@ class ClockSampler:
                 return int(ids[self.device])
         return self.device
 
-    def _poll_nvml(self):
+    def _make_nvml_poll(self):
         n = self.nvml
         bits = {
             "hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
@@ -163,6 +168,7 @@ class ClockSampler:
             sm_max = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
         except Exception:  # noqa: BLE001
             sm_max = float("nan")
+
         def poll():
             try:
                 sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
@@ -171,9 +177,11 @@ class ClockSampler:
             except Exception:  # noqa: BLE001
                 pass
 
-        self._poll = poll
+        return poll
+
+    def _poll_nvml(self):
         while not self.stop_flag:
-            poll()
+            self._poll()
             time.sleep(self.period_s)
 
     def poll_once(self):
@@ -210,7 +218,7 @@ class ClockSampler:
                 self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        if self.thread is None:
+        if self.thread is None and self._poll is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML bindings and no nvidia-smi"]}
         inside = [s for s in self.samples if s[0] >= self.t_begin]
         reasons: set = set()
@@ -398,10 +406,11 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     prof_tot: dict = {}
     n_out = n_slices = 0
     wall0 = time.perf_counter()
+    poll_every = max(1, int(os.environ.get("OBP_BENCH_POLL_EVERY", "1")))  # sample the clocks after every n-th step
     for _ in range(args.steps):
         acc = one_step()
-        if rank == 0 and os.environ.get("OBP_BENCH_POLL_BETWEEN_STEPS") == "1":
-            sampler.poll_once()
+        if rank == 0 and (_ % poll_every) == poll_every - 1:
+            sampler.poll_once()  # NVML: between steps, never inside one (see ClockSampler)
         if os.environ.get("OBP_BENCH_VERBOSE"):
             print(f"[bench] rank {rank} step e2e {acc['dt'] * 1e3:.2f} ms device {acc['dev_ms']:.2f} ms", file=sys.stderr, flush=True)
         e2e_s += acc["dt"]

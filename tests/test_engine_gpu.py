@@ -540,3 +540,46 @@ def test_wide_generator_rotation_across_words():
     qc.rzx(0.2, 64, 0)
     obs = SparsePauliOp.from_sparse_list([("XZ", [63, 64], 1.0), ("Y", [199], 0.5), ("ZX", [127, 128], -0.25)], nq)
     _compare(obs, [qc, qc])
+
+
+# ---- C-ABI protocol details -------------------------------------------------------------------------
+def test_submit_wait_protocol_and_replace_keeps_the_commit():
+    """obp_apply_ops_submit / _wait: nothing else may touch the context in between, and the pair returns what
+    obp_apply_ops returns.  obp_replace: new content, the last snapshot stays restorable."""
+    from qiskit_addon_obp_b200.engine import EngineError, TermTable
+    from qiskit_addon_obp_b200.gates import program_for
+
+    qc = QuantumCircuit(3)
+    qc.rx(0.3, 0)
+    qc.cx(0, 1)
+    qc.ry(-0.4, 1)
+    ops = np.concatenate([program_for(ins).template for ins in qc.data])
+    ops["qubit"][0, 0], ops["qubit"][1, :2], ops["qubit"][2, 0] = 0, (0, 1), 1
+    ops["flags"][-1] = 1
+    obs = SparsePauliOp(["ZZI", "IXY"], [1.0, 0.5])
+    a = TermTable.acquire(3, 1024)
+    b = TermTable.acquire(3, 1024)
+    try:
+        a.load(obs)
+        b.load(obs)
+        want = a.apply_ops(ops, 1e-8)
+        b.apply_ops_submit(ops, 1e-8)
+        with pytest.raises(EngineError, match="pending"):
+            b._check(b._lib.obp_snapshot(b._h), "obp_snapshot")  # (the raw call: the wrapper would drain first)
+        got = b.apply_ops_wait()
+        for f in ("n_in", "n_out", "raw_rows", "updates", "num_unique", "num_duplicate", "num_trimmed"):
+            assert getattr(got, f) == getattr(want, f), f
+        assert_same_operator(b.download(), a.download())
+        # replace: the commit survives
+        a.snapshot()
+        before = a.download()
+        a.load(SparsePauliOp(["XXX"], [2.0]), keep_snapshot=True)
+        assert a.download().as_dict() == {"XXX": 2.0}
+        a.restore()
+        assert_same_operator(a.download(), before)
+        a.load(SparsePauliOp(["XXX"], [2.0]))  # a plain load invalidates it
+        with pytest.raises(EngineError):
+            a.restore()
+    finally:
+        a.release()
+        b.release()
