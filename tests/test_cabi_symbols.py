@@ -78,3 +78,18 @@ def test_no_cpu_fallback_without_device(lib):
     with pytest.raises((EngineError, MemoryError)):
         backpropagate(SparsePauliOp("Z"), [qc])
     assert np.isfinite(1.0)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use it."""
+    import re
+
+    pkg = os.path.join(ROOT, "qiskit_addon_obp_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "obp_oracle" in text:
+                    offenders.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert offenders == []
