@@ -326,3 +326,12 @@ def test_slice_plan_full_cone_shortcut_and_unsupported_gate():
     assert [k for k, _ in prog.plan(1 << 5).steps] == ["ops"]
     kinds = [k for k, _ in prog.plan(0b1).steps]
     assert kinds[-1] == "error"
+
+
+@pytest.mark.parametrize("nq,n", [(1, 3), (5, 40), (70, 200), (130, 300)])
+def test_qwc_group_count_on_packed_words_matches_the_bool_version(nq, n):
+    from qiskit_addon_obp_b200.utils.qwc import _qwc_group_count_bool
+
+    rng = np.random.default_rng(nq + n)
+    op = SparsePauliOp((rng.random((n, nq)) < 0.3, rng.random((n, nq)) < 0.3), np.ones(n))
+    assert qwc_group_count(op) == _qwc_group_count_bool(op)
