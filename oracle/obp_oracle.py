@@ -16,7 +16,10 @@ Pinning: this oracle is checked (``tests/test_oracle_kat.py``) against every kno
 reference's own test-suite holds for the path and that can be stated without Qiskit objects —
 ``test/test_backpropagation.py:33-631`` (incl. the numeric KATs at :389-443 with their row order
 and accumulated errors), ``test/utils/test_simplify.py:24-136``, ``test/utils/test_operations.py``,
-``test/utils/test_metadata.py:183-265``.
+``test/utils/test_metadata.py:183-265`` — and against the executed notebook outputs the reference ships
+(``docs/guides/truncate_operator_terms.ipynb`` cells 10-49: slices absorbed / terms / QWC groups of seven
+runs; ``docs/guides/bound_error_using_p_norm.ipynb``: 116/10 and 84/6 terms/groups and the L2 expectation
+value 9.317829770853422 to the last digit; ``tests/test_notebook_anchors.py``).
 
 Every function cites the reference lines it follows.
 """
@@ -25,21 +28,212 @@ from __future__ import annotations
 
 import copy
 import itertools
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 
-from qiskit_addon_obp_b200.ir import (
-    QuantumCircuit,
-    SparsePauliOp,
-    topological_op_order,
-)
-from qiskit_addon_obp_b200.utils.metadata import OBPMetadata, SliceMetadata
-from qiskit_addon_obp_b200.utils.simplify import OperatorBudget, SimplifyMetadata
-from qiskit_addon_obp_b200.utils.truncating import TruncationErrorBudget
+# The only things taken from the product package are two passive containers: the bool[n, N] x/z +
+# complex128 operator (``SparsePauliOp`` work-alike) and the list-of-instructions circuit.  Everything
+# that *decides* a result — gate matrices, the gate order inside a slice, the budget replay, the
+# simplify/truncation arithmetic and the metadata records — is restated here, independently of the
+# product's host code, so that a wrong convention there cannot cancel out in an engine-vs-oracle test.
+from qiskit_addon_obp_b200.ir import QuantumCircuit, SparsePauliOp
 
 ATOL_DEFAULT = 1e-8  # [EXT] SparsePauliOp.atol
 RTOL_DEFAULT = 1e-5  # [EXT] SparsePauliOp.rtol
+
+
+# ---------------------------------------------------------------------------------------------
+# records (field-for-field: utils/simplify.py:26-77, utils/truncating.py:25-58, utils/metadata.py:25-222)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class SimplifyMetadata:
+    """``utils/simplify.py:26-40``."""
+
+    num_unique_paulis: int
+    num_duplicate_paulis: int
+    num_trimmed_paulis: int
+    sum_trimmed_coeffs: float
+
+
+@dataclass
+class OperatorBudget:
+    """``utils/simplify.py:43-77``."""
+
+    max_paulis: int | None = None
+    max_qwc_groups: int | None = None
+    simplify: bool = True
+    atol: float | None = None
+    rtol: float | None = None
+
+    def is_active(self) -> bool:  # :73-77
+        return self.max_paulis is not None or self.max_qwc_groups is not None
+
+
+@dataclass
+class TruncationErrorBudget:
+    """``utils/truncating.py:25-58``."""
+
+    per_slice_budget: list = field(default_factory=list)
+    max_error_total: float = 0.0
+    p_norm: int = 1
+    tol: float = 1e-8
+
+    def is_active(self) -> bool:  # :56-58
+        return (
+            any(budget > 0 for budget in self.per_slice_budget) and self.max_error_total > 0
+        )
+
+
+@dataclass
+class SliceMetadata:
+    """``utils/metadata.py:25-69``."""
+
+    slice_errors: list
+    raw_num_paulis: list
+    num_unique_paulis: list | None
+    num_duplicate_paulis: list | None
+    num_trimmed_paulis: list | None
+    sum_trimmed_coeffs: list | None
+    num_truncated_paulis: list
+    num_paulis: list
+    sum_paulis: int | None
+    num_qwc_groups: int | None
+
+
+@dataclass
+class OBPMetadata:
+    """``utils/metadata.py:72-222`` — the two budget functions written out as the reference has them
+    (``accumulated_error`` re-summed from zero inside every step of the replay, :152-157, :197-222)."""
+
+    truncation_error_budget: object
+    num_slices: int | None
+    operator_budget: object
+    backpropagation_history: list
+    num_backpropagated_slices: int
+
+    def accumulated_error(self, observable_idx: int, slice_idx: int | None = None) -> float:
+        if slice_idx is None:
+            slice_idx = self.num_backpropagated_slices
+        accumulated_error = 0.0
+        for i in range(slice_idx):  # :153-155
+            accumulated_error += self.backpropagation_history[i].slice_errors[observable_idx]
+        return accumulated_error
+
+    def left_over_error_budget(self, observable_idx: int, slice_idx: int | None = None) -> float:
+        if slice_idx is None:
+            slice_idx = self.num_backpropagated_slices
+        tb = self.truncation_error_budget
+        left_over = 0.0
+        for i in range(slice_idx + 1):  # :198
+            left_over = left_over + tb.per_slice_budget[i % len(tb.per_slice_budget)]  # :202-207
+            if i > 0:  # :210-213
+                left_over -= self.backpropagation_history[i - 1].slice_errors[observable_idx]
+            left_over = min(left_over, tb.max_error_total - self.accumulated_error(observable_idx, i))  # :216-220
+        return left_over
+
+    @classmethod
+    def from_json(cls, json_file: str) -> "OBPMetadata":  # :224-243
+        import json
+
+        with open(json_file) as fh:
+            data = json.load(fh)
+        data["truncation_error_budget"] = TruncationErrorBudget(**data["truncation_error_budget"])
+        data["operator_budget"] = OperatorBudget(**data["operator_budget"])
+        data["backpropagation_history"] = [SliceMetadata(**s) for s in data["backpropagation_history"]]
+        return cls(**data)
+
+
+# ---------------------------------------------------------------------------------------------
+# [EXT] Operator(gate).data — little-endian unitaries of Qiskit's standard gates, built here from
+# their Pauli closed forms (qubit 0 of the gate = least-significant index bit).  Independent of the
+# literal matrices in the product's ir.py; tests/test_oracle_kat.py compares the two tables.
+# ---------------------------------------------------------------------------------------------
+def _pauli_le(label: str) -> np.ndarray:
+    """Matrix of a little-endian Pauli label: label[0] acts on the gate's qubit 0."""
+    m = np.array([[1.0 + 0j]])
+    for ch in label:
+        m = np.kron(_P1[ch], m)
+    return m
+
+
+def _pauli_sum(terms: dict) -> np.ndarray:
+    return sum(c * _pauli_le(lbl) for lbl, c in terms.items())
+
+
+_ROT_GEN = {"rx": "X", "ry": "Y", "rz": "Z", "rxx": "XX", "ryy": "YY", "rzz": "ZZ", "rzx": "ZX"}  # rzx: Z on arg 0, X on arg 1
+
+
+def gate_matrix(name: str, params=()) -> np.ndarray:
+    """Unitary of a named Qiskit standard gate from its Pauli closed form."""
+    r2 = 1.0 / np.sqrt(2.0)
+    if name in _ROT_GEN:  # exp(-i theta/2 P)
+        t = params[0] / 2
+        g = _ROT_GEN[name]
+        return _pauli_sum({"I" * len(g): np.cos(t), g: -1j * np.sin(t)})
+    if name == "id":
+        return _pauli_le("I")
+    if name in ("x", "y", "z"):
+        return _pauli_le(name.upper())
+    if name == "h":
+        return _pauli_sum({"X": r2, "Z": r2})
+    phase_gates = {"s": np.pi / 2, "sdg": -np.pi / 2, "t": np.pi / 4, "tdg": -np.pi / 4}
+    if name in phase_gates or name == "p":  # diag(1, e^{i lam}) = (1+e)/2 I + (1-e)/2 Z
+        e = np.exp(1j * (params[0] if name == "p" else phase_gates[name]))
+        return _pauli_sum({"I": (1 + e) / 2, "Z": (1 - e) / 2})
+    if name in ("sx", "sxdg"):  # sqrt(X) = (1+i)/2 I + (1-i)/2 X
+        a = (1 + 1j) / 2 if name == "sx" else (1 - 1j) / 2
+        return _pauli_sum({"I": a, "X": np.conj(a)})
+    ctrl = {"cx": "X", "cy": "Y", "cz": "Z"}
+    if name in ctrl:  # |0><0|_0 (x) I + |1><1|_0 (x) P_1 = (II + Z_0 + P_1 - Z_0 P_1) / 2
+        p = ctrl[name]
+        return _pauli_sum({"II": 0.5, "ZI": 0.5, "I" + p: 0.5, "Z" + p: -0.5})
+    if name == "swap":
+        return _pauli_sum({"II": 0.5, "XX": 0.5, "YY": 0.5, "ZZ": 0.5})
+    if name == "iswap":  # exp(i pi/4 (XX + YY))
+        return _pauli_sum({"II": 0.5, "ZZ": 0.5, "XX": 0.5j, "YY": 0.5j})
+    if name == "ecr":  # (IX - XY)/sqrt(2) in Qiskit's big-endian labels = (X_0 - Y_0 X_1)/sqrt(2)
+        return _pauli_sum({"XI": r2, "YX": -r2})
+    if name == "cp":  # II + (e - 1) |11><11|
+        e = np.exp(1j * params[0]) - 1
+        return _pauli_sum({"II": 1 + e / 4, "ZI": -e / 4, "IZ": -e / 4, "ZZ": e / 4})
+    if name == "crz":  # |0><0|_0 (x) I + |1><1|_0 (x) RZ(theta)_1
+        c, s = np.cos(params[0] / 2), -1j * np.sin(params[0] / 2)
+        return _pauli_sum({"II": (1 + c) / 2, "ZI": (1 - c) / 2, "IZ": s / 2, "ZZ": -s / 2})
+    raise KeyError(f"oracle: no closed form for gate {name!r}")
+
+
+def _node_matrix(node) -> np.ndarray:
+    explicit = getattr(node, "_matrix", None)
+    return np.asarray(explicit, dtype=complex) if explicit is not None else gate_matrix(node.name, node.params)
+
+
+# ---------------------------------------------------------------------------------------------
+# [EXT] circuit_to_dag(slice).topological_op_nodes()  — backpropagation.py:170
+# ---------------------------------------------------------------------------------------------
+def gate_order(circuit) -> list:
+    """Instructions in lexicographical topological order (key: the qubit indices, zero-padded and
+    joined — tuples of ints compare the same way); a gate is ready once every earlier gate sharing a
+    qubit with it has been emitted.  **Parity unpinned** (SURVEY §8c (i)): how Qiskit's wire-input
+    nodes interleave with ready gates is not observable from any reference test; the order only
+    decides which gate's counters a slice reports and the last bits of fp sums."""
+    data = list(circuit.data)
+    blockers: list[set] = []
+    latest: dict = {}
+    for idx, ins in enumerate(data):
+        blockers.append({latest[q] for q in ins.qubits if q in latest})
+        for q in ins.qubits:
+            latest[q] = idx
+    emitted: list[int] = []
+    done: set = set()
+    remaining = set(range(len(data)))
+    while remaining:
+        ready = [i for i in remaining if blockers[i] <= done]
+        nxt = min(ready, key=lambda i: (tuple(data[i].qubits), i))
+        emitted.append(nxt)
+        done.add(nxt)
+        remaining.discard(nxt)
+    return [data[i] for i in emitted]
 
 _P1 = {
     "I": np.eye(2, dtype=complex),
@@ -119,10 +313,11 @@ def _decompose_cached(node) -> SparsePauliOp:
     """``from_operator`` per gate as in :213, memoised: the reference's Rust ``decompose_dense`` costs
     microseconds, this numpy restatement ~100 us — caching keeps the CPU baseline from being
     dominated by an artefact of the port."""
-    key = (node.name, node.params) if node._matrix is None else (node.name, node._matrix.tobytes())
+    explicit = getattr(node, "_matrix", None)
+    key = (node.name, tuple(node.params)) if explicit is None else (node.name, np.asarray(explicit).tobytes())
     op = _DECOMPOSE_CACHE.get(key)
     if op is None:
-        op = _DECOMPOSE_CACHE[key] = pauli_decompose(node.matrix)
+        op = _DECOMPOSE_CACHE[key] = pauli_decompose(_node_matrix(node))
     return op
 
 
@@ -310,6 +505,16 @@ def qwc_group_count(op: SparsePauliOp) -> int:
     return int(colour.max() + 1) if n else 0
 
 
+def _trunc_active(b) -> bool:
+    """``TruncationErrorBudget.is_active`` (``utils/truncating.py:56-58``) from the fields of any budget object."""
+    return any(x > 0 for x in b.per_slice_budget) and b.max_error_total > 0
+
+
+def _op_budget_active(b) -> bool:
+    """``OperatorBudget.is_active`` (``utils/simplify.py:73-77``)."""
+    return b.max_paulis is not None or b.max_qwc_groups is not None
+
+
 @dataclass
 class GateTrace:
     """Per applied gate bookkeeping used by the benchmark (term-gate update count)."""
@@ -368,7 +573,7 @@ def backpropagate(
         observables_tmp = list(observables_tmp)
         for i in range(n_obs):  # :168
             non_trivial = False
-            op_nodes = topological_op_order(slice_)[::-1]  # :170
+            op_nodes = gate_order(slice_)[::-1]  # :170
             for node in op_nodes:
                 if node.name == "barrier":  # :173
                     continue
@@ -405,7 +610,7 @@ def backpropagate(
                     break
             if stop:
                 break
-            if truncation_error_budget.is_active() and non_trivial:  # :244-251
+            if _trunc_active(truncation_error_budget) and non_trivial:  # :244-251
                 prev = len(observables_tmp[i])
                 sidx = metadata.num_backpropagated_slices
                 budget = metadata.left_over_error_budget(i, sidx)  # :388
@@ -420,7 +625,7 @@ def backpropagate(
             sm.num_paulis[i] = len(observables_tmp[i])  # :253
         if stop:
             break
-        if operator_budget.is_active():  # :266-275
+        if _op_budget_active(operator_budget):  # :266-275
             oversized = False
             if operator_budget.max_paulis is not None:
                 sm.sum_paulis = _union_size(observables_tmp)
@@ -479,7 +684,7 @@ def _validate(obs, slices, operator_budget):
             "Limiting the number of qubit-wise commmuting Pauli groups to less than 1 does not "
             "make sense."
         )
-    if operator_budget.is_active():
+    if _op_budget_active(operator_budget):
         allp = _unique_union(obs)
         if operator_budget.max_paulis is not None and len(allp) > operator_budget.max_paulis:
             raise ValueError(
@@ -499,7 +704,14 @@ def _validate(obs, slices, operator_budget):
 
 __all__ = [
     "GateTrace",
+    "OBPMetadata",
+    "OperatorBudget",
     "QuantumCircuit",
+    "SimplifyMetadata",
+    "SliceMetadata",
+    "TruncationErrorBudget",
+    "gate_matrix",
+    "gate_order",
     "adjoint",
     "apply_op_to",
     "apply_ple_to",

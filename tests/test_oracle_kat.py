@@ -156,3 +156,81 @@ def _embed_two(m, qs, nq):
                 row = rest | (ra << a) | (rb << b)
                 u[row, col] = m[ra + 2 * rb, ca + 2 * cb]
     return u
+
+
+# ---- the oracle's own conventions against the product's host code (two independent statements) -------
+def test_gate_tables_agree_and_match_closed_forms():
+    """Every named gate of the host IR (``ir.py``: literal little-endian matrices) against the oracle's
+    table (Pauli closed forms), plus textbook identities that fix the conventions themselves."""
+    from qiskit_addon_obp_b200 import ir
+
+    rng = np.random.default_rng(7)
+    names = [(n, ()) for n in ir._FIXED_1Q + ir._FIXED_2Q]
+    names += [(n, (float(rng.uniform(-3, 3)),)) for n in list(ir._ROT) + ["p", "cp", "crz"] for _ in range(3)]
+    for name, params in names:
+        nq = 1 if (name in ir._FIXED_1Q or name in ("rx", "ry", "rz", "p")) else 2
+        m_ir = ir.Instruction(name, tuple(range(nq)), params).matrix
+        m_or = oracle.gate_matrix(name, params)
+        np.testing.assert_allclose(m_ir, m_or, atol=1e-15, err_msg=name)
+        np.testing.assert_allclose(m_or @ m_or.conj().T, np.eye(2**nq), atol=1e-15, err_msg=f"{name} unitary")
+    g = oracle.gate_matrix
+    # index = q0 + 2*q1; cx: control = first argument flips the second: |q0=1,q1=0> (index 1) -> index 3
+    assert g("cx")[3, 1] == 1 and g("cx")[1, 3] == 1 and g("cx")[0, 0] == 1 and g("cx")[2, 2] == 1
+    assert g("cy")[3, 1] == 1j and g("cy")[1, 3] == -1j
+    np.testing.assert_allclose(g("cz"), np.diag([1, 1, 1, -1]))
+    np.testing.assert_allclose(g("swap")[[1, 2]][:, [2, 1]], np.eye(2))
+    np.testing.assert_allclose(g("iswap"), np.array([[1, 0, 0, 0], [0, 0, 1j, 0], [0, 1j, 0, 0], [0, 0, 0, 1]]))
+    np.testing.assert_allclose(  # Qiskit's documented ECR matrix
+        g("ecr"), np.array([[0, 1, 0, 1j], [1, 0, -1j, 0], [0, 1j, 0, 1], [-1j, 0, 1, 0]]) / np.sqrt(2)
+    )
+    np.testing.assert_allclose(g("sx") @ g("sx"), g("x"), atol=1e-15)
+    np.testing.assert_allclose(g("s") @ g("s"), g("z"), atol=1e-15)
+    np.testing.assert_allclose(g("t") @ g("t"), g("s"), atol=1e-15)
+    np.testing.assert_allclose(g("h") @ g("z") @ g("h"), g("x"), atol=1e-15)
+    np.testing.assert_allclose(g("rz", (0.3,)), np.diag([np.exp(-0.15j), np.exp(0.15j)]), atol=1e-15)
+    np.testing.assert_allclose(g("crz", (0.3,)), np.diag([1, np.exp(-0.15j), 1, np.exp(0.15j)]), atol=1e-15)
+    np.testing.assert_allclose(g("cp", (0.3,)), np.diag([1, 1, 1, np.exp(0.3j)]), atol=1e-15)
+    # rzx(t) = exp(-i t/2 X (x) Z) with Z on the first argument (index bit 0), X on the second
+    zx = np.kron(np.array([[0, 1], [1, 0]]), np.diag([1, -1]))
+    np.testing.assert_allclose(g("rzx", (0.7,)), np.cos(0.35) * np.eye(4) - 1j * np.sin(0.35) * zx, atol=1e-15)
+
+
+def test_gate_order_agrees_with_host_ir():
+    from qiskit_addon_obp_b200.ir import QuantumCircuit, topological_op_order
+
+    rng = np.random.default_rng(11)
+    for _ in range(50):
+        n = int(rng.integers(2, 9))
+        qc = QuantumCircuit(n)
+        for _ in range(int(rng.integers(1, 25))):
+            if rng.random() < 0.5:
+                qc.rx(0.1, int(rng.integers(n)))
+            else:
+                a, b = rng.choice(n, size=2, replace=False)
+                qc.cx(int(a), int(b))
+        got = oracle.gate_order(qc)
+        want = topological_op_order(qc)
+        assert [id(x) for x in got] == [id(x) for x in want]
+
+
+def test_oracle_budget_replay_on_the_reference_fixture():
+    """test/utils/test_metadata.py:183-265 on the oracle's own replay (the product's is pinned in test_host_logic)."""
+    import json
+    import os
+
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    md = oracle.OBPMetadata.from_json(os.path.join(golden, "metadata_fixture.json"))
+    want = json.load(open(os.path.join(golden, "metadata_expected.json")))
+    for obs in (0, 1):
+        n = len(md.backpropagation_history)
+        np.testing.assert_allclose([md.accumulated_error(obs, i) for i in range(n)], want["accumulated_error"][obs], rtol=0, atol=5e-11)
+        np.testing.assert_allclose([md.left_over_error_budget(obs, i) for i in range(n)], want["left_over_error_budget"][obs], rtol=0, atol=5e-11)
+
+
+def test_oracle_imports_only_containers_from_the_product():
+    import os
+    import re
+
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "obp_oracle.py")).read()
+    imports = re.findall(r"^from qiskit_addon_obp_b200[.\w]* import (.+)$", src, flags=re.M)
+    assert imports == ["QuantumCircuit, SparsePauliOp"], imports
