@@ -164,8 +164,23 @@ int obp_union_count(obp_ctx* const* ctxs, int32_t n_ctx, uint64_t* n_distinct);
 int obp_snapshot(obp_ctx* ctx);
 int obp_restore(obp_ctx* ctx);
 
-/* Grow the table to hold new_capacity terms (contents preserved). */
+/* Grow the table to hold new_capacity terms (contents preserved).  Failure-atomic: when device
+ * memory runs out the table keeps its old capacity and contents and OBP_ERR_OOM is returned (the
+ * caller may go on without growing).  Only if the old state cannot be re-established either is the
+ * context marked unusable: obp_is_broken() then returns 1, every other call fails, destroy it. */
 int obp_reserve(obp_ctx* ctx, uint64_t new_capacity);
+int obp_is_broken(const obp_ctx* ctx);
+
+/* Run-time switches of one context.  They select between code paths with identical results
+ * (utils/operations.py:103-105 + utils/simplify.py:115-165 either way); tests flip them to check
+ * every path against the oracle.
+ *   OBP_OPT_PROGRAM           1 (default): tables of <= 128 qubits run a slice's gate program in one
+ *                             persistent cooperative launch; 0: one kernel per gate / Clifford batch.
+ *   OBP_OPT_PROGRAM_MAX_ROWS  tables with at least this many dense rows use the stand-alone kernels
+ *                             (default 2^18). */
+#define OBP_OPT_PROGRAM 1
+#define OBP_OPT_PROGRAM_MAX_ROWS 2
+int obp_configure(obp_ctx* ctx, int32_t option, int64_t value);
 
 /* Row-order mode (off by default).  The reference's simplify() returns rows in the order of each
  * key's first appearance among the gate's k*k raw rows (utils/simplify.py:126,160-165 on top of the

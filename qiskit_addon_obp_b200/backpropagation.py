@@ -38,7 +38,8 @@ class TimeoutException(Exception):
 class RunInfo:
     """Work counters of the last :func:`backpropagate` call (used by ``bench.py``)."""
 
-    updates = 0  # term-gate updates: sum over applied gates of the term count at gate entry
+    updates = 0  # term-gate updates of committed work: sum over applied gates of the term count at gate entry
+    wasted_updates = 0  # updates of slice attempts that overflowed the table and were rolled back
     applied_gates = 0
     device_ms = 0.0  # CUDA-event time from the first table load to just before the download
     h2d_bytes = 0  # packed keys + coefficients uploaded
@@ -114,6 +115,10 @@ def backpropagate(
         capacity = max(capacity, min(8 * int(operator_budget.max_paulis), capacity * comm.n_ranks))
     if comm is not None and ordered:
         raise NotImplementedError("OBP_B200_ROW_ORDER=1 is not supported on a sharded table")
+    if comm is not None and hasattr(comm, "rank") and max_seconds is not None:
+        # the alarm would fire at a different point of the loop on every rank and leave the peers inside a
+        # collective; a timeout on a multi-process table needs a stop flag agreed at slice boundaries
+        raise NotImplementedError("max_seconds is not supported on a table sharded over several processes")
 
     metadata = OBPMetadata(
         truncation_error_budget=truncation_error_budget,
@@ -122,6 +127,9 @@ def backpropagate(
         backpropagation_history=[],
         num_backpropagated_slices=0,
     )
+    # slices the engine rejected before finishing them: (history index, observable, "lookahead" | "memory");
+    # a plain attribute, not a dataclass field, so the reference's JSON schema of OBPMetadata is unchanged
+    metadata.device_capacity_stops = []
     info = RunInfo()
     tables: list[TermTable] = []
     lengths = [len(o) for o in obs_in]  # len(observables_tmp[i]) as the reference sees it
@@ -170,7 +178,7 @@ def backpropagate(
                 )
                 metadata.backpropagation_history.append(sm)
                 prog = _slice_program(slice_, expand_all)
-                overflowed = False
+                overflow_peak: list[int | None] = [None] * n_obs
                 for i in range(n_obs):
                     plan = prog.plan(support_mask[i])  # gates inside the light cone (backpropagation.py:183)
                     applied = plan.applied
@@ -201,6 +209,7 @@ def backpropagate(
                             def prefetch(ns=next_slice, after=plan.support_after):
                                 _slice_program(ns, expand_all).plan(after)
 
+                        committed_work = (info.updates, info.applied_gates)
                         while True:
                             try:
                                 _run_slice(tables[i], prog, plan, atol, sm, i, info, raw, raw_first[i] and not ordered,
@@ -215,22 +224,33 @@ def backpropagate(
                                     sm.slice_errors[i] = err
                                     sm.num_truncated_paulis[i] = int(removed)
                                 break
-                            except CapacityError:
-                                # the table overflowed mid-slice: roll back to the committed state
+                            except CapacityError as exc:
+                                # the table overflowed mid-slice: roll back to the committed state; the work of the
+                                # discarded attempt is not counted as useful work (RunInfo.wasted_updates)
+                                info.wasted_updates += info.updates - committed_work[0]
+                                info.updates, info.applied_gates = committed_work
+                                prefetch = None
                                 tables[i].restore()
-                                if (
-                                    operator_budget.max_paulis is not None
-                                    and not trunc_active
-                                    and tables[i].capacity > operator_budget.max_paulis
-                                ):
-                                    # without truncation the term count cannot come back under
-                                    # max_paulis within this slice: the slice is oversized
-                                    overflowed = True
+                                peak = int(getattr(exc, "n_live", 0))
+                                if _stop_on_overflow(operator_budget, trunc_active, peak):
+                                    overflow_peak[i] = peak
                                     break
-                                _grow(tables[i])
-                        if overflowed:
-                            sm.sum_paulis = tables[i].capacity
-                            break
+                                try:
+                                    _grow(tables[i])
+                                except MemoryError:
+                                    if operator_budget.max_paulis is None or trunc_active or peak <= operator_budget.max_paulis:
+                                        raise
+                                    # device memory is exhausted while the slice already holds more terms than
+                                    # max_paulis: reject the slice, flagged as a memory-limited stop
+                                    overflow_peak[i] = peak
+                                    metadata.device_capacity_stops.append((len(metadata.backpropagation_history) - 1, i, "memory"))
+                                    break
+                        if overflow_peak[i] is not None:
+                            # the slice is oversized for this observable; its size is only known as a lower bound
+                            sm.num_paulis[i] = overflow_peak[i]
+                            if not any(s[:2] == (len(metadata.backpropagation_history) - 1, i) for s in metadata.device_capacity_stops):
+                                metadata.device_capacity_stops.append((len(metadata.backpropagation_history) - 1, i, "lookahead"))
+                            continue
                         support_mask[i] = plan.support_after
                         lengths[i] = len(tables[i])
                     if trunc_active and non_trivial:
@@ -246,10 +266,15 @@ def backpropagate(
                             f"[{metadata.num_backpropagated_slices:3}] size of the {i}-th observable: "
                             f"{sm.num_paulis[i]}"
                         )
-                if overflowed:
+                if any(p is not None for p in overflow_peak):
+                    # Deviation from backpropagation.py:266-275, 419-431: the reference finishes the
+                    # slice whatever its size and reports the exact count; the engine stops the slice for an
+                    # observable once it holds OBP_B200_OVERSIZE_LOOKAHEAD x max_paulis live terms (or device memory
+                    # is exhausted) and reports the count reached, a lower bound that already exceeds max_paulis.
+                    sm.sum_paulis = max(p for p in overflow_peak if p is not None)
                     LOGGER.info(
-                        f"[{metadata.num_backpropagated_slices:3}] Too many Pauli terms: more than "
-                        f"{sm.sum_paulis} (device table capacity reached mid-slice)"
+                        f"[{metadata.num_backpropagated_slices:3}] Too many Pauli terms: at least "
+                        f"{sm.sum_paulis} (slice stopped early, see OBPMetadata.device_capacity_stops)"
                     )
                     break
                 if operator_budget.is_active() and _observable_oversized(
@@ -302,6 +327,7 @@ def backpropagate(
             t.release()
 
     last_run.updates = info.updates
+    last_run.wasted_updates = info.wasted_updates
     last_run.applied_gates = info.applied_gates
     last_run.device_ms = info.device_ms
     last_run.h2d_bytes = info.h2d_bytes
@@ -314,12 +340,34 @@ def backpropagate(
     return (obs_out[0] if single else obs_out), slices_out, metadata
 
 
+def _stop_on_overflow(operator_budget: OperatorBudget, trunc_active: bool, peak_live: int) -> bool:
+    """Whether a mid-slice table overflow ends the backpropagation instead of growing the table.
+
+    Without truncation a slice's term count does not come back down by a large factor (only exact
+    cancellations remove terms), so once an observable holds ``OBP_B200_OVERSIZE_LOOKAHEAD`` (default 3)
+    times ``max_paulis`` live terms inside a slice, the slice is declared oversized without being finished.
+    ``OBP_B200_OVERSIZE_POLICY=exact`` turns this off: the table grows while device memory allows and the
+    slice is judged on its exact final count, like ``backpropagation.py:266-275``."""
+    if operator_budget.max_paulis is None or trunc_active:
+        return False
+    if os.environ.get("OBP_B200_OVERSIZE_POLICY", "lookahead") == "exact":
+        return False
+    factor = float(os.environ.get("OBP_B200_OVERSIZE_LOOKAHEAD", "3"))
+    return peak_live >= factor * operator_budget.max_paulis
+
+
 def _grow(table: TermTable) -> None:
-    """Double the table, bounded by free device memory."""
+    """Double the table, bounded by free device memory.  On a sharded table the verdict is agreed between the
+    ranks first (one rank must not leave the collective ``reserve`` its peers are about to enter)."""
     free, _ = engine.device_memory(table.device)
     per_term = int(engine.lib().obp_bytes_per_term(table.num_qubits))
     new_cap = min(2 * table.capacity, 0xFFFF0000)
-    if new_cap <= table.capacity or (new_cap - table.capacity) * per_term > 0.9 * free:
+    comm = getattr(table, "comm", None)
+    share = 1.25 / comm.n_ranks if comm is not None else 1.0
+    refuse = new_cap <= table.capacity or (new_cap - table.capacity) * per_term * share > 0.9 * free
+    if comm is not None:
+        refuse = bool(comm.allreduce_max({r: [1.0 if refuse else 0.0] for r in table.tables})[0] > 0)
+    if refuse:
         raise MemoryError(
             f"observable outgrew the device table ({table.capacity} terms) and it cannot be doubled"
         )
@@ -334,11 +382,11 @@ class SliceProgram:
     record of ``nodes[k]`` (``kind`` 0 for reset / LayerError, which have their own entry points).
     """
 
-    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "n_data", "generic", "touched", "all_idx",
+    __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "data_ref", "generic", "touched", "all_idx",
                  "masks", "touched_mask", "is_reset", "plans")
 
     def __init__(self, slice_: QuantumCircuit, raw: bool = False):
-        self.n_data = len(slice_.data)
+        self.data_ref = list(slice_.data)  # the instruction objects this program was compiled from (keeps them alive)
         classify = raw_program_for if raw else program_for
         self.nodes = [n for n in topological_op_order(slice_)[::-1] if n.name != "barrier"]
         self.qubit_sets = [frozenset(n.qubits) for n in self.nodes]
@@ -358,7 +406,7 @@ class SliceProgram:
         groups: dict[tuple, list[int]] = {}
         for k, node in enumerate(self.nodes):
             if not self.special[k]:
-                key = (node.name, node.params) if node._matrix is None else (node.name, id(node._matrix))
+                key = (node.name, node.params) if node._matrix is None else (node.name, node._matrix.tobytes())
                 groups.setdefault(key, []).append(k)
         qubit = self.recs["qubit"]
         for idxs in groups.values():
@@ -444,9 +492,15 @@ class SlicePlan:
 
 
 def _slice_program(slice_: QuantumCircuit, raw: bool = False) -> SliceProgram:
+    """The compiled program of a slice, cached on the circuit object and revalidated on every call.
+
+    The cache is valid only while ``slice_.data`` holds the very same instruction objects in the same order
+    (``Instruction`` is immutable, so an instruction cannot change behind its identity): replacing an
+    instruction in place, e.g. for a parameter sweep over the same slice objects, recompiles the slice.  The
+    check is one C-level list comparison by identity, ~1 us per slice."""
     attr = "_obp_program_raw" if raw else "_obp_program"
     prog = getattr(slice_, attr, None)
-    if prog is None or prog.n_data != len(slice_.data):
+    if prog is None or prog.data_ref != slice_.data:
         prog = SliceProgram(slice_, raw)
         setattr(slice_, attr, prog)
     return prog
@@ -486,7 +540,7 @@ def _run_slice(table: TermTable, prog: SliceProgram, plan: SlicePlan, atol: floa
                         run()
                     stats = table.apply_ops_wait()
             except CapacityError as exc:
-                info.updates += getattr(exc, "updates", 0)
+                info.updates += getattr(exc, "updates", 0)  # (moved to wasted_updates by the caller's rollback)
                 raise
             info.updates += int(stats.updates)
             if TRACE:

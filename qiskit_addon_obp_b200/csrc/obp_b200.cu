@@ -106,6 +106,8 @@ struct obp_ctx {
   u64* d_tbegin = nullptr;
   u64* h_tbegin = nullptr;  // pinned
   bool use_program = true;
+  u64 prog_max_rows = 1ull << 18;  // tables of at least this many rows run their gates as stand-alone kernels
+  bool broken = false;  // a failed obp_reserve could not restore the table: every entry point fails fast
   bool trace_host = false;  // OBP_B200_TRACE_HOST: print host enqueue / wait time per gate program
   int prog_min_grid = 148;  // smallest grid of the persistent program kernel (grid barriers cost more with more CTAs)
   int prog_reach_shift = 6;  // the grid is sized for rows << min(#rotations, this)
@@ -656,7 +658,8 @@ struct PendingOps {
   std::chrono::steady_clock::time_point t_host0;
 };
 
-#define OBP_NO_PENDING(ctx, what) \
+#define OBP_NO_PENDING(ctx, what)                                                                                       \
+  if ((ctx) && (ctx)->broken) return (ctx)->fail(OBP_ERR_OOM, what ": the context is unusable after a failed obp_reserve"); \
   if ((ctx) && (ctx)->pending) return (ctx)->fail(OBP_ERR_BADARG, what ": a submitted gate program is pending, call obp_apply_ops_wait first")
 
 
@@ -746,6 +749,7 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
       if (const char* e2 = getenv("OBP_B200_PROG_MIN_GRID")) ctx->prog_min_grid = std::max(1, atoi(e2));
       if (const char* e3 = getenv("OBP_B200_PROG_REACH_SHIFT")) ctx->prog_reach_shift = std::max(0, atoi(e3));
       if (const char* e6 = getenv("OBP_B200_PROG_DEBUG")) ctx->prog_debug = atoi(e6) & ~1;
+      if (const char* e7 = getenv("OBP_B200_PROG_MAX_ROWS")) ctx->prog_max_rows = (u64)std::max(0ll, atoll(e7));
     }
     init_frame(ctx);
     return set_counts(ctx, 0);
@@ -1008,7 +1012,10 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
     }
   }
   if (sync_rc) {
-    if (stats) stats->updates = updates;
+    if (stats) {
+      stats->updates = updates;      // work done before the overflow was noticed (the caller rolls the slice back)
+      stats->n_out = ctx->n_live;    // live rows when the table overflowed: a lower bound of the slice's size
+    }
     return sync_rc;
   }
   if (stats) {
@@ -1071,7 +1078,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   // tables of <= 128 qubits: record the program and run it with ONE persistent cooperative launch
   // (large tables keep the stand-alone kernels: a launch is cheap next to a pass over >= 2^18 rows and
   // k_rotate alone holds one more CTA per SM than the program kernel)
-  const bool prog_mode = ctx->use_program && ctx->prog_ctas_per_sm > 0 && ctx->W <= 2 && ctx->n_dense < (1ull << 18) && !ctx->flag_sync;
+  const bool prog_mode = ctx->use_program && ctx->prog_ctas_per_sm > 0 && ctx->W <= 2 && ctx->n_dense < ctx->prog_max_rows && !ctx->flag_sync;
   ProgRec prog;
   int n_rot_ops = 0;
   int last_split = -1;  // index of the last split rotation run with the device-side handshake
@@ -2372,6 +2379,36 @@ static int alloc_row_order_scratch(obp_ctx* ctx) {
   return OBP_OK;
 }
 
+// (re)allocate the buffers that hold no table data — index and compaction scratch — for `cap` rows
+static int alloc_scratch(obp_ctx* ctx, u64 cap) {
+  ctx->T = next_pow2(std::max<u64>(2 * cap, 1024));
+  CU(cudaMalloc(&ctx->index, ctx->T * sizeof(u64)));
+  CU(cudaMalloc(&ctx->spare16, cap * sizeof(ulonglong2)));
+  CU(cudaMalloc(&ctx->spare8, cap * sizeof(u64)));
+  CU(cudaMalloc(&ctx->dest, cap * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->blk, ((cap + OBP_CHUNK - 1) / OBP_CHUNK + 1) * sizeof(unsigned)));
+  return OBP_OK;
+}
+
+static void free_scratch(obp_ctx* ctx) {
+  cudaFree(ctx->index);
+  cudaFree(ctx->spare16);
+  cudaFree(ctx->spare8);
+  cudaFree(ctx->dest);
+  cudaFree(ctx->blk);
+  ctx->index = nullptr;
+  ctx->spare16 = nullptr;
+  ctx->spare8 = nullptr;
+  ctx->dest = nullptr;
+  ctx->blk = nullptr;
+}
+
+// Grow the table.  Failure-atomic: the data columns move one at a time (new buffer, copy, free the old
+// one — the peak footprint stays one column above the table), so at every point each column holds the n
+// live rows and has room for at least the OLD capacity.  If an allocation fails the table therefore
+// simply stays at its old capacity: the scratch buffers (which hold no data) are re-created at the old
+// size, the index is rebuilt and OBP_ERR_OOM is returned.  Only if even that fails is the context marked
+// broken; every entry point then fails fast and the Python wrapper destroys it instead of pooling it.
 int obp_reserve(obp_ctx* ctx, uint64_t new_capacity) {
   OBP_NO_PENDING(ctx, "obp_reserve");
   if (!ctx || new_capacity >= 0xffffffffull) return OBP_ERR_BADARG;
@@ -2386,48 +2423,50 @@ int obp_reserve(obp_ctx* ctx, uint64_t new_capacity) {
   }
   CU(cudaStreamSynchronize(ctx->stream));
   const u64 n = ctx->n_live;
-  // move the live columns into a bigger table, one column at a time to bound the peak footprint
-  ulonglong2* old_xz[OBP_MAX_WORDS];
-  for (int w = 0; w < OBP_MAX_WORDS; ++w) old_xz[w] = ctx->xz[w];
-  double2* old_coef = ctx->coef;
-  u64* old_hash = ctx->hash;
-  cudaFree(ctx->index);
-  cudaFree(ctx->spare16);
-  cudaFree(ctx->spare8);
-  cudaFree(ctx->dest);
-  cudaFree(ctx->blk);
-  ctx->index = nullptr;
-  ctx->spare16 = nullptr;
-  ctx->spare8 = nullptr;
-  ctx->dest = nullptr;
-  ctx->blk = nullptr;
-  const u64 cap = new_capacity;
-  for (int w = 0; w < ctx->W; ++w) {
-    ulonglong2* p = nullptr;
-    CU(cudaMalloc(&p, cap * sizeof(ulonglong2)));
-    CU(cudaMemcpy(p, old_xz[w], n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice));
-    cudaFree(old_xz[w]);
-    ctx->xz[w] = p;
+  const u64 old_cap = ctx->cap, cap = new_capacity;
+  free_scratch(ctx);
+  // one data column: bigger buffer, copy the live rows, release the old buffer
+  auto grow_column = [&](void** slot, size_t elem) -> int {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, cap * elem));
+    const cudaError_t e = cudaMemcpy(p, *slot, n * elem, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(p);
+      return ctx->fail(OBP_ERR_CUDA, std::string("obp_reserve copy: ") + cudaGetErrorString(e));
+    }
+    cudaFree(*slot);
+    *slot = p;
+    return OBP_OK;
+  };
+  rc = OBP_OK;
+  for (int w = 0; w < ctx->W && !rc; ++w) rc = grow_column((void**)&ctx->xz[w], sizeof(ulonglong2));
+  if (!rc) rc = grow_column((void**)&ctx->coef, sizeof(double2));
+  if (!rc) rc = grow_column((void**)&ctx->hash, sizeof(u64));
+  if (!rc) {
+    rc = alloc_scratch(ctx, cap);
+    if (rc) free_scratch(ctx);
   }
-  {
-    double2* p = nullptr;
-    CU(cudaMalloc(&p, cap * sizeof(double2)));
-    CU(cudaMemcpy(p, old_coef, n * sizeof(double2), cudaMemcpyDeviceToDevice));
-    cudaFree(old_coef);
-    ctx->coef = p;
-    u64* h = nullptr;
-    CU(cudaMalloc(&h, cap * sizeof(u64)));
-    CU(cudaMemcpy(h, old_hash, n * sizeof(u64), cudaMemcpyDeviceToDevice));
-    cudaFree(old_hash);
-    ctx->hash = h;
+  if (!rc) {
+    ctx->cap = cap;
+  } else {
+    // stay at the old capacity (every column still has room for it)
+    const std::string why = ctx->err;
+    cudaGetLastError();
+    const int rc2 = alloc_scratch(ctx, old_cap);
+    if (rc2) {
+      free_scratch(ctx);
+      ctx->broken = true;
+      return ctx->fail(rc, "obp_reserve: out of device memory and the table could not be put back (" + why + "); the context is unusable");
+    }
+    ctx->cap = old_cap;
+    const int rc3 = rebuild_index(ctx);
+    const int rc4 = rc3 ? rc3 : sync_state(ctx);
+    if (rc4) {
+      ctx->broken = true;
+      return rc4;
+    }
+    return ctx->fail(rc, "obp_reserve: " + why + " (the table keeps its capacity of " + std::to_string(old_cap) + " terms)");
   }
-  ctx->cap = cap;
-  ctx->T = next_pow2(std::max<u64>(2 * cap, 1024));
-  CU(cudaMalloc(&ctx->index, ctx->T * sizeof(u64)));
-  CU(cudaMalloc(&ctx->spare16, cap * sizeof(ulonglong2)));
-  CU(cudaMalloc(&ctx->spare8, cap * sizeof(u64)));
-  CU(cudaMalloc(&ctx->dest, cap * sizeof(unsigned)));
-  CU(cudaMalloc(&ctx->blk, ((cap + OBP_CHUNK - 1) / OBP_CHUNK + 1) * sizeof(unsigned)));
   if (ctx->row_order) {
     rc = alloc_row_order_scratch(ctx);
     if (rc) return rc;
@@ -2436,6 +2475,18 @@ int obp_reserve(obp_ctx* ctx, uint64_t new_capacity) {
   if (rc) return rc;
   return sync_state(ctx);
 }
+
+// Run-time switches of one context (tests flip them to force each code path against the oracle).
+int obp_configure(obp_ctx* ctx, int32_t option, int64_t value) {
+  if (!ctx) return OBP_ERR_BADARG;
+  switch (option) {
+    case OBP_OPT_PROGRAM: ctx->use_program = value != 0; return OBP_OK;
+    case OBP_OPT_PROGRAM_MAX_ROWS: ctx->prog_max_rows = value < 0 ? 0 : (u64)value; return OBP_OK;
+    default: return ctx->fail(OBP_ERR_BADARG, "obp_configure: unknown option");
+  }
+}
+
+int obp_is_broken(const obp_ctx* ctx) { return ctx && ctx->broken ? 1 : 0; }
 
 int obp_set_row_order(obp_ctx* ctx, int32_t enabled) {
   if (!ctx) return OBP_ERR_BADARG;

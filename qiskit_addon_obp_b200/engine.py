@@ -21,6 +21,7 @@ _LIB_PATH = os.environ.get(
 )  # the override selects another build of the same CUDA library (kernel A/B runs)
 
 OBP_OK = 0
+OBP_ERR_OOM = -3
 OBP_ERR_CAPACITY = -4
 OBP_OP_CLIFFORD = 1
 OBP_OP_ROTATION = 2
@@ -28,6 +29,8 @@ OBP_OP_GENERIC = 3  # host-side tag only: run through obp_apply_generic, never i
 OBP_FLAG_EXACT_COUNTERS = 1
 OBP_ATOL_MERGE_ONLY = -1.0
 OBP_ATOL_RAW = -2.0  # simplify=False: no merge, exact zeros stay
+OBP_OPT_PROGRAM = 1
+OBP_OPT_PROGRAM_MAX_ROWS = 2
 OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other", "program")
 
 #: numpy mirror of ``obp_op`` (104 bytes, natural C alignment)
@@ -135,6 +138,8 @@ def lib() -> C.CDLL:
         "obp_restore": ([vp], C.c_int),
         "obp_reserve": ([vp, C.c_uint64], C.c_int),
         "obp_set_row_order": ([vp, C.c_int32], C.c_int),
+        "obp_configure": ([vp, C.c_int32, C.c_int64], C.c_int),
+        "obp_is_broken": ([vp], C.c_int),
         "obp_profile_enable": ([vp, C.c_int32], C.c_int),
         "obp_profile_get": ([vp, C.POINTER(ObpProfile), C.c_int32], C.c_int),
         "obp_set_shard": ([vp, C.c_int32, C.c_int32], C.c_int),
@@ -176,7 +181,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters obp_reset_emit obp_reset_merge"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken"
 ).split()
 
 
@@ -243,8 +248,22 @@ class TermTable:
                 t.set_shard(1, 0)
                 t.set_shard_sync(False)
                 t.set_row_order(False)
+                t._apply_env_options()
                 return t
-        return cls(num_qubits, capacity, device)
+        t = cls(num_qubits, capacity, device)
+        t._apply_env_options()
+        return t
+
+    def _apply_env_options(self) -> None:
+        """Code-path switches from the environment, re-read at every acquire (pooled tables outlive a test):
+        ``OBP_B200_NO_PROGRAM=1`` — one kernel per gate instead of the persistent program kernel;
+        ``OBP_B200_PROG_MAX_ROWS=n`` — tables of at least n rows use the stand-alone kernels (default 2^18)."""
+        no_prog = os.environ.get("OBP_B200_NO_PROGRAM", "0") not in ("", "0")
+        self.configure(OBP_OPT_PROGRAM, 0 if no_prog else 1)
+        self.configure(OBP_OPT_PROGRAM_MAX_ROWS, int(os.environ.get("OBP_B200_PROG_MAX_ROWS", str(1 << 18))))
+
+    def configure(self, option: int, value: int) -> None:
+        self._check(self._lib.obp_configure(self._h, int(option), int(value)), "obp_configure")
 
     def _drain(self) -> None:
         """Wait for (and discard the result of) a gate program that was submitted but never waited for —
@@ -255,12 +274,12 @@ class TermTable:
             self._lib.obp_apply_ops_wait(self._h, None)  # a device error here resurfaces in the next call
 
     def release(self) -> None:
-        """Hand the table back to the pool (or destroy it when the pool is full)."""
+        """Hand the table back to the pool (or destroy it when the pool is full or the context is unusable)."""
         if not self._h.value:
             return
         self._drain()
         idle = _POOL.setdefault((self.device, self.num_qubits), [])
-        if len(idle) >= POOL_MAX_PER_KEY:
+        if len(idle) >= POOL_MAX_PER_KEY or self._lib.obp_is_broken(self._h):
             self.close()
         else:
             idle.append(self)
@@ -289,6 +308,8 @@ class TermTable:
         msg = (self._lib.obp_last_error(self._h) or b"").decode()
         if rc == OBP_ERR_CAPACITY:
             raise CapacityError(f"{what}: {msg}")
+        if rc == OBP_ERR_OOM:
+            raise MemoryError(f"{what}: {msg}")
         raise EngineError(f"{what} failed ({rc}): {msg}")
 
     def close(self):
@@ -386,6 +407,7 @@ class TermTable:
             self._check(rc, "obp_apply_ops")
         except CapacityError as exc:
             exc.updates = int(st.updates)  # the kernels ran before the overflow was detected
+            exc.n_live = int(st.n_out)  # live rows at that moment
             raise
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0:
@@ -421,6 +443,7 @@ class TermTable:
             self._check(rc, "obp_apply_ops_wait")
         except CapacityError as exc:
             exc.updates = int(st.updates)
+            exc.n_live = int(st.n_out)
             raise
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0:
@@ -553,6 +576,8 @@ class TermTable:
         if rc != OBP_ERR_CAPACITY:
             self._check(rc, "obp_apply_ops_sharded")
             self.n, self.n_dense = st.n_out, st.n_dense
+        else:
+            self.n = st.n_out  # live rows when the shard overflowed (the caller rolls back; used as a size lower bound)
         return st, done.value, peer.value, rc == OBP_ERR_CAPACITY
 
     def rotate_emit(self, op: np.ndarray, atol: float, d_records: int, cap_records: int) -> tuple[ObpShardCounters, bool]:

@@ -374,16 +374,29 @@ class Instruction:
     ``name`` follows Qiskit's gate names (``"rx"``, ``"cx"``, ``"barrier"``, ``"reset"``,
     ``"LayerError"``, ``"unitary"``...).  ``matrix`` is the little-endian unitary of the gate,
     i.e. what ``Operator(op_node.op).data`` is in ``backpropagation.py:213`` of the reference.
+
+    Immutable: compiled slice programs are cached against the identity of their instructions
+    (``backpropagation._slice_program``), so changing a gate means putting a new ``Instruction`` into
+    ``QuantumCircuit.data``.
     """
 
     __slots__ = ("name", "qubits", "params", "_matrix", "ple")
 
     def __init__(self, name, qubits, params=(), matrix=None, ple=None):
-        self.name = name
-        self.qubits = tuple(int(q) for q in qubits)
-        self.params = tuple(float(p) for p in params)
-        self._matrix = None if matrix is None else np.asarray(matrix, dtype=complex)
-        self.ple = ple
+        set_ = object.__setattr__
+        set_(self, "name", name)
+        set_(self, "qubits", tuple(int(q) for q in qubits))
+        set_(self, "params", tuple(float(p) for p in params))
+        if matrix is not None:
+            matrix = np.array(matrix, dtype=complex)  # private copy, frozen
+            matrix.setflags(write=False)
+        set_(self, "_matrix", matrix)
+        set_(self, "ple", ple)
+
+    def __setattr__(self, key, value):
+        raise AttributeError("Instruction is immutable: replace the entry of QuantumCircuit.data instead")
+
+    __delattr__ = __setattr__
 
     @property
     def matrix(self) -> np.ndarray:

@@ -463,7 +463,9 @@ class ShardedTable:
         ti, tf = self.comm.allreduce_pair(ints, floats)
         self.n, self.n_dense = int(ti[1]), int(ti[2])
         if ti[0] > 0:
-            raise CapacityError("sharded gate program: a shard overflowed its table")
+            exc = CapacityError("sharded gate program: a shard overflowed its table")
+            exc.updates, exc.n_live = int(ti[3]), self.n
+            raise exc
         out.updates = int(ti[3])
         self._fill_last(out, last, ops[-1], [int(v) for v in ti[4:8]], [float(tf[0]), float(tf[1])])
         self.t_phase["reduce"] += time.perf_counter() - t0

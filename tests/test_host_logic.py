@@ -335,3 +335,27 @@ def test_qwc_group_count_on_packed_words_matches_the_bool_version(nq, n):
     rng = np.random.default_rng(nq + n)
     op = SparsePauliOp((rng.random((n, nq)) < 0.3, rng.random((n, nq)) < 0.3), np.ones(n))
     assert qwc_group_count(op) == _qwc_group_count_bool(op)
+
+
+# ---- compiled-slice cache: valid only for the very same instruction objects ---------------
+def test_slice_program_cache_follows_in_place_edits():
+    from qiskit_addon_obp_b200.backpropagation import _slice_program
+
+    qc = QuantumCircuit(3)
+    qc.rx(0.3, 0)
+    qc.cx(0, 1)
+    p1 = _slice_program(qc)
+    assert _slice_program(qc) is p1
+    # same length, different angle: a parameter sweep that reuses the slice object
+    qc.data[0] = Instruction("rx", (0,), (0.7,))
+    p2 = _slice_program(qc)
+    assert p2 is not p1
+    assert float(p2.recs["u0"][[n.name for n in p2.nodes].index("rx")][0]) == pytest.approx(np.cos(0.35))
+    with pytest.raises(AttributeError):
+        qc.data[0].params = (0.9,)  # instructions cannot change behind their identity
+    m = np.eye(2, dtype=complex)
+    ins = Instruction("unitary", (1,), (), m)
+    m[0, 0] = -1  # the caller's array is not the instruction's
+    assert ins.matrix[0, 0] == 1
+    with pytest.raises(ValueError):
+        ins.matrix[0, 0] = 5
