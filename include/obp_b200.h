@@ -51,6 +51,8 @@ enum {
 };
 
 #define OBP_FLAG_EXACT_COUNTERS 1u /* produce the reference's simplify counters for this op */
+#define OBP_FLAG_OWN_SLOT 2u       /* do not fuse this Clifford-class gate with its neighbours: the term count
+                                      after exactly this gate is then reported by obp_last_op_sizes()       */
 
 typedef struct {
   int32_t kind;        /* OBP_OP_*                                                            */
@@ -133,6 +135,10 @@ int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, o
  * Between the two no other call may touch the context (they return OBP_ERR_BADARG).  Single-GPU tables. */
 int obp_apply_ops_submit(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol);
 int obp_apply_ops_wait(obp_ctx* ctx, obp_stats* stats);
+/* Live term count after every op of the last finished program (the size the reference logs at DEBUG level
+ * after each gate, backpropagation.py:239-242).  Gates fused into one pass share that pass's count unless they
+ * carried OBP_FLAG_OWN_SLOT.  Writes min(n_ops, max_ops) values, returns the number of ops in *n_ops. */
+int obp_last_op_sizes(obp_ctx* ctx, uint64_t* sizes, int32_t max_ops, int32_t* n_ops);
 
 /* Any other gate on 1-4 qubits (cp, crz, arbitrary unitaries): U = sum_j u_j * Pauli(codes[j]) with
  * codes[j] = local Pauli code (bit 2q = x, bit 2q+1 = z on qubits[q]) and coeffs[j] = (re, im).  Runs

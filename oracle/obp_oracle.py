@@ -521,6 +521,7 @@ class GateTrace:
 
     updates: int = 0
     applied_gates: int = 0
+    gate_sizes: list = field(default_factory=list)  # (slice position, observable, gate id, size after the gate), :239-242
 
 
 def backpropagate(
@@ -574,7 +575,7 @@ def backpropagate(
         for i in range(n_obs):  # :168
             non_trivial = False
             op_nodes = gate_order(slice_)[::-1]  # :170
-            for node in op_nodes:
+            for op_idx, node in enumerate(op_nodes):
                 if node.name == "barrier":  # :173
                     continue
                 op_qargs = list(node.qubits)
@@ -605,6 +606,10 @@ def backpropagate(
                     sm.num_duplicate_paulis[i] = smd.num_duplicate_paulis
                     sm.num_trimmed_paulis[i] = smd.num_trimmed_paulis
                     sm.sum_trimmed_coeffs[i] = smd.sum_trimmed_coeffs
+                if trace is not None:  # the DEBUG line of :239-242
+                    trace.gate_sizes.append(
+                        (len(metadata.backpropagation_history) - 1, i, len(op_nodes) - op_idx - 1, len(observables_tmp[i]))
+                    )
                 if max_updates is not None and trace is not None and trace.updates >= max_updates:
                     stop = True
                     break

@@ -20,7 +20,8 @@ from collections.abc import Sequence
 import numpy as np
 
 from . import engine
-from .engine import OBP_ATOL_RAW, OBP_FLAG_EXACT_COUNTERS, OBP_OP_GENERIC, OP_DTYPE, CapacityError, TermTable
+from .engine import (OBP_ATOL_RAW, OBP_FLAG_EXACT_COUNTERS, OBP_FLAG_OWN_SLOT, OBP_OP_GENERIC, OP_DTYPE, CapacityError,
+                     TermTable)
 from .gates import program_for, raw_program_for
 from .ir import QuantumCircuit, SparsePauliOp, topological_op_order
 from .sharded import ShardedTable, communicator_from_env
@@ -232,7 +233,13 @@ def backpropagate(
                                 prefetch = None
                                 tables[i].restore()
                                 peak = int(getattr(exc, "n_live", 0))
-                                if _stop_on_overflow(operator_budget, trunc_active, peak):
+                                stop = _stop_on_overflow(operator_budget, trunc_active, peak)
+                                LOGGER.info(
+                                    f"[{metadata.num_backpropagated_slices:3}] device table of the {i}-th observable "
+                                    f"overflowed mid-slice ({peak} live terms, capacity {tables[i].capacity}): "
+                                    + ("slice rejected" if stop else "growing the table")
+                                )
+                                if stop:
                                     overflow_peak[i] = peak
                                     break
                                 try:
@@ -383,12 +390,15 @@ class SliceProgram:
     """
 
     __slots__ = ("nodes", "qubit_sets", "recs", "special", "errors", "data_ref", "generic", "touched", "all_idx",
-                 "masks", "touched_mask", "is_reset", "plans")
+                 "masks", "touched_mask", "is_reset", "plans", "gate_ids")
 
     def __init__(self, slice_: QuantumCircuit, raw: bool = False):
         self.data_ref = list(slice_.data)  # the instruction objects this program was compiled from (keeps them alive)
         classify = raw_program_for if raw else program_for
-        self.nodes = [n for n in topological_op_order(slice_)[::-1] if n.name != "barrier"]
+        ordered_all = topological_op_order(slice_)[::-1]
+        self.nodes = [n for n in ordered_all if n.name != "barrier"]
+        # the id the reference's DEBUG line gives a gate: len(op_nodes) - op_idx - 1, barriers counted (:239-242)
+        self.gate_ids = [len(ordered_all) - idx - 1 for idx, n in enumerate(ordered_all) if n.name != "barrier"]
         self.qubit_sets = [frozenset(n.qubits) for n in self.nodes]
         self.touched = frozenset().union(*self.qubit_sets) if self.qubit_sets else frozenset()
         self.all_idx = list(range(len(self.nodes)))
@@ -475,19 +485,19 @@ class SlicePlan:
                 ops = prog.recs[seg]  # fancy index: a fresh array
                 if seg[-1] == last:
                     ops["flags"][-1] = OBP_FLAG_EXACT_COUNTERS
-                self.steps.append(("ops", ops))
+                self.steps.append(("ops", ops, list(seg)))
                 seg = []
 
         for k in applied:
             if not prog.special[k]:
                 if k in prog.errors:
                     cut()
-                    self.steps.append(("error", prog.errors[k]))
+                    self.steps.append(("error", prog.errors[k], None))
                     return
                 seg.append(k)
             else:
                 cut()
-                self.steps.append(("node", k))
+                self.steps.append(("node", k, None))
         cut()
 
 
@@ -521,13 +531,20 @@ def _run_slice(table: TermTable, prog: SliceProgram, plan: SlicePlan, atol: floa
         stats = table.apply_generic(node.qubits, g.codes, g.coeffs, atol, simplify=True)
         info.updates += int(stats.updates)
         info.applied_gates += 1
+        if LOGGER.isEnabledFor(logging.DEBUG) and not isinstance(table, ShardedTable):
+            _log_gate_size(prog.gate_ids[applied[0]], len(table))
         applied = applied[1:]
         plan = SlicePlan(prog, applied, plan.support_after)
 
     sharded = isinstance(table, ShardedTable)
-    for kind, what in plan.steps:
+    # the reference's per-gate DEBUG line (backpropagation.py:239-242): every gate then gets a pass of its own
+    log_gates = LOGGER.isEnabledFor(logging.DEBUG) and not sharded
+    for kind, what, seg in plan.steps:
         if kind == "ops":
             ops = what
+            if log_gates:
+                ops = ops.copy()
+                ops["flags"] |= OBP_FLAG_OWN_SLOT
             t0 = time.perf_counter() if TRACE else 0.0
             n_before = table.n
             try:
@@ -543,6 +560,9 @@ def _run_slice(table: TermTable, prog: SliceProgram, plan: SlicePlan, atol: floa
                 info.updates += getattr(exc, "updates", 0)  # (moved to wasted_updates by the caller's rollback)
                 raise
             info.updates += int(stats.updates)
+            if log_gates:
+                for k, size in zip(seg, table.last_op_sizes(len(ops))):
+                    _log_gate_size(prog.gate_ids[k], size)
             if TRACE:
                 dt = time.perf_counter() - t0
                 kinds = ops["kind"]
@@ -576,6 +596,8 @@ def _run_slice(table: TermTable, prog: SliceProgram, plan: SlicePlan, atol: floa
             gz[:, list(node.qubits)] = gens.z
             stats = table.apply_damping(gx, gz, np.exp(-2 * np.asarray(ple.rates, dtype=float)), -1.0 if raw else atol)
         info.updates += int(stats.updates)
+        if log_gates:
+            _log_gate_size(prog.gate_ids[k], len(table))
     if prefetch is not None:
         prefetch()
     info.applied_gates += len(applied)
@@ -593,6 +615,10 @@ def _run_slice(table: TermTable, prog: SliceProgram, plan: SlicePlan, atol: floa
         # sharded table, last gate Clifford-class: its coset count would need a cross-rank exchange
         sm.num_unique_paulis[i] = sm.num_duplicate_paulis[i] = sm.num_trimmed_paulis[i] = None
         sm.sum_trimmed_coeffs[i] = None
+
+
+def _log_gate_size(gate_id: int, size: int) -> None:
+    LOGGER.debug(f"Size of the observable after backpropagating gate id {gate_id} in the current layer: {size}")
 
 
 def _has_duplicates_or_zeros(op: SparsePauliOp, atol: float) -> bool:

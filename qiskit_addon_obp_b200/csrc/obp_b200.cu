@@ -105,6 +105,7 @@ struct obp_ctx {
   size_t stage_bytes = 0;
   u64* d_tbegin = nullptr;
   u64* h_tbegin = nullptr;  // pinned
+  std::vector<u64> last_op_sizes;  // live rows after every op of the last finished program
   bool use_program = true;
   u64 prog_max_rows = 1ull << 18;  // tables of at least this many rows run their gates as stand-alone kernels
   bool broken = false;  // a failed obp_reserve could not restore the table: every entry point fails fast
@@ -1011,6 +1012,9 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
       s_prev = s;
     }
   }
+  ctx->last_op_sizes.assign((size_t)P.n_ops, 0);
+  for (int k = 0; k < P.n_ops; ++k)
+    if (P.slot_of_op[k] >= 0 && P.slot_of_op[k] < P.n_slots) ctx->last_op_sizes[k] = ctx->h_ops[P.slot_of_op[k]].n_out;
   if (sync_rc) {
     if (stats) {
       stats->updates = updates;      // work done before the overflow was noticed (the caller rolls the slice back)
@@ -1302,6 +1306,19 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     if (op.kind == OBP_OP_CLIFFORD) {
       const bool exact = (op.flags & OBP_FLAG_EXACT_COUNTERS) != 0;
       slot_of_op[k] = n_slots;
+      if (!exact && (op.flags & OBP_FLAG_OWN_SLOT)) {
+        // per-gate size log: this gate gets a pass (and a counter slot) of its own
+        rc = release_all();
+        if (rc) return rc;
+        rc = flush();
+        if (rc) return rc;
+        slot_of_op[k] = n_slots;
+        rc = emit_gate(fused_from_op(op));
+        if (rc) return rc;
+        rc = flush();
+        if (rc) return rc;
+        continue;
+      }
       if (!exact && op.n_qubits == 1) {
         // hold it back: it commutes with everything that does not touch its qubit
         const int q = op.qubit[0];
@@ -1538,6 +1555,14 @@ int obp_apply_ops_wait(obp_ctx* ctx, obp_stats* stats) {
   const int rc = finish_ops(ctx, *P, stats);
   delete P;
   return rc;
+}
+
+int obp_last_op_sizes(obp_ctx* ctx, uint64_t* sizes, int32_t max_ops, int32_t* n_ops) {
+  if (!ctx || !n_ops) return OBP_ERR_BADARG;
+  *n_ops = (int32_t)ctx->last_op_sizes.size();
+  if (sizes)
+    for (int k = 0; k < *n_ops && k < max_ops; ++k) sizes[k] = ctx->last_op_sizes[k];
+  return OBP_OK;
 }
 
 int obp_apply_ops_sharded(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,

@@ -27,6 +27,7 @@ OBP_OP_CLIFFORD = 1
 OBP_OP_ROTATION = 2
 OBP_OP_GENERIC = 3  # host-side tag only: run through obp_apply_generic, never inside an obp_op program
 OBP_FLAG_EXACT_COUNTERS = 1
+OBP_FLAG_OWN_SLOT = 2
 OBP_ATOL_MERGE_ONLY = -1.0
 OBP_ATOL_RAW = -2.0  # simplify=False: no merge, exact zeros stay
 OBP_OPT_PROGRAM = 1
@@ -129,6 +130,7 @@ def lib() -> C.CDLL:
         "obp_apply_ops": ([vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_ops_submit": ([vp, vp, C.c_int32, C.c_double], C.c_int),
         "obp_apply_ops_wait": ([vp, C.POINTER(ObpStats)], C.c_int),
+        "obp_last_op_sizes": ([vp, u64p, C.c_int32, C.POINTER(C.c_int32)], C.c_int),
         "obp_apply_generic": ([vp, C.c_int32, vp, C.c_int32, vp, vp, C.c_double, C.c_int32, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_reset": ([vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_apply_damping": ([vp, vp, vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
@@ -181,7 +183,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes"
 ).split()
 
 
@@ -449,6 +451,18 @@ class TermTable:
         if self.n == 0:
             self.zero_operator = self.track_zero
         return st
+
+    def last_op_sizes(self, n_ops: int) -> list[int]:
+        """Live term count after every op of the program just waited for (exact per gate when the ops carried
+        ``OBP_FLAG_OWN_SLOT``): what the reference logs at DEBUG level after each gate."""
+        if self.zero_operator or n_ops == 0:
+            return [1 if self.zero_operator else self.n] * n_ops
+        buf = (C.c_uint64 * n_ops)()
+        got = C.c_int32()
+        self._check(self._lib.obp_last_op_sizes(self._h, buf, n_ops, C.byref(got)), "obp_last_op_sizes")
+        if got.value != n_ops:  # e.g. the program ran while the operator was already the zero operator
+            return [len(self)] * n_ops
+        return [int(v) for v in buf]
 
     def apply_generic(self, qubits, codes, coeffs, atol: float, simplify: bool = True) -> ObpStats:
         """A gate given as its Pauli sum (local codes + complex coefficients): raw k*k expansion (+ simplify)."""

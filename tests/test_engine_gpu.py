@@ -596,11 +596,27 @@ def test_program_and_standalone_kernels_agree_with_oracle(nq, mode, monkeypatch)
         monkeypatch.setenv("OBP_B200_NO_PROGRAM", "1")
     else:
         monkeypatch.setenv("OBP_B200_PROG_MAX_ROWS", "64" if "64" in mode else "2000")
-    rng = np.random.default_rng(4242 + nq)
-    slices = random_slices(nq, 9, rng, gates_per_slice=10, angles=[0.3, -0.45, 0.8, 1.1])
-    obs = random_observable(nq, 4, rng, weight=3)
+    lo = max(0, min(nq, 70) - 12)  # a 12-qubit window that straddles the 64-bit word boundary when there is one
+    win = list(range(lo, min(nq, lo + 12)))
+    slices = []
+    for k in range(4):
+        qc = QuantumCircuit(nq)
+        for q in win:
+            qc.rx(0.5 + 0.01 * q, q)
+        slices.append(qc)
+        qc = QuantumCircuit(nq)
+        for a, b in zip(win[k % 2 :: 2], win[k % 2 + 1 :: 2]):
+            qc.rzz(0.8, a, b)
+            qc.cx(a, b)
+        slices.append(qc)
+        qc = QuantumCircuit(nq)
+        for q in win:
+            qc.h(q)
+            qc.ry(0.4, q)
+        slices.append(qc)
+    obs = SparsePauliOp.from_sparse_list([("Z", [win[5]], 1.0), ("XY", [win[2], win[3]], 0.7)], nq)
     gl, md = _compare(obs, slices)
-    assert len(gl[0]) > 2000 or nq == 6, "the run must cross the row thresholds to mean anything"
+    assert len(gl[0]) > 3000 or nq == 6, f"the run must cross the row thresholds to mean anything ({len(gl[0])} terms)"
     _compare(obs, slices, truncation_error_budget=setup_budget(max_error_per_slice=1e-3))
 
 
@@ -654,11 +670,15 @@ def test_oversized_slice_exact_policy_matches_reference_metadata(monkeypatch):
     assert_same_metadata(md, md_w)
     assert md.backpropagation_history[-1].sum_paulis > 3 * 400, "the rejected slice must really overflow the first table"
     assert md.device_capacity_stops == []
-    assert bp.last_run.wasted_updates > 0 and bp.last_run.updates == _oracle_updates(obs, slices, budget, md_w)
+    # the attempts that overflowed are rolled back and not counted; the slice's final (complete) run is, as in the
+    # reference, whose per-gate sizes (backpropagation.py:239-242) include the slice it then rejects
+    tr = oracle.GateTrace()
+    oracle.backpropagate(obs, slices, operator_budget=budget, trace=tr)
+    assert bp.last_run.wasted_updates > 0 and bp.last_run.updates == tr.updates
     engine.clear_pool()
 
 
-def test_oversized_slice_lookahead_policy(monkeypatch):
+def test_oversized_slice_lookahead_policy(monkeypatch, caplog):
     """Look-ahead policy (default factor 3, here 1.5): a slice that reaches factor x max_paulis live terms is
     rejected without being finished.  Same operator, same slices absorbed, same history up to the rejected slice;
     that slice reports a lower bound of its size (> max_paulis, <= the exact count) and the stop is flagged in
@@ -669,7 +689,11 @@ def test_oversized_slice_lookahead_policy(monkeypatch):
     monkeypatch.setenv("OBP_B200_CAPACITY", "1024")
     monkeypatch.setenv("OBP_B200_OVERSIZE_LOOKAHEAD", "1.5")
     obs, slices, budget = _growing_workload(400)
-    got, rest, md = backpropagate(obs, slices, operator_budget=budget)
+    import logging
+
+    with caplog.at_level(logging.INFO, logger="qiskit_addon_obp_b200.backpropagation"):
+        got, rest, md = backpropagate(obs, slices, operator_budget=budget)
+    print("\n".join(r.getMessage() for r in caplog.records))
     want, rest_w, md_w = oracle.backpropagate(obs, slices, operator_budget=budget)
     assert len(rest) == len(rest_w)
     assert_same_operator(got, want)
@@ -682,14 +706,6 @@ def test_oversized_slice_lookahead_policy(monkeypatch):
     md_w.backpropagation_history.pop()
     assert_same_metadata(md, md_w)
     engine.clear_pool()
-
-
-def _oracle_updates(obs, slices, budget, md_w):
-    """Term-gate updates of the COMMITTED slices (the rejected slice's work is rolled back)."""
-    tr = oracle.GateTrace()
-    n = md_w.num_backpropagated_slices
-    oracle.backpropagate(obs, slices[len(slices) - n:], operator_budget=OperatorBudget(), trace=tr)
-    return tr.updates
 
 
 def test_reserve_failure_keeps_the_table(monkeypatch):
@@ -714,3 +730,32 @@ def test_reserve_failure_keeps_the_table(monkeypatch):
     got, _, _ = backpropagate(op, [qc])
     want, _, _ = oracle.backpropagate(op, [qc])
     assert_same_operator(got, want)
+
+
+def test_per_gate_debug_log_matches_reference_sizes(caplog):
+    """backpropagation.py:239-242: at DEBUG level the reference logs the observable's size after every applied
+    gate (this is how its term-gate update count is measured).  The engine then runs every gate
+    as a pass of its own and logs the same (gate id, size) sequence; results and counters are unchanged."""
+    import logging
+    import re
+
+    rng = np.random.default_rng(99)
+    nq = 7
+    slices = random_slices(nq, 5, rng, gates_per_slice=7)
+    slices[2].barrier()
+    slices[2].rx(0.2, 3)
+    ple = PauliLindbladError(["XX", "ZY"], [1e-2, 3e-3])
+    slices[3].append(PauliLindbladErrorInstruction(ple), [1, 3])
+    slices[4].cp(0.4, 0, 6)
+    obs = [random_observable(nq, 3, rng), SparsePauliOp("IIIZIII")]
+    tr = oracle.GateTrace()
+    want, _, md_w = oracle.backpropagate(obs, slices, trace=tr)
+    with caplog.at_level(logging.DEBUG, logger="qiskit_addon_obp_b200.backpropagation"):
+        got, _, md = backpropagate(obs, slices)
+    for g, w in zip(got, want):
+        assert_same_operator(g, w)
+    assert_same_metadata(md, md_w)
+    pat = re.compile(r"Size of the observable after backpropagating gate id (\d+) in the current layer: (\d+)")
+    logged = [tuple(map(int, m.groups())) for r in caplog.records if (m := pat.search(r.getMessage()))]
+    assert logged == [(gid, size) for _, _, gid, size in tr.gate_sizes]
+    assert sum(1 for _ in logged) == tr.applied_gates

@@ -294,9 +294,9 @@ def test_slice_plan_matches_the_reference_light_cone(seed):
         assert prog.plan(mask) is plan  # cached per (slice, support)
         # the steps partition the applied gates in order; the slice's last gate asks for exact counters
         seen = []
-        for kind, what in plan.steps:
+        for kind, what, seg in plan.steps:
             if kind == "ops":
-                assert len(what) > 0
+                assert len(what) > 0 and len(seg) == len(what)
                 seen += [None] * len(what)
             else:
                 assert kind == "node" and prog.special[what]
@@ -323,8 +323,8 @@ def test_slice_plan_full_cone_shortcut_and_unsupported_gate():
     bad.unitary(np.linalg.qr(np.random.default_rng(0).normal(size=(32, 32)) + 0j)[0], [0, 1, 2, 3, 4])
     bad.h(5)
     prog = SliceProgram(bad)
-    assert [k for k, _ in prog.plan(1 << 5).steps] == ["ops"]
-    kinds = [k for k, _ in prog.plan(0b1).steps]
+    assert [k for k, _, _ in prog.plan(1 << 5).steps] == ["ops"]
+    kinds = [k for k, _, _ in prog.plan(0b1).steps]
     assert kinds[-1] == "error"
 
 
