@@ -213,6 +213,10 @@ typedef struct {
 } obp_shard_counters;
 
 int obp_set_shard(obp_ctx* ctx, int32_t n_ranks, int32_t rank);
+/* Late sharding: while the operator is small every rank carries an identical copy of the whole table
+ * (no gate needs an exchange); obp_shard_split turns that copy into rank `rank`'s shard by dropping the
+ * rows other ranks own.  Invalidates the snapshot (it held the whole operator): call obp_snapshot again. */
+int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, uint64_t* n_out);
 /* Bytes of one exchange record: W x/z word pairs, the hash, the complex128 coefficient. */
 uint64_t obp_record_bytes(int n_qubits);
 /* obp_apply_ops on a sharded table: stops before the first rotation whose partner keys live on

@@ -1585,6 +1585,32 @@ int obp_set_shard(obp_ctx* ctx, int32_t n_ranks, int32_t rank) {
   return OBP_OK;
 }
 
+// Late sharding: a table that so far held the WHOLE operator (every rank an identical copy) keeps only the
+// rows this rank owns from now on.
+int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, uint64_t* n_out) {
+  OBP_NO_PENDING(ctx, "obp_shard_split");
+  if (!ctx) return OBP_ERR_BADARG;
+  if (ctx->n_ranks != 1) return ctx->fail(OBP_ERR_BADARG, "obp_shard_split: the table is already sharded");
+  int rc = obp_set_shard(ctx, n_ranks, rank);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->n_dense && ctx->n_ranks > 1) {
+    k_shard_drop<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), ctx->owner_shift, (u64)ctx->rank, ++ctx->epoch);
+    CU(cudaGetLastError());
+    rc = sync_state(ctx);
+    if (rc) return rc;
+    if (ctx->n_dense != ctx->n_live) {
+      rc = compact(ctx);
+      if (rc) return rc;
+      rc = sync_state(ctx);
+      if (rc) return rc;
+    }
+  }
+  ctx->snap.valid = false;  // the last commit held the whole operator: the caller commits again
+  if (n_out) *n_out = ctx->n_live;
+  return OBP_OK;
+}
+
 int obp_set_shard_sync(obp_ctx* ctx, int32_t device_flags) {
   if (!ctx) return OBP_ERR_BADARG;
   ctx->flag_sync = device_flags != 0;

@@ -1029,28 +1029,46 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, con
         }
       }
     }
+    // ---- the warp's records leave together: one atomicAdd on the (possibly remote) cursor reserves a contiguous
+    // run of the inbox, then ALL 32 lanes write that run word by word — consecutive lanes store consecutive u64,
+    // so the records cross NVLink as full 128-byte writes instead of one 8-byte store per word per lane.
     const unsigned bal = __ballot_sync(0xffffffffu, want_emit);
     if (bal) {
+      const unsigned cnt = (unsigned)__popc(bal);
       u64 wbase = 0;
-      if (lane == 0) wbase = atomicAdd(cursor, (u64)__popc(bal));
+      if (lane == 0) wbase = atomicAdd(cursor, (u64)cnt);
       wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (want_emit) {
-        n_emit++;
-        const u64 r = wbase + __popc(bal & ((1u << lane) - 1u));
-        if (r < rec_cap) {
-          u64* o = rec + r * RW;
-          for (int w = 0; w < t.W; ++w) {
+      if (want_emit) n_emit++;
+      const u64 h_out = want_emit ? (t.hash[i] ^ p.hG) : 0ull;
+      unsigned fit = cnt;  // records of this warp that fit the inbox
+      if (wbase + cnt > rec_cap) {
+        fit = wbase < rec_cap ? (unsigned)(rec_cap - wbase) : 0u;
+        overflow = true;
+      }
+      const unsigned total = fit * (unsigned)RW;
+      u64* o = rec + wbase * RW;
+      for (unsigned it = 0; it * 32u < total; ++it) {
+        const unsigned flat = it * 32u + lane;
+        const bool valid = flat < total;
+        const unsigned k = valid ? flat / (unsigned)RW : 0u, idx = valid ? flat % (unsigned)RW : 0u;
+        const int src = (int)__fns(bal, 0, (int)k + 1);  // lane that emitted the warp's k-th record
+        const u64 sh = __shfl_sync(0xffffffffu, h_out, src);
+        const u64 sre = __shfl_sync(0xffffffffu, (u64)__double_as_longlong(out_c.x), src);
+        const u64 sim = __shfl_sync(0xffffffffu, (u64)__double_as_longlong(out_c.y), src);
+        if (valid) {
+          u64 v;
+          if (idx < 2u * (unsigned)t.W) {
+            const int w = (int)(idx >> 1);
             u64 gx, gz;
             gen_word(p, w, gx, gz);
-            const ulonglong2 key = t.xz[w][i];
-            o[2 * w] = key.x ^ gx;
-            o[2 * w + 1] = key.y ^ gz;
+            const u64* kw = reinterpret_cast<const u64*>(&t.xz[w][base + (u64)src]);
+            v = (idx & 1u) ? (kw[1] ^ gz) : (kw[0] ^ gx);
+          } else if (idx == 2u * (unsigned)t.W) {
+            v = sh;
+          } else {
+            v = idx == 2u * (unsigned)t.W + 1u ? sre : sim;
           }
-          o[2 * t.W] = t.hash[i] ^ p.hG;
-          o[2 * t.W + 1] = (u64)__double_as_longlong(out_c.x);
-          o[2 * t.W + 2] = (u64)__double_as_longlong(out_c.y);
-        } else {
-          overflow = true;
+          o[flat] = v;
         }
       }
     }
@@ -1222,6 +1240,22 @@ __global__ void __launch_bounds__(OBP_BS) k_shard_filter(Tab t, int owner_shift,
   }
   const u64 f = warp_sum_u64(foreign);
   if ((threadIdx.x & 31) == 0 && f) atomicAdd(&t.st->removed, f);
+}
+
+// A replicated table becomes this rank's shard: live rows owned by another rank die (late sharding: while
+// the operator is small every rank carries all of it and no gate needs an exchange, see sharded.py).
+__global__ void __launch_bounds__(OBP_BS) k_shard_drop(Tab t, int owner_shift, u64 rank, u64 epoch) {
+  const u64 n = t.st->n_scan;
+  int deaths = 0;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    if ((t.hash[i] >> owner_shift) != rank && is_live(t.coef[i])) {
+      t.coef[i] = tombstone(epoch);
+      deaths++;
+    }
+  }
+  const long long dl = warp_sum_i64((long long)deaths);
+  if ((threadIdx.x & 31) == 0 && dl) atomicAdd(&t.st->n_live, (u64)(-dl));
+  finish_kernel(t, -1);
 }
 
 // ================================================================================================

@@ -146,6 +146,7 @@ def lib() -> C.CDLL:
         "obp_profile_get": ([vp, C.POINTER(ObpProfile), C.c_int32], C.c_int),
         "obp_set_shard": ([vp, C.c_int32, C.c_int32], C.c_int),
         "obp_record_bytes": ([C.c_int], C.c_uint64),
+        "obp_shard_split": ([vp, C.c_int32, C.c_int32, u64p], C.c_int),
         "obp_apply_ops_sharded": (
             [vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
             C.c_int,
@@ -183,7 +184,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split"
 ).split()
 
 
@@ -575,6 +576,13 @@ class TermTable:
     # -- sharded table (see sharded.py) ----------------------------------------------------------
     def set_shard(self, n_ranks: int, rank: int):
         self._check(self._lib.obp_set_shard(self._h, int(n_ranks), int(rank)), "obp_set_shard")
+
+    def shard_split(self, n_ranks: int, rank: int) -> int:
+        """A replicated table keeps only the rows rank ``rank`` of ``n_ranks`` owns (late sharding)."""
+        out = C.c_uint64()
+        self._check(self._lib.obp_shard_split(self._h, int(n_ranks), int(rank), C.byref(out)), "obp_shard_split")
+        self.n = self.n_dense = out.value
+        return out.value
 
     def apply_ops_sharded(self, ops: np.ndarray, atol: float) -> tuple[ObpStats, int, int, bool]:
         """Run ``ops`` up to the first rotation that needs a peer: ``(stats, n_done, peer_xor, overflowed)``.

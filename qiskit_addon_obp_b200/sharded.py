@@ -213,19 +213,20 @@ class ShardedTable:
         self.rec_u64 = int(lib().obp_record_bytes(self.num_qubits)) // 8
         per_rank = self._per_rank(capacity)
         self.tables = {r: TermTable.acquire(num_qubits, per_rank, comm.device) for r in comm.local_ranks}
-        for r, t in self.tables.items():
-            t.set_shard(comm.n_ranks, r)
-            t.track_zero = False  # an empty shard is normal; the zero-operator rule applies to the whole table
+        # Late sharding: while the operator holds fewer than `split_min` terms every rank carries an identical
+        # copy of the WHOLE table (same deterministic kernels on the same input: no exchange, no allreduce, exact
+        # counters); at the first commit at or above that size each rank drops the rows it does not own.
+        self.split = False
+        self.split_min = int(os.environ.get("OBP_B200_SHARD_MIN_TERMS", str(1 << 20)))
+        self._split_on_restore = False
+        self._skip_next_reserve = False
+        self._inboxes_ready = False
         self.p2p = os.environ.get("OBP_B200_P2P", "1") not in ("0", "")
         # one process per GPU: split rotations are ordered by device-side flags, the host never waits
         self.device_flags = (
             self.p2p and isinstance(comm, DistComm) and comm.backend == "nccl"
             and os.environ.get("OBP_B200_DEVICE_FLAGS", "1") not in ("0", "")
         )
-        if self.p2p:
-            self._setup_inboxes(per_rank)
-        for t in self.tables.values():
-            t.set_shard_sync(self.device_flags)
         self.n = 0
         self.n_dense = 0
         self.zero_operator = False
@@ -235,7 +236,57 @@ class ShardedTable:
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _per_rank(self, capacity: int) -> int:
-        return max(1 << 16, int(1.25 * capacity / self.comm.n_ranks) + 1)
+        # a rank's share of the table plus 25 % for imbalance — and room for the replicated phase
+        return max(1 << 16, int(1.25 * capacity / self.comm.n_ranks) + 1, min(int(capacity), 4 * self.split_min_env()))
+
+    @staticmethod
+    def split_min_env() -> int:
+        return int(os.environ.get("OBP_B200_SHARD_MIN_TERMS", str(1 << 20)))
+
+    def _reset_replicated(self) -> None:
+        """Back to the replicated phase (a recycled table starts a new run)."""
+        self.split = False
+        self._split_on_restore = self._skip_next_reserve = False
+        for t in self.tables.values():
+            t.set_shard(1, 0)
+            t.set_shard_sync(False)
+            t.track_zero = False
+
+    def _split_now(self) -> None:
+        """Every rank keeps its share (collective: all ranks reach this at the same commit)."""
+        for r, t in self.tables.items():
+            t.shard_split(self.comm.n_ranks, r)
+        if self.p2p and not self._inboxes_ready:
+            self._setup_inboxes(max(t.capacity for t in self.tables.values()))
+            self._inboxes_ready = True
+        for t in self.tables.values():
+            t.set_shard_sync(self.device_flags)
+        self.split = True
+        self._split_on_restore = False
+        self._sync_counts()
+        for t in self.tables.values():  # the commit the split invalidated
+            t.snapshot()
+        self._snap = (self.zero_operator, self.n)
+
+    def _maybe_split(self) -> None:
+        if not self.split and not self.zero_operator and self.comm.n_ranks > 1 and self.n >= self.split_min:
+            self._split_now()
+
+    def _rep(self):
+        """The replicated phase's representative table (all local copies are identical)."""
+        return self.tables[min(self.tables)]
+
+    def _rep_stats(self, stats_by_rank: dict) -> "_Stats":
+        st = stats_by_rank[min(stats_by_rank)]
+        out = _Stats()
+        for f in ("n_in", "raw_rows", "n_out", "n_dense", "updates", "num_unique", "num_duplicate", "num_trimmed"):
+            setattr(out, f, int(getattr(st, f)))
+        out.sum_trimmed = [float(st.sum_trimmed[0]), float(st.sum_trimmed[1])]
+        t = self._rep()
+        self.n, self.n_dense = t.n, t.n_dense
+        if self.n == 0:
+            self.zero_operator = True
+        return out
 
     @classmethod
     def acquire(cls, num_qubits, capacity, comm):
@@ -247,8 +298,12 @@ class ShardedTable:
                 t.n = t.n_dense = t.exchanges = t.exchanged_records = 0
                 t.zero_operator = False
                 t.t_phase = dict.fromkeys(t.t_phase, 0.0)
+                t.split_min = cls.split_min_env()
+                t._reset_replicated()
                 return t
-        return cls(num_qubits, capacity, comm)
+        t = cls(num_qubits, capacity, comm)
+        t._reset_replicated()
+        return t
 
     def _setup_inboxes(self, per_rank: int) -> None:
         """Every rank allocates its two inboxes and maps those of all its peers (collective)."""
@@ -281,8 +336,9 @@ class ShardedTable:
             self.close()
 
     def close(self):
-        if self.tables and self.p2p:
+        if self.tables and self.p2p and self._inboxes_ready:
             self._drop_inboxes()
+            self._inboxes_ready = False
         for t in self.tables.values():
             t.release()
         self.tables = {}
@@ -291,6 +347,10 @@ class ShardedTable:
         return 1 if self.zero_operator else self.n
 
     def _sync_counts(self):
+        if not self.split:
+            t = self._rep()
+            self.n, self.n_dense = int(t.n), int(t.n_dense)
+            return
         tot = self.comm.allreduce_sum_int({r: [t.n, t.n_dense] for r, t in self.tables.items()})
         self.n, self.n_dense = int(tot[0]), int(tot[1])
 
@@ -302,6 +362,27 @@ class ShardedTable:
     # -- I/O ----------------------------------------------------------------------------------------
     def load(self, op: SparsePauliOp, atol: float | None = None) -> _Stats:
         out = _Stats()
+        self._reset_replicated()
+        if atol != OBP_ATOL_RAW:
+            # replicated start: every rank loads the whole operator and keeps all of it for now
+            self._unsimplified = False
+            for t in self.tables.values():
+                if len(op) > t.capacity:
+                    t.reserve(2 * len(op))
+                t.load(op, atol)
+            self._sync_counts()
+            self.zero_operator = atol is not None and self.n == 0
+            out.n_in, out.n_out = len(op), self.n
+            self._maybe_split()
+            return out
+        self.split = True  # simplify=False deals the rows out at once (below): there is nothing to keep identical
+        for r, t in self.tables.items():
+            t.set_shard(self.comm.n_ranks, r)
+        if self.p2p and not self._inboxes_ready:
+            self._setup_inboxes(max(t.capacity for t in self.tables.values()))
+            self._inboxes_ready = True
+        for t in self.tables.values():
+            t.set_shard_sync(self.device_flags)
         if atol == OBP_ATOL_RAW:
             # simplify=False: nothing ever merges, so ownership by key hash is moot — deal the rows out evenly
             R = self.comm.n_ranks
@@ -330,6 +411,8 @@ class ShardedTable:
         if self.zero_operator:
             z = np.zeros((1, self.num_qubits), dtype=bool)
             return SparsePauliOp((z.copy(), z), np.array([0j]))
+        if not self.split:
+            return self._rep().download()
         return self.comm.gather_operators({r: t.download() for r, t in self.tables.items()})
 
     to_operator = download
@@ -347,6 +430,13 @@ class ShardedTable:
             k2 = int(ops[-1]["n_components"]) ** 2
             out.n_in, out.raw_rows, out.num_trimmed, out.n_out, out.updates = 1, k2, k2, 1, len(ops)
             return out
+        if not self.split:
+            try:
+                return self._rep_stats({r: t.apply_ops(ops, atol) for r, t in self.tables.items()})
+            except CapacityError:
+                # the whole operator no longer fits one rank's table: split at the caller's rollback, retry sharded
+                self._split_on_restore = self.comm.n_ranks > 1
+                raise
         if (
             self.comm.n_ranks > 1 and int(ops[-1]["kind"]) != OBP_OP_ROTATION and int(ops[-1]["flags"]) & 1
             and os.environ.get("OBP_B200_SHARDED_EXACT_COUNTERS", "0") == "1"
@@ -514,6 +604,8 @@ class ShardedTable:
         host traffic per gate; no BASELINE configuration has such gates."""
         out = _Stats()
         k2 = len(codes) ** 2
+        if not self.split and not self.zero_operator:
+            return self._rep_stats({r: t.apply_generic(qubits, codes, coeffs, atol, simplify=simplify) for r, t in self.tables.items()})
         if not simplify:
             # OperatorBudget(simplify=False): every rank expands the rows it holds, nothing moves or merges
             n_in = self.n
@@ -560,6 +652,8 @@ class ShardedTable:
         if self.zero_operator:
             out.n_in = out.raw_rows = out.num_trimmed = out.n_out = out.updates = 1
             return out
+        if not self.split:
+            return self._rep_stats({r: t.apply_reset(qubit, atol) for r, t in self.tables.items()})
         n_in = self.n
         if atol == OBP_ATOL_RAW:  # simplify=False: zero / clear in place on every rank, nothing merges
             for t in self.tables.values():
@@ -613,6 +707,8 @@ class ShardedTable:
         if self.zero_operator:
             out.n_in = out.raw_rows = out.num_trimmed = out.n_out = out.updates = 1
             return out
+        if not self.split:
+            return self._rep_stats({r: t.apply_damping(gen_x, gen_z, factors, atol) for r, t in self.tables.items()})
         n_in = self.n
         for t in self.tables.values():
             t.apply_damping(gen_x, gen_z, factors, atol)
@@ -629,6 +725,10 @@ class ShardedTable:
             self.zero_operator = False
             self.n = 0
             return 0.0, 1
+        if not self.split:
+            res = {r: t.truncate(budget, p_norm, tol) for r, t in self.tables.items()}
+            self._sync_counts()
+            return res[min(res)]
         before = self.n
         upper = float(self.comm.allreduce_max({r: [t.trunc_begin(p_norm)] for r, t in self.tables.items()})[0])
         lower, upper_error, lower_error = 0.0, budget, 0.0
@@ -646,6 +746,10 @@ class ShardedTable:
         return float(lower_error), before - self.n
 
     def snapshot(self):
+        """Commit.  The first commit at or above ``split_min`` terms also ends the replicated phase."""
+        if not self.split and not self.zero_operator and self.comm.n_ranks > 1 and self.n >= self.split_min:
+            self._split_now()  # (commits the shards itself)
+            return
         self._snap = (self.zero_operator, self.n)
         for t in self.tables.values():
             t.snapshot()
@@ -654,15 +758,24 @@ class ShardedTable:
         for t in self.tables.values():
             t.restore()
         self.zero_operator, self.n = self._snap
+        if self._split_on_restore and not self.split:
+            # the replicated table overflowed in the slice just rolled back: shard the committed state instead of
+            # growing every rank's copy; the caller's reserve() that follows is then unnecessary
+            self._split_now()
+            self._skip_next_reserve = True
 
     def reserve(self, capacity: int):
-        if self.p2p:
+        if self._skip_next_reserve:
+            self._skip_next_reserve = False
+            return
+        had_inboxes = self.p2p and self._inboxes_ready
+        if had_inboxes:
             self._drop_inboxes()
         for t in self.tables.values():
             t.reserve(self._per_rank(capacity))
         self.capacity = max(self.capacity, int(capacity))
-        if self.p2p:
-            self._setup_inboxes(self._per_rank(self.capacity))
+        if had_inboxes:
+            self._setup_inboxes(max(t.capacity for t in self.tables.values()))
 
     # -- measurement ------------------------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

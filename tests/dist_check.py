@@ -33,6 +33,7 @@ def log(*a):
         print(*a, flush=True)
 
 # ---- 1. parity -------------------------------------------------------------------------------------
+os.environ["OBP_B200_SHARD_MIN_TERMS"] = "0"  # tiny tables: shard from the first commit (exchanges from the start)
 for nq, seed in ((6, 0), (70, 1), (130, 2)):
     rng = np.random.default_rng(100 + seed)
     slices = random_slices(nq, 6, rng, gates_per_slice=8)
@@ -47,6 +48,15 @@ wl = W.config1_xy_chain()
 got, rest, md = backpropagate(wl.observables, wl.slices, **wl.kwargs())
 want, _, md_w = oracle.backpropagate(wl.observables, wl.slices, **wl.kwargs())
 assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
+# late sharding: replicated at first, split into shards mid-run
+os.environ["OBP_B200_SHARD_MIN_TERMS"] = "300"
+from test_engine_gpu import window_workload
+obs, slices = window_workload(70, 4)
+got, rest, md = backpropagate(obs, slices)
+want, rest_w, md_w = oracle.backpropagate(obs, slices)
+assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
+assert bpmod.last_run.exchanges > 0
+os.environ.pop("OBP_B200_SHARD_MIN_TERMS")
 dist.barrier()
 log(f"[dist_check] parity vs oracle OK on {world} ranks (NCCL, P2P inbox exchange = {p2p})")
 

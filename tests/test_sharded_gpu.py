@@ -17,6 +17,13 @@ from test_engine_gpu import random_observable, random_slices
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _shard_from_the_first_commit(monkeypatch):
+    """The tables of these tests are tiny: shard them at once (the default keeps a table replicated on every rank
+    until it holds 2^20 terms, see test_late_sharding_* for that path)."""
+    monkeypatch.setenv("OBP_B200_SHARD_MIN_TERMS", "0")
+
+
 def _compare(monkeypatch, ranks, obs, slices, p2p=True, **kw):
     monkeypatch.setenv("OBP_B200_SHARDS", str(ranks))
     monkeypatch.setenv("OBP_B200_P2P", "1" if p2p else "0")
@@ -236,3 +243,46 @@ def test_sharded_exact_counters_for_clifford_ending_slices(monkeypatch):
     want, _, md_w = oracle.backpropagate(obs, slices)
     assert_same_operator(got, want)
     assert_same_metadata(md_g, md_w)  # no counter may be missing
+
+
+# ---- late sharding: replicated while small, split at a commit or when a rank's copy overflows --------------
+@pytest.mark.parametrize("min_terms", [40, 400, 10**9])
+@pytest.mark.parametrize("ranks", [2, 8])
+def test_late_sharding_splits_mid_run(monkeypatch, ranks, min_terms):
+    """The operator starts as an identical copy on every rank and is split into shards at the first commit at or
+    above OBP_B200_SHARD_MIN_TERMS terms (never, for 10^9): same operator and metadata as the oracle either way,
+    and — unlike a table sharded from the start — exact simplify counters for the slices run replicated."""
+    from qiskit_addon_obp_b200 import backpropagation as bp
+
+    monkeypatch.setenv("OBP_B200_SHARD_MIN_TERMS", str(min_terms))
+    from test_engine_gpu import window_workload
+
+    obs, slices = window_workload(70, 4)
+    got, md = _compare(monkeypatch, ranks, obs, slices)
+    sizes = [s.num_paulis[0] for s in md.backpropagation_history]
+    assert sizes[-1] > 400, sizes
+    if min_terms == 10**9:
+        assert bp.last_run.exchanges == 0
+        assert all(s.num_unique_paulis[0] is not None for s in md.backpropagation_history)
+    else:
+        assert bp.last_run.exchanges > 0
+    _compare(monkeypatch, ranks, obs, slices, truncation_error_budget=setup_budget(max_error_per_slice=2e-3))
+
+
+def test_late_sharding_split_on_overflow(monkeypatch):
+    """A replicated copy that outgrows one rank's table is rolled back and split instead of grown."""
+    from qiskit_addon_obp_b200 import backpropagation as bp
+    from qiskit_addon_obp_b200 import engine, sharded
+
+    sharded.close_all()
+    engine.clear_pool()
+    monkeypatch.setenv("OBP_B200_SHARD_MIN_TERMS", "100000")  # never reached by size ...
+    monkeypatch.setenv("OBP_B200_CAPACITY", "70000")          # ... but a rank holds at most max(2^16, ...) rows
+    from test_engine_gpu import window_workload
+
+    obs, slices = window_workload(70, 5)
+    got, md = _compare(monkeypatch, 4, obs, slices)
+    assert max(s.num_paulis[0] for s in md.backpropagation_history) > 2**16
+    assert bp.last_run.exchanges > 0 and bp.last_run.wasted_updates > 0
+    sharded.close_all()
+    engine.clear_pool()
