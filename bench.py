@@ -18,9 +18,16 @@ Engine arm (default) prints one JSON line with
 here) on the host cores, on the same workload, each step a bounded sample.
 
 N > 1 (torchrun): every rank backpropagates its own observable of the workload (independent
-observables partition the path with no data-path collective): weak scaling.  With
-``--sharded`` the ranks instead share ONE observable as a hash-sharded table (strong scaling; meant for
-tables far beyond one GPU's L2, e.g. ``--workload config4 --max-paulis 20000000``).
+observables partition the path with no data-path collective): weak scaling — that is the
+top-level line.  The same run then measures the north-star split as the ``sharded`` object: BASELINE
+config 4 (1000-qubit near-Clifford brickwork, ``max_paulis=1e8``) with ONE observable hash-sharded over
+the N ranks (pairwise P2P record exchange per branching gate), after a parity check of the sharded path
+against the oracle over NCCL; ``ms_1gpu`` is the same job on one unsharded table (rank 0 alone, same
+run), ``speedup`` their ratio.  At N = 1 the object holds the single-table time only.  ``--sharded``
+instead makes the top-level line itself a sharded run of ``--workload``.
+
+N = 1 also reports ``other_configs``: BASELINE configs 1, 3, 4 (2e7 terms) and 5 (1e6) through the same
+public call, outside the headline's timed region.
 """
 
 from __future__ import annotations
@@ -71,6 +78,11 @@ def make_workloads(name: str, rank: int, args) -> list:
     if name == "config5":
         return [wl.config5_magic_sweep(theta=t, depth=args.depth or 40, max_paulis=args.max_paulis, seed=rank) for t in thetas]
     raise SystemExit(f"unknown workload {name}")
+
+
+def bench_config(args, wls) -> dict:
+    """What is measured — the same dictionary in the engine arm and in the reference arm."""
+    return {"workload": workload_name(wls), "theta": args.theta, "max_paulis": args.max_paulis}
 
 
 def workload_name(wls) -> str:
@@ -278,7 +290,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "vs_baseline": None,
         "dtype": "complex128 (f64) coefficients, bool keys",
         "data": "synthetic",
-        "config": {"workload": workload_name(wls), "theta": args.theta, "max_paulis": args.max_paulis},
+        "config": bench_config(args, wls),
         "cpu_baseline": {
             "value": value,
             "unit": UNIT,
@@ -326,13 +338,264 @@ def large_table_roofline(backpropagate, bpmod, peak: float) -> dict:
         "term_updates": rot["term_updates"],
         "ms": rot["ms"],
         "updates_per_s_whole_run": bpmod.last_run.updates / (bpmod.last_run.device_ms * 1e-3),
-        "traffic": {
-            "dram_bytes_per_launch": 300.4e6,
-            "rows_per_launch": 4.5e6,
-            "algorithmic_bytes_per_launch": 4.5e6 * btg,
-            "source": "ncu --set full, profiles/r1d_k_rotate_big_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
-        },
+        "traffic": None,
+        "traffic_source": "profiles/README.md (ncu --set full capture of k_rotate on a table of this size)",
     }
+
+
+
+def other_configs(backpropagate, bpmod, torch, device, flush_buf, peak: float) -> dict:
+    """BASELINE configs 1, 3, 4 and 5 through the same public call (N = 1, outside the headline's timed
+    region): one warm-up call, then `reps` timed calls each; device-resident and end-to-end time, updates/s
+    and the algorithmic HBM fraction of the kernel class that took the most device time.  Config 1 is small
+    enough for the CPU port to run the WHOLE job: its wall time is measured beside the engine's (same work)."""
+    from qiskit_addon_obp_b200 import workloads as wl
+
+    cases = [
+        ("config1", wl.config1_xy_chain(), 5, True),
+        ("config3", wl.config3_square_lattice(), 2, True),
+        ("config4@2e7", wl.config4_near_clifford(depth=200, max_paulis=20_000_000), 2, False),
+        ("config5@1e6", wl.config5_magic_sweep(theta=np.pi / 16, depth=40, max_paulis=1_000_000), 2, True),
+    ]
+    out = {}
+    for name, w, reps, download in cases:
+        os.environ["OBP_B200_DOWNLOAD"] = "1" if download else "0"
+        try:
+            backpropagate(w.observables, w.slices, **w.kwargs())  # warm-up: tables, compiled slices
+            dev_ms = wall = 0.0
+            updates = 0
+            prof: dict = {}
+            for _ in range(reps):
+                flush_l2(torch, device, flush_buf)
+                t0 = time.perf_counter()
+                res, rest, md = backpropagate(w.observables, w.slices, **w.kwargs())
+                torch.cuda.synchronize(device)
+                wall += time.perf_counter() - t0
+                r = bpmod.last_run
+                dev_ms += r.device_ms
+                updates += r.updates
+                for k, v in (r.profile or {}).items():
+                    a = prof.setdefault(k, {"ms": 0.0, "term_updates": 0})
+                    a["ms"] += v["ms"]
+                    a["term_updates"] += v["term_updates"]
+            btg = algorithmic_bytes_per_update(w.num_qubits)
+            top = max((k for k in prof if k != "program"), key=lambda k: prof[k]["ms"], default=None)
+            entry = {
+                "workload": w.name,
+                "slices_absorbed": md.num_backpropagated_slices,
+                "terms_out": len(res) if download else int(md.backpropagation_history[md.num_backpropagated_slices - 1].num_paulis[0]),
+                "updates_per_call": updates / reps,
+                "device_ms": dev_ms / reps,
+                "e2e_ms": 1e3 * wall / reps if download else None,
+                "updates_per_s": updates / (dev_ms * 1e-3) if dev_ms > 0 else None,
+                "kernel_ms": {k: round(v["ms"] / reps, 3) for k, v in prof.items() if v["ms"] > 0},
+            }
+            if top is not None and prof[top]["ms"] > 0 and prof[top]["term_updates"]:
+                ach = prof[top]["term_updates"] * btg / (prof[top]["ms"] * 1e-3) / 1e9
+                entry["dominant_kernel"] = {"class": top, "achieved_gbs_algorithmic": ach, "frac": ach / peak,
+                                            "bytes_per_term_gate_update": btg}
+            if name == "config1":
+                t0 = time.perf_counter()
+                u, _ = cpu_sample([w], 10**12)
+                t_cpu = time.perf_counter() - t0
+                entry["cpu_full_run"] = {"kind": "port", "cores": 1, "wall_ms": 1e3 * t_cpu, "updates": u,
+                                         "same_work": True, "e2e_speedup": t_cpu / (wall / reps)}
+            out[name] = entry
+        except Exception as exc:  # noqa: BLE001 - a side measurement must not take the headline line down
+            out[name] = {"workload": w.name, "error": f"{type(exc).__name__}: {exc}"}
+    os.environ.pop("OBP_B200_DOWNLOAD", None)
+    return out
+
+
+def sharded_parity_check(backpropagate, bpmod) -> tuple[bool, str]:
+    """The sharded path against the oracle over NCCL, on every rank (the oracle only checks here): small circuits
+    sharded from the first commit, and one that starts replicated and is split mid-run."""
+    from oracle import obp_oracle as oracle
+    from qiskit_addon_obp_b200 import workloads as wl
+    from qiskit_addon_obp_b200.ir import QuantumCircuit, SparsePauliOp
+
+    def window(nq, rounds):
+        lo = max(0, min(nq, 70) - 12)
+        win = list(range(lo, min(nq, lo + 12)))
+        slices = []
+        for k in range(rounds):
+            qc = QuantumCircuit(nq)
+            for q in win:
+                qc.rx(0.5 + 0.01 * q, q)
+            slices.append(qc)
+            qc = QuantumCircuit(nq)
+            for a, b in zip(win[k % 2 :: 2], win[k % 2 + 1 :: 2]):
+                qc.rzz(0.8, a, b)
+                qc.cx(a, b)
+            slices.append(qc)
+            qc = QuantumCircuit(nq)
+            for q in win:
+                qc.h(q)
+                qc.ry(0.4, q)
+            slices.append(qc)
+        return SparsePauliOp.from_sparse_list([("Z", [win[5]], 1.0), ("XY", [win[2], win[3]], 0.7)], nq), slices
+
+    def same(got, want, md, md_w) -> str:
+        a, b = got.as_dict(), want.as_dict()
+        if set(a) != set(b):
+            return f"key sets differ ({len(a)} vs {len(b)})"
+        err = max((abs(a[k] - b[k]) - 1e-10 * abs(b[k]) for k in a), default=0.0)
+        if err > 1e-12:
+            return f"coefficients differ by {err:.3e}"
+        if md.num_backpropagated_slices != md_w.num_backpropagated_slices:
+            return "slices absorbed differ"
+        for g, w in zip(md.backpropagation_history, md_w.backpropagation_history):
+            if g.num_paulis != w.num_paulis or g.sum_paulis != w.sum_paulis:
+                return "per-slice term counts differ"
+            if max(abs(x - y) for x, y in zip(g.slice_errors, w.slice_errors)) > 1e-9:
+                return "slice errors differ"
+        return ""
+
+    cases = []
+    c1 = wl.config1_xy_chain()
+    cases.append(("config1", "0", c1.observables, c1.slices, c1.kwargs()))
+    c4 = wl.config4_near_clifford(num_qubits=1000, depth=10, t_prob=0.01, max_paulis=4000, per_slice=1e-4)
+    cases.append(("config4 small", "0", c4.observables, c4.slices, c4.kwargs()))
+    obs, sl = window(70, 4)
+    cases.append(("70q window, sharded at once", "0", obs, sl, {}))
+    cases.append(("70q window, split mid-run", "300", obs, sl, {}))
+    exchanges = 0
+    try:
+        for name, min_terms, o, sl, kw in cases:
+            os.environ["OBP_B200_SHARD_MIN_TERMS"] = min_terms
+            got, rest, md = backpropagate(o, sl, **kw)
+            exchanges += bpmod.last_run.exchanges
+            want, rest_w, md_w = oracle.backpropagate(o, sl, **kw)
+            msg = same(got, want, md, md_w) if len(rest) == len(rest_w) else "remaining slices differ"
+            if msg:
+                return False, f"{name}: {msg}"
+        if exchanges == 0:
+            return False, "no record exchange took place"
+        return True, f"{len(cases)} cases vs the oracle, {exchanges} record exchanges"
+    except Exception as exc:  # noqa: BLE001
+        return False, f"{type(exc).__name__}: {exc}"
+    finally:
+        os.environ.pop("OBP_B200_SHARD_MIN_TERMS", None)
+
+
+def sharded_block(args, rank: int, world: int, device, torch, dist, backpropagate, bpmod, flush_buf) -> dict | None:
+    """The north-star multi-GPU split, measured in the same run (see the module docstring)."""
+    from qiskit_addon_obp_b200 import engine
+    from qiskit_addon_obp_b200 import sharded as sh
+    from qiskit_addon_obp_b200 import workloads as wl
+
+    w = wl.config4_near_clifford(depth=200, max_paulis=args.sharded_max_paulis)
+    os.environ["OBP_B200_DOWNLOAD"] = "0"  # 1e8 terms x 272 B: the result stays on the device(s)
+    os.environ.pop("OBP_B200_SHARDED", None)
+    engine.clear_pool()
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    def run(n_warm: int, n_steps: int) -> dict:
+        acc = {"dev_ms": 0.0, "wall_ms": 0.0, "updates": 0, "prof": {}, "exchanges": 0, "records": 0, "slices": 0, "peak": 0}
+        for k in range(n_warm + n_steps):
+            flush_l2(torch, device, flush_buf)
+            barrier()
+            t0 = time.perf_counter()
+            _, _, md = backpropagate(w.observables, w.slices, **w.kwargs())
+            torch.cuda.synchronize(device)
+            barrier()
+            if k < n_warm:
+                continue
+            r = bpmod.last_run
+            acc["wall_ms"] += 1e3 * (time.perf_counter() - t0)
+            acc["dev_ms"] += r.device_ms
+            acc["updates"] += r.updates
+            acc["exchanges"] += r.exchanges
+            acc["records"] += r.exchanged_records
+            acc["slices"] = md.num_backpropagated_slices
+            acc["peak"] = max(s.num_paulis[0] for s in md.backpropagation_history)
+            for c, v in (r.profile or {}).items():
+                acc["prof"][c] = acc["prof"].get(c, 0.0) + v["ms"]
+        for f in ("dev_ms", "wall_ms", "updates", "exchanges", "records"):
+            acc[f] /= n_steps
+        acc["prof"] = {c: round(v / n_steps, 3) for c, v in acc["prof"].items() if v > 0}
+        return acc
+
+    out: dict = {"workload": w.name, "n_gpus": world}
+    try:
+        # ---- one unsharded table: rank 0 alone (its peers wait at the barrier inside run()) ----------------
+        single = None
+        if rank == 0 or world == 1:
+            pass
+        # every rank enters run() (it holds the barriers); only rank 0 does the work
+        if world == 1:
+            single = run(1, 2)
+        else:
+            single = _rank0_only(run, rank, barrier, 1, 2, w, backpropagate)
+        engine.clear_pool()
+        if world == 1:
+            out.update({"ms_1gpu": single["dev_ms"], "ms_per_step": single["dev_ms"], "speedup": 1.0,
+                        "updates_per_step": single["updates"], "slices_absorbed": single["slices"],
+                        "peak_terms": single["peak"], "kernel_ms_1gpu": single["prof"],
+                        "note": "N = 1: one unsharded table; run with --gpus N for the hash-sharded table"})
+            return out
+        # ---- the same job, one observable hash-sharded over all ranks ----------------------------------------
+        os.environ["OBP_B200_SHARDED"] = "1"
+        ok, detail = sharded_parity_check(backpropagate, bpmod)
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        shard = run(1, 3)
+        t = torch.tensor([shard["dev_ms"], shard["wall_ms"]] + [shard["prof"].get(c, 0.0) for c in engine.OBP_K_NAMES],
+                         dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms1 = torch.tensor([single["dev_ms"] if single else 0.0, float(single["updates"]) if single else 0.0],
+                           dtype=torch.float64, device=device)
+        dist.all_reduce(ms1, op=dist.ReduceOp.MAX)
+        kernel_ms = {c: round(float(v), 3) for c, v in zip(engine.OBP_K_NAMES, t[2:]) if float(v) > 0}
+        dev_ms = float(t[0])
+        out.update({
+            "ms_1gpu": float(ms1[0]),
+            "ms_per_step": dev_ms,
+            "wall_ms_per_step": float(t[1]),
+            "speedup": float(ms1[0]) / dev_ms if dev_ms > 0 else None,
+            "updates_per_step": shard["updates"],
+            "updates_per_s": shard["updates"] / (dev_ms * 1e-3) if dev_ms > 0 else None,
+            "slices_absorbed": shard["slices"],
+            "peak_terms": shard["peak"],
+            "parity_ok": bool(float(flag[0]) > 0),
+            "parity_detail": detail,
+            "phases_ms": {
+                "clifford": kernel_ms.get("clifford", 0.0),
+                "rotate_emit_merge_finish": kernel_ms.get("rotate", 0.0),
+                "other_kernels": round(sum(v for c, v in kernel_ms.items() if c not in ("clifford", "rotate")), 3),
+                "host_and_wait": round(max(0.0, dev_ms - sum(kernel_ms.values())), 3),
+                "note": "max over ranks of CUDA-event time per kernel class; a split rotation is three kernels (emit into the "
+                        "peer's inbox over NVLink, merge, finish) timed as one class; host_and_wait = device-timed span minus the kernel classes",
+            },
+            "kernel_ms_1gpu": single["prof"] if single else None,
+            "exchanges_per_step": shard["exchanges"],
+            "exchanged_records_per_step": shard["records"],
+            "shard_min_terms": sh.ShardedTable.split_min_env(),
+            "timing": "CUDA events on each rank's stream from the observable upload to the end of the last slice, max over ranks; "
+                      "result left on the devices (OBP_B200_DOWNLOAD=0)",
+        })
+        sh.close_all()
+        return out
+    except Exception as exc:  # noqa: BLE001 - report, never take the headline line down
+        out["error"] = f"{type(exc).__name__}: {exc}"
+        return out
+    finally:
+        os.environ.pop("OBP_B200_DOWNLOAD", None)
+        os.environ.pop("OBP_B200_SHARDED", None)
+
+
+def _rank0_only(run, rank, barrier, n_warm, n_steps, w, backpropagate):
+    """run() on rank 0 while the other ranks only keep its barriers company."""
+    if rank == 0:
+        return run(n_warm, n_steps)
+    for _ in range(2 * (n_warm + n_steps)):
+        barrier()
+    return None
 
 
 def run_engine(args, rank: int, local_rank: int, world: int) -> None:
@@ -368,7 +631,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     def one_step():
         """One pass of the hot path over the step's workload(s) through the public API."""
         flush_l2(torch, device, flush_buf)
-        acc = {"dt": 0.0, "dev_ms": 0.0, "updates": 0, "h2d": 0, "d2h": 0, "n_out": 0, "slices": 0, "prof": {}}
+        acc = {"dt": 0.0, "dev_ms": 0.0, "updates": 0, "wasted": 0, "h2d": 0, "d2h": 0, "n_out": 0, "slices": 0, "prof": {}}
         for wl in wls:
             t0 = time.perf_counter()
             out, rest, md = backpropagate(wl.observables, wl.slices, **wl.kwargs())
@@ -377,6 +640,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             r = bpmod.last_run
             acc["dev_ms"] += r.device_ms
             acc["updates"] += r.updates
+            acc["wasted"] += getattr(r, "wasted_updates", 0)
             acc["h2d"] += r.h2d_bytes
             acc["d2h"] += r.d2h_bytes
             acc["n_out"] += len(out) if not isinstance(out, list) else sum(len(o) for o in out)
@@ -402,7 +666,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     gc.disable()
     sampler.mark_begin()
     e2e_s, dev_ms, updates = 0.0, 0.0, 0
-    h2d = d2h = 0
+    h2d = d2h = wasted = 0
     prof_tot: dict = {}
     n_out = n_slices = 0
     wall0 = time.perf_counter()
@@ -416,6 +680,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
         e2e_s += acc["dt"]
         dev_ms += acc["dev_ms"]
         updates += acc["updates"]
+        wasted += acc["wasted"]
         h2d += acc["h2d"]
         d2h += acc["d2h"]
         for k, v in acc["prof"].items():
@@ -469,13 +734,12 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "vs_baseline": None,
             "dtype": "u64 keys + f64 complex coefficients",
             "data": "synthetic",
-            "config": {
-                "workload": workload_name(wls),
-                "theta": args.theta,
-                "max_paulis": args.max_paulis,
+            "config": bench_config(args, wls),
+            "run": {
                 "slices_absorbed": n_slices,
                 "terms_out": n_out,
                 "updates_per_step": updates_all / max(1, args.steps),
+                "wasted_updates_per_step": wasted / max(1, args.steps),
                 "parallelism": (
                     f"one observable hash-sharded over {world} GPUs (pairwise P2P record exchange per branching gate)"
                     if sharded
@@ -506,22 +770,17 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                 "avg_pass_ms": rot["ms"] / max(1, rot["passes"]),
                 "timing": "tables <= 128 qubits: %globaltimer stamps at the grid barriers of the persistent program "
                 "kernel; wider tables: CUDA events around the k_rotate launches",
-                # one `ncu --set full` capture of the persistent program kernel on this workload (theta_h = 0.3,
-                # the 88-rotation slice entered with 94 842 terms: 23 070 231 term-gate updates in one launch)
-                "traffic": {
-                    "dram_bytes_per_launch": 171.7e6,
-                    "algorithmic_bytes_per_launch": 23070231 * 96.0,
-                    "kernel": "k_program<2>",
-                    "note": "the table (<= 1.5e6 rows x 56 B) stays in the 126 MB L2: DRAM moves 8 % of the algorithmic bytes; "
-                            "the pass is bound by the dependent L2 round trips between grid barriers, not by bytes",
-                    "source": "profiles/r1i_k_program_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
-                } if args.workload == "config2" and btg == 96 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch is not re-measured here: see the ncu capture
+                "traffic": None,
+                "traffic_source": "profiles/README.md (ncu --set full captures of the rotation kernels, per launch)",
             },
             "clocks": clocks,
             "wall_s": wall,
         }
         if world == 1 and not args.no_large_table and args.workload == "config2":
             line["roofline_large_table"] = large_table_roofline(backpropagate, bpmod, peak)
+        if world == 1 and not args.no_other_configs and args.workload == "config2":
+            line["other_configs"] = other_configs(backpropagate, bpmod, torch, device, flush_buf, peak)
         if world == 1 and not args.no_cpu_baseline:
             u, t = cpu_sample(wls, args.cpu_updates)
             line["cpu_baseline"] = {
@@ -531,6 +790,13 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                 "kind": "port",
                 "sample": f"first {u} term-gate updates of the same workload ({t:.1f} s of the numpy oracle port, 1 thread)",
             }
+    else:
+        line = None
+    if not args.no_sharded_block and not sharded and args.workload == "config2":
+        blk = sharded_block(args, rank, world, device, torch, dist if world > 1 else None, backpropagate, bpmod, flush_buf)
+        if rank == 0:
+            line["sharded"] = blk
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -552,6 +818,9 @@ def main() -> None:
                     "host copy would be tens of GB (e2e is then not an end-to-end number and is reported as null)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-table", action="store_true", help="skip the extra HBM-regime roofline pass")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs 1/3/4/5 side measurements (N = 1)")
+    ap.add_argument("--no-sharded-block", action="store_true", help="skip the config-4 hash-sharded strong-scaling measurement")
+    ap.add_argument("--sharded-max-paulis", type=int, default=100_000_000, help="max_paulis of the sharded config-4 measurement")
     ap.add_argument("--sharded", action="store_true", help="N>1: shard ONE observable over all ranks instead of one observable per rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -165,6 +165,13 @@ int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double
 /* Distinct keys over several observables: _observable_oversized (backpropagation.py:419-428). */
 int obp_union_count(obp_ctx* const* ctxs, int32_t n_ctx, uint64_t* n_distinct);
 
+/* Number of qubit-wise commuting groups of n Pauli terms given as packed words [n][W] (the union of all
+ * observables' distinct keys, in the caller's row order): len(all_paulis.group_commuting(qubit_wise=True))
+ * of backpropagation.py:368-375, 433-440 — greedy colouring of the qubit-wise non-commutation graph,
+ * vertices by descending degree, ties in row order.  Needs no context; n <= 2^20. */
+int obp_qwc_group_count(int device, int n_qubits, const uint64_t* x_words, const uint64_t* z_words, uint64_t n,
+                        uint64_t* n_groups);
+
 /* Commit / roll back: the deepcopy at backpropagation.py:279-280 and the discarded slice of
  * :266-275.  obp_snapshot copies the live terms aside; obp_restore brings them back. */
 int obp_snapshot(obp_ctx* ctx);

@@ -60,18 +60,31 @@ TRACE = bool(os.environ.get("OBP_B200_TRACE"))
 last_run = RunInfo()
 
 
-def _default_capacity(num_qubits: int, operator_budget: OperatorBudget, n_obs: int, device: int) -> int:
+def _default_capacity(num_qubits: int, operator_budget: OperatorBudget, n_obs: int, device: int, comm=None) -> int:
+    """Rows of one observable's table (the whole table when it is sharded over the ranks of ``comm``).
+
+    With ``max_paulis`` set, 4 x max_paulis: a slice is given up once it holds 3 x max_paulis live terms
+    (``_stop_on_overflow``) and compaction keeps the dense rows below 1.25 x the live ones.  Bounded by device
+    memory: 60 % of what is free, divided by the bytes one term costs (table, snapshot, scratch, index — and the
+    two exchange inboxes of a shard)."""
     env = os.environ.get("OBP_B200_CAPACITY")
     if env:
         return int(env)
     free, _ = engine.device_memory(device)
     per_term = int(engine.lib().obp_bytes_per_term(num_qubits))
+    n_ranks = 1
+    if comm is not None and hasattr(comm, "rank"):  # one GPU per rank
+        n_ranks = comm.n_ranks
+        if os.environ.get("OBP_B200_P2P", "1") not in ("0", ""):
+            per_term += 2 * int(engine.lib().obp_record_bytes(num_qubits))
     limit = max(1 << 16, int(0.6 * free / per_term / max(1, n_obs)))
+    if n_ranks > 1:
+        limit = int(limit * n_ranks / 1.25)  # a rank holds 1.25 / n_ranks of the table (imbalance margin)
     if operator_budget.max_paulis is not None:
-        want = max(1 << 20, 8 * int(operator_budget.max_paulis))
+        want = max(1 << 20, 4 * int(operator_budget.max_paulis))
     else:
         want = 1 << 22
-    return int(min(want, limit, 0xFFFF0000))
+    return int(min(want, limit, 0xFFFF0000 * n_ranks))
 
 
 def backpropagate(
@@ -109,11 +122,8 @@ def backpropagate(
     # reduce_op (utils/operations.py:176-181): support set, error for a pure identity observable
     support_mask = [sum(1 << q for q in _support(o)) for o in obs_in]  # qubit sets as integer bit masks
     device = engine.default_device()
-    capacity = _default_capacity(num_qubits, operator_budget, n_obs, device)
     comm = communicator_from_env(device)  # None: one table per observable on this GPU
-    if comm is not None and hasattr(comm, "rank") and operator_budget.max_paulis is not None:
-        # one GPU per rank: the whole table may be n_ranks times what a single device holds
-        capacity = max(capacity, min(8 * int(operator_budget.max_paulis), capacity * comm.n_ranks))
+    capacity = _default_capacity(num_qubits, operator_budget, n_obs, device, comm)
     if comm is not None and ordered:
         raise NotImplementedError("OBP_B200_ROW_ORDER=1 is not supported on a sharded table")
     if comm is not None and hasattr(comm, "rank") and max_seconds is not None:

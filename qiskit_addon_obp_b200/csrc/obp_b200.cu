@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "obp_kernels.cuh"
+#include "obp_qwc.cuh"
 
 namespace {
 
@@ -663,6 +664,37 @@ struct PendingOps {
   if ((ctx) && (ctx)->broken) return (ctx)->fail(OBP_ERR_OOM, what ": the context is unusable after a failed obp_reserve"); \
   if ((ctx) && (ctx)->pending) return (ctx)->fail(OBP_ERR_BADARG, what ": a submitted gate program is pending, call obp_apply_ops_wait first")
 
+
+namespace {
+template <int W>
+int qwc_run(const ulonglong2* d_keys, ulonglong2* d_sorted, unsigned* d_degree, unsigned* d_order, unsigned* d_colour,
+            unsigned* d_ncol, unsigned n, int n_sm, std::vector<unsigned>& order, unsigned* n_colours, std::string& err) {
+  auto fail = [&](const char* what, cudaError_t e) {
+    err = std::string("obp_qwc_group_count: ") + what + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? OBP_ERR_OOM : OBP_ERR_CUDA;
+  };
+  cudaError_t e;
+  const unsigned nt = (n + OBP_QWC_TILE - 1) / OBP_QWC_TILE;
+  const unsigned gy = std::max(1u, std::min(nt, (unsigned)(n_sm * 4 + nt - 1) / nt));
+  k_qwc_degree<W><<<dim3(nt, gy), OBP_QWC_TILE>>>(d_keys, n, d_degree);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail("degree kernel", e);
+  std::vector<unsigned> degree(n);
+  if ((e = cudaMemcpy(degree.data(), d_degree, n * sizeof(unsigned), cudaMemcpyDeviceToHost)) != cudaSuccess) return fail("degrees", e);
+  // colouring order: descending degree, ties in row order (stable)
+  order.resize(n);
+  for (unsigned i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return degree[a] > degree[b]; });
+  if ((e = cudaMemcpy(d_order, order.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("order", e);
+  k_qwc_gather<<<std::min(nt * W, (unsigned)n_sm * 8), 256>>>(d_keys, d_order, n, W, d_sorted);
+  const size_t smem = (size_t)((n + 31) / 32) * sizeof(unsigned);
+  if ((e = cudaFuncSetAttribute(k_qwc_colour<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+    return fail("shared memory for the colour bit map", e);
+  k_qwc_colour<W><<<1, 1024, smem>>>(d_sorted, n, d_colour, d_ncol);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail("colour kernel", e);
+  if ((e = cudaMemcpy(n_colours, d_ncol, sizeof(unsigned), cudaMemcpyDeviceToHost)) != cudaSuccess) return fail("result", e);
+  return OBP_OK;
+}
+}  // namespace
 
 // =================================================================================================
 // C-ABI
@@ -2605,6 +2637,76 @@ int obp_union_count(obp_ctx* const* ctxs, int32_t n_ctx, uint64_t* n_distinct) {
   if (rc) return ctx->fail(rc, sc->err);
   *n_distinct = sc->h_ops[0].keys_present;
   return OBP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Qubit-wise commuting groups (backpropagation.py:368-375, 433-440), see obp_qwc.cuh.  Stand-alone: the
+// rows are the union of all observables' keys in the caller's order (ties of the greedy colouring are
+// broken by row order, like rustworkx does on Qiskit's row order).
+int obp_qwc_group_count(int device, int n_qubits, const uint64_t* x_words, const uint64_t* z_words, uint64_t n,
+                        uint64_t* n_groups) {
+  if (!n_groups || n_qubits < 1 || n_qubits > 64 * OBP_MAX_WORDS || (n && (!x_words || !z_words))) {
+    g_create_error = "obp_qwc_group_count: bad argument";
+    return OBP_ERR_BADARG;
+  }
+  *n_groups = 0;
+  if (n == 0) return OBP_OK;
+  if (n > (1ull << 20)) {  // the colour bit map lives in shared memory; beyond this the O(n^2) pass is impractical anyway
+    g_create_error = "obp_qwc_group_count: more than 2^20 terms";
+    return OBP_ERR_UNSUPPORTED;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_create_error = "obp_qwc_group_count: cudaSetDevice failed";
+    return OBP_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  int n_sm = 148;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    n_sm = prop.multiProcessorCount;
+    if (prop.major < 10) {
+      g_create_error = "obp_b200 requires an sm_100a (Blackwell B200) device";
+      return OBP_ERR_UNSUPPORTED;
+    }
+  }
+  const int W = (n_qubits + 63) / 64;
+  int Wp = 1;
+  while (Wp < W) Wp <<= 1;  // kernels are instantiated for 1, 2, 4, 8, 16 words: pad with identity words
+  std::vector<ulonglong2> keys((size_t)n * Wp, make_ulonglong2(0ull, 0ull));
+  for (u64 i = 0; i < n; ++i)
+    for (int w = 0; w < W; ++w) keys[(size_t)i * Wp + w] = make_ulonglong2(x_words[i * W + w], z_words[i * W + w]);
+  ulonglong2 *d_keys = nullptr, *d_sorted = nullptr;
+  unsigned *d_u = nullptr;  // degree | order | colour | n_colours
+  int rc = OBP_OK;
+  cudaError_t e;
+  const size_t kb = keys.size() * sizeof(ulonglong2);
+  if ((e = cudaMalloc(&d_keys, kb)) != cudaSuccess || (e = cudaMalloc(&d_sorted, kb)) != cudaSuccess ||
+      (e = cudaMalloc(&d_u, (3 * n + 1) * sizeof(unsigned))) != cudaSuccess) {
+    g_create_error = std::string("obp_qwc_group_count: cudaMalloc: ") + cudaGetErrorString(e);
+    rc = OBP_ERR_OOM;
+  }
+  if (!rc && ((e = cudaMemcpy(d_keys, keys.data(), kb, cudaMemcpyHostToDevice)) != cudaSuccess ||
+              (e = cudaMemset(d_u, 0, (3 * n + 1) * sizeof(unsigned))) != cudaSuccess)) {
+    g_create_error = std::string("obp_qwc_group_count: upload: ") + cudaGetErrorString(e);
+    rc = OBP_ERR_CUDA;
+  }
+  unsigned ncol = 0;
+  if (!rc) {
+    std::vector<unsigned> order;
+    unsigned *dg = d_u, *od = d_u + n, *co = d_u + 2 * n, *nc = d_u + 3 * n;
+    const unsigned nn = (unsigned)n;
+    switch (Wp) {
+      case 1: rc = qwc_run<1>(d_keys, d_sorted, dg, od, co, nc, nn, n_sm, order, &ncol, g_create_error); break;
+      case 2: rc = qwc_run<2>(d_keys, d_sorted, dg, od, co, nc, nn, n_sm, order, &ncol, g_create_error); break;
+      case 4: rc = qwc_run<4>(d_keys, d_sorted, dg, od, co, nc, nn, n_sm, order, &ncol, g_create_error); break;
+      case 8: rc = qwc_run<8>(d_keys, d_sorted, dg, od, co, nc, nn, n_sm, order, &ncol, g_create_error); break;
+      default: rc = qwc_run<16>(d_keys, d_sorted, dg, od, co, nc, nn, n_sm, order, &ncol, g_create_error); break;
+    }
+  }
+  cudaFree(d_keys);
+  cudaFree(d_sorted);
+  cudaFree(d_u);
+  *n_groups = ncol;
+  return rc;
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
         "obp_apply_damping": ([vp, vp, vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats)], C.c_int),
         "obp_truncate": ([vp, C.c_double, C.c_int32, C.c_double, f64p, u64p, u64p], C.c_int),
         "obp_union_count": ([C.POINTER(vp), C.c_int32, u64p], C.c_int),
+        "obp_qwc_group_count": ([C.c_int, C.c_int, vp, vp, C.c_uint64, u64p], C.c_int),
         "obp_snapshot": ([vp], C.c_int),
         "obp_restore": ([vp], C.c_int),
         "obp_reserve": ([vp, C.c_uint64], C.c_int),
@@ -184,7 +185,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count"
 ).split()
 
 
@@ -738,6 +739,22 @@ class TermTable:
             yield table, md
         finally:
             table.release()
+
+
+def qwc_group_count(op: SparsePauliOp, device: int | None = None) -> int:
+    """``len(op.group_commuting(qubit_wise=True))`` on the device (``backpropagation.py:368-375, 433-440``)."""
+    xw, zw = op.packed()
+    xw = np.ascontiguousarray(xw, dtype="<u8")
+    zw = np.ascontiguousarray(zw, dtype="<u8")
+    out = C.c_uint64()
+    rc = lib().obp_qwc_group_count(
+        default_device() if device is None else int(device), op.num_qubits,
+        xw.ctypes.data_as(C.c_void_p), zw.ctypes.data_as(C.c_void_p), len(op), C.byref(out),
+    )
+    if rc != OBP_OK:
+        msg = (lib().obp_last_error(None) or b"").decode()
+        raise (MemoryError if rc == OBP_ERR_OOM else EngineError)(f"obp_qwc_group_count failed ({rc}): {msg}")
+    return int(out.value)
 
 
 def union_count(tables: list[TermTable]) -> int:

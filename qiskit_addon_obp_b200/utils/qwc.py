@@ -1,11 +1,20 @@
-"""Number of qubit-wise commuting groups (host side).
+"""Number of qubit-wise commuting groups.
 
 The reference calls ``len(op.group_commuting(qubit_wise=True))`` ([EXT] Qiskit + rustworkx,
 ``backpropagation.py:369,434``): build the graph whose edges join Paulis that do *not* commute
-qubit-wise and colour it greedily, largest degree first (stable).  This stays on the host like
-the reference's own graph colouring; it is O(n^2) (on packed 64-qubit words) and meant for the operators
-for which ``max_qwc_groups`` is practical (up to ~10^5 terms).  Row order follows the engine's table order, so on operators where
-the greedy colouring is order-sensitive the count can differ from Qiskit's.
+qubit-wise and colour it greedily, largest degree first, ties in row order.
+
+Operators of ``OBP_B200_QWC_DEVICE_MIN`` (default 256) terms and more are counted on the GPU
+(``obp_qwc_group_count``: all n^2 pair tests on packed words across the whole device, then the sequential
+colouring in one CTA; ``csrc/obp_qwc.cuh``) and there is no CPU fallback for them.  Smaller ones — the input
+validation of ``backpropagate`` sees a handful of terms before any device table exists — are counted right
+here with the same algorithm on the same packed words.
+
+Row order: ties of the colouring are broken by the order of the rows handed in.  In row-order mode
+(``OBP_B200_ROW_ORDER=1``) that is exactly the reference's order; on the fast path it is the table's order, so
+on an operator whose greedy colouring is order-sensitive the count can differ from Qiskit's (the reference's
+notebook outputs — 10/10/14/20/9/9/10+8 and 10/6 groups — reproduce in both modes,
+``tests/test_notebook_anchors.py``).
 """
 
 from __future__ import annotations
@@ -16,6 +25,17 @@ from ..ir import SparsePauliOp
 
 
 def qwc_group_count(op: SparsePauliOp) -> int:
+    """``len(op.group_commuting(qubit_wise=True))``: on the device from ``OBP_B200_QWC_DEVICE_MIN`` terms up."""
+    import os
+
+    if len(op) >= int(os.environ.get("OBP_B200_QWC_DEVICE_MIN", "256")):
+        from .. import engine
+
+        return engine.qwc_group_count(op)
+    return _qwc_group_count_host(op)
+
+
+def _qwc_group_count_host(op: SparsePauliOp) -> int:
     """Greedy colouring (largest degree first, stable) of the graph joining Paulis that do not commute qubit-wise.
 
     Two Paulis clash iff on some qubit both are non-identity and different.  On the packed words that is

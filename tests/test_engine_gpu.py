@@ -766,3 +766,42 @@ def test_per_gate_debug_log_matches_reference_sizes(caplog):
     logged = [tuple(map(int, m.groups())) for r in caplog.records if (m := pat.search(r.getMessage()))]
     assert logged == [(gid, size) for _, _, gid, size in tr.gate_sizes]
     assert sum(1 for _ in logged) == tr.applied_gates
+
+
+# ---- QWC groups on the device (backpropagation.py:433-440) --------------------------
+@pytest.mark.parametrize("nq,n,dens", [(1, 3, 0.9), (5, 40, 0.4), (10, 700, 0.35), (64, 1500, 0.05), (70, 3000, 0.04),
+                                       (127, 5000, 0.02), (300, 2000, 0.01), (1000, 1200, 0.004)])
+def test_qwc_group_count_device_matches_host_and_oracle(nq, n, dens, monkeypatch):
+    """obp_qwc_group_count (degrees over all pairs + greedy colouring by descending degree, ties in row order)
+    against the host statement on packed words and the oracle's restatement on the bool arrays."""
+    from qiskit_addon_obp_b200 import engine
+    from qiskit_addon_obp_b200.utils.qwc import _qwc_group_count_host, qwc_group_count
+
+    rng = np.random.default_rng(nq * 7 + n)
+    x = rng.random((n, nq)) < dens
+    z = rng.random((n, nq)) < dens
+    op = SparsePauliOp((x, z), np.ones(n))
+    want = _qwc_group_count_host(op)
+    assert engine.qwc_group_count(op) == want
+    if n <= 1500:
+        assert oracle.qwc_group_count(op) == want
+    # a different row order may legitimately give another count; the same order must not
+    perm = rng.permutation(n)
+    op2 = SparsePauliOp((x[perm], z[perm]), np.ones(n))
+    assert engine.qwc_group_count(op2) == _qwc_group_count_host(op2)
+    monkeypatch.setenv("OBP_B200_QWC_DEVICE_MIN", "0")
+    assert qwc_group_count(op) == want
+
+
+def test_max_qwc_groups_through_backpropagate_on_device(monkeypatch):
+    """max_qwc_groups with every count taken on the device (threshold 0), against the oracle's history."""
+    monkeypatch.setenv("OBP_B200_QWC_DEVICE_MIN", "0")
+    obs, slices = window_workload(20, 3)
+    for row_order in ("0", "1"):
+        monkeypatch.setenv("OBP_B200_ROW_ORDER", row_order)
+        got, rest, md = backpropagate(obs, slices, operator_budget=OperatorBudget(max_qwc_groups=60))
+        want, rest_w, md_w = oracle.backpropagate(obs, slices, operator_budget=OperatorBudget(max_qwc_groups=60))
+        assert len(rest) == len(rest_w) and 0 < len(rest) < len(slices)
+        assert_same_operator(got, want)
+        if row_order == "1":  # the reference's row order: the greedy count is then the reference's, slice by slice
+            assert [s.num_qwc_groups for s in md.backpropagation_history] == [s.num_qwc_groups for s in md_w.backpropagation_history]

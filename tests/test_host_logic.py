@@ -330,11 +330,11 @@ def test_slice_plan_full_cone_shortcut_and_unsupported_gate():
 
 @pytest.mark.parametrize("nq,n", [(1, 3), (5, 40), (70, 200), (130, 300)])
 def test_qwc_group_count_on_packed_words_matches_the_bool_version(nq, n):
-    from qiskit_addon_obp_b200.utils.qwc import _qwc_group_count_bool
+    from qiskit_addon_obp_b200.utils.qwc import _qwc_group_count_bool, _qwc_group_count_host
 
     rng = np.random.default_rng(nq + n)
     op = SparsePauliOp((rng.random((n, nq)) < 0.3, rng.random((n, nq)) < 0.3), np.ones(n))
-    assert qwc_group_count(op) == _qwc_group_count_bool(op)
+    assert _qwc_group_count_host(op) == _qwc_group_count_bool(op)
 
 
 # ---- compiled-slice cache: valid only for the very same instruction objects ---------------
