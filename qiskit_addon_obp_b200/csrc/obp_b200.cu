@@ -89,6 +89,9 @@ struct obp_ctx {
   u64 xseq = 0;            // split rotations run so far (identical on all ranks)
   bool shard_rot_open = false;
   int rot_ctas_per_sm = 0;  // resident CTAs of k_rotate per SM (occupancy API)
+  int rotp_ctas_per_sm = 0; // the same for k_rotate_pipe
+  bool rot_pipe = true;     // tables beyond the L2 use the software-pipelined rotation kernel
+  u64 rot_pipe_min_rows = 1ull << 20;
   int prog_ctas_per_sm = 0; // resident CTAs of k_program per SM; 0 = cooperative launch unavailable
   unsigned char* d_prog = nullptr;  // persistent program: entries + parameter pool (device)
   unsigned char* h_prog = nullptr;  // pinned staging of the same
@@ -758,7 +761,7 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     int rc = ensure_ops(ctx, 256);  // also allocates the table state (d_st / h_st) and the start stamp
     if (rc) return rc;
     CU(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 2));
-    CU(cudaMalloc(&ctx->d_partial, sizeof(double) * (size_t)ctx->n_sm * 8));
+    CU(cudaMalloc(&ctx->d_partial, sizeof(double) * (size_t)ctx->n_sm * 8 * OBP_TRUNC_NODES));
     CU(cudaMalloc(&ctx->d_scalar, sizeof(double) * 2));
     CU(cudaMalloc(&ctx->d_cols, sizeof(u64) * 2 * 64 * ctx->W));
     CU(cudaMalloc(&ctx->d_cnt, sizeof(ShardCnt)));
@@ -767,6 +770,8 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     if (rc) return rc;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->rot_ctas_per_sm, k_rotate, OBP_BS, 0));
     if (ctx->rot_ctas_per_sm < 1) ctx->rot_ctas_per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->rotp_ctas_per_sm, k_rotate_pipe, OBP_BS, 0));
+    if (ctx->rotp_ctas_per_sm < 1) ctx->rotp_ctas_per_sm = 1;
     if (ctx->W <= 2 && prop.cooperativeLaunch) {
       if (ctx->W == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prog_ctas_per_sm, k_program<1>, OBP_BS, 0));
       else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prog_ctas_per_sm, k_program<2>, OBP_BS, 0));
@@ -1480,7 +1485,10 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
         prog.add(PROG_ROTATE, n_slots, &p, sizeof(p), OBP_K_ROTATE);
       } else {
         Bracket br(ctx, OBP_K_ROTATE);
-        k_rotate<<<grid_for(ctx, bound, ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(t, p);  // one wave
+        if (ctx->rot_pipe && p.ngw <= 2 && ctx->n_dense >= ctx->rot_pipe_min_rows)
+          k_rotate_pipe<<<grid_for(ctx, bound, ctx->rotp_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(t, p);  // one wave
+        else
+          k_rotate<<<grid_for(ctx, bound, ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(t, p);  // one wave
         CU(cudaGetLastError());
       }
       slot_of_op[k] = n_slots;
@@ -2323,14 +2331,19 @@ int obp_truncate(obp_ctx* ctx, double budget, int32_t p_norm, double tol, double
     const u64 before = ctx->n_live;
     Tab t = make_tab(ctx);
     double* a = (double*)ctx->spare16;
-    // two CTAs per SM at most: every bisection step ends in two grid barriers, which cost more with more CTAs
-    int g = std::min(grid_for(ctx, ctx->n_dense), std::min(ctx->trunc_ctas_per_sm, 2) * ctx->n_sm);
+    // two CTAs per SM at most (a pass ends in two grid barriers, which cost more with more CTAs); a small table
+    // runs in ONE CTA: its barriers are __syncthreads
+    int g = ctx->n_dense <= OBP_TRUNC_ONE_CTA ? 1
+                                               : std::min(grid_for(ctx, ctx->n_dense), std::min(ctx->trunc_ctas_per_sm, 2) * ctx->n_sm);
     u64 ep = ++ctx->epoch;
     void* args[] = {(void*)&t, (void*)&a, (void*)&ctx->d_partial, (void*)&ctx->d_ts, (void*)&budget, (void*)&p_norm,
                     (void*)&tol, (void*)&ep};
     {
       Bracket br(ctx, OBP_K_TRUNCATE);
-      CU(cudaLaunchCooperativeKernel((void*)k_trunc_search, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
+      if (g == 1)  // no grid barrier inside: an ordinary launch (a cooperative one costs several microseconds more)
+        k_trunc_search<<<1, OBP_BS, 0, ctx->stream>>>(t, a, ctx->d_partial, ctx->d_ts, budget, p_norm, tol, ep);
+      else
+        CU(cudaLaunchCooperativeKernel((void*)k_trunc_search, dim3(g), dim3(OBP_BS), args, 0, ctx->stream));
     }
     CU(cudaMemcpyAsync(ctx->h_ts, ctx->d_ts, sizeof(TruncState), cudaMemcpyDeviceToHost, ctx->stream));
     int rc1 = sync_state(ctx);
@@ -2565,6 +2578,8 @@ int obp_configure(obp_ctx* ctx, int32_t option, int64_t value) {
   switch (option) {
     case OBP_OPT_PROGRAM: ctx->use_program = value != 0; return OBP_OK;
     case OBP_OPT_PROGRAM_MAX_ROWS: ctx->prog_max_rows = value < 0 ? 0 : (u64)value; return OBP_OK;
+    case OBP_OPT_ROTATE_PIPE: ctx->rot_pipe = value != 0; return OBP_OK;
+    case OBP_OPT_ROTATE_PIPE_MIN_ROWS: ctx->rot_pipe_min_rows = value < 0 ? 0 : (u64)value; return OBP_OK;
     default: return ctx->fail(OBP_ERR_BADARG, "obp_configure: unknown option");
   }
 }

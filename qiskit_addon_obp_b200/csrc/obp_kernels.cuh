@@ -113,13 +113,15 @@ __device__ __forceinline__ void gen_word(const RotP& p, int w, u64& gx, u64& gz)
 
 // Find the row holding key(i) ^ G.  Returns its row id or -1.  *fresh is set when the row was
 // killed during this epoch (it was live when the kernel started).
+// `have_e0`: the entry of the first slot was loaded ahead of time (pipelined kernel) and is passed as e0.
 __device__ __forceinline__ long long find_partner(const Tab& t, const RotP& p, u64 i, u64 h2,
-                                                  u64 n_scan, double2& cq, bool& fresh) {
+                                                  u64 n_scan, double2& cq, bool& fresh, bool have_e0 = false,
+                                                  u64 e0 = 0) {
   const u64 fp = h2 >> 32;
   u64 s = h2 & t.mask;
   fresh = false;
   for (u64 probes = 0; probes <= t.mask; ++probes) {
-    const u64 e = ld_volatile(&t.index[s]);
+    const u64 e = (have_e0 && probes == 0) ? e0 : ld_volatile(&t.index[s]);
     if (e == OBP_EMPTY) return -1;
     if ((e >> 32) == fp) {
       const u64 j = e & 0xffffffffull;
@@ -307,6 +309,192 @@ __device__ __forceinline__ void rotate_body(const Tab& t, const RotP& p, const u
     }
   }
   if (lane == 0 && dl) atomicAdd(live_ctr, (u64)dl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rotate_body_pipe — the same pass as rotate_body for tables far beyond the L2, as a three-stage software
+// pipeline over the rows a thread visits (row t+2: streaming loads of coefficient / generator word / hash;
+// row t+1: commutation test and the load of its FIRST index slot; row t: partner loads, update, append).
+// In rotate_body an anticommuting row waits for two dependent DRAM round trips back to back (index slot,
+// then partner key + coefficient); here the index slot of the next row is in flight while the partner of the
+// current one is, so a thread keeps two random accesses and one streaming batch outstanding instead of one.
+// Same arithmetic, same counters, same append protocol.  Generators on at most two 64-bit words (every one-
+// and two-qubit rotation); wider ones use rotate_body.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rotate_body_pipe(const Tab& t, const RotP& p, const u64 n, u64* live_ctr) {
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
+  int dlive = 0;
+  double sum_re = 0.0, sum_im = 0.0;
+  bool overflow = false;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const ulonglong2* __restrict__ col0 = t.xz[p.gw[0]];
+  const ulonglong2* __restrict__ col1 = t.xz[p.ngw > 1 ? p.gw[1] : p.gw[0]];
+  const bool two = p.ngw > 1;
+  const u64 first = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+  // stage registers.  C: streaming loads issued; B: + commutation data and first index entry; A: being finished
+  double2 cC = make_double2(0.0, 0.0), cB = cC, cA = cC;
+  ulonglong2 k0C = make_ulonglong2(0ull, 0ull), k1C = k0C, k0B = k0C, k1B = k0C;
+  u64 hC = 0, hB = 0, eB = OBP_EMPTY, eA = OBP_EMPTY, h2A = 0;
+  int metaB = 0, metaA = 0;  // bit 0: needs the partner; bits 1-2: E; bit 3: s; bit 4: own_bit; bit 5: row in range and live
+  auto load_stream = [&](u64 i) {
+    if (i < n) {
+      cC = t.coef[i];
+      k0C = col0[i];
+      if (two) k1C = col1[i];
+      hC = t.hash[i];
+    } else {
+      cC = make_double2(0.0, 0.0);  // reads as a dead row
+      hC = 0;
+    }
+  };
+  // commutation test of the row in stage B and, if it needs its partner, the load of its first index slot
+  auto probe = [&](u64 i) {
+    metaB = 0;
+    eB = OBP_EMPTY;
+    if (i < n && is_live(cB)) {
+      int sp = 0, E = p.yG, own_bit = 0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k < p.ngw) {
+          const ulonglong2 key = k == 0 ? k0B : k1B;
+          const u64 m = p.gx[k] | p.gz[k];
+          sp += __popcll(key.x & p.gz[k]) + __popcll(key.y & p.gx[k]);
+          E += __popcll(key.x & key.y & m) - __popcll((key.x ^ p.gx[k]) & (key.y ^ p.gz[k]) & m) +
+               2 * __popcll(key.y & p.gx[k]);
+          if (k == p.canon_slot) own_bit = ((p.canon_z ? key.y : key.x) & p.canon_bit) != 0;
+        }
+      }
+      const int s = sp & 1;
+      const int need = (p.exact || s) ? 1 : 0;
+      metaB = need | ((E & 3) << 1) | (s << 3) | (own_bit << 4) | 32;
+      if (need) eB = __ldcg(&t.index[(hB ^ p.hG) & t.mask]);
+    }
+  };
+  // prologue: rows `first` (-> B, probed) and `first + stride` (-> C)
+  load_stream(first + lane);
+  cB = cC; k0B = k0C; k1B = k1C; hB = hC;
+  load_stream(first + stride + lane);
+  probe(first + lane);
+  for (u64 base = first; base < n; base += stride) {
+    const u64 i = base + lane;
+    // rotate the pipeline: A <- B, B <- C, C <- new loads
+    cA = cB; eA = eB; metaA = metaB; h2A = hB ^ p.hG;
+    cB = cC; k0B = k0C; k1B = k1C; hB = hC;
+    load_stream(i + 2 * stride);
+    probe(i + stride);
+    bool want_append = false;
+    double2 app_c = make_double2(0.0, 0.0);
+    if (metaA & 32) {
+      const double2 c = cA;
+      const int s = (metaA >> 3) & 1, E = (metaA >> 1) & 3, own_bit = (metaA >> 4) & 1;
+      if (!(metaA & 1)) {
+        // commuting row, fast mode: only its own key can change (row filter)
+        const RowSet rp = rot_rows_self(c, s, p);
+        if (rp.nself < 2) {
+          if (rp.nself == 0 || is_small(rp.self, p.atol)) {
+            t.coef[i] = tombstone(p.epoch);
+            dlive--;
+          } else {
+            t.coef[i] = rp.self;
+          }
+        }
+      } else {
+        const RowSet rp = rot_rows(c, E, s, p);
+        double2 cq;
+        bool fresh;
+        const long long j = find_partner(t, p, i, h2A, n, cq, fresh, true, eA);
+        if (j >= 0 && !fresh && !own_bit) {
+          const RowSet rq = rot_rows(cq, (4 - E) & 3, s, p);
+          const bool pres_p = rp.nself > 0 || rq.ncross > 0;
+          const bool pres_q = rq.nself > 0 || rp.ncross > 0;
+          double2 np_ = rp.self, nq_ = rq.self;
+          if (rq.ncross) np_ = rp.nself ? cadd(np_, rq.cross) : rq.cross;
+          if (rp.ncross) nq_ = rq.nself ? cadd(nq_, rp.cross) : rp.cross;
+          rows_surv += rp.nself + rp.ncross + rq.nself + rq.ncross;
+          keys_present += (unsigned)pres_p + (unsigned)pres_q;
+          if (pres_p && !is_small(np_, p.atol)) {
+            t.coef[i] = np_;
+          } else {
+            if (pres_p) { cancelled++; sum_re += np_.x; sum_im += np_.y; }
+            t.coef[i] = tombstone(p.epoch);
+            dlive--;
+          }
+          if (pres_q && !is_small(nq_, p.atol)) {
+            t.coef[j] = nq_;
+          } else {
+            if (pres_q) { cancelled++; sum_re += nq_.x; sum_im += nq_.y; }
+            t.coef[j] = tombstone(p.epoch);
+            dlive--;
+          }
+        } else if (j < 0) {
+          rows_surv += rp.nself + rp.ncross;
+          keys_present += (unsigned)(rp.nself > 0) + (unsigned)(rp.ncross > 0);
+          if (rp.nself > 0 && !is_small(rp.self, p.atol)) {
+            if (rp.self.x != c.x || rp.self.y != c.y) t.coef[i] = rp.self;
+          } else {
+            if (rp.nself > 0) { cancelled++; sum_re += rp.self.x; sum_im += rp.self.y; }
+            t.coef[i] = tombstone(p.epoch);
+            dlive--;
+          }
+          if (rp.ncross > 0) {
+            if (!is_small(rp.cross, p.atol)) {
+              want_append = true;
+              app_c = rp.cross;
+            } else {
+              cancelled++; sum_re += rp.cross.x; sum_im += rp.cross.y;
+            }
+          }
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, want_append);
+    if (bal) {
+      u64 wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&t.st->n_append, (u64)__popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (want_append) {
+        const u64 row = wbase + __popc(bal & ((1u << lane) - 1u));
+        if (row < t.cap) {
+          for (int w = 0; w < t.W; ++w) {
+            u64 gx, gz;
+            gen_word(p, w, gx, gz);
+            ulonglong2 key = t.xz[w][i];
+            key.x ^= gx;
+            key.y ^= gz;
+            t.xz[w][row] = key;
+          }
+          t.coef[row] = app_c;
+          t.hash[row] = h2A;
+          if (!index_insert(t, h2A, row)) atomicOr(&t.st->error, OBP_ERR_BIT_INDEX);
+          dlive++;
+        } else {
+          overflow = true;
+        }
+      }
+    }
+  }
+  if (overflow) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
+  const long long dl = warp_sum_i64((long long)dlive);
+  if (p.exact) {
+    const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present), cz = warp_sum_u64(cancelled);
+    const double sr = warp_sum_f64(sum_re), si = warp_sum_f64(sum_im);
+    if (lane == 0) {
+      OpStat* o = &t.ops[p.slot];
+      if (a) atomicAdd(&o->rows_surv, a);
+      if (b) atomicAdd(&o->keys_present, b);
+      if (cz) { atomicAdd(&o->cancelled, cz); atomicAdd(&o->sum_re, sr); atomicAdd(&o->sum_im, si); }
+    }
+  }
+  if (lane == 0 && dl) atomicAdd(live_ctr, (u64)dl);
+}
+
+#ifndef OBP_ROTP_MINB
+#define OBP_ROTP_MINB 3
+#endif
+__global__ void __launch_bounds__(OBP_BS, OBP_ROTP_MINB) k_rotate_pipe(Tab t, const __grid_constant__ RotP p) {
+  rotate_body_pipe(t, p, t.st->n_scan, &t.st->n_live);
+  finish_kernel(t, p.slot);
 }
 
 __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate(Tab t, const __grid_constant__ RotP p) {
@@ -1568,22 +1756,49 @@ __global__ void __launch_bounds__(OBP_BS) k_pack_rows(Tab t, u64* __restrict__ o
 
 // ================================================================================================
 // k_trunc_search — truncate_binary_search (utils/truncating.py:171-204) in ONE cooperative launch:
-// |c|^p and its maximum, the whole bisection (one masked sum per step, fixed reduction tree, grid
-// barrier between the steps) and the final kill pass.  The host-driven version needs two launches
-// and one synchronisation per step (~30 steps per slice).
+// |c|^p and its maximum, the whole bisection and the final kill pass.
+//
+// The bisection is a chain of ~27 dependent masked sums; each needs every CTA's partial sum, i.e. two grid
+// barriers.  Instead of one step per pass, a pass evaluates the masked sums of ALL thresholds the next
+// OBP_TRUNC_LEVELS steps can ask for: the 2^L - 1 nodes of the decision tree below the current
+// (upper, lower), each `mid` computed with the reference's own expression (upper + lower) / 2 from its
+// parent's bounds, so every threshold — and every sum, accumulated per threshold with the same fixed
+// reduction tree — is bit-identical to what the one-step-per-pass search would produce.  CTA 0 then walks
+// the tree with the reference's loop (`<`, `>`, the isclose exit, :179-196) for up to L steps.  6 passes
+// instead of 27; a table of <= OBP_TRUNC_ONE_CTA rows runs in a single CTA with no grid barrier at all.
 // ================================================================================================
+#define OBP_TRUNC_LEVELS 5
+#define OBP_TRUNC_NODES ((1 << OBP_TRUNC_LEVELS) - 1)
+#define OBP_TRUNC_ONE_CTA 8192
+
 struct TruncState {
   double upper, lower, upper_err, lower_err;
   u64 steps;
 };
 
+// np.isclose(upper_error, lower_error, atol=tol) with the default rtol = 1e-5 (:181)
+__device__ __forceinline__ bool trunc_done(double upper, double lower, double ue, double le, double tol) {
+  const bool close = fabs(ue - le) <= tol + 1e-5 * fabs(le);
+  return !((upper - lower) > tol) || close;
+}
+
 __global__ void __launch_bounds__(OBP_BS) k_trunc_search(Tab t, double* __restrict__ a, double* __restrict__ partial,
                                                           TruncState* __restrict__ ts, double budget, int p_norm,
                                                           double tol, u64 epoch) {
   namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  __shared__ double s_w[OBP_BS / 32];
+  const bool one_cta = gridDim.x == 1;
+  auto barrier = [&]() {
+    if (one_cta) {
+      __syncthreads();
+    } else {
+      __threadfence();
+      cg::this_grid().sync();
+    }
+  };
+  __shared__ double s_w[OBP_BS / 32][OBP_TRUNC_NODES];
+  __shared__ double s_thr[OBP_TRUNC_NODES], s_tot[OBP_TRUNC_NODES];
   const u64 n = t.st->n_scan;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // ---- a = |c|^p, global maximum ----------------------------------------------------------------
   double mx = 0.0;
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
@@ -1598,9 +1813,8 @@ __global__ void __launch_bounds__(OBP_BS) k_trunc_search(Tab t, double* __restri
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(&t.st->amax_bits, (u64)__double_as_longlong(mx));
-  __threadfence();
-  grid.sync();
+  if (lane == 0 && mx > 0.0) atomicMax(&t.st->amax_bits, (u64)__double_as_longlong(mx));
+  barrier();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ts->upper = __longlong_as_double((long long)ld_volatile(&t.st->amax_bits));
     ts->lower = 0.0;
@@ -1608,63 +1822,98 @@ __global__ void __launch_bounds__(OBP_BS) k_trunc_search(Tab t, double* __restri
     ts->lower_err = 0.0;
     ts->steps = 0;
   }
-  __threadfence();
-  grid.sync();
-  // ---- bisection (:179-196); every CTA evaluates the same exit test on the same state -----------
-  for (int it = 0; it < 4096; ++it) {
+  barrier();
+  // ---- bisection, OBP_TRUNC_LEVELS steps per pass ---------------------------------------------------
+  for (int round = 0; round < 4096; ++round) {
     const double upper = *(volatile double*)&ts->upper, lower = *(volatile double*)&ts->lower;
     const double ue = *(volatile double*)&ts->upper_err, le = *(volatile double*)&ts->lower_err;
-    const bool close = fabs(ue - le) <= tol + 1e-5 * fabs(le);  // np.isclose(upper_error, lower_error, atol=tol)
-    if (!((upper - lower) > tol) || close) break;
-    const double mid = (upper + lower) / 2;
-    double acc = 0.0;
-    for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
-      const double v = a[i];
-      if (v >= 0.0 && v < mid) acc += v;
-    }
-    acc = warp_sum_f64(acc);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
-    __syncthreads();
+    if (trunc_done(upper, lower, ue, le, tol)) break;  // every CTA evaluates the same test on the same state
+    // decision tree in heap order: node k has bounds (up[k], lo[k]); child 2k+1 = "mid_error > budget"
+    // (upper = mid), child 2k+2 = "mid_error <= budget" (lower = mid)
     if (threadIdx.x == 0) {
-      double tot = 0.0;
+      double up[OBP_TRUNC_NODES], lo[OBP_TRUNC_NODES];
+      up[0] = upper;
+      lo[0] = lower;
 #pragma unroll
-      for (int w = 0; w < OBP_BS / 32; ++w) tot += s_w[w];
-      partial[blockIdx.x] = tot;
-    }
-    __threadfence();
-    grid.sync();
-    if (blockIdx.x == 0) {  // fixed-order reduction of the per-CTA partial sums by the whole CTA
-      double s = 0.0;
-      for (unsigned b = threadIdx.x; b < gridDim.x; b += OBP_BS) s += *(volatile double*)&partial[b];
-      s = warp_sum_f64(s);
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < OBP_BS / 32; ++w) tot += s_w[w];
-        const double mid_err = p_norm == 1 ? tot : pow(tot, 1.0 / (double)p_norm);
-        if (mid_err <= budget) { ts->lower = mid; ts->lower_err = mid_err; }
-        else { ts->upper = mid; ts->upper_err = mid_err; }
-        ts->steps = (u64)it + 1;
+      for (int k = 0; k < OBP_TRUNC_NODES; ++k) {
+        const double mid = (up[k] + lo[k]) / 2;  // :185
+        s_thr[k] = mid;
+        if (2 * k + 2 < OBP_TRUNC_NODES) {
+          up[2 * k + 1] = mid; lo[2 * k + 1] = lo[k];
+          up[2 * k + 2] = up[k]; lo[2 * k + 2] = mid;
+        }
       }
     }
-    __threadfence();
-    grid.sync();
+    __syncthreads();
+    double thr[OBP_TRUNC_NODES], acc[OBP_TRUNC_NODES];
+#pragma unroll
+    for (int k = 0; k < OBP_TRUNC_NODES; ++k) { thr[k] = s_thr[k]; acc[k] = 0.0; }
+    for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+      const double v = a[i];
+      if (v >= 0.0) {
+#pragma unroll
+        for (int k = 0; k < OBP_TRUNC_NODES; ++k)
+          if (v < thr[k]) acc[k] += v;  // strict <, :187
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < OBP_TRUNC_NODES; ++k) {
+      const double r = warp_sum_f64(acc[k]);
+      if (lane == 0) s_w[warp][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < OBP_TRUNC_NODES) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < OBP_BS / 32; ++w) tot += s_w[w][threadIdx.x];
+      if (one_cta) s_tot[threadIdx.x] = tot;
+      else partial[(size_t)blockIdx.x * OBP_TRUNC_NODES + threadIdx.x] = tot;
+    }
+    barrier();
+    if (blockIdx.x == 0) {
+      if (!one_cta) {
+        // fixed-order reduction of the per-CTA partial sums: warp w takes the thresholds w, w + 8, ...
+        for (int k = (int)warp; k < OBP_TRUNC_NODES; k += OBP_BS / 32) {
+          double sum = 0.0;
+          for (unsigned b = lane; b < gridDim.x; b += 32u) sum += *(volatile double*)&partial[(size_t)b * OBP_TRUNC_NODES + k];
+          sum = warp_sum_f64(sum);
+          if (lane == 0) s_tot[k] = sum;
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        double up = upper, lo = lower, uerr = ue, lerr = le;
+        u64 steps = ts->steps;
+        int k = 0;
+        for (int lvl = 0; lvl < OBP_TRUNC_LEVELS; ++lvl) {
+          if (trunc_done(up, lo, uerr, lerr, tol)) break;
+          const double mid = s_thr[k], tot = s_tot[k];
+          const double mid_err = p_norm == 1 ? tot : pow(tot, 1.0 / (double)p_norm);
+          if (mid_err <= budget) { lo = mid; lerr = mid_err; k = 2 * k + 2; }
+          else { up = mid; uerr = mid_err; k = 2 * k + 1; }
+          ++steps;
+        }
+        ts->upper = up;
+        ts->lower = lo;
+        ts->upper_err = uerr;
+        ts->lower_err = lerr;
+        ts->steps = steps;
+      }
+    }
+    barrier();
   }
   // ---- keep a > lower (:199) -----------------------------------------------------------------------
-  const double thr = *(volatile double*)&ts->lower;
+  const double thr_keep = *(volatile double*)&ts->lower;
   unsigned removed = 0;
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
     const double v = a[i];
-    if (v >= 0.0 && !(v > thr)) {
+    if (v >= 0.0 && !(v > thr_keep)) {
       t.coef[i] = tombstone(epoch);
       removed++;
     }
   }
   const u64 r = warp_sum_u64(removed);
-  if ((threadIdx.x & 31) == 0 && r) {
+  if (lane == 0 && r) {
     atomicAdd(&t.st->removed, r);
     atomicAdd(&t.st->n_live, (u64)(-(long long)r));
   }

@@ -611,14 +611,16 @@ def window_workload(nq, rounds):
 
 
 # ---- every code path of the gate kernels against the oracle ----------------------
-@pytest.mark.parametrize("mode", ["no-program", "switch-at-64-rows", "switch-at-2000-rows"])
+@pytest.mark.parametrize("mode", ["no-program", "no-program-pipelined", "switch-at-64-rows", "switch-at-2000-rows"])
 @pytest.mark.parametrize("nq", [6, 64, 70, 127])
 def test_program_and_standalone_kernels_agree_with_oracle(nq, mode, monkeypatch):
     """Tables of <= 128 qubits run a slice either inside the persistent program kernel or as stand-alone
     k_rotate / k_clifford_reg launches (>= 2^18 rows by default).  Forced here: everything stand-alone, and a
     row threshold low enough that the run changes path part-way — all against the oracle, counters included."""
-    if mode == "no-program":
+    if mode.startswith("no-program"):
         monkeypatch.setenv("OBP_B200_NO_PROGRAM", "1")
+        # k_rotate_pipe (the software-pipelined kernel of tables beyond the L2) forced on from the first row, or off
+        monkeypatch.setenv("OBP_B200_ROT_PIPE_MIN_ROWS", "0" if mode.endswith("pipelined") else str(1 << 40))
     else:
         monkeypatch.setenv("OBP_B200_PROG_MAX_ROWS", "64" if "64" in mode else "2000")
     obs, slices = window_workload(nq, 4)
@@ -805,3 +807,18 @@ def test_max_qwc_groups_through_backpropagate_on_device(monkeypatch):
         assert_same_operator(got, want)
         if row_order == "1":  # the reference's row order: the greedy count is then the reference's, slice by slice
             assert [s.num_qwc_groups for s in md.backpropagation_history] == [s.num_qwc_groups for s in md_w.backpropagation_history]
+
+
+@pytest.mark.parametrize("nq", [130, 200, 1000])
+def test_pipelined_rotation_kernel_wide_tables(nq, monkeypatch):
+    """k_rotate_pipe on tables wider than 128 qubits (W = 3, 4, 16), incl. generators that straddle two words."""
+    monkeypatch.setenv("OBP_B200_ROT_PIPE_MIN_ROWS", "0")
+    rng = np.random.default_rng(nq)
+    slices = random_slices(nq, 6, rng, gates_per_slice=8)
+    for k, qc in enumerate(slices):
+        qc.rzz(0.37, 63, 64)  # generator on two words
+        qc.rxx(-0.6, 127, 128)
+        qc.rx(0.45, 64 + k)
+    obs = SparsePauliOp.from_sparse_list([("ZY", [63, 64], 1.0), ("X", [128], 0.5), ("ZZ", [64, 127], -0.3)], nq)
+    _compare(obs, slices)
+    _compare(obs, slices, truncation_error_budget=setup_budget(max_error_per_slice=1e-3))
