@@ -190,13 +190,9 @@ int obp_is_broken(const obp_ctx* ctx);
  *   OBP_OPT_PROGRAM           1 (default): tables of <= 128 qubits run a slice's gate program in one
  *                             persistent cooperative launch; 0: one kernel per gate / Clifford batch.
  *   OBP_OPT_PROGRAM_MAX_ROWS  tables with at least this many dense rows use the stand-alone kernels
- *                             (default 2^18).
- *   OBP_OPT_ROTATE_PIPE       1 (default): stand-alone rotations on tables of at least
- *   OBP_OPT_ROTATE_PIPE_MIN_ROWS rows (default 2^20) run the software-pipelined kernel k_rotate_pipe. */
+ *                             (default 2^18). */
 #define OBP_OPT_PROGRAM 1
 #define OBP_OPT_PROGRAM_MAX_ROWS 2
-#define OBP_OPT_ROTATE_PIPE 3
-#define OBP_OPT_ROTATE_PIPE_MIN_ROWS 4
 int obp_configure(obp_ctx* ctx, int32_t option, int64_t value);
 
 /* Row-order mode (off by default).  The reference's simplify() returns rows in the order of each

@@ -89,9 +89,6 @@ struct obp_ctx {
   u64 xseq = 0;            // split rotations run so far (identical on all ranks)
   bool shard_rot_open = false;
   int rot_ctas_per_sm = 0;  // resident CTAs of k_rotate per SM (occupancy API)
-  int rotp_ctas_per_sm = 0; // the same for k_rotate_pipe
-  bool rot_pipe = true;     // tables beyond the L2 use the software-pipelined rotation kernel
-  u64 rot_pipe_min_rows = 1ull << 20;
   int prog_ctas_per_sm = 0; // resident CTAs of k_program per SM; 0 = cooperative launch unavailable
   unsigned char* d_prog = nullptr;  // persistent program: entries + parameter pool (device)
   unsigned char* h_prog = nullptr;  // pinned staging of the same
@@ -770,8 +767,6 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     if (rc) return rc;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->rot_ctas_per_sm, k_rotate, OBP_BS, 0));
     if (ctx->rot_ctas_per_sm < 1) ctx->rot_ctas_per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->rotp_ctas_per_sm, k_rotate_pipe, OBP_BS, 0));
-    if (ctx->rotp_ctas_per_sm < 1) ctx->rotp_ctas_per_sm = 1;
     if (ctx->W <= 2 && prop.cooperativeLaunch) {
       if (ctx->W == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prog_ctas_per_sm, k_program<1>, OBP_BS, 0));
       else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prog_ctas_per_sm, k_program<2>, OBP_BS, 0));
@@ -1485,10 +1480,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
         prog.add(PROG_ROTATE, n_slots, &p, sizeof(p), OBP_K_ROTATE);
       } else {
         Bracket br(ctx, OBP_K_ROTATE);
-        if (ctx->rot_pipe && p.ngw <= 2 && ctx->n_dense >= ctx->rot_pipe_min_rows)
-          k_rotate_pipe<<<grid_for(ctx, bound, ctx->rotp_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(t, p);  // one wave
-        else
-          k_rotate<<<grid_for(ctx, bound, ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(t, p);  // one wave
+        k_rotate<<<grid_for(ctx, bound, ctx->rot_ctas_per_sm), OBP_BS, 0, ctx->stream>>>(t, p);  // one wave
         CU(cudaGetLastError());
       }
       slot_of_op[k] = n_slots;
@@ -2578,8 +2570,6 @@ int obp_configure(obp_ctx* ctx, int32_t option, int64_t value) {
   switch (option) {
     case OBP_OPT_PROGRAM: ctx->use_program = value != 0; return OBP_OK;
     case OBP_OPT_PROGRAM_MAX_ROWS: ctx->prog_max_rows = value < 0 ? 0 : (u64)value; return OBP_OK;
-    case OBP_OPT_ROTATE_PIPE: ctx->rot_pipe = value != 0; return OBP_OK;
-    case OBP_OPT_ROTATE_PIPE_MIN_ROWS: ctx->rot_pipe_min_rows = value < 0 ? 0 : (u64)value; return OBP_OK;
     default: return ctx->fail(OBP_ERR_BADARG, "obp_configure: unknown option");
   }
 }

@@ -113,15 +113,13 @@ __device__ __forceinline__ void gen_word(const RotP& p, int w, u64& gx, u64& gz)
 
 // Find the row holding key(i) ^ G.  Returns its row id or -1.  *fresh is set when the row was
 // killed during this epoch (it was live when the kernel started).
-// `have_e0`: the entry of the first slot was loaded ahead of time (pipelined kernel) and is passed as e0.
 __device__ __forceinline__ long long find_partner(const Tab& t, const RotP& p, u64 i, u64 h2,
-                                                  u64 n_scan, double2& cq, bool& fresh, bool have_e0 = false,
-                                                  u64 e0 = 0) {
+                                                  u64 n_scan, double2& cq, bool& fresh) {
   const u64 fp = h2 >> 32;
   u64 s = h2 & t.mask;
   fresh = false;
   for (u64 probes = 0; probes <= t.mask; ++probes) {
-    const u64 e = (have_e0 && probes == 0) ? e0 : ld_volatile(&t.index[s]);
+    const u64 e = ld_volatile(&t.index[s]);
     if (e == OBP_EMPTY) return -1;
     if ((e >> 32) == fp) {
       const u64 j = e & 0xffffffffull;
@@ -309,192 +307,6 @@ __device__ __forceinline__ void rotate_body(const Tab& t, const RotP& p, const u
     }
   }
   if (lane == 0 && dl) atomicAdd(live_ctr, (u64)dl);
-}
-
-// ------------------------------------------------------------------------------------------------
-// rotate_body_pipe — the same pass as rotate_body for tables far beyond the L2, as a three-stage software
-// pipeline over the rows a thread visits (row t+2: streaming loads of coefficient / generator word / hash;
-// row t+1: commutation test and the load of its FIRST index slot; row t: partner loads, update, append).
-// In rotate_body an anticommuting row waits for two dependent DRAM round trips back to back (index slot,
-// then partner key + coefficient); here the index slot of the next row is in flight while the partner of the
-// current one is, so a thread keeps two random accesses and one streaming batch outstanding instead of one.
-// Same arithmetic, same counters, same append protocol.  Generators on at most two 64-bit words (every one-
-// and two-qubit rotation); wider ones use rotate_body.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rotate_body_pipe(const Tab& t, const RotP& p, const u64 n, u64* live_ctr) {
-  const unsigned lane = threadIdx.x & 31u;
-  unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
-  int dlive = 0;
-  double sum_re = 0.0, sum_im = 0.0;
-  bool overflow = false;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  const ulonglong2* __restrict__ col0 = t.xz[p.gw[0]];
-  const ulonglong2* __restrict__ col1 = t.xz[p.ngw > 1 ? p.gw[1] : p.gw[0]];
-  const bool two = p.ngw > 1;
-  const u64 first = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
-  // stage registers.  C: streaming loads issued; B: + commutation data and first index entry; A: being finished
-  double2 cC = make_double2(0.0, 0.0), cB = cC, cA = cC;
-  ulonglong2 k0C = make_ulonglong2(0ull, 0ull), k1C = k0C, k0B = k0C, k1B = k0C;
-  u64 hC = 0, hB = 0, eB = OBP_EMPTY, eA = OBP_EMPTY, h2A = 0;
-  int metaB = 0, metaA = 0;  // bit 0: needs the partner; bits 1-2: E; bit 3: s; bit 4: own_bit; bit 5: row in range and live
-  auto load_stream = [&](u64 i) {
-    if (i < n) {
-      cC = t.coef[i];
-      k0C = col0[i];
-      if (two) k1C = col1[i];
-      hC = t.hash[i];
-    } else {
-      cC = make_double2(0.0, 0.0);  // reads as a dead row
-      hC = 0;
-    }
-  };
-  // commutation test of the row in stage B and, if it needs its partner, the load of its first index slot
-  auto probe = [&](u64 i) {
-    metaB = 0;
-    eB = OBP_EMPTY;
-    if (i < n && is_live(cB)) {
-      int sp = 0, E = p.yG, own_bit = 0;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (k < p.ngw) {
-          const ulonglong2 key = k == 0 ? k0B : k1B;
-          const u64 m = p.gx[k] | p.gz[k];
-          sp += __popcll(key.x & p.gz[k]) + __popcll(key.y & p.gx[k]);
-          E += __popcll(key.x & key.y & m) - __popcll((key.x ^ p.gx[k]) & (key.y ^ p.gz[k]) & m) +
-               2 * __popcll(key.y & p.gx[k]);
-          if (k == p.canon_slot) own_bit = ((p.canon_z ? key.y : key.x) & p.canon_bit) != 0;
-        }
-      }
-      const int s = sp & 1;
-      const int need = (p.exact || s) ? 1 : 0;
-      metaB = need | ((E & 3) << 1) | (s << 3) | (own_bit << 4) | 32;
-      if (need) eB = __ldcg(&t.index[(hB ^ p.hG) & t.mask]);
-    }
-  };
-  // prologue: rows `first` (-> B, probed) and `first + stride` (-> C)
-  load_stream(first + lane);
-  cB = cC; k0B = k0C; k1B = k1C; hB = hC;
-  load_stream(first + stride + lane);
-  probe(first + lane);
-  for (u64 base = first; base < n; base += stride) {
-    const u64 i = base + lane;
-    // rotate the pipeline: A <- B, B <- C, C <- new loads
-    cA = cB; eA = eB; metaA = metaB; h2A = hB ^ p.hG;
-    cB = cC; k0B = k0C; k1B = k1C; hB = hC;
-    load_stream(i + 2 * stride);
-    probe(i + stride);
-    bool want_append = false;
-    double2 app_c = make_double2(0.0, 0.0);
-    if (metaA & 32) {
-      const double2 c = cA;
-      const int s = (metaA >> 3) & 1, E = (metaA >> 1) & 3, own_bit = (metaA >> 4) & 1;
-      if (!(metaA & 1)) {
-        // commuting row, fast mode: only its own key can change (row filter)
-        const RowSet rp = rot_rows_self(c, s, p);
-        if (rp.nself < 2) {
-          if (rp.nself == 0 || is_small(rp.self, p.atol)) {
-            t.coef[i] = tombstone(p.epoch);
-            dlive--;
-          } else {
-            t.coef[i] = rp.self;
-          }
-        }
-      } else {
-        const RowSet rp = rot_rows(c, E, s, p);
-        double2 cq;
-        bool fresh;
-        const long long j = find_partner(t, p, i, h2A, n, cq, fresh, true, eA);
-        if (j >= 0 && !fresh && !own_bit) {
-          const RowSet rq = rot_rows(cq, (4 - E) & 3, s, p);
-          const bool pres_p = rp.nself > 0 || rq.ncross > 0;
-          const bool pres_q = rq.nself > 0 || rp.ncross > 0;
-          double2 np_ = rp.self, nq_ = rq.self;
-          if (rq.ncross) np_ = rp.nself ? cadd(np_, rq.cross) : rq.cross;
-          if (rp.ncross) nq_ = rq.nself ? cadd(nq_, rp.cross) : rp.cross;
-          rows_surv += rp.nself + rp.ncross + rq.nself + rq.ncross;
-          keys_present += (unsigned)pres_p + (unsigned)pres_q;
-          if (pres_p && !is_small(np_, p.atol)) {
-            t.coef[i] = np_;
-          } else {
-            if (pres_p) { cancelled++; sum_re += np_.x; sum_im += np_.y; }
-            t.coef[i] = tombstone(p.epoch);
-            dlive--;
-          }
-          if (pres_q && !is_small(nq_, p.atol)) {
-            t.coef[j] = nq_;
-          } else {
-            if (pres_q) { cancelled++; sum_re += nq_.x; sum_im += nq_.y; }
-            t.coef[j] = tombstone(p.epoch);
-            dlive--;
-          }
-        } else if (j < 0) {
-          rows_surv += rp.nself + rp.ncross;
-          keys_present += (unsigned)(rp.nself > 0) + (unsigned)(rp.ncross > 0);
-          if (rp.nself > 0 && !is_small(rp.self, p.atol)) {
-            if (rp.self.x != c.x || rp.self.y != c.y) t.coef[i] = rp.self;
-          } else {
-            if (rp.nself > 0) { cancelled++; sum_re += rp.self.x; sum_im += rp.self.y; }
-            t.coef[i] = tombstone(p.epoch);
-            dlive--;
-          }
-          if (rp.ncross > 0) {
-            if (!is_small(rp.cross, p.atol)) {
-              want_append = true;
-              app_c = rp.cross;
-            } else {
-              cancelled++; sum_re += rp.cross.x; sum_im += rp.cross.y;
-            }
-          }
-        }
-      }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, want_append);
-    if (bal) {
-      u64 wbase = 0;
-      if (lane == 0) wbase = atomicAdd(&t.st->n_append, (u64)__popc(bal));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (want_append) {
-        const u64 row = wbase + __popc(bal & ((1u << lane) - 1u));
-        if (row < t.cap) {
-          for (int w = 0; w < t.W; ++w) {
-            u64 gx, gz;
-            gen_word(p, w, gx, gz);
-            ulonglong2 key = t.xz[w][i];
-            key.x ^= gx;
-            key.y ^= gz;
-            t.xz[w][row] = key;
-          }
-          t.coef[row] = app_c;
-          t.hash[row] = h2A;
-          if (!index_insert(t, h2A, row)) atomicOr(&t.st->error, OBP_ERR_BIT_INDEX);
-          dlive++;
-        } else {
-          overflow = true;
-        }
-      }
-    }
-  }
-  if (overflow) atomicOr(&t.st->error, OBP_ERR_BIT_CAP);
-  const long long dl = warp_sum_i64((long long)dlive);
-  if (p.exact) {
-    const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present), cz = warp_sum_u64(cancelled);
-    const double sr = warp_sum_f64(sum_re), si = warp_sum_f64(sum_im);
-    if (lane == 0) {
-      OpStat* o = &t.ops[p.slot];
-      if (a) atomicAdd(&o->rows_surv, a);
-      if (b) atomicAdd(&o->keys_present, b);
-      if (cz) { atomicAdd(&o->cancelled, cz); atomicAdd(&o->sum_re, sr); atomicAdd(&o->sum_im, si); }
-    }
-  }
-  if (lane == 0 && dl) atomicAdd(live_ctr, (u64)dl);
-}
-
-#ifndef OBP_ROTP_MINB
-#define OBP_ROTP_MINB 3
-#endif
-__global__ void __launch_bounds__(OBP_BS, OBP_ROTP_MINB) k_rotate_pipe(Tab t, const __grid_constant__ RotP p) {
-  rotate_body_pipe(t, p, t.st->n_scan, &t.st->n_live);
-  finish_kernel(t, p.slot);
 }
 
 __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate(Tab t, const __grid_constant__ RotP p) {

@@ -32,8 +32,6 @@ OBP_ATOL_MERGE_ONLY = -1.0
 OBP_ATOL_RAW = -2.0  # simplify=False: no merge, exact zeros stay
 OBP_OPT_PROGRAM = 1
 OBP_OPT_PROGRAM_MAX_ROWS = 2
-OBP_OPT_ROTATE_PIPE = 3
-OBP_OPT_ROTATE_PIPE_MIN_ROWS = 4
 OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other", "program")
 
 #: numpy mirror of ``obp_op`` (104 bytes, natural C alignment)
@@ -267,9 +265,6 @@ class TermTable:
         no_prog = os.environ.get("OBP_B200_NO_PROGRAM", "0") not in ("", "0")
         self.configure(OBP_OPT_PROGRAM, 0 if no_prog else 1)
         self.configure(OBP_OPT_PROGRAM_MAX_ROWS, int(os.environ.get("OBP_B200_PROG_MAX_ROWS", str(1 << 18))))
-        # OBP_B200_ROT_PIPE=0 / OBP_B200_ROT_PIPE_MIN_ROWS=n: software-pipelined rotation kernel off / from n rows up
-        self.configure(OBP_OPT_ROTATE_PIPE, 0 if os.environ.get("OBP_B200_ROT_PIPE", "1") in ("", "0") else 1)
-        self.configure(OBP_OPT_ROTATE_PIPE_MIN_ROWS, int(os.environ.get("OBP_B200_ROT_PIPE_MIN_ROWS", str(1 << 20))))
 
     def configure(self, option: int, value: int) -> None:
         self._check(self._lib.obp_configure(self._h, int(option), int(value)), "obp_configure")

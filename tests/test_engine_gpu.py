@@ -611,16 +611,14 @@ def window_workload(nq, rounds):
 
 
 # ---- every code path of the gate kernels against the oracle ----------------------
-@pytest.mark.parametrize("mode", ["no-program", "no-program-pipelined", "switch-at-64-rows", "switch-at-2000-rows"])
+@pytest.mark.parametrize("mode", ["no-program", "switch-at-64-rows", "switch-at-2000-rows"])
 @pytest.mark.parametrize("nq", [6, 64, 70, 127])
 def test_program_and_standalone_kernels_agree_with_oracle(nq, mode, monkeypatch):
     """Tables of <= 128 qubits run a slice either inside the persistent program kernel or as stand-alone
     k_rotate / k_clifford_reg launches (>= 2^18 rows by default).  Forced here: everything stand-alone, and a
     row threshold low enough that the run changes path part-way — all against the oracle, counters included."""
-    if mode.startswith("no-program"):
+    if mode == "no-program":
         monkeypatch.setenv("OBP_B200_NO_PROGRAM", "1")
-        # k_rotate_pipe (the software-pipelined kernel of tables beyond the L2) forced on from the first row, or off
-        monkeypatch.setenv("OBP_B200_ROT_PIPE_MIN_ROWS", "0" if mode.endswith("pipelined") else str(1 << 40))
     else:
         monkeypatch.setenv("OBP_B200_PROG_MAX_ROWS", "64" if "64" in mode else "2000")
     obs, slices = window_workload(nq, 4)
@@ -810,9 +808,8 @@ def test_max_qwc_groups_through_backpropagate_on_device(monkeypatch):
 
 
 @pytest.mark.parametrize("nq", [130, 200, 1000])
-def test_pipelined_rotation_kernel_wide_tables(nq, monkeypatch):
-    """k_rotate_pipe on tables wider than 128 qubits (W = 3, 4, 16), incl. generators that straddle two words."""
-    monkeypatch.setenv("OBP_B200_ROT_PIPE_MIN_ROWS", "0")
+def test_rotation_kernel_wide_tables(nq):
+    """Stand-alone k_rotate on tables wider than 128 qubits (W = 3, 4, 16), incl. generators that straddle two words."""
     rng = np.random.default_rng(nq)
     slices = random_slices(nq, 6, rng, gates_per_slice=8)
     for k, qc in enumerate(slices):
