@@ -466,9 +466,14 @@ def sharded_parity_check(backpropagate, bpmod) -> tuple[bool, str]:
     obs, sl = window(70, 4)
     cases.append(("70q window, sharded at once", "0", obs, sl, {}))
     cases.append(("70q window, split mid-run", "300", obs, sl, {}))
+    cases.append(("70q window, split mid-run, hash shard function", "300/noplan", obs, sl, {}))
     exchanges = 0
+    saved_download = os.environ.get("OBP_B200_DOWNLOAD")
+    os.environ["OBP_B200_DOWNLOAD"] = "1"  # the check needs the operators back
     try:
         for name, min_terms, o, sl, kw in cases:
+            os.environ["OBP_B200_SHARD_PLAN"] = "0" if min_terms.endswith("/noplan") else "1"
+            min_terms = min_terms.split("/")[0]
             os.environ["OBP_B200_SHARD_MIN_TERMS"] = min_terms
             got, rest, md = backpropagate(o, sl, **kw)
             exchanges += bpmod.last_run.exchanges
@@ -483,6 +488,11 @@ def sharded_parity_check(backpropagate, bpmod) -> tuple[bool, str]:
         return False, f"{type(exc).__name__}: {exc}"
     finally:
         os.environ.pop("OBP_B200_SHARD_MIN_TERMS", None)
+        os.environ.pop("OBP_B200_SHARD_PLAN", None)
+        if saved_download is None:
+            os.environ.pop("OBP_B200_DOWNLOAD", None)
+        else:
+            os.environ["OBP_B200_DOWNLOAD"] = saved_download
 
 
 def sharded_block(args, rank: int, world: int, device, torch, dist, backpropagate, bpmod, flush_buf) -> dict | None:
@@ -583,6 +593,8 @@ def sharded_block(args, rank: int, world: int, device, torch, dist, backpropagat
             "exchanges_per_step": shard["exchanges"],
             "exchanged_records_per_step": shard["records"],
             "shard_min_terms": sh.ShardedTable.split_min_env(),
+            "shard_function": "planned at the split: owner bits of every upcoming rotation generator are zero, so a rotation "
+                              "never moves a term to another rank (exchanges_per_step counts the ones outside the plan)",
             "timing": "CUDA events on each rank's stream from the observable upload to the end of the last slice, max over ranks; "
                       "result left on the devices (OBP_B200_DOWNLOAD=0)",
         })

@@ -222,8 +222,17 @@ typedef struct {
 int obp_set_shard(obp_ctx* ctx, int32_t n_ranks, int32_t rank);
 /* Late sharding: while the operator is small every rank carries an identical copy of the whole table
  * (no gate needs an exchange); obp_shard_split turns that copy into rank `rank`'s shard by dropping the
- * rows other ranks own.  Invalidates the snapshot (it held the whole operator): call obp_snapshot again. */
-int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, uint64_t* n_out);
+ * rows other ranks own.  future_ops (optional, n_future records): the gates the run applies next, in
+ * order.  The hash frame is then re-drawn such that the owner bits of the generator of every rotation
+ * among them are zero — a rotation P -> P xor G keeps owner(P xor G) = owner(P) — so those rotations run
+ * rank-local without any record exchange; *n_covered = how many rotations the plan covers.  Rotations
+ * outside the plan still work through the exchange path.  Invalidates the snapshot (it held the whole
+ * operator): call obp_snapshot again. */
+int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, const obp_op* future_ops, int32_t n_future,
+                    uint64_t* n_out, int32_t* n_covered);
+/* Statistics since the context was created: rotations that needed a record exchange with a peer, and records
+ * this rank emitted (the latter as of the last call that synchronised with the device). */
+int obp_shard_stats(obp_ctx* ctx, uint64_t* n_exchange_rotations, uint64_t* n_records_emitted);
 /* Bytes of one exchange record: W x/z word pairs, the hash, the complex128 coefficient. */
 uint64_t obp_record_bytes(int n_qubits);
 /* obp_apply_ops on a sharded table: stops before the first rotation whose partner keys live on

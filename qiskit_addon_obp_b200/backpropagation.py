@@ -220,6 +220,10 @@ def backpropagate(
                             def prefetch(ns=next_slice, after=plan.support_after):
                                 _slice_program(ns, expand_all).plan(after)
 
+                        if comm is not None:
+                            # a table that is split into shards during this slice (overflow of the replicated copy)
+                            # plans its shard function against the gates from this slice on
+                            tables[i].lookahead = (reversed_slices, slice_pos, support_mask[i], expand_all)
                         committed_work = (info.updates, info.applied_gates)
                         while True:
                             try:
@@ -301,6 +305,8 @@ def backpropagate(
                 # commit (backpropagation.py:279-285): the snapshot is the deepcopy of the reference
                 for i in range(n_obs):
                     if loaded[i]:
+                        if comm is not None:  # (a split at this commit plans against the gates still to come)
+                            tables[i].lookahead = (reversed_slices, slice_pos + 1, support_mask[i], expand_all)
                         tables[i].snapshot()
                 loaded_committed = list(loaded)
                 metadata.num_backpropagated_slices += 1
@@ -625,6 +631,26 @@ def _run_slice(table: TermTable, prog: SliceProgram, plan: SlicePlan, atol: floa
         # sharded table, last gate Clifford-class: its coset count would need a cross-rank exchange
         sm.num_unique_paulis[i] = sm.num_duplicate_paulis[i] = sm.num_trimmed_paulis[i] = None
         sm.sum_trimmed_coeffs[i] = None
+
+
+def future_ops(lookahead, max_slices: int = 48) -> np.ndarray | None:
+    """The gate records the run applies next (light cone included), for a sharded table that plans its shard
+    function (``obp_shard_split``).  Stops at the first gate with an entry point of its own (generic gates, reset,
+    noise layers) and after ``max_slices`` slices; rotations beyond the plan still work, through the exchange path."""
+    if lookahead is None:
+        return None
+    reversed_slices, start, support, expand_all = lookahead
+    if expand_all:
+        return None
+    chunks = []
+    for sl in reversed_slices[start : start + max_slices]:
+        plan = _slice_program(sl, False).plan(support)
+        for kind, what, _ in plan.steps:
+            if kind != "ops":
+                return np.concatenate(chunks) if chunks else None
+            chunks.append(what)
+        support = plan.support_after
+    return np.concatenate(chunks) if chunks else None
 
 
 def _log_gate_size(gate_id: int, size: int) -> None:

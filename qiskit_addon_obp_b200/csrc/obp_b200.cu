@@ -87,6 +87,7 @@ struct obp_ctx {
   bool last_split_is_last_op = false;  // the program just run ended on a handshake split rotation (counters in h_cnt)
   bool flag_sync = false;  // split rotations are ordered by device-side flags, no host barrier
   u64 xseq = 0;            // split rotations run so far (identical on all ranks)
+  u64 n_split_rot = 0;     // rotations that needed a record exchange (statistics)
   bool shard_rot_open = false;
   int rot_ctas_per_sm = 0;  // resident CTAs of k_rotate per SM (occupancy API)
   int prog_ctas_per_sm = 0; // resident CTAs of k_program per SM; 0 = cooperative launch unavailable
@@ -378,6 +379,7 @@ int set_counts(obp_ctx* ctx, u64 n) {
   DevState s;
   memset(&s, 0, sizeof(s));
   s.n_scan = s.n_append = s.n_live = n;
+  s.emitted_total = ctx->h_st->emitted_total;  // (a statistic, not table state)
   *ctx->h_st = s;
   CU(cudaMemcpyAsync(ctx->d_st, ctx->h_st, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -695,6 +697,129 @@ int qwc_run(const ulonglong2* d_keys, ulonglong2* d_sorted, unsigned* d_degree, 
   return OBP_OK;
 }
 }  // namespace
+
+// ---- exchange-free sharding: a shard function orthogonal to the rotations to come -------------------
+// owner(P) = top bits of the GF(2)-linear row hash, and a rotation with generator G moves a key to the
+// owner  owner(P) ^ owner(G).  The hash frame is ours to choose: if the top bits of h(G_t) vanish for every
+// rotation G_t the run is going to apply, no rotation ever sends a term to another rank and the shards evolve
+// without any communication.  h(G_t) is a fixed linear function of the frame columns at split time (Clifford
+// gates only re-express the frame), so the condition is a linear system on each top bit plane
+// a in GF(2)^{2N}:  <a, G'_t> = 0  for the generators pulled back to the split-time frame.  It is solved
+// without building a 2N x 2N tableau: run the frame forward over the future gates with random WIDE columns
+// (OBP_PLAN_WORDS x 64 bits), collect the wide hashes s(G_t), take L in their null space, and set
+// a[b] = parity(L . s_col[b]) — then <a, G'_t> = parity(L . s(G_t)) = 0 exactly, by linearity.
+#define OBP_PLAN_WORDS 16  // 1024-bit columns: up to ~1000 planned rotations
+
+struct WideCol {
+  u64 w[OBP_PLAN_WORDS];
+  WideCol& operator^=(const WideCol& o) {
+    for (int k = 0; k < OBP_PLAN_WORDS; ++k) w[k] ^= o.w[k];
+    return *this;
+  }
+};
+
+void wide_frame_update(std::vector<WideCol>& sx, std::vector<WideCol>& sz, const obp_op& op) {
+  const int nb = 2 * op.n_qubits;
+  WideCol old_col[4], new_col[4];
+  for (int j = 0; j < op.n_qubits; ++j) {
+    old_col[2 * j] = sx[op.qubit[j]];
+    old_col[2 * j + 1] = sz[op.qubit[j]];
+  }
+  unsigned inv[16];
+  for (unsigned v = 0; v < (1u << nb); ++v) inv[(op.lut >> (4 * v)) & 15ull] = v;
+  for (int j = 0; j < nb; ++j) {
+    const unsigned pre = inv[1u << j];
+    WideCol c;
+    memset(&c, 0, sizeof(c));
+    for (int i = 0; i < nb; ++i)
+      if (pre & (1u << i)) c ^= old_col[i];
+    new_col[j] = c;
+  }
+  for (int j = 0; j < op.n_qubits; ++j) {
+    sx[op.qubit[j]] = new_col[2 * j];
+    sz[op.qubit[j]] = new_col[2 * j + 1];
+  }
+}
+
+// Top-bit planes for `n_bits` owner bits: planes[i][2q] / [2q+1] = owner bit i of the x / z column of qubit q.
+// Returns the number of rotations the plan covers (all of them unless the wide hash ran out of dimensions).
+int plan_owner_planes(int nq, const obp_op* ops, int n_ops, int n_bits, std::vector<std::vector<unsigned char>>& planes) {
+  u64 seed = 0x5EEDC0DE5EEDull;
+  std::vector<WideCol> sx(nq), sz(nq);
+  for (int q = 0; q < nq; ++q)
+    for (int k = 0; k < OBP_PLAN_WORDS; ++k) {
+      sx[q].w[k] = splitmix64(seed);
+      sz[q].w[k] = splitmix64(seed);
+    }
+  const std::vector<WideCol> sx0 = sx, sz0 = sz;  // the columns at split time
+  // Gaussian elimination of the rotation hashes as they come: basis rows in echelon form, pivot per row
+  const int dims = 64 * OBP_PLAN_WORDS;
+  std::vector<WideCol> basis;
+  std::vector<int> pivot;
+  int covered = 0;
+  for (int k = 0; k < n_ops; ++k) {
+    const obp_op& op = ops[k];
+    if (op.kind == OBP_OP_CLIFFORD) {
+      wide_frame_update(sx, sz, op);
+      continue;
+    }
+    if (op.kind != OBP_OP_ROTATION) break;
+    if ((int)basis.size() >= dims - n_bits - 8) break;  // keep a null space to choose from
+    WideCol g;
+    memset(&g, 0, sizeof(g));
+    for (int j = 0; j < op.n_qubits; ++j) {
+      const unsigned code = (op.gen_local >> (2 * j)) & 3u;
+      if (code & 1u) g ^= sx[op.qubit[j]];
+      if (code & 2u) g ^= sz[op.qubit[j]];
+    }
+    for (size_t r = 0; r < basis.size(); ++r)
+      if ((g.w[pivot[r] >> 6] >> (pivot[r] & 63)) & 1ull) g ^= basis[r];
+    int pv = -1;
+    for (int b = 0; b < dims && pv < 0; ++b)
+      if ((g.w[b >> 6] >> (b & 63)) & 1ull) pv = b;
+    if (pv >= 0) {
+      // keep the basis reduced: clear the new pivot from the older rows
+      for (size_t r = 0; r < basis.size(); ++r)
+        if ((basis[r].w[pv >> 6] >> (pv & 63)) & 1ull) basis[r] ^= g;
+      basis.push_back(g);
+      pivot.push_back(pv);
+    }
+    covered++;
+  }
+  // null space vectors: one per free coordinate f:  L = e_f + sum over basis rows r with bit f set of e_pivot[r]
+  std::vector<char> is_pivot(dims, 0);
+  for (int pv : pivot) is_pivot[pv] = 1;
+  std::vector<int> free_coords;
+  for (int b = 0; b < dims; ++b)
+    if (!is_pivot[b]) free_coords.push_back(b);
+  planes.assign(n_bits, std::vector<unsigned char>(2 * (size_t)nq, 0));
+  for (int i = 0; i < n_bits; ++i) {
+    // a random combination of free-coordinate null vectors (different per owner bit, never empty)
+    WideCol L;
+    memset(&L, 0, sizeof(L));
+    int used = 0;
+    for (size_t f = 0; f < free_coords.size(); ++f) {
+      const bool take = (splitmix64(seed) & 3ull) == 0 || (int)f == i;
+      if (!take) continue;
+      const int fc = free_coords[f];
+      L.w[fc >> 6] ^= 1ull << (fc & 63);
+      for (size_t r = 0; r < basis.size(); ++r)
+        if ((basis[r].w[fc >> 6] >> (fc & 63)) & 1ull) L.w[pivot[r] >> 6] ^= 1ull << (pivot[r] & 63);
+      used++;
+    }
+    (void)used;
+    auto par = [&](const WideCol& c) {
+      u64 acc = 0;
+      for (int k = 0; k < OBP_PLAN_WORDS; ++k) acc ^= c.w[k] & L.w[k];
+      return (unsigned char)(__builtin_popcountll(acc) & 1);
+    };
+    for (int q = 0; q < nq; ++q) {
+      planes[i][2 * q] = par(sx0[q]);
+      planes[i][2 * q + 1] = par(sz0[q]);
+    }
+  }
+  return covered;
+}
 
 // =================================================================================================
 // C-ABI
@@ -1439,6 +1564,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
         // headers (cta_wait_flag / finish_kernel_flag), the host does not synchronise.
         const int peer_rank = ctx->rank ^ (int)(p.hG >> ctx->owner_shift);
         const u64 seq = ++ctx->xseq;
+        ctx->n_split_rot++;
         const int b = (int)(seq & 1ull);
         if (!ctx->inbox[b] || !ctx->peer_inbox[b][peer_rank]) return ctx->fail(OBP_ERR_BADARG, "sharded table: peer inbox not attached");
         u64* peer = ctx->peer_inbox[b][peer_rank];
@@ -1618,26 +1744,63 @@ int obp_set_shard(obp_ctx* ctx, int32_t n_ranks, int32_t rank) {
 }
 
 // Late sharding: a table that so far held the WHOLE operator (every rank an identical copy) keeps only the
-// rows this rank owns from now on.
-int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, uint64_t* n_out) {
+// rows this rank owns from now on.  `future_ops` (optional) are the gates the run is going to apply next, in
+// order: the hash frame is re-drawn so that the owner bits of every rotation generator among them vanish
+// (plan_owner_planes above) — those rotations then never need a record exchange — and every row is re-hashed
+// under the new frame before the foreign ones are dropped.  *n_covered = rotations the plan covers.
+int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, const obp_op* future_ops, int32_t n_future,
+                    uint64_t* n_out, int32_t* n_covered) {
   OBP_NO_PENDING(ctx, "obp_shard_split");
   if (!ctx) return OBP_ERR_BADARG;
   if (ctx->n_ranks != 1) return ctx->fail(OBP_ERR_BADARG, "obp_shard_split: the table is already sharded");
   int rc = obp_set_shard(ctx, n_ranks, rank);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
+  if (n_covered) *n_covered = 0;
+  int bits = 0;
+  while ((1 << bits) < n_ranks) ++bits;
+  if (future_ops && n_future > 0 && bits > 0) {
+    for (int k = 0; k < n_future; ++k) {
+      const int vrc = validate_op(ctx, future_ops[k]);
+      if (vrc) return vrc;
+    }
+    std::vector<std::vector<unsigned char>> planes;
+    const int covered = plan_owner_planes(ctx->nq, future_ops, n_future, bits, planes);
+    if (n_covered) *n_covered = covered;
+    // a fresh frame: random low bits, planned owner bits on top (bit 63 - i = owner bit i counted from the top)
+    u64 seed = 0x0B9B200C0FFEEull ^ (0x9E3779B97F4A7C15ull * (ctx->epoch + 1));
+    for (int q = 0; q < ctx->nq; ++q) {
+      u64 cx = splitmix64(seed) >> bits, cz = splitmix64(seed) >> bits;
+      for (int i = 0; i < bits; ++i) {
+        cx |= (u64)planes[i][2 * q] << (63 - i);
+        cz |= (u64)planes[i][2 * q + 1] << (63 - i);
+      }
+      ctx->hx[q] = cx;
+      ctx->hz[q] = cz;
+    }
+    ctx->cols_dirty = true;
+    rc = upload_cols(ctx);
+    if (rc) return rc;
+    if (ctx->n_dense) {
+      k_hash_rows<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), ctx->d_cols, ctx->n_dense);
+      CU(cudaGetLastError());
+    }
+  }
   if (ctx->n_dense && ctx->n_ranks > 1) {
     k_shard_drop<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), ctx->owner_shift, (u64)ctx->rank, ++ctx->epoch);
     CU(cudaGetLastError());
     rc = sync_state(ctx);
     if (rc) return rc;
-    if (ctx->n_dense != ctx->n_live) {
-      rc = compact(ctx);
-      if (rc) return rc;
-      rc = sync_state(ctx);
-      if (rc) return rc;
-    }
   }
+  // rows moved or were re-hashed: dense again, index rebuilt under the current hashes
+  if (ctx->n_dense != ctx->n_live) {
+    rc = compact(ctx);
+  } else {
+    rc = rebuild_index(ctx);
+  }
+  if (rc) return rc;
+  rc = sync_state(ctx);
+  if (rc) return rc;
   ctx->snap.valid = false;  // the last commit held the whole operator: the caller commits again
   if (n_out) *n_out = ctx->n_live;
   return OBP_OK;
@@ -1646,6 +1809,13 @@ int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, uint64_t* n_out
 int obp_set_shard_sync(obp_ctx* ctx, int32_t device_flags) {
   if (!ctx) return OBP_ERR_BADARG;
   ctx->flag_sync = device_flags != 0;
+  return OBP_OK;
+}
+
+int obp_shard_stats(obp_ctx* ctx, uint64_t* n_exchange_rotations, uint64_t* n_records_emitted) {
+  if (!ctx) return OBP_ERR_BADARG;
+  if (n_exchange_rotations) *n_exchange_rotations = ctx->n_split_rot;
+  if (n_records_emitted) *n_records_emitted = ctx->h_st->emitted_total;  // as of the last synchronisation
   return OBP_OK;
 }
 
@@ -1903,6 +2073,7 @@ int obp_rotate_emit_p2p(obp_ctx* ctx, const obp_op* op, double atol, int32_t pee
   p.slot = -1;
   ctx->shard_rot = p;
   ctx->shard_rot_open = true;
+  ctx->n_split_rot++;
   const u64 n_in = ctx->n_live;
   u64* peer = ctx->peer_inbox[b][peer_rank];
   CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));

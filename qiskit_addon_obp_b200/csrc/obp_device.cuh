@@ -34,6 +34,7 @@ struct DevState {
   u64 scan_total;
   unsigned int ticket;  // last-block-done counter
   unsigned int error;   // OBP_ERR_BIT_*
+  u64 emitted_total;    // sharded table: records this rank has emitted to peers so far (monotonic, statistics)
 };
 
 // Result block: [DevState | pad to 64 | program start stamp | pad to 128 | OpStat slots...], the same layout on

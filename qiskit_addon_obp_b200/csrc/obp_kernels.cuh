@@ -1080,6 +1080,7 @@ __global__ void __launch_bounds__(OBP_BS, OBP_ROT_MINB) k_rotate_emit(Tab t, con
     if (a) atomicAdd(&cnt->rows_surv, a);
     if (b) atomicAdd(&cnt->keys_present, b);
     if (ne && cursor != &cnt->n_records) atomicAdd(&cnt->n_records, ne);
+    if (ne) atomicAdd(&t.st->emitted_total, ne);
     if (dl) atomicAdd(&t.st->n_live, (u64)dl);
   }
   // records written into a peer's memory must be visible before the kernel ends / the flag is raised

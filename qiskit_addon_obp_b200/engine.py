@@ -147,7 +147,8 @@ def lib() -> C.CDLL:
         "obp_profile_get": ([vp, C.POINTER(ObpProfile), C.c_int32], C.c_int),
         "obp_set_shard": ([vp, C.c_int32, C.c_int32], C.c_int),
         "obp_record_bytes": ([C.c_int], C.c_uint64),
-        "obp_shard_split": ([vp, C.c_int32, C.c_int32, u64p], C.c_int),
+        "obp_shard_stats": ([vp, u64p, u64p], C.c_int),
+        "obp_shard_split": ([vp, C.c_int32, C.c_int32, vp, C.c_int32, u64p, C.POINTER(C.c_int32)], C.c_int),
         "obp_apply_ops_sharded": (
             [vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
             C.c_int,
@@ -185,7 +186,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count obp_shard_stats"
 ).split()
 
 
@@ -578,12 +579,27 @@ class TermTable:
     def set_shard(self, n_ranks: int, rank: int):
         self._check(self._lib.obp_set_shard(self._h, int(n_ranks), int(rank)), "obp_set_shard")
 
-    def shard_split(self, n_ranks: int, rank: int) -> int:
-        """A replicated table keeps only the rows rank ``rank`` of ``n_ranks`` owns (late sharding)."""
-        out = C.c_uint64()
-        self._check(self._lib.obp_shard_split(self._h, int(n_ranks), int(rank), C.byref(out)), "obp_shard_split")
+    def shard_stats(self) -> tuple[int, int]:
+        """``(rotations that needed a record exchange, records emitted)`` since the context was created."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.obp_shard_stats(self._h, C.byref(a), C.byref(b)), "obp_shard_stats")
+        return a.value, b.value
+
+    def shard_split(self, n_ranks: int, rank: int, future_ops: np.ndarray | None = None) -> tuple[int, int]:
+        """A replicated table keeps only the rows rank ``rank`` of ``n_ranks`` owns (late sharding).  With
+        ``future_ops`` (the gate records the run applies next) the shard function is planned so that none of
+        their rotations needs a record exchange.  Returns ``(rows kept, rotations covered by the plan)``."""
+        out, cov = C.c_uint64(), C.c_int32()
+        ops_p, n_ops = None, 0
+        if future_ops is not None and len(future_ops):
+            future_ops = np.ascontiguousarray(future_ops, dtype=OP_DTYPE)
+            ops_p, n_ops = future_ops.ctypes.data_as(C.c_void_p), len(future_ops)
+        self._check(
+            self._lib.obp_shard_split(self._h, int(n_ranks), int(rank), ops_p, n_ops, C.byref(out), C.byref(cov)),
+            "obp_shard_split",
+        )
         self.n = self.n_dense = out.value
-        return out.value
+        return out.value, cov.value
 
     def apply_ops_sharded(self, ops: np.ndarray, atol: float) -> tuple[ObpStats, int, int, bool]:
         """Run ``ops`` up to the first rotation that needs a peer: ``(stats, n_done, peer_xor, overflowed)``.

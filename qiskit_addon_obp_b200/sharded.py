@@ -221,6 +221,8 @@ class ShardedTable:
         self._split_on_restore = False
         self._skip_next_reserve = False
         self._inboxes_ready = False
+        self.lookahead = None  # set by the driver: (reversed slices, next slice, support, expand_all), see _split_now
+        self.planned_rotations = 0  # rotations the shard function was planned against (they need no exchange)
         self.p2p = os.environ.get("OBP_B200_P2P", "1") not in ("0", "")
         # one process per GPU: split rotations are ordered by device-side flags, the host never waits
         self.device_flags = (
@@ -230,8 +232,9 @@ class ShardedTable:
         self.n = 0
         self.n_dense = 0
         self.zero_operator = False
-        self.exchanges = 0  # rotations that needed a record exchange
-        self.exchanged_records = 0
+        self._xstat0 = {r: t.shard_stats() for r, t in self.tables.items()}  # counters at the start of this run
+        self._host_exchanges = 0  # host-ordered exchange paths (staged / barrier): counted here
+        self._host_records = 0
         self.t_phase = {"local": 0.0, "emit": 0.0, "barrier": 0.0, "merge": 0.0, "reduce": 0.0}  # host seconds
 
     # -- plumbing ---------------------------------------------------------------------------------
@@ -253,9 +256,16 @@ class ShardedTable:
             t.track_zero = False
 
     def _split_now(self) -> None:
-        """Every rank keeps its share (collective: all ranks reach this at the same commit)."""
+        """Every rank keeps its share (collective: all ranks reach this at the same commit).  The shard function is
+        planned against the gates the run is about to apply (``OBP_B200_SHARD_PLAN=0`` turns that off): the owner
+        bits of their rotation generators are zero, so those rotations never move a term to another rank."""
+        ops = None
+        if os.environ.get("OBP_B200_SHARD_PLAN", "1") not in ("0", ""):
+            from .backpropagation import future_ops
+
+            ops = future_ops(self.lookahead)
         for r, t in self.tables.items():
-            t.shard_split(self.comm.n_ranks, r)
+            _, self.planned_rotations = t.shard_split(self.comm.n_ranks, r, ops)
         if self.p2p and not self._inboxes_ready:
             self._setup_inboxes(max(t.capacity for t in self.tables.values()))
             self._inboxes_ready = True
@@ -295,10 +305,13 @@ class ShardedTable:
         for k, t in enumerate(pool):
             if t.num_qubits == int(num_qubits) and t.capacity >= int(capacity):
                 pool.pop(k)
-                t.n = t.n_dense = t.exchanges = t.exchanged_records = 0
+                t.n = t.n_dense = 0
+                t._host_exchanges = t._host_records = 0
+                t._xstat0 = {r: m.shard_stats() for r, m in t.tables.items()}
                 t.zero_operator = False
                 t.t_phase = dict.fromkeys(t.t_phase, 0.0)
                 t.split_min = cls.split_min_env()
+                t.lookahead, t.planned_rotations = None, 0
                 t._reset_replicated()
                 return t
         t = cls(num_qubits, capacity, comm)
@@ -345,6 +358,21 @@ class ShardedTable:
 
     def __len__(self) -> int:
         return 1 if self.zero_operator else self.n
+
+    @property
+    def exchanges(self) -> int:
+        """Rotations of this run that needed a record exchange (per rank: every rank takes part in each of them)."""
+        if self.device_flags and self.tables:
+            r = min(self.tables)
+            return self.tables[r].shard_stats()[0] - self._xstat0[r][0]
+        return self._host_exchanges
+
+    @property
+    def exchanged_records(self) -> int:
+        """Records emitted by the local rank(s) during this run."""
+        if self.device_flags and self.tables:
+            return sum(t.shard_stats()[1] - self._xstat0[r][1] for r, t in self.tables.items())
+        return self._host_records
 
     def _sync_counts(self):
         if not self.split:
@@ -538,8 +566,8 @@ class ShardedTable:
                     merge[r], over = t.rotate_merge(buf.data_ptr() if n_rec else 0, n_rec)
                     failed |= over
                 del bufs, recv
-            self.exchanges += 1
-            self.exchanged_records += sum(counts.values())
+            self._host_exchanges += 1
+            self._host_records += sum(counts.values())
             last = {"kind": "split", "emit": emit, "merge": merge, "op": op[0]}
             pos += 1
         # one combined reduction per program: overflow flag, row counts, update count, last-op counters

@@ -55,7 +55,12 @@ obs, slices = window_workload(70, 4)
 got, rest, md = backpropagate(obs, slices)
 want, rest_w, md_w = oracle.backpropagate(obs, slices)
 assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
-assert bpmod.last_run.exchanges > 0
+assert bpmod.last_run.exchanges == 0, "planned shard function: no rotation after the split needs an exchange"
+os.environ["OBP_B200_SHARD_PLAN"] = "0"  # the same run with a plain hash shard function: records cross NVLink
+got, rest, md = backpropagate(obs, slices)
+assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
+assert bpmod.last_run.exchanges > 0 and bpmod.last_run.exchanged_records > 0
+os.environ.pop("OBP_B200_SHARD_PLAN")
 os.environ.pop("OBP_B200_SHARD_MIN_TERMS")
 dist.barrier()
 log(f"[dist_check] parity vs oracle OK on {world} ranks (NCCL, P2P inbox exchange = {p2p})")

@@ -246,15 +246,18 @@ def test_sharded_exact_counters_for_clifford_ending_slices(monkeypatch):
 
 
 # ---- late sharding: replicated while small, split at a commit or when a rank's copy overflows --------------
+@pytest.mark.parametrize("plan", [False, True], ids=["hash-sharded", "planned"])
 @pytest.mark.parametrize("min_terms", [40, 400, 10**9])
 @pytest.mark.parametrize("ranks", [2, 8])
-def test_late_sharding_splits_mid_run(monkeypatch, ranks, min_terms):
+def test_late_sharding_splits_mid_run(monkeypatch, ranks, min_terms, plan):
     """The operator starts as an identical copy on every rank and is split into shards at the first commit at or
     above OBP_B200_SHARD_MIN_TERMS terms (never, for 10^9): same operator and metadata as the oracle either way,
     and — unlike a table sharded from the start — exact simplify counters for the slices run replicated."""
     from qiskit_addon_obp_b200 import backpropagation as bp
 
     monkeypatch.setenv("OBP_B200_SHARD_MIN_TERMS", str(min_terms))
+    # planned: the shard function is drawn orthogonal to the rotations still to come — no exchange at all
+    monkeypatch.setenv("OBP_B200_SHARD_PLAN", "1" if plan else "0")
     from test_engine_gpu import window_workload
 
     obs, slices = window_workload(70, 4)
@@ -264,6 +267,8 @@ def test_late_sharding_splits_mid_run(monkeypatch, ranks, min_terms):
     if min_terms == 10**9:
         assert bp.last_run.exchanges == 0
         assert all(s.num_unique_paulis[0] is not None for s in md.backpropagation_history)
+    elif plan:
+        assert bp.last_run.exchanges == 0, "every rotation after the split was in the plan"
     else:
         assert bp.last_run.exchanges > 0
     _compare(monkeypatch, ranks, obs, slices, truncation_error_budget=setup_budget(max_error_per_slice=2e-3))
@@ -276,6 +281,7 @@ def test_late_sharding_split_on_overflow(monkeypatch):
 
     sharded.close_all()
     engine.clear_pool()
+    monkeypatch.setenv("OBP_B200_SHARD_PLAN", "0")
     monkeypatch.setenv("OBP_B200_SHARD_MIN_TERMS", "100000")  # never reached by size ...
     monkeypatch.setenv("OBP_B200_CAPACITY", "70000")          # ... but a rank holds at most max(2^16, ...) rows
     from test_engine_gpu import window_workload
@@ -286,3 +292,33 @@ def test_late_sharding_split_on_overflow(monkeypatch):
     assert bp.last_run.exchanges > 0 and bp.last_run.wasted_updates > 0
     sharded.close_all()
     engine.clear_pool()
+
+
+def test_planned_sharding_balance_and_fallback(monkeypatch):
+    """A planned shard function spreads the rows over the ranks like a hash, and rotations beyond the planning
+    horizon (here: a plan of one slice) fall back to the record exchange — same results either way."""
+    from qiskit_addon_obp_b200 import backpropagation as bp
+    from qiskit_addon_obp_b200 import sharded
+    from test_engine_gpu import window_workload
+
+    monkeypatch.setenv("OBP_B200_SHARD_MIN_TERMS", "60")
+    obs, slices = window_workload(70, 4)
+    # 1. full plan: no exchange; per-rank row counts within a factor of two of the mean
+    seen = {}
+    orig = sharded.ShardedTable._split_now
+
+    def spy(self):
+        orig(self)
+        seen["rows"] = [t.n for t in self.tables.values()]
+        seen["planned"] = self.planned_rotations
+
+    monkeypatch.setattr(sharded.ShardedTable, "_split_now", spy)
+    _compare(monkeypatch, 4, obs, slices)
+    assert bp.last_run.exchanges == 0 and seen["planned"] > 0
+    mean = sum(seen["rows"]) / 4
+    assert max(seen["rows"]) <= 2 * mean and min(seen["rows"]) >= mean / 4, seen
+    # 2. a one-slice horizon: later rotations are not in the plan and exchange records
+    real = bp.future_ops
+    monkeypatch.setattr(bp, "future_ops", lambda la, max_slices=48: real(la, 1))
+    _compare(monkeypatch, 4, obs, slices)
+    assert bp.last_run.exchanges > 0
