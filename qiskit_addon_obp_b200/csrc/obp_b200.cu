@@ -743,7 +743,8 @@ void wide_frame_update(std::vector<WideCol>& sx, std::vector<WideCol>& sz, const
 
 // Top-bit planes for `n_bits` owner bits: planes[i][2q] / [2q+1] = owner bit i of the x / z column of qubit q.
 // Returns the number of rotations the plan covers (all of them unless the wide hash ran out of dimensions).
-int plan_owner_planes(int nq, const obp_op* ops, int n_ops, int n_bits, std::vector<std::vector<unsigned char>>& planes) {
+int plan_owner_planes(int nq, const obp_op* ops, int n_ops, int n_bits, int max_rotations,
+                      std::vector<std::vector<unsigned char>>& planes) {
   u64 seed = 0x5EEDC0DE5EEDull;
   std::vector<WideCol> sx(nq), sz(nq);
   for (int q = 0; q < nq; ++q)
@@ -764,6 +765,7 @@ int plan_owner_planes(int nq, const obp_op* ops, int n_ops, int n_bits, std::vec
       continue;
     }
     if (op.kind != OBP_OP_ROTATION) break;
+    if (covered >= max_rotations) break;
     if ((int)basis.size() >= dims - n_bits - 8) break;  // keep a null space to choose from
     WideCol g;
     memset(&g, 0, sizeof(g));
@@ -1764,11 +1766,44 @@ int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, const obp_op* f
       const int vrc = validate_op(ctx, future_ops[k]);
       if (vrc) return vrc;
     }
+    if (bits > OBP_MAX_OWNER_BITS) return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_shard_split: planning supports up to 64 ranks");
+    // The plan must also spread the rows that exist now.  In a circuit whose future generators span the same space
+    // as the past ones (periodic Trotter layers) a function that is blind to every future generator is blind to the
+    // differences between the existing rows too: judge each candidate on the owner histogram of the current table
+    // and halve the number of rotations it covers until no rank would get more than 1.5 x its share (a plan that
+    // covers nothing is the plain hash shard function).
     std::vector<std::vector<unsigned char>> planes;
-    const int covered = plan_owner_planes(ctx->nq, future_ops, n_future, bits, planes);
+    int n_rot_future = 0;
+    for (int k = 0; k < n_future; ++k) n_rot_future += future_ops[k].kind == OBP_OP_ROTATION;
+    int covered = 0;
+    u64* d_counts = ctx->d_cols;  // scratch: 2 * 64 * W u64, at least 128 entries
+    std::vector<u64> counts((size_t)1 << bits);
+    for (int target = n_rot_future;; target /= 2) {
+      covered = plan_owner_planes(ctx->nq, future_ops, n_future, bits, target, planes);
+      if (ctx->n_live == 0 || target == 0) break;
+      OwnerPlanes pl;
+      memset(&pl, 0, sizeof(pl));
+      pl.bits = bits;
+      for (int i = 0; i < bits; ++i)
+        for (int q = 0; q < ctx->nq; ++q) {
+          if (planes[i][2 * q]) pl.mask[i][q / 64].x |= 1ull << (q % 64);
+          if (planes[i][2 * q + 1]) pl.mask[i][q / 64].y |= 1ull << (q % 64);
+        }
+      CU(cudaMemsetAsync(d_counts, 0, counts.size() * sizeof(u64), ctx->stream));
+      k_owner_hist<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), pl, d_counts);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(counts.data(), d_counts, counts.size() * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      const u64 mx = *std::max_element(counts.begin(), counts.end());
+      const double share = (double)ctx->n_live / (double)counts.size();
+      if ((double)mx <= 1.5 * share + 4.0 * std::sqrt(share) + 8.0) break;  // (small tables are allowed their scatter)
+    }
+    ctx->cols_dirty = true;  // d_cols served as scratch
     if (n_covered) *n_covered = covered;
     // a fresh frame: random low bits, planned owner bits on top (bit 63 - i = owner bit i counted from the top)
-    u64 seed = 0x0B9B200C0FFEEull ^ (0x9E3779B97F4A7C15ull * (ctx->epoch + 1));
+    // (the seed must be the same on every rank: records carry hashes across ranks — only quantities the replicated
+    // copies share may enter it, never a context's own history such as its epoch counter)
+    u64 seed = 0x0B9B200C0FFEEull ^ (0x9E3779B97F4A7C15ull * (ctx->n_live + 1));
     for (int q = 0; q < ctx->nq; ++q) {
       u64 cx = splitmix64(seed) >> bits, cz = splitmix64(seed) >> bits;
       for (int i = 0; i < bits; ++i) {

@@ -1259,6 +1259,37 @@ __global__ void __launch_bounds__(OBP_BS) k_shard_drop(Tab t, int owner_shift, u
   finish_kernel(t, -1);
 }
 
+// Rows per owner under a candidate shard function given as owner-bit planes on the KEY bits (the plan of
+// obp_shard_split is judged on how evenly it spreads the rows before any hash is rewritten).
+#define OBP_MAX_OWNER_BITS 6
+struct OwnerPlanes {
+  int bits;
+  ulonglong2 mask[OBP_MAX_OWNER_BITS][OBP_MAX_WORDS];  // {x mask, z mask} of owner bit i on key word w
+};
+
+__global__ void __launch_bounds__(OBP_BS) k_owner_hist(Tab t, const __grid_constant__ OwnerPlanes pl, u64* __restrict__ counts) {
+  __shared__ unsigned s_cnt[1 << OBP_MAX_OWNER_BITS];
+  for (int k = threadIdx.x; k < (1 << pl.bits); k += OBP_BS) s_cnt[k] = 0;
+  __syncthreads();
+  const u64 n = t.st->n_scan;
+  for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < n; i += (u64)gridDim.x * OBP_BS) {
+    if (!is_live(t.coef[i])) continue;
+    unsigned owner = 0;
+    for (int b = 0; b < pl.bits; ++b) {
+      int par = 0;
+      for (int w = 0; w < t.W; ++w) {
+        const ulonglong2 key = t.xz[w][i];
+        par += __popcll(key.x & pl.mask[b][w].x) + __popcll(key.y & pl.mask[b][w].y);
+      }
+      owner |= (unsigned)(par & 1) << (pl.bits - 1 - b);  // bit 0 of the plan = most significant owner bit (hash bit 63)
+    }
+    atomicAdd(&s_cnt[owner], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < (1 << pl.bits); k += OBP_BS)
+    if (s_cnt[k]) atomicAdd(&counts[k], (u64)s_cnt[k]);
+}
+
 // ================================================================================================
 // k_program — one persistent cooperative launch for a whole gate program (W <= 2)
 //
