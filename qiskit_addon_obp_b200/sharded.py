@@ -260,12 +260,17 @@ class ShardedTable:
         planned against the gates the run is about to apply (``OBP_B200_SHARD_PLAN=0`` turns that off): the owner
         bits of their rotation generators are zero, so those rotations never move a term to another rank."""
         ops = None
+        t0 = time.perf_counter()
         if os.environ.get("OBP_B200_SHARD_PLAN", "1") not in ("0", ""):
             from .backpropagation import future_ops
 
             ops = future_ops(self.lookahead)
+        t1 = time.perf_counter()
         for r, t in self.tables.items():
             _, self.planned_rotations = t.shard_split(self.comm.n_ranks, r, ops)
+        t2 = time.perf_counter()
+        self.t_phase["plan"] = self.t_phase.get("plan", 0.0) + (t1 - t0)
+        self.t_phase["split"] = self.t_phase.get("split", 0.0) + (t2 - t1)
         if self.p2p and not self._inboxes_ready:
             self._setup_inboxes(max(t.capacity for t in self.tables.values()))
             self._inboxes_ready = True
@@ -277,6 +282,11 @@ class ShardedTable:
         for t in self.tables.values():  # the commit the split invalidated
             t.snapshot()
         self._snap = (self.zero_operator, self.n)
+        self.t_phase["split_total"] = self.t_phase.get("split_total", 0.0) + (time.perf_counter() - t0)
+        if os.environ.get("OBP_B200_TRACE"):
+            print(f"[obp trace] split into {self.comm.n_ranks} shards at {self.n} terms: local rows "
+                  f"{[t.n for t in self.tables.values()]}, plan covers {self.planned_rotations} rotations "
+                  f"({len(ops) if ops is not None else 0} gates looked ahead)", flush=True)
 
     def _maybe_split(self) -> None:
         if not self.split and not self.zero_operator and self.comm.n_ranks > 1 and self.n >= self.split_min:
@@ -343,10 +353,13 @@ class ShardedTable:
             print(f"[obp trace] sharded table: {self.exchanges} exchanges, {self.exchanged_records} records, host seconds "
                   + ", ".join(f"{k} {v:.3f}" for k, v in self.t_phase.items()), flush=True)
         pool = self.comm.__dict__.setdefault("_idle_tables", [])
-        if self.tables and len(pool) < 2:
-            pool.append(self)
-        else:
-            self.close()
+        if not self.tables:
+            return
+        # keep the most recently used tables: the one just released is the likeliest to be asked for again (every rank
+        # releases in the same order, so the collective close() of the evicted one lines up)
+        pool.append(self)
+        while len(pool) > 2:
+            pool.pop(0).close()
 
     def close(self):
         if self.tables and self.p2p and self._inboxes_ready:

@@ -48,18 +48,25 @@ wl = W.config1_xy_chain()
 got, rest, md = backpropagate(wl.observables, wl.slices, **wl.kwargs())
 want, _, md_w = oracle.backpropagate(wl.observables, wl.slices, **wl.kwargs())
 assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
-# late sharding: replicated at first, split into shards mid-run
-os.environ["OBP_B200_SHARD_MIN_TERMS"] = "300"
+# late sharding: replicated at first, split into shards mid-run.  (a) a periodic circuit: the planner cannot cover
+# its rotations without putting every row on one rank, records cross NVLink; (b) the same with the plain hash shard
+# function; (c) a near-Clifford brickwork: the planned shard function covers every rotation, no exchange at all
 from test_engine_gpu import window_workload
+os.environ["OBP_B200_SHARD_MIN_TERMS"] = "300"
 obs, slices = window_workload(70, 4)
-got, rest, md = backpropagate(obs, slices)
 want, rest_w, md_w = oracle.backpropagate(obs, slices)
+for plan in ("1", "0"):
+    os.environ["OBP_B200_SHARD_PLAN"] = plan
+    got, rest, md = backpropagate(obs, slices)
+    assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
+    assert bpmod.last_run.exchanges > 0 and bpmod.last_run.exchanged_records > 0
+os.environ["OBP_B200_SHARD_PLAN"] = "1"
+os.environ["OBP_B200_SHARD_MIN_TERMS"] = "200"
+wl = W.config4_near_clifford(num_qubits=200, depth=24, t_prob=0.05, max_paulis=20_000, n_observable_terms=4)
+got, rest, md = backpropagate(wl.observables, wl.slices, **wl.kwargs())
+want, _, md_w = oracle.backpropagate(wl.observables, wl.slices, **wl.kwargs())
 assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
 assert bpmod.last_run.exchanges == 0, "planned shard function: no rotation after the split needs an exchange"
-os.environ["OBP_B200_SHARD_PLAN"] = "0"  # the same run with a plain hash shard function: records cross NVLink
-got, rest, md = backpropagate(obs, slices)
-assert_same_operator(got, want); assert_same_metadata(md, md_w, allow_missing_counters=True)
-assert bpmod.last_run.exchanges > 0 and bpmod.last_run.exchanged_records > 0
 os.environ.pop("OBP_B200_SHARD_PLAN")
 os.environ.pop("OBP_B200_SHARD_MIN_TERMS")
 dist.barrier()
