@@ -217,7 +217,7 @@ class ShardedTable:
         # copy of the WHOLE table (same deterministic kernels on the same input: no exchange, no allreduce, exact
         # counters); at the first commit at or above that size each rank drops the rows it does not own.
         self.split = False
-        self.split_min = int(os.environ.get("OBP_B200_SHARD_MIN_TERMS", str(1 << 20)))
+        self.split_min = int(os.environ.get("OBP_B200_SHARD_MIN_TERMS", str(1 << 17)))
         self._split_on_restore = False
         self._skip_next_reserve = False
         self._inboxes_ready = False
@@ -244,7 +244,7 @@ class ShardedTable:
 
     @staticmethod
     def split_min_env() -> int:
-        return int(os.environ.get("OBP_B200_SHARD_MIN_TERMS", str(1 << 20)))
+        return int(os.environ.get("OBP_B200_SHARD_MIN_TERMS", str(1 << 17)))
 
     def _reset_replicated(self) -> None:
         """Back to the replicated phase (a recycled table starts a new run)."""
