@@ -171,6 +171,37 @@ def test_random_circuit_truncation(nq, p):
     _compare(obs, slices, truncation_error_budget=setup_budget(max_error_total=0.05, num_slices=8, p_norm=p))
 
 
+@pytest.mark.parametrize("nq", [5, 40, 70, 127])
+@pytest.mark.parametrize("layers", [True, False], ids=["slice-in-smem", "gate-by-gate"])
+def test_rotation_layers(nq, layers, monkeypatch):
+    """Slices made of rotations only (RX / RY / RZ / RZZ / RXX layers): the slice-in-shared-memory path
+    (k_slice_smem: the table partitioned so that whole cosets live in one CTA, all gates between __syncthreads)
+    and the gate-by-gate passes against the oracle.  Small angles and a loose atol put coefficients inside the
+    trim band of the intermediate gates."""
+    monkeypatch.setenv("OBP_B200_NO_SEGMENTS", "0" if layers else "1")
+    rng = np.random.default_rng(4000 + nq)
+    slices = []
+    for k in range(6):
+        qc = QuantumCircuit(nq)
+        kind = k % 3
+        if kind == 0:
+            for q in range(nq):
+                getattr(qc, ("rx", "ry", "rz")[int(rng.integers(3))])(float(rng.choice([0.1, 0.3, -0.7, 1e-3])), q)
+        elif kind == 1:
+            for q in range(k % 2, nq - 1, 2):
+                getattr(qc, ("rzz", "rxx", "ryy")[int(rng.integers(3))])(float(rng.choice([0.2, -0.4, 2e-3])), q, q + 1)
+        else:
+            for q in range(0, nq - 1, 2):
+                qc.cx(q, q + 1)
+            for q in range(nq):
+                qc.rx(0.25, q)
+        slices.append(qc)
+    obs = random_observable(nq, 3, rng, weight=min(nq, 4))
+    _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=20000))
+    _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=20000, atol=1e-4))
+    _compare(obs, slices, truncation_error_budget=TruncationErrorBudget([0.01], 0.1, 2, 1e-8))
+
+
 def test_clifford_only_counters():
     """Clifford gates: keys move, nothing merges; counters come from the coset count kernel."""
     rng = np.random.default_rng(5)
