@@ -513,7 +513,7 @@ def sharded_block(args, rank: int, world: int, device, torch, dist, backpropagat
             torch.cuda.synchronize(device)
 
     def run(n_warm: int, n_steps: int) -> dict:
-        acc = {"dev_ms": 0.0, "wall_ms": 0.0, "updates": 0, "prof": {}, "exchanges": 0, "records": 0, "slices": 0, "peak": 0}
+        acc = {"dev_ms": 0.0, "wall_ms": 0.0, "updates": 0, "wasted": 0, "prof": {}, "exchanges": 0, "records": 0, "slices": 0, "peak": 0}
         for k in range(n_warm + n_steps):
             flush_l2(torch, device, flush_buf)
             barrier()
@@ -527,13 +527,14 @@ def sharded_block(args, rank: int, world: int, device, torch, dist, backpropagat
             acc["wall_ms"] += 1e3 * (time.perf_counter() - t0)
             acc["dev_ms"] += r.device_ms
             acc["updates"] += r.updates
+            acc["wasted"] += r.wasted_updates
             acc["exchanges"] += r.exchanges
             acc["records"] += r.exchanged_records
             acc["slices"] = md.num_backpropagated_slices
             acc["peak"] = max(s.num_paulis[0] for s in md.backpropagation_history)
             for c, v in (r.profile or {}).items():
                 acc["prof"][c] = acc["prof"].get(c, 0.0) + v["ms"]
-        for f in ("dev_ms", "wall_ms", "updates", "exchanges", "records"):
+        for f in ("dev_ms", "wall_ms", "updates", "wasted", "exchanges", "records"):
             acc[f] /= n_steps
         acc["prof"] = {c: round(v / n_steps, 3) for c, v in acc["prof"].items() if v > 0}
         return acc
@@ -576,6 +577,7 @@ def sharded_block(args, rank: int, world: int, device, torch, dist, backpropagat
             "wall_ms_per_step": float(t[1]),
             "speedup": float(ms1[0]) / dev_ms if dev_ms > 0 else None,
             "updates_per_step": shard["updates"],
+            "wasted_updates_per_step": shard["wasted"],
             "updates_per_s": shard["updates"] / (dev_ms * 1e-3) if dev_ms > 0 else None,
             "slices_absorbed": shard["slices"],
             "peak_terms": shard["peak"],

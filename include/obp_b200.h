@@ -190,10 +190,25 @@ int obp_is_broken(const obp_ctx* ctx);
  *   OBP_OPT_PROGRAM           1 (default): tables of <= 128 qubits run a slice's gate program in one
  *                             persistent cooperative launch; 0: one kernel per gate / Clifford batch.
  *   OBP_OPT_PROGRAM_MAX_ROWS  tables with at least this many dense rows use the stand-alone kernels
- *                             (default 2^18). */
+ *                             (default 2^18).
+ *   OBP_OPT_SEGMENTS          1 (default): a call that consists of rotations only (an RX / RZ / RZZ ... layer of a
+ *                             Trotter step; tables of <= 128 qubits) is applied in shared memory: the table is
+ *                             partitioned so that every key a term can mix with shares its partition, one CTA
+ *                             applies all gates to a partition and writes the survivors out once (obp_segment.cuh);
+ *                             0: one pass over the table per gate.  Results are identical either way.
+ *   OBP_OPT_SEGMENT_MIN_GATES shorter runs use the per-gate kernels (default 6).
+ *   OBP_OPT_SEGMENT_CAP_ROWS  rows a partition may hold, 0 = what the shared memory allows (test hook: small values
+ *                             force the retry with more partitions and the fall-back to the per-gate kernels). */
 #define OBP_OPT_PROGRAM 1
 #define OBP_OPT_PROGRAM_MAX_ROWS 2
+#define OBP_OPT_SEGMENTS 3
+#define OBP_OPT_SEGMENT_MIN_GATES 4
+#define OBP_OPT_SEGMENT_CAP_ROWS 5
 int obp_configure(obp_ctx* ctx, int32_t option, int64_t value);
+
+/* Runs of rotations applied in shared memory since the context was created: committed runs, runs repeated with
+ * four times as many partitions (a partition outgrew its shared memory), runs handed to the per-gate kernels. */
+int obp_segment_stats(obp_ctx* ctx, uint64_t* n_runs, uint64_t* n_retries, uint64_t* n_fallbacks);
 
 /* Row-order mode (off by default).  The reference's simplify() returns rows in the order of each
  * key's first appearance among the gate's k*k raw rows (utils/simplify.py:126,160-165 on top of the
@@ -293,12 +308,15 @@ int obp_trunc_finish(obp_ctx* ctx, double threshold, uint64_t* n_removed, uint64
 /* ---- measurement --------------------------------------------------------------------------- */
 
 enum { OBP_K_ROTATE = 0, OBP_K_CLIFFORD = 1, OBP_K_TRUNCATE = 2, OBP_K_COMPACT = 3,
-       OBP_K_INDEX = 4, OBP_K_OTHER = 5, OBP_K_PROGRAM = 6, OBP_K_COUNT = 7 };
+       OBP_K_INDEX = 4, OBP_K_OTHER = 5, OBP_K_PROGRAM = 6, OBP_K_SEGMENT = 7, OBP_K_COUNT = 8 };
 
 /* OBP_K_PROGRAM is the persistent cooperative kernel that runs a whole gate program in one launch
  * (tables of up to 128 qubits): it counts as ONE launch; the table passes it makes are counted per
  * class in `passes`, and their device time (from %globaltimer stamps taken inside the kernel at
- * each grid barrier) is attributed to the class of each pass in `ms`. */
+ * each grid barrier) is attributed to the class of each pass in `ms`.
+ * OBP_K_SEGMENT is a run of rotations applied in shared memory (five launches per run: partition count /
+ * scan / scatter, the run itself, bookkeeping); `passes` counts its gates, `term_updates` the live terms at
+ * the entry of every gate, `ms` the five kernels together (CUDA events). */
 typedef struct {
   uint64_t launches[OBP_K_COUNT];  /* kernel launches per class since the last reset           */
   uint64_t passes[OBP_K_COUNT];    /* passes over the table per class (= launches for stand-alone kernels) */

@@ -49,6 +49,9 @@ class RunInfo:
     sharded = False  # the observable was a hash-sharded table: `updates` is already the global count
     exchanges = 0  # sharded: rotations that needed a record exchange
     exchanged_records = 0
+    #: rotation-only gate programs applied in shared memory: (committed runs, runs retried with smaller partitions,
+    #: runs handed to the per-gate kernels)
+    segments = (0, 0, 0)
 
 
 #: set True (bench.py does) to bracket every kernel launch with CUDA events
@@ -167,6 +170,7 @@ def backpropagate(
             cap_i = max(capacity, 2 * len(obs_in[i]))
             if comm is None:
                 tables.append(TermTable.acquire(num_qubits, cap_i, device))
+                tables[-1]._seg0 = tables[-1].segment_stats()  # (pooled contexts keep counting)
                 tables[-1].set_row_order(ordered)
             else:
                 tables.append(ShardedTable.acquire(num_qubits, cap_i, comm))
@@ -346,6 +350,8 @@ def backpropagate(
         for t in tables:
             info.exchanges += getattr(t, "exchanges", 0)
             info.exchanged_records += getattr(t, "exchanged_records", 0)
+            if hasattr(t, "_seg0"):
+                info.segments = tuple(a + b - c for a, b, c in zip(info.segments, t.segment_stats(), t._seg0))
             t.profile_enable(False)
             t.release()
 
@@ -359,6 +365,7 @@ def backpropagate(
     last_run.sharded = comm is not None
     last_run.exchanges = info.exchanges
     last_run.exchanged_records = info.exchanged_records
+    last_run.segments = info.segments
     obs_out = [restore_types(o) for o in obs_out]
     return (obs_out[0] if single else obs_out), slices_out, metadata
 

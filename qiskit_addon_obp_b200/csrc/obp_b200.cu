@@ -10,6 +10,7 @@
 
 #include "obp_kernels.cuh"
 #include "obp_qwc.cuh"
+#include "obp_segment.cuh"
 
 namespace {
 
@@ -111,6 +112,18 @@ struct obp_ctx {
   bool use_program = true;
   u64 prog_max_rows = 1ull << 18;  // tables of at least this many rows run their gates as stand-alone kernels
   bool broken = false;  // a failed obp_reserve could not restore the table: every entry point fails fast
+  // ---- runs of rotations applied in shared memory (obp_segment.cuh) ----
+  bool use_segments = true;
+  int seg_min_gates = 6;        // shorter runs go through the per-gate kernels
+  int seg_cap_rows = 0;         // test hook: rows a partition may hold (0: what the shared memory allows)
+  int seg_smem_max = 0;         // opt-in shared memory per CTA of k_seg_main (0: path unavailable)
+  double seg_growth = 4.0;      // rows out / rows in of the last run (sizes the next run's partitions)
+  ulonglong2* alt_xz[2] = {nullptr, nullptr};  // the run's output columns (swapped with the table's on success)
+  double2* alt_coef = nullptr;
+  u64* alt_hash = nullptr;
+  unsigned char* d_seg = nullptr;  // [cnt | off | cur] (OBP_SEG_MAXP + 1 u32 each) | SegRes
+  bool index_stale = false;        // the table's columns were replaced by a run: the index is rebuilt before its next use
+  u64 n_seg_runs = 0, n_seg_retries = 0, n_seg_fallbacks = 0;
   bool trace_host = false;  // OBP_B200_TRACE_HOST: print host enqueue / wait time per gate program
   int prog_min_grid = 148;  // smallest grid of the persistent program kernel (grid barriers cost more with more CTAs)
   int prog_reach_shift = 6;  // the grid is sized for rows << min(#rotations, this)
@@ -305,12 +318,16 @@ void init_frame(obp_ctx* ctx) {
 
 // (re)build the index from the live rows (no duplicates expected)
 int rebuild_index(obp_ctx* ctx) {
+  ctx->index_stale = false;
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
   Bracket b(ctx, OBP_K_INDEX);
   k_index_build<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), 0, -1.0, ctx->epoch, -1, nullptr);
   CU(cudaGetLastError());
   return OBP_OK;
 }
+
+// a run of rotations in shared memory replaces the table's columns and leaves the index behind
+int ensure_index(obp_ctx* ctx) { return ctx->index_stale ? rebuild_index(ctx) : OBP_OK; }
 
 // move every row i with dest[i] != NONE to row dest[i] (all columns), then rebuild the index;
 // st->scan_total holds the new row count
@@ -399,10 +416,20 @@ int alloc_table(obp_ctx* ctx, u64 cap) {
   CU(cudaMalloc(&ctx->dest, cap * sizeof(unsigned)));
   CU(cudaMalloc(&ctx->blk, ((cap + OBP_CHUNK - 1) / OBP_CHUNK + 1) * sizeof(unsigned)));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  ctx->index_stale = false;
   return OBP_OK;
 }
 
+void free_seg_columns(obp_ctx* ctx) {
+  for (int w = 0; w < 2; ++w) { cudaFree(ctx->alt_xz[w]); ctx->alt_xz[w] = nullptr; }
+  cudaFree(ctx->alt_coef);
+  cudaFree(ctx->alt_hash);
+  ctx->alt_coef = nullptr;
+  ctx->alt_hash = nullptr;
+}
+
 void free_table(obp_ctx* ctx) {
+  free_seg_columns(ctx);
   for (int w = 0; w < OBP_MAX_WORDS; ++w) {
     if (ctx->xz[w]) cudaFree(ctx->xz[w]);
     ctx->xz[w] = nullptr;
@@ -659,6 +686,10 @@ struct PendingOps {
   int n_ops = 0, n_entries = 0, n_slots = 0, last_split = -1;
   u64 n_start = 0;
   bool prog_mode = false;
+  bool segment = false;   // a run of rotations in shared memory (slot n_slots reports its outcome)
+  int seg_P = 0;          // its partition count
+  int seg_try = 0;
+  double atol = 0.0;
   std::chrono::steady_clock::time_point t_host0;
 };
 
@@ -900,6 +931,18 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     }
     if (prop.cooperativeLaunch)
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->trunc_ctas_per_sm, k_trunc_search, OBP_BS, 0));
+    if (ctx->W <= 2) {
+      // the slice-in-shared-memory kernel opts in to (nearly) the whole shared memory of an SM
+      int optin = 0;
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+      const int want = std::min(optin, 227 * 1024) - 1024;
+      if (want >= 64 * 1024 &&
+          cudaFuncSetAttribute(k_seg_main<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) == cudaSuccess &&
+          cudaFuncSetAttribute(k_seg_main<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) == cudaSuccess)
+        ctx->seg_smem_max = want;
+      else
+        cudaGetLastError();
+    }
     CU(cudaMalloc(&ctx->d_ts, sizeof(TruncState)));
     CU(cudaMallocHost(&ctx->h_ts, sizeof(TruncState)));
     {
@@ -910,6 +953,9 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
       if (const char* e3 = getenv("OBP_B200_PROG_REACH_SHIFT")) ctx->prog_reach_shift = std::max(0, atoi(e3));
       if (const char* e6 = getenv("OBP_B200_PROG_DEBUG")) ctx->prog_debug = atoi(e6) & ~1;
       if (const char* e7 = getenv("OBP_B200_PROG_MAX_ROWS")) ctx->prog_max_rows = (u64)std::max(0ll, atoll(e7));
+      if (const char* e8 = getenv("OBP_B200_NO_SEGMENTS")) ctx->use_segments = !(e8[0] && e8[0] != '0');
+      if (const char* e9 = getenv("OBP_B200_SEG_MIN_GATES")) ctx->seg_min_gates = std::max(1, atoi(e9));
+      if (const char* e10 = getenv("OBP_B200_SEG_CAP_ROWS")) ctx->seg_cap_rows = std::max(0, atoi(e10));
     }
     init_frame(ctx);
     return set_counts(ctx, 0);
@@ -934,6 +980,7 @@ void obp_destroy(obp_ctx* ctx) {
   cudaFree(ctx->d_cols);
   cudaFree(ctx->d_cnt);
   cudaFree(ctx->d_prog);
+  cudaFree(ctx->d_seg);
   cudaFree(ctx->d_stage);
   cudaFree(ctx->ord_minidx);
   cudaFree(ctx->ord_flag);
@@ -1010,6 +1057,7 @@ static int load_impl(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_wo
   if (rc) return rc;
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  ctx->index_stale = false;
   Tab t = make_tab(ctx);
   if (n && atol == OBP_ATOL_RAW) {  // simplify=False: rows as given, duplicates and zeros included
     Bracket b(ctx, OBP_K_INDEX, 2);
@@ -1129,13 +1177,105 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
 // Runs ops[0, n_ops) — or, on a sharded table, up to the first rotation whose partner keys live on
 // another rank: *n_done = ops executed, *peer_xor = owner bits of that rotation's generator hash.
 // Second half of a gate program: wait for the device, account, compact if needed, fill the statistics.
+
+// ---- runs of rotations in shared memory (obp_segment.cuh) -------------------------------------------------------
+static bool segment_eligible(const obp_ctx* ctx, const obp_op* ops, int n_ops) {
+  if (!ctx->use_segments || ctx->seg_smem_max <= 0 || ctx->W > 2 || ctx->n_ranks != 1 || ctx->row_order || ctx->flag_sync) return false;
+  if (n_ops < ctx->seg_min_gates || n_ops > OBP_SEG_MAXG || ctx->n_live == 0 || ctx->n_dense >= (1ull << 31)) return false;
+  for (int k = 0; k < n_ops; ++k) {
+    if (ops[k].kind != OBP_OP_ROTATION) return false;
+    const unsigned allowed = (k == n_ops - 1) ? OBP_FLAG_EXACT_COUNTERS : 0u;
+    if (ops[k].flags & ~allowed) return false;
+  }
+  return true;
+}
+
+// bytes of dynamic shared memory k_seg_main needs for `cap` rows per partition
+static size_t seg_smem_bytes(int W, int cap, int n_index, int ng) {
+  return (size_t)cap * (16 * W + 16 + 8 + 1) + (size_t)ng * sizeof(SegGate) + (size_t)((ng + 1) & ~1) * 4 + (size_t)n_index * 2 + 64;
+}
+
+// The partition map of a run: a GF(2)-linear map keys -> OBP_SEG_FBITS bits that vanishes on every generator.
+// Key bit positions: word w, plane (x = 0, z = 1), bit b -> 128 w + 64 plane + b.
+static void seg_partition_map(const std::vector<SegGate>& gates, int W, u64 fmask[OBP_SEG_FBITS][4]) {
+  struct V { u64 w[4]; };
+  std::vector<V> basis;     // reduced row echelon form of the generators
+  std::vector<int> pivot;
+  auto test = [](const V& v, int b) { return (v.w[b >> 6] >> (b & 63)) & 1ull; };
+  for (const SegGate& g : gates) {
+    V v{{g.gx[0], g.gz[0], W == 2 ? g.gx[1] : 0ull, W == 2 ? g.gz[1] : 0ull}};
+    for (size_t k = 0; k < basis.size(); ++k)
+      if (test(v, pivot[k]))
+        for (int j = 0; j < 4; ++j) v.w[j] ^= basis[k].w[j];
+    int pv = -1;
+    for (int j = 0; j < 4 && pv < 0; ++j)
+      if (v.w[j]) pv = 64 * j + __builtin_ctzll(v.w[j]);
+    if (pv < 0) continue;  // dependent on the generators before it
+    for (size_t k = 0; k < basis.size(); ++k)
+      if (test(basis[k], pv))
+        for (int j = 0; j < 4; ++j) basis[k].w[j] ^= v.w[j];
+    basis.push_back(v);
+    pivot.push_back(pv);
+  }
+  // random weights on the free positions, the pivots follow from f(G) = 0
+  unsigned r[256];
+  u64 seed = 0x5E6B200D15EA5Eull;
+  for (int b = 0; b < 256; ++b) r[b] = (unsigned)(splitmix64(seed) & ((1u << OBP_SEG_FBITS) - 1u));
+  for (int pv : pivot) r[pv] = 0;
+  for (size_t k = 0; k < basis.size(); ++k) {
+    unsigned acc = 0;
+    for (int b = 0; b < 256; ++b)
+      if (b != pivot[k] && test(basis[k], b)) acc ^= r[b];  // (no other pivot occurs in a reduced row)
+    r[pivot[k]] = acc;
+  }
+  for (int j = 0; j < OBP_SEG_FBITS; ++j)
+    for (int q = 0; q < 4; ++q) {
+      u64 m = 0;
+      for (int b = 0; b < 64; ++b)
+        if ((r[64 * q + b] >> j) & 1u) m |= 1ull << b;
+      fmask[j][q] = m;
+    }
+}
+
+static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,
+                          int32_t* n_done, int32_t* peer_xor, bool defer);
+static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats, bool defer,
+                         int force_P, int n_try);
+
 static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
   int rc;
   if (stats) memset(stats, 0, sizeof(*stats));
   const auto t_host1 = std::chrono::steady_clock::now();
   // state + start stamp + counters (+ the per-op barrier stamps while profiling) in one copy
-  const bool by_kernel = P.prog_mode && P.n_entries > 0;
-  const int sync_rc = sync_state(ctx, P.n_slots + (ctx->prof_on ? P.n_entries : 0), by_kernel);
+  const bool by_kernel = (P.prog_mode && P.n_entries > 0) || P.segment;
+  const int sync_rc = sync_state(ctx, P.n_slots + (P.segment ? 1 : 0) + (ctx->prof_on ? P.n_entries : 0), by_kernel);
+  if (P.segment && !sync_rc) {
+    // a run of rotations in shared memory: slot n_slots holds its outcome.  The input table is untouched until here.
+    const unsigned ovf = (unsigned)ctx->h_ops[P.n_slots].n_out;
+    if (ovf) {
+      std::vector<obp_op> ops = P.ops;  // (P may be ctx->pending's storage)
+      const int n_ops = P.n_ops, n_try = P.seg_try;
+      const double atol = P.atol;
+      if (!(ovf & 2u) && n_try < 1 && (u64)P.seg_P * 4 <= OBP_SEG_MAXP) {
+        ctx->n_seg_retries++;
+        return apply_segment(ctx, ops.data(), n_ops, atol, stats, false, P.seg_P * 4, n_try + 1);  // smaller partitions
+      }
+      ctx->n_seg_fallbacks++;
+      ctx->seg_growth = 16.0;
+      const bool keep = ctx->use_segments;
+      ctx->use_segments = false;
+      rc = apply_ops_impl(ctx, ops.data(), n_ops, atol, stats, nullptr, nullptr, false);  // the per-gate kernels
+      ctx->use_segments = keep;
+      return rc;
+    }
+    // commit: the output columns become the table (the old columns are the next run's output)
+    for (int w = 0; w < ctx->W; ++w) std::swap(ctx->xz[w], ctx->alt_xz[w]);
+    std::swap(ctx->coef, ctx->alt_coef);
+    std::swap(ctx->hash, ctx->alt_hash);
+    ctx->index_stale = true;
+    ctx->n_seg_runs++;
+    ctx->seg_growth = (double)ctx->n_live / (double)std::max<u64>(P.n_start, 1);
+  }
   if (ctx->trace_host) {
     const auto t_host2 = std::chrono::steady_clock::now();
     fprintf(stderr, "[obp host] ops %d slots %d: enqueue %.1f us, wait %.1f us\n", P.n_ops, P.n_slots,
@@ -1167,7 +1307,7 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
     for (int k = 0, s_prev = -1; k < P.n_ops; ++k) {
       const int s = P.slot_of_op[k];
       if (s != s_prev && s_prev >= 0) nin = ctx->h_ops[s_prev].n_out;
-      ctx->prof.term_updates[P.ops[k].kind == OBP_OP_ROTATION ? OBP_K_ROTATE : OBP_K_CLIFFORD] += nin;
+      ctx->prof.term_updates[P.segment ? OBP_K_SEGMENT : P.ops[k].kind == OBP_OP_ROTATION ? OBP_K_ROTATE : OBP_K_CLIFFORD] += nin;
       s_prev = s;
     }
   }
@@ -1221,6 +1361,143 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
   return OBP_OK;
 }
 
+// A run of rotations (the whole call) applied in shared memory: partition the table by a linear map that vanishes on
+// every generator, one CTA per partition applies all gates, the survivors go to the second set of columns
+// (obp_segment.cuh).  The table is committed in finish_ops once the outcome is known.
+static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats, bool defer,
+                         int force_P, int n_try) {
+  const auto t_host0 = std::chrono::steady_clock::now();
+  const int W = ctx->W, ng = n_ops;
+  int rc = ensure_ops(ctx, ng + 2);
+  if (rc) return rc;
+  // second set of columns and the partition scratch: allocated on first use (a failed allocation turns the path off)
+  if (!ctx->alt_coef) {
+    bool ok = true;
+    for (int w = 0; w < W && ok; ++w) ok = cudaMalloc(&ctx->alt_xz[w], ctx->cap * sizeof(ulonglong2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->alt_coef, ctx->cap * sizeof(double2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->alt_hash, ctx->cap * sizeof(u64)) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      free_seg_columns(ctx);
+      ctx->use_segments = false;
+      return apply_ops_impl(ctx, ops, n_ops, atol, stats, nullptr, nullptr, defer);
+    }
+  }
+  const size_t part_bytes = (3 * (size_t)(OBP_SEG_MAXP + 1) * sizeof(unsigned) + 255) & ~(size_t)255;
+  if (!ctx->d_seg) CU(cudaMalloc(&ctx->d_seg, part_bytes + sizeof(SegRes)));
+  unsigned* d_cnt = (unsigned*)ctx->d_seg;
+  unsigned* d_off = d_cnt + (OBP_SEG_MAXP + 1);
+  unsigned* d_cur = d_off + (OBP_SEG_MAXP + 1);
+  SegRes* d_res = (SegRes*)(ctx->d_seg + part_bytes);
+
+  // gate parameters
+  std::vector<SegGate> gates((size_t)ng);
+  for (int k = 0; k < ng; ++k) {
+    const RotP p = build_rotp(ctx, ops[k], atol);
+    SegGate& g = gates[k];
+    memset(&g, 0, sizeof(g));
+    for (int q = 0; q < p.ngw; ++q) { g.gx[p.gw[q]] = p.gx[q]; g.gz[p.gw[q]] = p.gz[q]; }
+    g.hG = p.hG;
+    g.u0r = p.u0r; g.u0i = p.u0i; g.u1r = p.u1r; g.u1i = p.u1i;
+    g.yG = p.yG;
+    g.simple = p.simple;
+  }
+  SegP sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.ng = ng;
+  sp.exact_last = (ops[ng - 1].flags & OBP_FLAG_EXACT_COUNTERS) ? 1 : 0;
+  sp.slot0 = 0;
+  sp.n_dense = ctx->n_dense;
+  sp.out_cap = ctx->cap;
+  sp.atol = atol;
+  seg_partition_map(gates, W, sp.fmask);
+  // partition geometry: as many rows per partition as the shared memory holds, the index at most 3/8 full
+  int cap_rows = 4096, n_index = 8192;
+  while (cap_rows > 64 && seg_smem_bytes(W, cap_rows, n_index, ng) > (size_t)ctx->seg_smem_max) cap_rows -= 64;
+  if (ctx->seg_cap_rows > 0) cap_rows = std::min(cap_rows, std::max(ctx->seg_cap_rows, 8));
+  n_index = (int)next_pow2((u64)std::max(2 * cap_rows, 64));
+  sp.cap_rows = cap_rows;
+  sp.n_index = n_index;
+  const size_t smem = seg_smem_bytes(W, cap_rows, n_index, ng);
+  const int n_ctas = ctx->n_sm;  // one CTA per SM (the partition fills its shared memory)
+  int P = force_P;
+  if (P <= 0) {
+    const double growth = std::min(16.0, std::max(2.0, ctx->seg_growth)) * 1.5;
+    const double want = (double)ctx->n_live * growth / (0.5 * cap_rows);
+    P = (int)std::min<double>((double)OBP_SEG_MAXP, std::max<double>((double)n_ctas, std::ceil(want)));
+  }
+  P = std::max(1, std::min(P, OBP_SEG_MAXP));
+  sp.P = P;
+
+  // upload the gates through the program staging buffer
+  const size_t need = gates.size() * sizeof(SegGate);
+  if (need > ctx->prog_alloc) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_prog);
+    if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
+    ctx->d_prog = ctx->h_prog = nullptr;
+    ctx->prog_alloc = 0;
+    const size_t na = std::max<size_t>(2 * need, 1 << 16);
+    CU(cudaMalloc(&ctx->d_prog, na));
+    CU(cudaMallocHost(&ctx->h_prog, na));
+    ctx->prog_alloc = na;
+  }
+  memcpy(ctx->h_prog, gates.data(), need);
+  CU(cudaMemcpyAsync(ctx->d_prog, ctx->h_prog, need, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_seg, 0, part_bytes + sizeof(SegRes), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * (size_t)(ng + 1), ctx->stream));
+  Tab t = make_tab(ctx);
+  SegOut out;
+  out.xz[0] = ctx->alt_xz[0];
+  out.xz[1] = ctx->alt_xz[1];
+  out.coef = ctx->alt_coef;
+  out.hash = ctx->alt_hash;
+  unsigned* part = ctx->dest;
+  unsigned* perm = (unsigned*)ctx->spare8;
+  const SegGate* d_gates = (const SegGate*)ctx->d_prog;
+  {
+    Bracket br(ctx, OBP_K_SEGMENT, 5);
+    ctx->prof.passes[OBP_K_SEGMENT] += (u64)(ng - 1);  // (one pass per gate, in shared memory)
+    const int g1 = grid_for(ctx, ctx->n_dense);
+    const int gm = std::min(P, n_ctas);
+    if (W == 1) {
+      k_seg_count<1><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt);
+      k_seg_scan<<<1, 1024, 0, ctx->stream>>>(d_cnt, d_off, d_cur, P);
+      k_seg_scatter<<<g1, OBP_BS, 0, ctx->stream>>>(part, d_off, d_cur, perm, ctx->n_dense);
+      k_seg_main<1><<<gm, OBP_SEG_THREADS, smem, ctx->stream>>>(t, out, sp, d_gates, d_off, perm, d_res);
+    } else {
+      k_seg_count<2><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt);
+      k_seg_scan<<<1, 1024, 0, ctx->stream>>>(d_cnt, d_off, d_cur, P);
+      k_seg_scatter<<<g1, OBP_BS, 0, ctx->stream>>>(part, d_off, d_cur, perm, ctx->n_dense);
+      k_seg_main<2><<<gm, OBP_SEG_THREADS, smem, ctx->stream>>>(t, out, sp, d_gates, d_off, perm, d_res);
+    }
+    k_seg_finish<<<1, 256, 0, ctx->stream>>>(ctx->d_st, ctx->d_ops, d_res, 0, ng, ctx->n_live, ctx->h_res_dev, ng + 1);
+    CU(cudaGetLastError());
+  }
+  PendingOps P_;
+  P_.ops.assign(ops, ops + n_ops);
+  P_.slot_of_op.resize((size_t)n_ops);
+  for (int k = 0; k < n_ops; ++k) P_.slot_of_op[k] = k;
+  P_.slot_gates.assign((size_t)n_ops, 1);
+  P_.n_ops = n_ops;
+  P_.n_entries = 0;
+  P_.n_slots = n_ops;
+  P_.last_split = -1;
+  P_.n_start = ctx->n_live;
+  P_.prog_mode = false;
+  P_.segment = true;
+  P_.seg_P = P;
+  P_.seg_try = n_try;
+  P_.atol = atol;
+  P_.t_host0 = t_host0;
+  if (defer) {
+    delete ctx->pending;
+    ctx->pending = new PendingOps(std::move(P_));
+    return OBP_OK;
+  }
+  return finish_ops(ctx, P_, stats);
+}
+
 static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,
                           int32_t* n_done, int32_t* peer_xor, bool defer = false) {
   if (!ctx || (n_ops && !ops) || n_ops < 0) return OBP_ERR_BADARG;
@@ -1236,6 +1513,11 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   for (int k = 0; k < n_ops; ++k) {
     const int vrc = validate_op(ctx, ops[k]);
     if (vrc) return vrc;
+  }
+  if (segment_eligible(ctx, ops, n_ops) && !n_done) return apply_segment(ctx, ops, n_ops, atol, stats, defer, 0, 0);
+  {
+    const int irc = ensure_index(ctx);
+    if (irc) return irc;
   }
   const auto t_host0 = std::chrono::steady_clock::now();
   // tables of <= 128 qubits: record the program and run it with ONE persistent cooperative launch
@@ -1758,6 +2040,7 @@ int obp_shard_split(obp_ctx* ctx, int32_t n_ranks, int32_t rank, const obp_op* f
   int rc = obp_set_shard(ctx, n_ranks, rank);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   if (n_covered) *n_covered = 0;
   int bits = 0;
   while ((1 << bits) < n_ranks) ++bits;
@@ -1894,6 +2177,7 @@ int obp_rotate_emit(obp_ctx* ctx, const obp_op* op, double atol, void* d_records
                     obp_shard_counters* out) {
   if (!ctx || !op || op->kind != OBP_OP_ROTATION || (cap_records && !d_records)) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   int rc = validate_op(ctx, *op);
   if (rc) return rc;
   RotP p = build_rotp(ctx, *op, atol);
@@ -1922,6 +2206,7 @@ int obp_rotate_merge(obp_ctx* ctx, const void* d_records, uint64_t n_records, ob
   if (!ctx || (n_records && !d_records)) return OBP_ERR_BADARG;
   if (!ctx->shard_rot_open) return ctx->fail(OBP_ERR_BADARG, "obp_rotate_merge: no rotation in flight");
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   ctx->shard_rot_open = false;
   const u64 n_in = ctx->n_live;
   CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(ShardCnt), ctx->stream));
@@ -1956,6 +2241,7 @@ int obp_reset_emit(obp_ctx* ctx, int32_t qubit, double atol, void* d_records, ui
                    obp_shard_counters* out) {
   if (!ctx || qubit < 0 || qubit >= ctx->nq || !peer_xor || (cap_records && !d_records)) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   *peer_xor = ctx->n_ranks > 1 ? (int32_t)(ctx->hz[qubit] >> ctx->owner_shift) : 0;
   if (*peer_xor == 0) return OBP_OK;
   int rc = ensure_ops(ctx, 2);
@@ -1992,6 +2278,7 @@ int obp_reset_emit(obp_ctx* ctx, int32_t qubit, double atol, void* d_records, ui
 int obp_reset_merge(obp_ctx* ctx, double atol, const void* d_records, uint64_t n_records, obp_shard_counters* out) {
   if (!ctx || (n_records && !d_records)) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   const u64 n_in = ctx->n_live;
   int rc = ensure_ops(ctx, 2);
   if (rc) return rc;
@@ -2101,6 +2388,7 @@ int obp_rotate_emit_p2p(obp_ctx* ctx, const obp_op* op, double atol, int32_t pee
   const int b = ctx->xchg_parity;
   if (!ctx->inbox[b] || !ctx->peer_inbox[b][peer_rank]) return ctx->fail(OBP_ERR_BADARG, "obp_rotate_emit_p2p: peer inbox not attached");
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   int rc = validate_op(ctx, *op);
   if (rc) return rc;
   RotP p = build_rotp(ctx, *op, atol);
@@ -2131,6 +2419,7 @@ int obp_rotate_merge_inbox(obp_ctx* ctx, obp_shard_counters* out) {
   const int b = ctx->xchg_parity;
   if (!ctx->inbox[b]) return ctx->fail(OBP_ERR_BADARG, "obp_rotate_merge_inbox: no inbox");
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   ctx->shard_rot_open = false;
   ctx->xchg_parity ^= 1;
   const u64 n_in = ctx->n_live;
@@ -2172,6 +2461,7 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
   if (ctx->n_ranks > 1 && simplify)
     return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_generic: with simplify, not available on a sharded table");
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   GenP p;
   memset(&p, 0, sizeof(p));
   p.m = n_qubits;
@@ -2219,6 +2509,7 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
   CU(cudaMemcpyAsync(ctx->d_st, ctx->h_st, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  ctx->index_stale = false;
   if (!simplify) {  // OperatorBudget(simplify=False): keep every raw row, zeros included
     if (raw) {
       Bracket br(ctx, OBP_K_OTHER);
@@ -2292,6 +2583,7 @@ static int reset_in_row_order(obp_ctx* ctx, int32_t qubit, double atol, obp_stat
   if (rc) return rc;
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
+  ctx->index_stale = false;
   Tab t = make_tab(ctx);
   if (n_in) {
     Bracket br(ctx, OBP_K_OTHER, 4);
@@ -2332,6 +2624,7 @@ int obp_apply_reset(obp_ctx* ctx, int32_t qubit, double atol, obp_stats* stats) 
   OBP_NO_PENDING(ctx, "obp_apply_reset");
   if (!ctx || qubit < 0 || qubit >= ctx->nq) return OBP_ERR_BADARG;
   CU(cudaSetDevice(ctx->device));
+  { const int irc = ensure_index(ctx); if (irc) return irc; }
   if (atol == OBP_ATOL_RAW) {  // simplify=False: zero the X/Y rows, clear the qubit, merge nothing
     const u64 n_rows = ctx->n_live;
     {
@@ -2719,6 +3012,7 @@ int obp_reserve(obp_ctx* ctx, uint64_t new_capacity) {
   const u64 n = ctx->n_live;
   const u64 old_cap = ctx->cap, cap = new_capacity;
   free_scratch(ctx);
+  free_seg_columns(ctx);  // (sized by the capacity; allocated again by the next run of rotations that wants them)
   // one data column: bigger buffer, copy the live rows, release the old buffer
   auto grow_column = [&](void** slot, size_t elem) -> int {
     void* p = nullptr;
@@ -2776,8 +3070,19 @@ int obp_configure(obp_ctx* ctx, int32_t option, int64_t value) {
   switch (option) {
     case OBP_OPT_PROGRAM: ctx->use_program = value != 0; return OBP_OK;
     case OBP_OPT_PROGRAM_MAX_ROWS: ctx->prog_max_rows = value < 0 ? 0 : (u64)value; return OBP_OK;
+    case OBP_OPT_SEGMENTS: ctx->use_segments = value != 0; return OBP_OK;
+    case OBP_OPT_SEGMENT_MIN_GATES: ctx->seg_min_gates = value < 1 ? 1 : (int)std::min<int64_t>(value, 1 << 20); return OBP_OK;
+    case OBP_OPT_SEGMENT_CAP_ROWS: ctx->seg_cap_rows = value < 0 ? 0 : (int)std::min<int64_t>(value, 4096); return OBP_OK;
     default: return ctx->fail(OBP_ERR_BADARG, "obp_configure: unknown option");
   }
+}
+
+int obp_segment_stats(obp_ctx* ctx, uint64_t* n_runs, uint64_t* n_retries, uint64_t* n_fallbacks) {
+  if (!ctx) return OBP_ERR_BADARG;
+  if (n_runs) *n_runs = ctx->n_seg_runs;
+  if (n_retries) *n_retries = ctx->n_seg_retries;
+  if (n_fallbacks) *n_fallbacks = ctx->n_seg_fallbacks;
+  return OBP_OK;
 }
 
 int obp_is_broken(const obp_ctx* ctx) { return ctx && ctx->broken ? 1 : 0; }

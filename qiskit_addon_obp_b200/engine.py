@@ -32,7 +32,10 @@ OBP_ATOL_MERGE_ONLY = -1.0
 OBP_ATOL_RAW = -2.0  # simplify=False: no merge, exact zeros stay
 OBP_OPT_PROGRAM = 1
 OBP_OPT_PROGRAM_MAX_ROWS = 2
-OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other", "program")
+OBP_OPT_SEGMENTS = 3
+OBP_OPT_SEGMENT_MIN_GATES = 4
+OBP_OPT_SEGMENT_CAP_ROWS = 5
+OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other", "program", "segment")
 
 #: numpy mirror of ``obp_op`` (104 bytes, natural C alignment)
 OP_DTYPE = np.dtype(
@@ -73,10 +76,10 @@ class ObpStats(C.Structure):
 
 class ObpProfile(C.Structure):
     _fields_ = [
-        ("launches", C.c_uint64 * 7),
-        ("passes", C.c_uint64 * 7),
-        ("ms", C.c_double * 7),
-        ("term_updates", C.c_uint64 * 7),
+        ("launches", C.c_uint64 * 8),
+        ("passes", C.c_uint64 * 8),
+        ("ms", C.c_double * 8),
+        ("term_updates", C.c_uint64 * 8),
     ]
 
 
@@ -148,6 +151,7 @@ def lib() -> C.CDLL:
         "obp_set_shard": ([vp, C.c_int32, C.c_int32], C.c_int),
         "obp_record_bytes": ([C.c_int], C.c_uint64),
         "obp_shard_stats": ([vp, u64p, u64p], C.c_int),
+        "obp_segment_stats": ([vp, u64p, u64p, u64p], C.c_int),
         "obp_shard_split": ([vp, C.c_int32, C.c_int32, vp, C.c_int32, u64p, C.POINTER(C.c_int32)], C.c_int),
         "obp_apply_ops_sharded": (
             [vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
@@ -186,7 +190,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count obp_shard_stats"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count obp_shard_stats obp_segment_stats"
 ).split()
 
 
@@ -266,6 +270,10 @@ class TermTable:
         no_prog = os.environ.get("OBP_B200_NO_PROGRAM", "0") not in ("", "0")
         self.configure(OBP_OPT_PROGRAM, 0 if no_prog else 1)
         self.configure(OBP_OPT_PROGRAM_MAX_ROWS, int(os.environ.get("OBP_B200_PROG_MAX_ROWS", str(1 << 18))))
+        # runs of rotations applied in shared memory (OBP_B200_NO_SEGMENTS=1: one pass over the table per gate)
+        self.configure(OBP_OPT_SEGMENTS, 0 if os.environ.get("OBP_B200_NO_SEGMENTS", "0") not in ("", "0") else 1)
+        self.configure(OBP_OPT_SEGMENT_MIN_GATES, int(os.environ.get("OBP_B200_SEG_MIN_GATES", "6")))
+        self.configure(OBP_OPT_SEGMENT_CAP_ROWS, int(os.environ.get("OBP_B200_SEG_CAP_ROWS", "0")))
 
     def configure(self, option: int, value: int) -> None:
         self._check(self._lib.obp_configure(self._h, int(option), int(value)), "obp_configure")
@@ -578,6 +586,13 @@ class TermTable:
     # -- sharded table (see sharded.py) ----------------------------------------------------------
     def set_shard(self, n_ranks: int, rank: int):
         self._check(self._lib.obp_set_shard(self._h, int(n_ranks), int(rank)), "obp_set_shard")
+
+    def segment_stats(self) -> tuple[int, int, int]:
+        """``(runs of rotations applied in shared memory, runs retried with smaller partitions, runs handed to the
+        per-gate kernels)`` since the context was created."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.obp_segment_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "obp_segment_stats")
+        return a.value, b.value, c.value
 
     def shard_stats(self) -> tuple[int, int]:
         """``(rotations that needed a record exchange, records emitted)`` since the context was created."""

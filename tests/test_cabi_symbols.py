@@ -57,7 +57,7 @@ def test_op_record_layout_matches_header():
         "group_size": 44, "group_elems": 48, "row_scale": 56, "gen_local": 64, "reserved": 68, "u0": 72, "u1": 88,
     }  # fmt: skip
     assert ctypes.sizeof(ObpStats) == 80
-    assert ctypes.sizeof(ObpProfile) == 7 * 8 * 4
+    assert ctypes.sizeof(ObpProfile) == 8 * 8 * 4  # OBP_K_COUNT classes x four arrays
 
 
 def test_no_cpu_fallback_without_device(lib):

@@ -172,13 +172,17 @@ def test_random_circuit_truncation(nq, p):
 
 
 @pytest.mark.parametrize("nq", [5, 40, 70, 127])
-@pytest.mark.parametrize("layers", [True, False], ids=["slice-in-smem", "gate-by-gate"])
-def test_rotation_layers(nq, layers, monkeypatch):
+@pytest.mark.parametrize("mode", ["slice-in-smem", "tiny-partitions", "gate-by-gate"])
+def test_rotation_layers(nq, mode, monkeypatch):
     """Slices made of rotations only (RX / RY / RZ / RZZ / RXX layers): the slice-in-shared-memory path
     (k_slice_smem: the table partitioned so that whole cosets live in one CTA, all gates between __syncthreads)
     and the gate-by-gate passes against the oracle.  Small angles and a loose atol put coefficients inside the
     trim band of the intermediate gates."""
-    monkeypatch.setenv("OBP_B200_NO_SEGMENTS", "0" if layers else "1")
+    monkeypatch.setenv("OBP_B200_NO_SEGMENTS", "1" if mode == "gate-by-gate" else "0")
+    # partitions of 24 rows: runs outgrow them, are retried with four times as many partitions and finally fall
+    # back to the per-gate kernels (the input table must come through untouched)
+    monkeypatch.setenv("OBP_B200_SEG_CAP_ROWS", "24" if mode == "tiny-partitions" else "0")
+    monkeypatch.setenv("OBP_B200_SEG_MIN_GATES", "2")
     rng = np.random.default_rng(4000 + nq)
     slices = []
     for k in range(6):

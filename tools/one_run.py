@@ -11,4 +11,4 @@ mp = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1_000_000
 wl = W.config2_kicked_ising(theta_h=th, max_paulis=mp)
 for _ in range(2):
     backpropagate(wl.observables, wl.slices, **wl.kwargs())
-    print("updates", bpmod.last_run.updates, "device_ms", round(bpmod.last_run.device_ms, 3))
+    print("updates", bpmod.last_run.updates, "device_ms", round(bpmod.last_run.device_ms, 3), "segments", bpmod.last_run.segments)
