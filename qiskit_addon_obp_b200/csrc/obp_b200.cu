@@ -932,16 +932,19 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
     if (prop.cooperativeLaunch)
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->trunc_ctas_per_sm, k_trunc_search, OBP_BS, 0));
     if (ctx->W <= 2) {
-      // the slice-in-shared-memory kernel opts in to (nearly) the whole shared memory of an SM
+      // the slice-in-shared-memory kernels opt in to (nearly) the whole shared memory of an SM
       int optin = 0;
       cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
       const int want = std::min(optin, 227 * 1024) - 1024;
-      if (want >= 64 * 1024 &&
-          cudaFuncSetAttribute(k_seg_main<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) == cudaSuccess &&
-          cudaFuncSetAttribute(k_seg_main<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) == cudaSuccess)
-        ctx->seg_smem_max = want;
-      else
-        cudaGetLastError();
+      bool ok = want >= 64 * 1024;
+      const void* fns[4] = {(const void*)k_seg_main<1, 128, 4>, (const void*)k_seg_main<2, 128, 4>,
+                            (const void*)k_seg_main<1, 512, 1>, (const void*)k_seg_main<2, 512, 1>};
+      for (int k = 0; k < 4 && ok; ++k) {
+        ok = cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, k < 2 ? want / 4 : want) == cudaSuccess &&
+             cudaFuncSetAttribute(fns[k], cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess;
+      }
+      if (ok) ctx->seg_smem_max = want;
+      else cudaGetLastError();
     }
     CU(cudaMalloc(&ctx->d_ts, sizeof(TruncState)));
     CU(cudaMallocHost(&ctx->h_ts, sizeof(TruncState)));
@@ -1192,7 +1195,16 @@ static bool segment_eligible(const obp_ctx* ctx, const obp_op* ops, int n_ops) {
 
 // bytes of dynamic shared memory k_seg_main needs for `cap` rows per partition
 static size_t seg_smem_bytes(int W, int cap, int n_index, int ng) {
-  return (size_t)cap * (16 * W + 16 + 8 + 1) + (size_t)ng * sizeof(SegGate) + (size_t)((ng + 1) & ~1) * 4 + (size_t)n_index * 2 + 64;
+  return (size_t)cap * (16 * W + 16 + 8 + 1) + 2 * (size_t)((ng + 1) & ~1) * 4 + (size_t)n_index * 2 + 64;
+}
+
+// the largest partition (rows, multiple of 64) whose arrays and index (at most half full) fit `budget` bytes
+static void seg_geometry(int W, int ng, size_t budget, int limit_rows, int* cap_rows, int* n_index) {
+  int cap = 4096;
+  while (cap > 64 && seg_smem_bytes(W, cap, (int)next_pow2((u64)2 * cap), ng) > budget) cap -= 64;
+  if (limit_rows > 0) cap = std::min(cap, std::max(limit_rows, 8));
+  *cap_rows = cap;
+  *n_index = (int)next_pow2((u64)std::max(2 * cap, 64));
 }
 
 // The partition map of a run: a GF(2)-linear map keys -> OBP_SEG_FBITS bits that vanishes on every generator.
@@ -1224,8 +1236,11 @@ static void seg_partition_map(const std::vector<SegGate>& gates, int W, u64 fmas
   for (int pv : pivot) r[pv] = 0;
   for (size_t k = 0; k < basis.size(); ++k) {
     unsigned acc = 0;
-    for (int b = 0; b < 256; ++b)
-      if (b != pivot[k] && test(basis[k], b)) acc ^= r[b];  // (no other pivot occurs in a reduced row)
+    for (int j = 0; j < 4; ++j)
+      for (u64 w = basis[k].w[j]; w; w &= w - 1) {
+        const int b = 64 * j + __builtin_ctzll(w);
+        if (b != pivot[k]) acc ^= r[b];  // (no other pivot occurs in a reduced row)
+      }
     r[pivot[k]] = acc;
   }
   for (int j = 0; j < OBP_SEG_FBITS; ++j)
@@ -1254,12 +1269,8 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
     const unsigned ovf = (unsigned)ctx->h_ops[P.n_slots].n_out;
     if (ovf) {
       std::vector<obp_op> ops = P.ops;  // (P may be ctx->pending's storage)
-      const int n_ops = P.n_ops, n_try = P.seg_try;
+      const int n_ops = P.n_ops;
       const double atol = P.atol;
-      if (!(ovf & 2u) && n_try < 1 && (u64)P.seg_P * 4 <= OBP_SEG_MAXP) {
-        ctx->n_seg_retries++;
-        return apply_segment(ctx, ops.data(), n_ops, atol, stats, false, P.seg_P * 4, n_try + 1);  // smaller partitions
-      }
       ctx->n_seg_fallbacks++;
       ctx->seg_growth = 16.0;
       const bool keep = ctx->use_segments;
@@ -1274,6 +1285,7 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
     std::swap(ctx->hash, ctx->alt_hash);
     ctx->index_stale = true;
     ctx->n_seg_runs++;
+    ctx->n_seg_retries += ctx->h_ops[P.n_slots].keys_present;  // partitions that needed the big CTAs
     ctx->seg_growth = (double)ctx->n_live / (double)std::max<u64>(P.n_start, 1);
   }
   if (ctx->trace_host) {
@@ -1383,14 +1395,19 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
       return apply_ops_impl(ctx, ops, n_ops, atol, stats, nullptr, nullptr, defer);
     }
   }
-  const size_t part_bytes = (3 * (size_t)(OBP_SEG_MAXP + 1) * sizeof(unsigned) + 255) & ~(size_t)255;
-  if (!ctx->d_seg) CU(cudaMalloc(&ctx->d_seg, part_bytes + sizeof(SegRes)));
+  const size_t part_bytes = (4 * (size_t)(OBP_SEG_MAXP + 1) * sizeof(unsigned) + 255) & ~(size_t)255;
+  if (!ctx->d_seg) {
+    CU(cudaMalloc(&ctx->d_seg, part_bytes + sizeof(SegRes)));
+    CU(cudaMemsetAsync(ctx->d_seg, 0, part_bytes + sizeof(SegRes), ctx->stream));  // (every run leaves it clean again)
+  }
   unsigned* d_cnt = (unsigned*)ctx->d_seg;
   unsigned* d_off = d_cnt + (OBP_SEG_MAXP + 1);
   unsigned* d_cur = d_off + (OBP_SEG_MAXP + 1);
+  unsigned* d_redo = d_cur + (OBP_SEG_MAXP + 1);
   SegRes* d_res = (SegRes*)(ctx->d_seg + part_bytes);
 
-  // gate parameters
+  // gate parameters (a kernel parameter of the run)
+  static thread_local SegGates gs;  // 24 KB: kept off the stack
   std::vector<SegGate> gates((size_t)ng);
   for (int k = 0; k < ng; ++k) {
     const RotP p = build_rotp(ctx, ops[k], atol);
@@ -1401,6 +1418,11 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
     g.u0r = p.u0r; g.u0i = p.u0i; g.u1r = p.u1r; g.u1i = p.u1i;
     g.yG = p.yG;
     g.simple = p.simple;
+    // no raw row of a term with |c|^2 above this can fall under the zero filter: the smallest factor is
+    // min(|u0|^2, |u1|^2) (|u0||u1| lies between them)
+    const double f0 = p.u0r * p.u0r + p.u0i * p.u0i, f1 = p.u1r * p.u1r + p.u1i * p.u1i, fmin = std::min(f0, f1);
+    g.thr_self = g.thr_all = atol < 0.0 ? -1.0 : (fmin > 0.0 ? atol * atol * (1.0 + 1e-6) / (fmin * fmin) : HUGE_VAL);
+    gs.g[k] = g;
   }
   SegP sp;
   memset(&sp, 0, sizeof(sp));
@@ -1411,41 +1433,23 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   sp.out_cap = ctx->cap;
   sp.atol = atol;
   seg_partition_map(gates, W, sp.fmask);
-  // partition geometry: as many rows per partition as the shared memory holds, the index at most 3/8 full
-  int cap_rows = 4096, n_index = 8192;
-  while (cap_rows > 64 && seg_smem_bytes(W, cap_rows, n_index, ng) > (size_t)ctx->seg_smem_max) cap_rows -= 64;
-  if (ctx->seg_cap_rows > 0) cap_rows = std::min(cap_rows, std::max(ctx->seg_cap_rows, 8));
-  n_index = (int)next_pow2((u64)std::max(2 * cap_rows, 64));
-  sp.cap_rows = cap_rows;
-  sp.n_index = n_index;
-  const size_t smem = seg_smem_bytes(W, cap_rows, n_index, ng);
-  const int n_ctas = ctx->n_sm;  // one CTA per SM (the partition fills its shared memory)
+  // Geometry.  First launch: 128-thread CTAs, four per SM (a quarter of the shared memory each), partitions sized for
+  // ~256 rows after the run's growth; second launch: the partitions that outgrew those, one 512-thread CTA per SM.
+  SegP sp2 = sp;
+  seg_geometry(W, ng, std::min<size_t>((size_t)ctx->seg_smem_max / 4, 55 * 1024), ctx->seg_cap_rows, &sp.cap_rows, &sp.n_index);  // (228 KB per SM, 1 KB reserved per CTA)
+  seg_geometry(W, ng, (size_t)ctx->seg_smem_max, 4 * ctx->seg_cap_rows, &sp2.cap_rows, &sp2.n_index);
+  const size_t smem1 = seg_smem_bytes(W, sp.cap_rows, sp.n_index, ng), smem2 = seg_smem_bytes(W, sp2.cap_rows, sp2.n_index, ng);
+  const int n_ctas1 = 4 * ctx->n_sm, n_ctas2 = ctx->n_sm;
   int P = force_P;
   if (P <= 0) {
-    const double growth = std::min(16.0, std::max(2.0, ctx->seg_growth)) * 1.5;
-    const double want = (double)ctx->n_live * growth / (0.5 * cap_rows);
-    P = (int)std::min<double>((double)OBP_SEG_MAXP, std::max<double>((double)n_ctas, std::ceil(want)));
+    const double growth = std::min(32.0, std::max(1.5, ctx->seg_growth));
+    const double rows_per_part = std::min(256.0, 0.35 * sp.cap_rows);
+    const double want = (double)ctx->n_live * growth / rows_per_part;
+    P = (int)std::min<double>((double)OBP_SEG_MAXP, std::max<double>((double)n_ctas1, std::ceil(want)));
   }
   P = std::max(1, std::min(P, OBP_SEG_MAXP));
-  sp.P = P;
+  sp.P = sp2.P = P;
 
-  // upload the gates through the program staging buffer
-  const size_t need = gates.size() * sizeof(SegGate);
-  if (need > ctx->prog_alloc) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_prog);
-    if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
-    ctx->d_prog = ctx->h_prog = nullptr;
-    ctx->prog_alloc = 0;
-    const size_t na = std::max<size_t>(2 * need, 1 << 16);
-    CU(cudaMalloc(&ctx->d_prog, na));
-    CU(cudaMallocHost(&ctx->h_prog, na));
-    ctx->prog_alloc = na;
-  }
-  memcpy(ctx->h_prog, gates.data(), need);
-  CU(cudaMemcpyAsync(ctx->d_prog, ctx->h_prog, need, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_seg, 0, part_bytes + sizeof(SegRes), ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * (size_t)(ng + 1), ctx->stream));
   Tab t = make_tab(ctx);
   SegOut out;
   out.xz[0] = ctx->alt_xz[0];
@@ -1454,24 +1458,31 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   out.hash = ctx->alt_hash;
   unsigned* part = ctx->dest;
   unsigned* perm = (unsigned*)ctx->spare8;
-  const SegGate* d_gates = (const SegGate*)ctx->d_prog;
   {
-    Bracket br(ctx, OBP_K_SEGMENT, 5);
+    Bracket br(ctx, OBP_K_SEGMENT, 4);
     ctx->prof.passes[OBP_K_SEGMENT] += (u64)(ng - 1);  // (one pass per gate, in shared memory)
     const int g1 = grid_for(ctx, ctx->n_dense);
-    const int gm = std::min(P, n_ctas);
+    const int gm = std::min(P, n_ctas1);
+    const unsigned* none = nullptr;
+    SegFin fin0;
+    memset(&fin0, 0, sizeof(fin0));
+    SegFin fin = fin0;
+    fin.st = ctx->d_st;
+    fin.cnt = d_cnt;
+    fin.n_live_in = ctx->n_live;
+    fin.host_res = ctx->h_res_dev;
+    fin.n_res_ops = ng + 1;
     if (W == 1) {
-      k_seg_count<1><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt);
-      k_seg_scan<<<1, 1024, 0, ctx->stream>>>(d_cnt, d_off, d_cur, P);
+      k_seg_count<1><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt, d_off, d_cur, d_res);
       k_seg_scatter<<<g1, OBP_BS, 0, ctx->stream>>>(part, d_off, d_cur, perm, ctx->n_dense);
-      k_seg_main<1><<<gm, OBP_SEG_THREADS, smem, ctx->stream>>>(t, out, sp, d_gates, d_off, perm, d_res);
+      k_seg_main<1, 128, 4><<<gm, 128, smem1, ctx->stream>>>(t, out, sp, gs, d_off, perm, d_res, none, none, d_redo, fin0);
+      k_seg_main<1, 512, 1><<<n_ctas2, 512, smem2, ctx->stream>>>(t, out, sp2, gs, d_off, perm, d_res, d_redo, &d_res->n_redo, nullptr, fin);
     } else {
-      k_seg_count<2><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt);
-      k_seg_scan<<<1, 1024, 0, ctx->stream>>>(d_cnt, d_off, d_cur, P);
+      k_seg_count<2><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt, d_off, d_cur, d_res);
       k_seg_scatter<<<g1, OBP_BS, 0, ctx->stream>>>(part, d_off, d_cur, perm, ctx->n_dense);
-      k_seg_main<2><<<gm, OBP_SEG_THREADS, smem, ctx->stream>>>(t, out, sp, d_gates, d_off, perm, d_res);
+      k_seg_main<2, 128, 4><<<gm, 128, smem1, ctx->stream>>>(t, out, sp, gs, d_off, perm, d_res, none, none, d_redo, fin0);
+      k_seg_main<2, 512, 1><<<n_ctas2, 512, smem2, ctx->stream>>>(t, out, sp2, gs, d_off, perm, d_res, d_redo, &d_res->n_redo, nullptr, fin);
     }
-    k_seg_finish<<<1, 256, 0, ctx->stream>>>(ctx->d_st, ctx->d_ops, d_res, 0, ng, ctx->n_live, ctx->h_res_dev, ng + 1);
     CU(cudaGetLastError());
   }
   PendingOps P_;

@@ -96,6 +96,39 @@ __device__ __forceinline__ RowSet rot_rows_t(double2 c, int E, int s, const RotP
   return r;
 }
 
+// The same four raw rows when the caller knows that none of them can fall under the zero filter (|c| times the
+// smallest factor is above atol with a margin): the same products and the same sums, no magnitude tests.
+template <bool SIMPLE>
+__device__ __forceinline__ RowSet rot_rows_nofilter_t(double2 c, int E, int s, const RotP& p) {
+  double2 r00, r11, r01, r10;
+  if (SIMPLE) {
+    const double a = p.u0r, b = p.u1i;
+    const double2 t0 = make_double2(__dmul_rn(c.x, a), __dmul_rn(c.y, a));
+    const double2 t1 = make_double2(-__dmul_rn(c.y, b), __dmul_rn(c.x, b));
+    r00 = make_double2(__dmul_rn(t0.x, a), __dmul_rn(t0.y, a));
+    r11 = make_double2(__dmul_rn(t1.y, b), -__dmul_rn(t1.x, b));
+    r01 = make_double2(__dmul_rn(t0.y, b), -__dmul_rn(t0.x, b));
+    r10 = make_double2(__dmul_rn(t1.x, a), __dmul_rn(t1.y, a));
+  } else {
+    const double2 u0 = make_double2(p.u0r, p.u0i), u1 = make_double2(p.u1r, p.u1i);
+    const double2 t0 = cmul(c, u0), t1 = cmul(c, u1);
+    r00 = cmul(t0, cconj(u0));
+    r11 = cmul(t1, cconj(u1));
+    r01 = cmul(t0, cconj(u1));
+    r10 = cmul(t1, cconj(u0));
+  }
+  if (s) r11 = make_double2(-r11.x, -r11.y);
+  RowSet r;
+  r.self = cadd(r00, r11);
+  r.nself = 2;
+  r.cross = cadd(mul_mi_pow(r01, E), mul_mi_pow(r10, E + 2 * s));
+  r.ncross = 2;
+  return r;
+}
+__device__ __forceinline__ RowSet rot_rows_nofilter(double2 c, int E, int s, const RotP& p) {
+  return p.simple ? rot_rows_nofilter_t<true>(c, E, s, p) : rot_rows_nofilter_t<false>(c, E, s, p);
+}
+
 __device__ __forceinline__ RowSet rot_rows(double2 c, int E, int s, const RotP& p) {
   return p.simple ? rot_rows_t<true, true>(c, E, s, p) : rot_rows_t<false, true>(c, E, s, p);
 }

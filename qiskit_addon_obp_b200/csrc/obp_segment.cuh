@@ -18,25 +18,38 @@
 // out, compacted, to the table's second set of columns.  Global memory is read once and written once per RUN instead
 // of once per GATE; the per-gate cost is a shared-memory pass over the partition.
 //
-// Kernels: k_seg_count (partition id per live row + histogram), k_seg_scan (offsets), k_seg_scatter (row ids in
-// partition order), k_seg_main<W> (the run), k_seg_finish (per-gate row counts, table state, result block).
-// The input table is never modified: if a partition outgrows its shared memory (or the output its capacity) the run
+// A partition's pass is a chain of dependent shared-memory accesses and fp64 operations (~1 us per gate) whatever its
+// size, so the run is spread over MANY SMALL CTAs — 128 threads, four per SM, partitions of a few hundred rows —
+// which overlap each other's latencies; the few partitions that outgrow a small CTA's shared memory (a big coset
+// class) are listed and run again by a second launch of one 512-thread CTA per SM with the whole shared memory.
+//
+// Four launches per run: k_seg_count (partition id per live row + histogram; its last CTA turns the histogram into
+// offsets), k_seg_scatter (row ids in partition order), k_seg_main<W, 128, 4> (the run), k_seg_main<W, 512, 1> (the
+// listed partitions again; its last CTA writes the per-gate row counts, the table state and the host's result
+// block).  The gates travel as a kernel parameter (constant bank), nothing is copied or cleared in between.
+// The input table is never modified: if a partition outgrows even the big CTA (or the output its capacity) the run
 // reports it and the host applies the same gates through the per-gate kernels instead.
 #pragma once
 #include "obp_kernels.cuh"
 
-#define OBP_SEG_THREADS 512
-#define OBP_SEG_MAXG 192    // gates per run (their parameters are staged in shared memory)
-#define OBP_SEG_MAXP 8192   // partitions per run
+#define OBP_SEG_MAXG 250    // gates per run (a row records the gate that killed it in one byte; 24 KB of kernel parameters)
+#define OBP_SEG_MAXP 16384  // partitions per run
 #define OBP_SEG_FBITS 16    // output bits of the partition map
 #define OBP_SEG_ALIVE 255u
 
-struct SegGate {  // 80 bytes
+struct SegGate {  // 96 bytes
   u64 gx[2], gz[2];  // generator on table words 0 and 1 (zero where it is the identity)
   u64 hG;            // hash of the generator
   double u0r, u0i, u1r, u1i;
   int yG;
   int simple;
+  // |c|^2 above which no raw row of a term can fall under the zero filter (1e-6 relative margin; rows below take the
+  // exact path): thr_self for the two rows of the term's own key (|c||u0|^2, |c||u1|^2), thr_all for all four
+  double thr_self, thr_all;
+};
+
+struct SegGates {  // the run's gates: a kernel parameter (constant bank: uniform loads, no staging)
+  SegGate g[OBP_SEG_MAXG];
 };
 
 struct SegP {
@@ -55,6 +68,8 @@ struct SegP {
 struct SegRes {  // device-side result of a run (zeroed before)
   u64 out_rows;          // output cursor
   unsigned overflow;     // 1: a partition outgrew shared memory, 2: the output outgrew its columns, 4: a local index filled up
+  unsigned n_redo;       // partitions that outgrew the small CTAs and were run again by the big ones
+  unsigned ticket;       // last-block-done counter (k_seg_count, second k_seg_main)
   unsigned pad;
   long long delta[OBP_SEG_MAXG];  // change of the live-row count by every gate
 };
@@ -77,9 +92,17 @@ __device__ __forceinline__ unsigned seg_part(const SegP& s, const ulonglong2* ke
   return (v * (unsigned)s.P) >> OBP_SEG_FBITS;
 }
 
+// Partition id of every live row + histogram; the last CTA to finish turns the histogram into offsets (off[p],
+// off[P] = live rows) and clears the scatter cursors.  CTA 0 also zeroes the run's counter slots.
 template <int W>
 __global__ void __launch_bounds__(OBP_BS) k_seg_count(Tab t, const __grid_constant__ SegP s, unsigned* __restrict__ part,
-                                                      unsigned* __restrict__ cnt) {
+                                                      unsigned* __restrict__ cnt, unsigned* __restrict__ off,
+                                                      unsigned* __restrict__ cur, SegRes* __restrict__ res) {
+  if (blockIdx.x == 0) {
+    u64* w = reinterpret_cast<u64*>(t.ops + s.slot0);
+    const int n_words = (s.ng + 1) * (int)(sizeof(OpStat) / sizeof(u64));
+    for (int k = threadIdx.x; k < n_words; k += OBP_BS) w[k] = 0;
+  }
   for (u64 i = (u64)blockIdx.x * OBP_BS + threadIdx.x; i < s.n_dense; i += (u64)gridDim.x * OBP_BS) {
     const double2 c = t.coef[i];
     unsigned p = 0xffffffffu;
@@ -92,19 +115,22 @@ __global__ void __launch_bounds__(OBP_BS) k_seg_count(Tab t, const __grid_consta
     }
     part[i] = p;
   }
-}
-
-// exclusive scan of the partition sizes (P <= OBP_SEG_MAXP): off[p], off[P] = live rows; cur[p] = 0
-__global__ void __launch_bounds__(1024) k_seg_scan(const unsigned* __restrict__ cnt, unsigned* __restrict__ off,
-                                                   unsigned* __restrict__ cur, int P) {
-  __shared__ unsigned s_tot[1024];
-  const int per = (P + 1023) / 1024;
+  __shared__ bool s_last;
+  __shared__ unsigned s_tot[OBP_BS];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&res->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int P = s.P;
+  const int per = (P + OBP_BS - 1) / OBP_BS;
   const int p0 = threadIdx.x * per, p1 = min(P, p0 + per);
   unsigned local = 0;
-  for (int p = p0; p < p1; ++p) local += cnt[p];
+  for (int p = p0; p < p1; ++p) local += __ldcg(&cnt[p]);
   s_tot[threadIdx.x] = local;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
+  for (int d = 1; d < OBP_BS; d <<= 1) {
     const unsigned v = threadIdx.x >= (unsigned)d ? s_tot[threadIdx.x - d] : 0u;
     __syncthreads();
     s_tot[threadIdx.x] += v;
@@ -114,9 +140,12 @@ __global__ void __launch_bounds__(1024) k_seg_scan(const unsigned* __restrict__ 
   for (int p = p0; p < p1; ++p) {
     off[p] = run;
     cur[p] = 0;
-    run += cnt[p];
+    run += __ldcg(&cnt[p]);
   }
-  if (threadIdx.x == 1023) off[P] = s_tot[1023];
+  if (threadIdx.x == OBP_BS - 1) {
+    off[P] = s_tot[OBP_BS - 1];
+    res->ticket = 0;
+  }
 }
 
 __global__ void __launch_bounds__(OBP_BS) k_seg_scatter(const unsigned* __restrict__ part, const unsigned* __restrict__ off,
@@ -135,8 +164,7 @@ struct SegSmem {
   u64* hash;
   unsigned short* idx;
   unsigned char* died;  // OBP_SEG_ALIVE, or the gate that killed the row
-  SegGate* gate;
-  int* dg;              // per-gate change of the live-row count, summed over the CTA's partitions
+  int* dg;              // per-gate change of the live-row count, summed over the CTA's finished partitions
 };
 
 // Row of the partition holding `key ^ flips` with hash h2 that was present when pass g started (alive, or killed
@@ -181,21 +209,37 @@ __device__ __forceinline__ bool seg_insert(const SegSmem<W>& m, unsigned idx_mas
   return false;
 }
 
-template <int W>
-__global__ void __launch_bounds__(OBP_SEG_THREADS, 1)
-k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __restrict__ gates,
-           const unsigned* __restrict__ off, const unsigned* __restrict__ perm, SegRes* __restrict__ res) {
+// One launch of the run.  plist == nullptr: every partition p < s.P (the first launch, small CTAs, several per SM);
+// else the n = *plist_n partitions listed in plist (the second launch: the partitions that outgrew the small CTAs'
+// shared memory, one big CTA per SM).  A partition that does not fit is appended to redo_list (first launch) or
+// fails the run (second launch, redo_list == nullptr).
+struct SegFin {  // what the last CTA of the second launch needs for the run's bookkeeping
+  DevState* st;
+  unsigned* cnt;     // partition histogram: cleared for the next run
+  u64 n_live_in;
+  u64* host_res;     // the host's mapped result block
+  int n_res_ops;
+};
+
+template <int W, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_constant__ SegGates gs,
+           const unsigned* __restrict__ off, const unsigned* __restrict__ perm, SegRes* __restrict__ res,
+           const unsigned* __restrict__ plist, const unsigned* __restrict__ plist_n, unsigned* __restrict__ redo_list,
+           const SegFin fin) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CAP = s.cap_rows;
+  const int ngp = (s.ng + 1) & ~1;
   SegSmem<W> m;
+  int* dgp;  // per-gate change of the live-row count inside the current partition
   {
     unsigned char* p = smem_raw;
 #pragma unroll
     for (int w = 0; w < W; ++w) { m.xz[w] = reinterpret_cast<ulonglong2*>(p); p += (size_t)CAP * 16; }
     m.coef = reinterpret_cast<double2*>(p); p += (size_t)CAP * 16;
-    m.gate = reinterpret_cast<SegGate*>(p); p += (size_t)s.ng * sizeof(SegGate);
     m.hash = reinterpret_cast<u64*>(p); p += (size_t)CAP * 8;
-    m.dg = reinterpret_cast<int*>(p); p += (size_t)((s.ng + 1) & ~1) * 4;
+    m.dg = reinterpret_cast<int*>(p); p += (size_t)ngp * 4;
+    dgp = reinterpret_cast<int*>(p); p += (size_t)ngp * 4;
     m.idx = reinterpret_cast<unsigned short*>(p); p += (size_t)s.n_index * 2;
     m.died = p;
   }
@@ -205,33 +249,38 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
   __shared__ u64 s_base;         // first output row of the partition
   const unsigned idx_mask = (unsigned)s.n_index - 1u;
   const unsigned lane = threadIdx.x & 31u;
-  const int nt = blockDim.x;
-  // gate parameters and the per-gate counters: once per CTA
-  for (int k = threadIdx.x; k < s.ng * (int)(sizeof(SegGate) / 8); k += nt)
-    reinterpret_cast<u64*>(m.gate)[k] = reinterpret_cast<const u64*>(gates)[k];
-  for (int k = threadIdx.x; k < s.ng; k += nt) m.dg[k] = 0;
-  // exact counters of the last gate (thread-local over all partitions of this CTA)
+  for (int k = threadIdx.x; k < ngp; k += NT) m.dg[k] = 0;
+  // exact counters of the last gate: thread-local, over all partitions this CTA completes
   unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
   double sum_re = 0.0, sum_im = 0.0;
+  const int n_list = plist ? (int)*plist_n : s.P;
+  auto redo = [&](int part) {
+    if (threadIdx.x == 0) {
+      if (redo_list) redo_list[atomicAdd(&res->n_redo, 1u)] = (unsigned)part;
+      else atomicOr(&res->overflow, 1u);
+    }
+  };
   __syncthreads();
 
-  for (int part = blockIdx.x; part < s.P; part += gridDim.x) {
+  for (int it = blockIdx.x; it < n_list; it += gridDim.x) {
+    const int part = plist ? (int)plist[it] : it;
     const unsigned o0 = off[part];
     const int n_in = (int)(off[part + 1] - o0);
     if (n_in == 0) continue;
     if (n_in > CAP) {
-      if (threadIdx.x == 0) atomicOr(&res->overflow, 1u);
+      redo(part);
       continue;
     }
     // ---- gather the partition ----------------------------------------------------------------------------------
-    for (int k = threadIdx.x; k < s.n_index / 4; k += nt) reinterpret_cast<u64*>(m.idx)[k] = 0ull;
+    for (int k = threadIdx.x; k < s.n_index / 4; k += NT) reinterpret_cast<u64*>(m.idx)[k] = 0ull;
+    for (int k = threadIdx.x; k < ngp; k += NT) dgp[k] = 0;
     if (threadIdx.x == 0) {
       s_add[0] = 0; s_add[1] = 0; s_add[2] = 0;
       s_live = n_in;
       s_out = 0;
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < n_in; r += nt) {
+    for (int r = threadIdx.x; r < n_in; r += NT) {
       const u64 i = perm[o0 + r];
 #pragma unroll
       for (int w = 0; w < W; ++w) m.xz[w][r] = t.xz[w][i];
@@ -243,10 +292,13 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
     }
     __syncthreads();
     // ---- the gates --------------------------------------------------------------------------------------------
+    unsigned p_rows_surv = 0, p_keys_present = 0, p_cancelled = 0;
+    double p_sum_re = 0.0, p_sum_im = 0.0;
     int n_pass = n_in;
+    int add_i = 1;  // s_add slot the current pass appends to (the next one is cleared meanwhile)
     bool failed = false;
     for (int g = 0; g < s.ng && !failed; ++g) {
-      const SegGate& G = m.gate[g];
+      const SegGate& G = gs.g[g];
       RotP pg;  // the fields rot_rows() reads
       pg.u0r = G.u0r; pg.u0i = G.u0i; pg.u1r = G.u1r; pg.u1i = G.u1i;
       pg.atol = s.atol;
@@ -257,81 +309,93 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
 #pragma unroll
       for (int w = 0; w < W; ++w) { gx[w] = G.gx[w]; gz[w] = G.gz[w]; }
       const int yG = G.yG;
-      int* add_w = &s_add[(g + 1) % 3];
-      if (threadIdx.x == 0) s_add[(g + 2) % 3] = 0;
+      const double thr_self = G.thr_self, thr_all = G.thr_all;
+      int* add_w = &s_add[add_i];
+      if (threadIdx.x == 0) s_add[add_i == 2 ? 0 : add_i + 1] = 0;
       int dlive = 0;
-      for (int base = (int)(threadIdx.x & ~31u); base < n_pass; base += nt) {
+      for (int base = (int)(threadIdx.x & ~31u); base < n_pass; base += NT) {
         const int r = base + (int)lane;
         bool want_append = false;
         double2 app_c = make_double2(0.0, 0.0);
         ulonglong2 pk[W];  // partner key
         u64 h2 = 0;
         if (r < n_pass && m.died[r] == OBP_SEG_ALIVE) {
-          const double2 c = m.coef[r];
-          int sp = 0, E = yG;
+          int sp = 0;
 #pragma unroll
           for (int w = 0; w < W; ++w) {
-            const ulonglong2 key = m.xz[w][r];
-            const u64 mm = gx[w] | gz[w];
-            sp += __popcll(key.x & gz[w]) + __popcll(key.y & gx[w]);
-            E += __popcll(key.x & key.y & mm) - __popcll((key.x ^ gx[w]) & (key.y ^ gz[w]) & mm) + 2 * __popcll(key.y & gx[w]);
-            pk[w] = make_ulonglong2(key.x ^ gx[w], key.y ^ gz[w]);
+            if ((gx[w] | gz[w]) != 0ull) {  // (uniform: the generator's words)
+              const ulonglong2 key = m.xz[w][r];
+              sp += __popcll(key.x & gz[w]) + __popcll(key.y & gx[w]);
+            }
           }
           const int sgn = sp & 1;
-          E &= 3;
+          const double2 c = m.coef[r];
+          const double m2 = fma(c.x, c.x, c.y * c.y);
           if (!exact && !sgn) {
-            // commuting row, fast mode: only its own key can change (row filter)
-            const RowSet rp = rot_rows_self(c, sgn, pg);
-            if (rp.nself < 2) {
-              if (rp.nself == 0 || is_small(rp.self, s.atol)) {
-                m.died[r] = (unsigned char)g;
-                dlive--;
-              } else {
-                m.coef[r] = rp.self;
+            // commuting row, fast mode: only its own key can change (row filter) — and only a tiny coefficient does
+            if (!(m2 > thr_self)) {
+              const RowSet rp = rot_rows_self(c, sgn, pg);
+              if (rp.nself < 2) {
+                if (rp.nself == 0 || is_small(rp.self, s.atol)) {
+                  m.died[r] = (unsigned char)g;
+                  dlive--;
+                } else {
+                  m.coef[r] = rp.self;
+                }
               }
             }
           } else {
-            const RowSet rp = rot_rows(c, E, sgn, pg);
+            int E = yG;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+              const ulonglong2 key = m.xz[w][r];
+              const u64 mm = gx[w] | gz[w];
+              E += __popcll(key.x & key.y & mm) - __popcll((key.x ^ gx[w]) & (key.y ^ gz[w]) & mm) + 2 * __popcll(key.y & gx[w]);
+              pk[w] = make_ulonglong2(key.x ^ gx[w], key.y ^ gz[w]);
+            }
+            E &= 3;
+            const RowSet rp = m2 > thr_all ? rot_rows_nofilter(c, E, sgn, pg) : rot_rows(c, E, sgn, pg);
             h2 = m.hash[r] ^ hG;
             bool fresh;
             const int j = seg_find<W>(m, idx_mask, h2, pk, n_pass, (unsigned)g, fresh);
             if (j >= 0 && !fresh && r < j) {
               // both rows live, this thread owns the pair (the row with the smaller id)
               const double2 cq = m.coef[j];
-              const RowSet rq = rot_rows(cq, (4 - E) & 3, sgn, pg);
+              const RowSet rq = fma(cq.x, cq.x, cq.y * cq.y) > thr_all ? rot_rows_nofilter(cq, (4 - E) & 3, sgn, pg)
+                                                                       : rot_rows(cq, (4 - E) & 3, sgn, pg);
               const bool pres_p = rp.nself > 0 || rq.ncross > 0;
               const bool pres_q = rq.nself > 0 || rp.ncross > 0;
               double2 np_ = rp.self, nq_ = rq.self;
               if (rq.ncross) np_ = rp.nself ? cadd(np_, rq.cross) : rq.cross;
               if (rp.ncross) nq_ = rq.nself ? cadd(nq_, rp.cross) : rp.cross;
               if (exact) {
-                rows_surv += rp.nself + rp.ncross + rq.nself + rq.ncross;
-                keys_present += (unsigned)pres_p + (unsigned)pres_q;
+                p_rows_surv += rp.nself + rp.ncross + rq.nself + rq.ncross;
+                p_keys_present += (unsigned)pres_p + (unsigned)pres_q;
               }
               if (pres_p && !is_small(np_, s.atol)) {
                 m.coef[r] = np_;
               } else {
-                if (pres_p && exact) { cancelled++; sum_re += np_.x; sum_im += np_.y; }
+                if (pres_p && exact) { p_cancelled++; p_sum_re += np_.x; p_sum_im += np_.y; }
                 m.died[r] = (unsigned char)g;
                 dlive--;
               }
               if (pres_q && !is_small(nq_, s.atol)) {
                 m.coef[j] = nq_;
               } else {
-                if (pres_q && exact) { cancelled++; sum_re += nq_.x; sum_im += nq_.y; }
+                if (pres_q && exact) { p_cancelled++; p_sum_re += nq_.x; p_sum_im += nq_.y; }
                 m.died[j] = (unsigned char)g;
                 dlive--;
               }
             } else if (j < 0) {
               // partner key absent: update this row, append the partner if it survives
               if (exact) {
-                rows_surv += rp.nself + rp.ncross;
-                keys_present += (unsigned)(rp.nself > 0) + (unsigned)(rp.ncross > 0);
+                p_rows_surv += rp.nself + rp.ncross;
+                p_keys_present += (unsigned)(rp.nself > 0) + (unsigned)(rp.ncross > 0);
               }
               if (rp.nself > 0 && !is_small(rp.self, s.atol)) {
                 m.coef[r] = rp.self;
               } else {
-                if (rp.nself > 0 && exact) { cancelled++; sum_re += rp.self.x; sum_im += rp.self.y; }
+                if (rp.nself > 0 && exact) { p_cancelled++; p_sum_re += rp.self.x; p_sum_im += rp.self.y; }
                 m.died[r] = (unsigned char)g;
                 dlive--;
               }
@@ -340,7 +404,7 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
                   want_append = true;
                   app_c = rp.cross;
                 } else if (exact) {
-                  cancelled++; sum_re += rp.cross.x; sum_im += rp.cross.y;
+                  p_cancelled++; p_sum_re += rp.cross.x; p_sum_im += rp.cross.y;
                 }
               }
             }
@@ -364,21 +428,22 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
               if (!seg_insert<W>(m, idx_mask, h2, row)) atomicOr(&res->overflow, 4u);
               dlive++;
             }
-            // (a row beyond the partition's capacity is not stored: n_pass > CAP after this pass ends the run)
+            // (a row beyond the partition's capacity is not stored: n_pass > CAP after this pass ends the attempt)
           }
         }
       }
-      const int dl = (int)warp_sum_i64((long long)dlive);
+      const int dl = __reduce_add_sync(0xffffffffu, dlive);
       if (lane == 0 && dl) {
-        atomicAdd(&m.dg[g], dl);
+        atomicAdd(&dgp[g], dl);
         atomicAdd(&s_live, dl);
       }
       __syncthreads();
       n_pass += *add_w;
+      add_i = add_i == 2 ? 0 : add_i + 1;
       failed = n_pass > CAP;  // (uniform: every thread reads the same, stable counter)
     }
     if (failed) {
-      if (threadIdx.x == 0) atomicOr(&res->overflow, 1u);
+      redo(part);
       __syncthreads();
       continue;
     }
@@ -391,7 +456,7 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
       __syncthreads();
       continue;
     }
-    for (int base = (int)(threadIdx.x & ~31u); base < n_pass; base += nt) {
+    for (int base = (int)(threadIdx.x & ~31u); base < n_pass; base += NT) {
       const int r = base + (int)lane;
       const bool alive = r < n_pass && m.died[r] == OBP_SEG_ALIVE;
       const unsigned bal = __ballot_sync(0xffffffffu, alive);
@@ -407,11 +472,18 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
         out.hash[o] = m.hash[r];
       }
     }
+    // the partition is done: its counters join the CTA's
+    for (int k = threadIdx.x; k < s.ng; k += NT) m.dg[k] += dgp[k];
+    rows_surv += p_rows_surv;
+    keys_present += p_keys_present;
+    cancelled += p_cancelled;
+    sum_re += p_sum_re;
+    sum_im += p_sum_im;
     __syncthreads();  // the next partition reuses the shared arrays
   }
   // ---- counters ---------------------------------------------------------------------------------------------------
   __syncthreads();
-  for (int k = threadIdx.x; k < s.ng; k += nt)
+  for (int k = threadIdx.x; k < s.ng; k += NT)
     if (m.dg[k]) atomicAdd(reinterpret_cast<unsigned long long*>(&res->delta[k]), (unsigned long long)(long long)m.dg[k]);
   if (s.exact_last) {
     const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present), cz = warp_sum_u64(cancelled);
@@ -423,32 +495,48 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
       if (cz) { atomicAdd(&o->cancelled, cz); atomicAdd(&o->sum_re, sr); atomicAdd(&o->sum_im, si); }
     }
   }
-}
-
-// Per-gate live-row counts, the table state (only if the run succeeded) and the result block for the host.
-// Slot slot0 + ng reports the outcome: n_out = 0 ok / overflow bits, rows_surv = output rows.
-__global__ void __launch_bounds__(256) k_seg_finish(DevState* st, OpStat* ops, const SegRes* __restrict__ res, int slot0, int ng,
-                                                    u64 n_live_in, u64* __restrict__ host_res, int n_res_ops) {
+  if (fin.st == nullptr) return;
+  // ---- second launch: the last CTA to finish does the run's bookkeeping ----------------------------------------------
+  // Per-gate live-row counts, the table state (only if the run succeeded), the result block for the host; the
+  // partition scratch is left clean for the next run.  Slot slot0 + ng reports the outcome: n_out = 0 ok / overflow
+  // bits, rows_surv = output rows, keys_present = partitions that needed the big CTAs.
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&res->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  OpStat* ops = t.ops + s.slot0;
   if (threadIdx.x == 0) {
-    long long run = (long long)n_live_in;
-    for (int g = 0; g < ng; ++g) {
-      run += res->delta[g];
-      ops[slot0 + g].n_out = (u64)run;
+    long long run = (long long)fin.n_live_in;
+    for (int g = 0; g < s.ng; ++g) {
+      run += (long long)__ldcg(reinterpret_cast<const unsigned long long*>(&res->delta[g]));
+      ops[g].n_out = (u64)run;
     }
-    OpStat* f = &ops[slot0 + ng];
-    f->n_out = res->overflow;
-    f->rows_surv = res->out_rows;
-    if (res->overflow == 0u) {
-      st->n_scan = res->out_rows;
-      st->n_append = res->out_rows;
-      st->n_live = res->out_rows;
+    const unsigned ovf = __ldcg(&res->overflow);
+    const u64 n_rows = __ldcg(reinterpret_cast<const unsigned long long*>(&res->out_rows));
+    OpStat* f = &ops[s.ng];
+    f->n_out = ovf;
+    f->rows_surv = n_rows;
+    f->keys_present = __ldcg(&res->n_redo);
+    if (ovf == 0u) {
+      fin.st->n_scan = n_rows;
+      fin.st->n_append = n_rows;
+      fin.st->n_live = n_rows;
     }
     __threadfence();
   }
   __syncthreads();
-  if (host_res) {
-    const u64* src = reinterpret_cast<const u64*>(st);  // DevState | start stamp | counter slots: one block
-    const int n_words = (int)((OBP_RES_HDR + (size_t)n_res_ops * sizeof(OpStat)) / sizeof(u64));
-    for (int k = threadIdx.x; k < n_words; k += blockDim.x) host_res[k] = src[k];
+  if (fin.host_res) {
+    const u64* src = reinterpret_cast<const u64*>(fin.st);  // DevState | start stamp | counter slots: one block
+    const int n_words = (int)((OBP_RES_HDR + (size_t)fin.n_res_ops * sizeof(OpStat)) / sizeof(u64));
+    for (int k = threadIdx.x; k < n_words; k += NT) fin.host_res[k] = __ldcg(&src[k]);
+  }
+  for (int k = threadIdx.x; k <= s.P; k += NT) fin.cnt[k] = 0u;
+  {
+    u64* w = reinterpret_cast<u64*>(res);
+    for (int k = threadIdx.x; k < (int)(sizeof(SegRes) / sizeof(u64)); k += NT) w[k] = 0ull;
   }
 }
+
