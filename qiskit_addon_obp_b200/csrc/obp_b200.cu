@@ -123,6 +123,7 @@ struct obp_ctx {
   u64* alt_hash = nullptr;
   unsigned char* d_seg = nullptr;  // [cnt | off | cur] (OBP_SEG_MAXP + 1 u32 each) | SegRes
   bool index_stale = false;        // the table's columns were replaced by a run: the index is rebuilt before its next use
+  u64 T_eff = 0;                   // index slots in use (a power of two <= T): a lazy rebuild after a run sizes the index to the rows
   u64 n_seg_runs = 0, n_seg_retries = 0, n_seg_fallbacks = 0;
   bool trace_host = false;  // OBP_B200_TRACE_HOST: print host enqueue / wait time per gate program
   int prog_min_grid = 148;  // smallest grid of the persistent program kernel (grid barriers cost more with more CTAs)
@@ -175,7 +176,7 @@ Tab make_tab(const obp_ctx* c) {
   t.coef = c->coef;
   t.hash = c->hash;
   t.index = c->index;
-  t.mask = c->T - 1;
+  t.mask = (c->T_eff ? c->T_eff : c->T) - 1;
   t.cap = c->cap;
   t.W = c->W;
   t.st = c->d_st;
@@ -319,6 +320,7 @@ void init_frame(obp_ctx* ctx) {
 // (re)build the index from the live rows (no duplicates expected)
 int rebuild_index(obp_ctx* ctx) {
   ctx->index_stale = false;
+  ctx->T_eff = ctx->T;
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
   Bracket b(ctx, OBP_K_INDEX);
   k_index_build<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), 0, -1.0, ctx->epoch, -1, nullptr);
@@ -327,7 +329,21 @@ int rebuild_index(obp_ctx* ctx) {
 }
 
 // a run of rotations in shared memory replaces the table's columns and leaves the index behind
-int ensure_index(obp_ctx* ctx) { return ctx->index_stale ? rebuild_index(ctx) : OBP_OK; }
+// need_rows: the rows the index must be able to hold before anybody rebuilds it again (0: the whole capacity).  The
+// rebuild that follows a run clears and fills only as many slots as those rows want (a 10^4-row table in a context
+// sized for 4 * 10^6 terms would otherwise pay a 64 MB memset per slice).
+int ensure_index(obp_ctx* ctx, u64 need_rows = 0) {
+  if (need_rows == 0 || need_rows > ctx->cap) need_rows = ctx->cap;
+  const u64 want = std::min<u64>(ctx->T, next_pow2(std::max<u64>(4 * need_rows, 1ull << 16)));
+  if (!ctx->index_stale && (ctx->T_eff == 0 || ctx->T_eff >= std::min<u64>(ctx->T, 2 * need_rows))) return OBP_OK;
+  ctx->index_stale = false;
+  ctx->T_eff = want;
+  CU(cudaMemsetAsync(ctx->index, 0xFF, want * sizeof(u64), ctx->stream));
+  Bracket b(ctx, OBP_K_INDEX);
+  k_index_build<<<grid_for(ctx, ctx->n_dense), OBP_BS, 0, ctx->stream>>>(make_tab(ctx), 0, -1.0, ctx->epoch, -1, nullptr);
+  CU(cudaGetLastError());
+  return OBP_OK;
+}
 
 // move every row i with dest[i] != NONE to row dest[i] (all columns), then rebuild the index;
 // st->scan_total holds the new row count
@@ -407,6 +423,7 @@ int set_counts(obp_ctx* ctx, u64 n) {
 int alloc_table(obp_ctx* ctx, u64 cap) {
   ctx->cap = cap;
   ctx->T = next_pow2(std::max<u64>(2 * cap, 1024));
+  ctx->T_eff = ctx->T;
   for (int w = 0; w < ctx->W; ++w) CU(cudaMalloc(&ctx->xz[w], cap * sizeof(ulonglong2)));
   CU(cudaMalloc(&ctx->coef, cap * sizeof(double2)));
   CU(cudaMalloc(&ctx->hash, cap * sizeof(u64)));
@@ -417,6 +434,7 @@ int alloc_table(obp_ctx* ctx, u64 cap) {
   CU(cudaMalloc(&ctx->blk, ((cap + OBP_CHUNK - 1) / OBP_CHUNK + 1) * sizeof(unsigned)));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
   ctx->index_stale = false;
+  ctx->T_eff = ctx->T;
   return OBP_OK;
 }
 
@@ -1061,6 +1079,7 @@ static int load_impl(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_wo
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
   ctx->index_stale = false;
+  ctx->T_eff = ctx->T;
   Tab t = make_tab(ctx);
   if (n && atol == OBP_ATOL_RAW) {  // simplify=False: rows as given, duplicates and zeros included
     Bracket b(ctx, OBP_K_INDEX, 2);
@@ -1195,7 +1214,7 @@ static bool segment_eligible(const obp_ctx* ctx, const obp_op* ops, int n_ops) {
 
 // bytes of dynamic shared memory k_seg_main needs for `cap` rows per partition
 static size_t seg_smem_bytes(int W, int cap, int n_index, int ng) {
-  return (size_t)cap * (16 * W + 16 + 8 + 1) + 2 * (size_t)((ng + 1) & ~1) * 4 + (size_t)n_index * 2 + 64;
+  return (size_t)cap * (16 * W + 16 + 8 + 1) + (size_t)ng * sizeof(SegGate) + 2 * (size_t)((ng + 1) & ~1) * 4 + (size_t)n_index * 2 + 64;
 }
 
 // the largest partition (rows, multiple of 64) whose arrays and index (at most half full) fit `budget` bytes
@@ -1211,35 +1230,44 @@ static void seg_geometry(int W, int ng, size_t budget, int limit_rows, int* cap_
 // Key bit positions: word w, plane (x = 0, z = 1), bit b -> 128 w + 64 plane + b.
 static void seg_partition_map(const std::vector<SegGate>& gates, int W, u64 fmask[OBP_SEG_FBITS][4]) {
   struct V { u64 w[4]; };
-  std::vector<V> basis;     // reduced row echelon form of the generators
+  std::vector<V> basis;     // row echelon form of the generators: a row holds no pivot of the rows before it
   std::vector<int> pivot;
-  auto test = [](const V& v, int b) { return (v.w[b >> 6] >> (b & 63)) & 1ull; };
+  int row_of_pivot[256];
+  for (int b = 0; b < 256; ++b) row_of_pivot[b] = -1;
   for (const SegGate& g : gates) {
     V v{{g.gx[0], g.gz[0], W == 2 ? g.gx[1] : 0ull, W == 2 ? g.gz[1] : 0ull}};
-    for (size_t k = 0; k < basis.size(); ++k)
-      if (test(v, pivot[k]))
-        for (int j = 0; j < 4; ++j) v.w[j] ^= basis[k].w[j];
+    // reduce by the rows whose pivot v holds (generators on disjoint qubits: none — the common case costs O(weight))
+    for (bool again = true; again;) {
+      again = false;
+      for (int j = 0; j < 4 && !again; ++j)
+        for (u64 w = v.w[j]; w; w &= w - 1) {
+          const int k = row_of_pivot[64 * j + __builtin_ctzll(w)];
+          if (k >= 0) {
+            for (int q = 0; q < 4; ++q) v.w[q] ^= basis[(size_t)k].w[q];
+            again = true;
+            break;
+          }
+        }
+    }
     int pv = -1;
     for (int j = 0; j < 4 && pv < 0; ++j)
       if (v.w[j]) pv = 64 * j + __builtin_ctzll(v.w[j]);
     if (pv < 0) continue;  // dependent on the generators before it
-    for (size_t k = 0; k < basis.size(); ++k)
-      if (test(basis[k], pv))
-        for (int j = 0; j < 4; ++j) basis[k].w[j] ^= v.w[j];
+    row_of_pivot[pv] = (int)basis.size();
     basis.push_back(v);
     pivot.push_back(pv);
   }
-  // random weights on the free positions, the pivots follow from f(G) = 0
+  // random weights on the free positions; the pivots follow from f(G) = 0, last row first (a row may hold pivots of
+  // LATER rows only, and those are settled by then)
   unsigned r[256];
   u64 seed = 0x5E6B200D15EA5Eull;
   for (int b = 0; b < 256; ++b) r[b] = (unsigned)(splitmix64(seed) & ((1u << OBP_SEG_FBITS) - 1u));
-  for (int pv : pivot) r[pv] = 0;
-  for (size_t k = 0; k < basis.size(); ++k) {
+  for (size_t k = basis.size(); k-- > 0;) {
     unsigned acc = 0;
     for (int j = 0; j < 4; ++j)
       for (u64 w = basis[k].w[j]; w; w &= w - 1) {
         const int b = 64 * j + __builtin_ctzll(w);
-        if (b != pivot[k]) acc ^= r[b];  // (no other pivot occurs in a reduced row)
+        if (b != pivot[k]) acc ^= r[b];
       }
     r[pivot[k]] = acc;
   }
@@ -1406,8 +1434,7 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   unsigned* d_redo = d_cur + (OBP_SEG_MAXP + 1);
   SegRes* d_res = (SegRes*)(ctx->d_seg + part_bytes);
 
-  // gate parameters (a kernel parameter of the run)
-  static thread_local SegGates gs;  // 24 KB: kept off the stack
+  // gate parameters
   std::vector<SegGate> gates((size_t)ng);
   for (int k = 0; k < ng; ++k) {
     const RotP p = build_rotp(ctx, ops[k], atol);
@@ -1422,13 +1449,13 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
     // min(|u0|^2, |u1|^2) (|u0||u1| lies between them)
     const double f0 = p.u0r * p.u0r + p.u0i * p.u0i, f1 = p.u1r * p.u1r + p.u1i * p.u1i, fmin = std::min(f0, f1);
     g.thr_self = g.thr_all = atol < 0.0 ? -1.0 : (fmin > 0.0 ? atol * atol * (1.0 + 1e-6) / (fmin * fmin) : HUGE_VAL);
-    gs.g[k] = g;
   }
   SegP sp;
   memset(&sp, 0, sizeof(sp));
   sp.ng = ng;
   sp.exact_last = (ops[ng - 1].flags & OBP_FLAG_EXACT_COUNTERS) ? 1 : 0;
   sp.slot0 = 0;
+  if (const char* e = getenv("OBP_B200_SEG_DEBUG")) sp.dbg = atoi(e);
   sp.n_dense = ctx->n_dense;
   sp.out_cap = ctx->cap;
   sp.atol = atol;
@@ -1450,6 +1477,22 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   P = std::max(1, std::min(P, OBP_SEG_MAXP));
   sp.P = sp2.P = P;
 
+  // upload the gates through the program staging buffer
+  const size_t need = gates.size() * sizeof(SegGate);
+  if (need > ctx->prog_alloc) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_prog);
+    if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
+    ctx->d_prog = ctx->h_prog = nullptr;
+    ctx->prog_alloc = 0;
+    const size_t na = std::max<size_t>(2 * need, 1 << 16);
+    CU(cudaMalloc(&ctx->d_prog, na));
+    CU(cudaMallocHost(&ctx->h_prog, na));
+    ctx->prog_alloc = na;
+  }
+  memcpy(ctx->h_prog, gates.data(), need);
+  CU(cudaMemcpyAsync(ctx->d_prog, ctx->h_prog, need, cudaMemcpyHostToDevice, ctx->stream));
+  const SegGate* gs = (const SegGate*)ctx->d_prog;
   Tab t = make_tab(ctx);
   SegOut out;
   out.xz[0] = ctx->alt_xz[0];
@@ -1527,7 +1570,11 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   }
   if (segment_eligible(ctx, ops, n_ops) && !n_done) return apply_segment(ctx, ops, n_ops, atol, stats, defer, 0, 0);
   {
-    const int irc = ensure_index(ctx);
+    // rows this program can reach: every rotation may double the table
+    int n_rot = 0;
+    for (int k = 0; k < n_ops; ++k) n_rot += ops[k].kind == OBP_OP_ROTATION ? 1 : 0;
+    const u64 reach = n_rot >= 40 ? ctx->cap : std::min<u64>(ctx->cap, std::max<u64>(ctx->n_dense, 1) << n_rot);
+    const int irc = ensure_index(ctx, reach);
     if (irc) return irc;
   }
   const auto t_host0 = std::chrono::steady_clock::now();
@@ -2521,6 +2568,7 @@ int obp_apply_generic(obp_ctx* ctx, int32_t n_qubits, const int32_t* qubits, int
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
   ctx->index_stale = false;
+  ctx->T_eff = ctx->T;
   if (!simplify) {  // OperatorBudget(simplify=False): keep every raw row, zeros included
     if (raw) {
       Bracket br(ctx, OBP_K_OTHER);
@@ -2595,6 +2643,7 @@ static int reset_in_row_order(obp_ctx* ctx, int32_t qubit, double atol, obp_stat
   CU(cudaMemsetAsync(ctx->d_ops, 0, sizeof(OpStat) * 2, ctx->stream));
   CU(cudaMemsetAsync(ctx->index, 0xFF, ctx->T * sizeof(u64), ctx->stream));
   ctx->index_stale = false;
+  ctx->T_eff = ctx->T;
   Tab t = make_tab(ctx);
   if (n_in) {
     Bracket br(ctx, OBP_K_OTHER, 4);
@@ -2980,6 +3029,7 @@ static int alloc_row_order_scratch(obp_ctx* ctx) {
 // (re)allocate the buffers that hold no table data — index and compaction scratch — for `cap` rows
 static int alloc_scratch(obp_ctx* ctx, u64 cap) {
   ctx->T = next_pow2(std::max<u64>(2 * cap, 1024));
+  ctx->T_eff = ctx->T;
   CU(cudaMalloc(&ctx->index, ctx->T * sizeof(u64)));
   CU(cudaMalloc(&ctx->spare16, cap * sizeof(ulonglong2)));
   CU(cudaMalloc(&ctx->spare8, cap * sizeof(u64)));

@@ -26,13 +26,13 @@
 // Four launches per run: k_seg_count (partition id per live row + histogram; its last CTA turns the histogram into
 // offsets), k_seg_scatter (row ids in partition order), k_seg_main<W, 128, 4> (the run), k_seg_main<W, 512, 1> (the
 // listed partitions again; its last CTA writes the per-gate row counts, the table state and the host's result
-// block).  The gates travel as a kernel parameter (constant bank), nothing is copied or cleared in between.
+// block).  One small upload (the gates) precedes them; nothing is cleared in between.
 // The input table is never modified: if a partition outgrows even the big CTA (or the output its capacity) the run
 // reports it and the host applies the same gates through the per-gate kernels instead.
 #pragma once
 #include "obp_kernels.cuh"
 
-#define OBP_SEG_MAXG 250    // gates per run (a row records the gate that killed it in one byte; 24 KB of kernel parameters)
+#define OBP_SEG_MAXG 250    // gates per run (a row records the gate that killed it in one byte)
 #define OBP_SEG_MAXP 16384  // partitions per run
 #define OBP_SEG_FBITS 16    // output bits of the partition map
 #define OBP_SEG_ALIVE 255u
@@ -48,9 +48,9 @@ struct SegGate {  // 96 bytes
   double thr_self, thr_all;
 };
 
-struct SegGates {  // the run's gates: a kernel parameter (constant bank: uniform loads, no staging)
-  SegGate g[OBP_SEG_MAXG];
-};
+
+
+static_assert(sizeof(SegGate) == 96, "SegGate is staged with 16-byte copies");
 
 struct SegP {
   int ng;            // gates
@@ -59,6 +59,8 @@ struct SegP {
   int n_index;       // local index slots (power of two)
   int exact_last;    // the last gate reports the reference's simplify counters
   int slot0;         // counter slot of gate 0 (gate g: slot0 + g)
+  int dbg;           // timing experiments (OBP_B200_SEG_DEBUG; results are wrong): 1 no row work, 2 no partner path
+  int pad;
   u64 n_dense;       // rows of the input table
   u64 out_cap;       // rows the output columns hold
   double atol;
@@ -171,8 +173,7 @@ struct SegSmem {
 // during pass g), or -1.
 template <int W>
 __device__ __forceinline__ int seg_find(const SegSmem<W>& m, unsigned idx_mask, u64 h2, const ulonglong2* want, int n_pass,
-                                        unsigned g, bool& fresh) {
-  unsigned s = (unsigned)h2 & idx_mask;
+                                        unsigned g, bool& fresh, unsigned s) {
   fresh = false;
   for (unsigned probes = 0; probes <= idx_mask; ++probes) {
     const unsigned v = m.idx[s];
@@ -223,7 +224,7 @@ struct SegFin {  // what the last CTA of the second launch needs for the run's b
 
 template <int W, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
-k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_constant__ SegGates gs,
+k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __restrict__ gates,
            const unsigned* __restrict__ off, const unsigned* __restrict__ perm, SegRes* __restrict__ res,
            const unsigned* __restrict__ plist, const unsigned* __restrict__ plist_n, unsigned* __restrict__ redo_list,
            const SegFin fin) {
@@ -232,11 +233,13 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
   const int ngp = (s.ng + 1) & ~1;
   SegSmem<W> m;
   int* dgp;  // per-gate change of the live-row count inside the current partition
+  SegGate* sgate;  // the run's gates, staged once per CTA (a pass starts with broadcast loads from here)
   {
     unsigned char* p = smem_raw;
 #pragma unroll
     for (int w = 0; w < W; ++w) { m.xz[w] = reinterpret_cast<ulonglong2*>(p); p += (size_t)CAP * 16; }
     m.coef = reinterpret_cast<double2*>(p); p += (size_t)CAP * 16;
+    sgate = reinterpret_cast<SegGate*>(p); p += (size_t)s.ng * sizeof(SegGate);
     m.hash = reinterpret_cast<u64*>(p); p += (size_t)CAP * 8;
     m.dg = reinterpret_cast<int*>(p); p += (size_t)ngp * 4;
     dgp = reinterpret_cast<int*>(p); p += (size_t)ngp * 4;
@@ -250,6 +253,8 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
   const unsigned idx_mask = (unsigned)s.n_index - 1u;
   const unsigned lane = threadIdx.x & 31u;
   for (int k = threadIdx.x; k < ngp; k += NT) m.dg[k] = 0;
+  for (int k = threadIdx.x; k < s.ng * (int)(sizeof(SegGate) / 16); k += NT)
+    reinterpret_cast<uint4*>(sgate)[k] = reinterpret_cast<const uint4*>(gates)[k];
   // exact counters of the last gate: thread-local, over all partitions this CTA completes
   unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
   double sum_re = 0.0, sum_im = 0.0;
@@ -298,7 +303,7 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
     int add_i = 1;  // s_add slot the current pass appends to (the next one is cleared meanwhile)
     bool failed = false;
     for (int g = 0; g < s.ng && !failed; ++g) {
-      const SegGate& G = gs.g[g];
+      const SegGate& G = sgate[g];
       RotP pg;  // the fields rot_rows() reads
       pg.u0r = G.u0r; pg.u0i = G.u0i; pg.u1r = G.u1r; pg.u1i = G.u1i;
       pg.atol = s.atol;
@@ -319,19 +324,24 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
         double2 app_c = make_double2(0.0, 0.0);
         ulonglong2 pk[W];  // partner key
         u64 h2 = 0;
-        if (r < n_pass && m.died[r] == OBP_SEG_ALIVE) {
-          int sp = 0;
-#pragma unroll
-          for (int w = 0; w < W; ++w) {
-            if ((gx[w] | gz[w]) != 0ull) {  // (uniform: the generator's words)
-              const ulonglong2 key = m.xz[w][r];
-              sp += __popcll(key.x & gz[w]) + __popcll(key.y & gx[w]);
-            }
-          }
-          const int sgn = sp & 1;
+        if (s.dbg != 1 && r < n_pass) {
+          // the row's own data: independent shared-memory loads, issued together
+          const unsigned died_r = m.died[r];
           const double2 c = m.coef[r];
+          ulonglong2 key[W];
+#pragma unroll
+          for (int w = 0; w < W; ++w) key[w] = m.xz[w][r];
+          const u64 h_own = m.hash[r];
+          // commutation parity: popc(a) + popc(b) = popc(a ^ b) mod 2, so one 32-bit popcount of the folded words
+          // decides it (POPC issues at a quarter of the ALU rate)
+          u64 fold = 0;
+#pragma unroll
+          for (int w = 0; w < W; ++w) fold ^= (key[w].x & gz[w]) ^ (key[w].y & gx[w]);
+          const int sgn = s.dbg == 2 ? 0 : (__popc((unsigned)fold ^ (unsigned)(fold >> 32)) & 1);
           const double m2 = fma(c.x, c.x, c.y * c.y);
-          if (!exact && !sgn) {
+          if (died_r != OBP_SEG_ALIVE) {
+            // dead row
+          } else if (!exact && !sgn) {
             // commuting row, fast mode: only its own key can change (row filter) — and only a tiny coefficient does
             if (!(m2 > thr_self)) {
               const RowSet rp = rot_rows_self(c, sgn, pg);
@@ -348,21 +358,47 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
             int E = yG;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
-              const ulonglong2 key = m.xz[w][r];
               const u64 mm = gx[w] | gz[w];
-              E += __popcll(key.x & key.y & mm) - __popcll((key.x ^ gx[w]) & (key.y ^ gz[w]) & mm) + 2 * __popcll(key.y & gx[w]);
-              pk[w] = make_ulonglong2(key.x ^ gx[w], key.y ^ gz[w]);
+              E += __popcll(key[w].x & key[w].y & mm) - __popcll((key[w].x ^ gx[w]) & (key[w].y ^ gz[w]) & mm) +
+                   2 * __popcll(key[w].y & gx[w]);
+              pk[w] = make_ulonglong2(key[w].x ^ gx[w], key[w].y ^ gz[w]);
             }
             E &= 3;
-            const RowSet rp = m2 > thr_all ? rot_rows_nofilter(c, E, sgn, pg) : rot_rows(c, E, sgn, pg);
-            h2 = m.hash[r] ^ hG;
-            bool fresh;
-            const int j = seg_find<W>(m, idx_mask, h2, pk, n_pass, (unsigned)g, fresh);
+            h2 = h_own ^ hG;
+            // partner lookup: the first slot of the probe chain inline (the candidate's hash, key, state and coefficient
+            // are independent loads), the rest of the chain only on a mismatch
+            int j = -1;
+            bool fresh = false;
+            double2 cq = make_double2(0.0, 0.0);
+            {
+              const unsigned s0 = (unsigned)h2 & idx_mask;
+              const unsigned v0 = m.idx[s0];
+              if (v0 != 0u) {
+                const int j0 = (int)v0 - 1;
+                const u64 hj = m.hash[j0];
+                ulonglong2 kj[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) kj[w] = m.xz[w][j0];
+                const unsigned dj = m.died[j0];
+                const double2 cj = m.coef[j0];
+                bool eq = j0 < n_pass && hj == h2;
+#pragma unroll
+                for (int w = 0; w < W; ++w) eq = eq && kj[w].x == pk[w].x && kj[w].y == pk[w].y;
+                if (eq && (dj == OBP_SEG_ALIVE || dj == (unsigned)g)) {
+                  j = j0;
+                  fresh = dj == (unsigned)g;
+                  cq = cj;
+                } else {
+                  j = seg_find<W>(m, idx_mask, h2, pk, n_pass, (unsigned)g, fresh, (s0 + 1) & idx_mask);
+                  if (j >= 0) cq = m.coef[j];
+                }
+              }
+            }
             if (j >= 0 && !fresh && r < j) {
               // both rows live, this thread owns the pair (the row with the smaller id)
-              const double2 cq = m.coef[j];
-              const RowSet rq = fma(cq.x, cq.x, cq.y * cq.y) > thr_all ? rot_rows_nofilter(cq, (4 - E) & 3, sgn, pg)
-                                                                       : rot_rows(cq, (4 - E) & 3, sgn, pg);
+              const bool big = m2 > thr_all && fma(cq.x, cq.x, cq.y * cq.y) > thr_all;
+              const RowSet rp = big ? rot_rows_nofilter(c, E, sgn, pg) : rot_rows(c, E, sgn, pg);
+              const RowSet rq = big ? rot_rows_nofilter(cq, (4 - E) & 3, sgn, pg) : rot_rows(cq, (4 - E) & 3, sgn, pg);
               const bool pres_p = rp.nself > 0 || rq.ncross > 0;
               const bool pres_q = rq.nself > 0 || rp.ncross > 0;
               double2 np_ = rp.self, nq_ = rq.self;
@@ -388,6 +424,7 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
               }
             } else if (j < 0) {
               // partner key absent: update this row, append the partner if it survives
+              const RowSet rp = m2 > thr_all ? rot_rows_nofilter(c, E, sgn, pg) : rot_rows(c, E, sgn, pg);
               if (exact) {
                 p_rows_surv += rp.nself + rp.ncross;
                 p_keys_present += (unsigned)(rp.nself > 0) + (unsigned)(rp.ncross > 0);
@@ -495,7 +532,7 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
       if (cz) { atomicAdd(&o->cancelled, cz); atomicAdd(&o->sum_re, sr); atomicAdd(&o->sum_im, si); }
     }
   }
-  if (fin.st == nullptr) return;
+  if (fin.st == nullptr || NT < 256) return;  // (the bookkeeping below wants one thread per gate)
   // ---- second launch: the last CTA to finish does the run's bookkeeping ----------------------------------------------
   // Per-gate live-row counts, the table state (only if the run succeeded), the result block for the host; the
   // partition scratch is left clean for the next run.  Slot slot0 + ng reports the outcome: n_out = 0 ok / overflow
@@ -508,12 +545,22 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
   if (!s_last) return;
   __threadfence();
   OpStat* ops = t.ops + s.slot0;
-  if (threadIdx.x == 0) {
-    long long run = (long long)fin.n_live_in;
-    for (int g = 0; g < s.ng; ++g) {
-      run += (long long)__ldcg(reinterpret_cast<const unsigned long long*>(&res->delta[g]));
-      ops[g].n_out = (u64)run;
+  {
+    // live rows after every gate: inclusive scan of the per-gate changes (one gate per thread, ng <= 250 < NT)
+    long long* sc = reinterpret_cast<long long*>(smem_raw);
+    long long v = 0;
+    if ((int)threadIdx.x < s.ng) v = (long long)__ldcg(reinterpret_cast<const unsigned long long*>(&res->delta[threadIdx.x]));
+    sc[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < NT; d <<= 1) {
+      const long long a = (int)threadIdx.x >= d ? sc[threadIdx.x - d] : 0ll;
+      __syncthreads();
+      sc[threadIdx.x] += a;
+      __syncthreads();
     }
+    if ((int)threadIdx.x < s.ng) ops[threadIdx.x].n_out = (u64)((long long)fin.n_live_in + sc[threadIdx.x]);
+  }
+  if (threadIdx.x == 0) {
     const unsigned ovf = __ldcg(&res->overflow);
     const u64 n_rows = __ldcg(reinterpret_cast<const unsigned long long*>(&res->out_rows));
     OpStat* f = &ops[s.ng];
@@ -525,8 +572,8 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const __grid_const
       fin.st->n_append = n_rows;
       fin.st->n_live = n_rows;
     }
-    __threadfence();
   }
+  __threadfence();
   __syncthreads();
   if (fin.host_res) {
     const u64* src = reinterpret_cast<const u64*>(fin.st);  // DevState | start stamp | counter slots: one block
