@@ -118,6 +118,7 @@ struct obp_ctx {
   int seg_cap_rows = 0;         // test hook: rows a partition may hold (0: what the shared memory allows)
   int seg_smem_max = 0;         // opt-in shared memory per CTA of k_seg_main (0: path unavailable)
   double seg_growth = 4.0;      // rows out / rows in of the last run (sizes the next run's partitions)
+  u64 seg_block_rows = ~0ull;   // a run on this many live rows fell back to the per-gate kernels: no attempts at or above it
   ulonglong2* alt_xz[2] = {nullptr, nullptr};  // the run's output columns (swapped with the table's on success)
   double2* alt_coef = nullptr;
   u64* alt_hash = nullptr;
@@ -1059,6 +1060,10 @@ static int load_impl(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_wo
   if (n > ctx->cap) return ctx->fail(OBP_ERR_CAPACITY, "obp_load: more rows than capacity");
   CU(cudaSetDevice(ctx->device));
   if (!keep_snapshot) ctx->snap.valid = false;  // (the snapshot carries its own hash frame: it survives a replace)
+  if (!keep_snapshot) {  // a new observable: what the last one taught about runs in shared memory no longer holds
+    ctx->seg_block_rows = ~0ull;
+    ctx->seg_growth = 4.0;
+  }
   init_frame(ctx);
   int rc = upload_cols(ctx);
   if (rc) return rc;
@@ -1204,6 +1209,7 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
 static bool segment_eligible(const obp_ctx* ctx, const obp_op* ops, int n_ops) {
   if (!ctx->use_segments || ctx->seg_smem_max <= 0 || ctx->W > 2 || ctx->n_ranks != 1 || ctx->row_order || ctx->flag_sync) return false;
   if (n_ops < ctx->seg_min_gates || n_ops > OBP_SEG_MAXG || ctx->n_live == 0 || ctx->n_dense >= (1ull << 31)) return false;
+  if (ctx->n_live >= ctx->seg_block_rows) return false;
   for (int k = 0; k < n_ops; ++k) {
     if (ops[k].kind != OBP_OP_ROTATION) return false;
     const unsigned allowed = (k == n_ops - 1) ? OBP_FLAG_EXACT_COUNTERS : 0u;
@@ -1301,6 +1307,8 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
       const double atol = P.atol;
       ctx->n_seg_fallbacks++;
       ctx->seg_growth = 16.0;
+      // (the observable of this run grows classes no CTA can hold: stay with the per-gate kernels from half this size on)
+      ctx->seg_block_rows = std::max<u64>(P.n_start / 2, 64);
       const bool keep = ctx->use_segments;
       ctx->use_segments = false;
       rc = apply_ops_impl(ctx, ops.data(), n_ops, atol, stats, nullptr, nullptr, false);  // the per-gate kernels
@@ -1476,6 +1484,7 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   }
   P = std::max(1, std::min(P, OBP_SEG_MAXP));
   sp.P = sp2.P = P;
+  sp.cap_rows_big = sp2.cap_rows_big = sp2.cap_rows;
 
   // upload the gates through the program staging buffer
   const size_t need = gates.size() * sizeof(SegGate);

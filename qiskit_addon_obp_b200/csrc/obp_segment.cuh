@@ -33,7 +33,7 @@
 #include "obp_kernels.cuh"
 
 #define OBP_SEG_MAXG 250    // gates per run (a row records the gate that killed it in one byte)
-#define OBP_SEG_MAXP 16384  // partitions per run
+#define OBP_SEG_MAXP 65536  // partitions per run
 #define OBP_SEG_FBITS 16    // output bits of the partition map
 #define OBP_SEG_ALIVE 255u
 
@@ -59,6 +59,8 @@ struct SegP {
   int n_index;       // local index slots (power of two)
   int exact_last;    // the last gate reports the reference's simplify counters
   int slot0;         // counter slot of gate 0 (gate g: slot0 + g)
+  int cap_rows_big;  // rows a partition may hold in the big CTAs of the second launch (a bigger one cannot be run at all)
+  int pad2;
   int dbg;           // timing experiments (OBP_B200_SEG_DEBUG; results are wrong): 1 no row work, 2 no partner path
   int pad;
   u64 n_dense;       // rows of the input table
@@ -128,8 +130,13 @@ __global__ void __launch_bounds__(OBP_BS) k_seg_count(Tab t, const __grid_consta
   const int P = s.P;
   const int per = (P + OBP_BS - 1) / OBP_BS;
   const int p0 = threadIdx.x * per, p1 = min(P, p0 + per);
-  unsigned local = 0;
-  for (int p = p0; p < p1; ++p) local += __ldcg(&cnt[p]);
+  unsigned local = 0, biggest = 0;
+  for (int p = p0; p < p1; ++p) {
+    const unsigned c = __ldcg(&cnt[p]);
+    local += c;
+    biggest = max(biggest, c);
+  }
+  if (biggest > (unsigned)s.cap_rows_big) atomicOr(&res->overflow, 8u);  // hopeless: the launches that follow return at once
   s_tot[threadIdx.x] = local;
   __syncthreads();
   for (int d = 1; d < OBP_BS; d <<= 1) {
@@ -258,7 +265,10 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
   // exact counters of the last gate: thread-local, over all partitions this CTA completes
   unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
   double sum_re = 0.0, sum_im = 0.0;
-  const int n_list = plist ? (int)*plist_n : s.P;
+  // a run that has already failed (a partition too big for any CTA, or a partition of the second launch) is not continued;
+  // one thread looks, so that the whole CTA takes the same decision
+  __shared__ int s_abort;
+  if (threadIdx.x == 0) s_abort = __ldcg(&res->overflow) != 0u;
   auto redo = [&](int part) {
     if (threadIdx.x == 0) {
       if (redo_list) redo_list[atomicAdd(&res->n_redo, 1u)] = (unsigned)part;
@@ -266,9 +276,17 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
     }
   };
   __syncthreads();
+  const int n_list = s_abort ? 0 : (plist ? (int)*plist_n : s.P);
 
   for (int it = blockIdx.x; it < n_list; it += gridDim.x) {
     const int part = plist ? (int)plist[it] : it;
+    if (plist) {
+      if (threadIdx.x == 0) s_abort = __ldcg(&res->overflow) != 0u;
+      __syncthreads();
+      const bool ab = s_abort != 0;
+      __syncthreads();  // (nobody rewrites the flag before everybody has read it)
+      if (ab) break;
+    }
     const unsigned o0 = off[part];
     const int n_in = (int)(off[part + 1] - o0);
     if (n_in == 0) continue;
