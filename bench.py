@@ -370,7 +370,7 @@ def large_table_roofline(backpropagate, bpmod, peak: float) -> dict:
     out = rotation_roofline(bpmod.last_run.profile or {}, btg, peak)
     out["workload"] = w.name
     out["updates_per_s_whole_run"] = bpmod.last_run.updates / (bpmod.last_run.device_ms * 1e-3)
-    out["segments"] = dict(zip(("runs", "partitions_redone", "fallbacks"), bpmod.last_run.segments))
+    out["segments"] = dict(zip(("runs", "runs_cut_into_pieces", "fallbacks_to_per_gate_kernels"), bpmod.last_run.segments))
     out["traffic_source"] = "profiles/README.md (ncu --set full captures of the rotation kernels on tables of this size)"
     return out
 
@@ -814,7 +814,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                              timing="k_rotate inside the persistent program kernel: %globaltimer stamps at its grid barriers; stand-alone "
                                     "k_rotate and the k_seg_* launches of a run: CUDA events on the table's stream",
                              traffic_source="profiles/README.md (ncu --set full captures of the rotation kernels, per launch)"),
-            "segments": dict(zip(("runs", "partitions_redone", "fallbacks"), seg_tot)),
+            "segments": dict(zip(("runs", "runs_cut_into_pieces", "fallbacks_to_per_gate_kernels"), seg_tot)),
             "clocks": clocks,
             "wall_s": wall,
         }

@@ -206,8 +206,8 @@ int obp_is_broken(const obp_ctx* ctx);
 #define OBP_OPT_SEGMENT_CAP_ROWS 5
 int obp_configure(obp_ctx* ctx, int32_t option, int64_t value);
 
-/* Runs of rotations applied in shared memory since the context was created: committed runs, runs repeated with
- * four times as many partitions (a partition outgrew its shared memory), runs handed to the per-gate kernels. */
+/* Runs of rotations applied in shared memory since the context was created: committed runs, failed runs repeated in
+ * shorter pieces (too many rows shared a partition), runs handed to the per-gate kernels. */
 int obp_segment_stats(obp_ctx* ctx, uint64_t* n_runs, uint64_t* n_retries, uint64_t* n_fallbacks);
 
 /* Row-order mode (off by default).  The reference's simplify() returns rows in the order of each

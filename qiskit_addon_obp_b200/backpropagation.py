@@ -49,7 +49,7 @@ class RunInfo:
     sharded = False  # the observable was a hash-sharded table: `updates` is already the global count
     exchanges = 0  # sharded: rotations that needed a record exchange
     exchanged_records = 0
-    #: rotation-only gate programs applied in shared memory: (committed runs, runs retried with smaller partitions,
+    #: rotation-only gate programs applied in shared memory: (committed runs, failed runs repeated in shorter pieces,
     #: runs handed to the per-gate kernels)
     segments = (0, 0, 0)
 

@@ -118,6 +118,10 @@ struct obp_ctx {
   int seg_cap_rows = 0;         // test hook: rows a partition may hold (0: what the shared memory allows)
   int seg_smem_max = 0;         // opt-in shared memory per CTA of k_seg_main (0: path unavailable)
   double seg_growth = 4.0;      // rows out / rows in of the last run (sizes the next run's partitions)
+  int seg_max_gates = OBP_SEG_MAXG;  // longer runs are cut into pieces of at most this many gates (halved when a run fails:
+                                     // fewer generators leave a finer partition map, i.e. smaller coset classes)
+  u64 carry_updates = 0;             // term-gate updates of the pieces of a cut run that were finished before the last one
+  std::vector<u64> carry_sizes;      // ... and their per-op row counts
   u64 seg_block_rows = ~0ull;   // a run on this many live rows fell back to the per-gate kernels: no attempts at or above it
   ulonglong2* alt_xz[2] = {nullptr, nullptr};  // the run's output columns (swapped with the table's on success)
   double2* alt_coef = nullptr;
@@ -1062,6 +1066,7 @@ static int load_impl(obp_ctx* ctx, const uint64_t* x_words, const uint64_t* z_wo
   if (!keep_snapshot) ctx->snap.valid = false;  // (the snapshot carries its own hash frame: it survives a replace)
   if (!keep_snapshot) {  // a new observable: what the last one taught about runs in shared memory no longer holds
     ctx->seg_block_rows = ~0ull;
+    ctx->seg_max_gates = OBP_SEG_MAXG;
     ctx->seg_growth = 4.0;
   }
   init_frame(ctx);
@@ -1208,7 +1213,7 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
 // ---- runs of rotations in shared memory (obp_segment.cuh) -------------------------------------------------------
 static bool segment_eligible(const obp_ctx* ctx, const obp_op* ops, int n_ops) {
   if (!ctx->use_segments || ctx->seg_smem_max <= 0 || ctx->W > 2 || ctx->n_ranks != 1 || ctx->row_order || ctx->flag_sync) return false;
-  if (n_ops < ctx->seg_min_gates || n_ops > OBP_SEG_MAXG || ctx->n_live == 0 || ctx->n_dense >= (1ull << 31)) return false;
+  if (n_ops < ctx->seg_min_gates || ctx->n_live == 0 || ctx->n_dense >= (1ull << 31)) return false;
   if (ctx->n_live >= ctx->seg_block_rows) return false;
   for (int k = 0; k < n_ops; ++k) {
     if (ops[k].kind != OBP_OP_ROTATION) return false;
@@ -1290,6 +1295,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
                           int32_t* n_done, int32_t* peer_xor, bool defer);
 static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats, bool defer,
                          int force_P, int n_try);
+static int apply_in_pieces(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats, bool defer, int piece);
 
 static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
   int rc;
@@ -1305,10 +1311,21 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
       std::vector<obp_op> ops = P.ops;  // (P may be ctx->pending's storage)
       const int n_ops = P.n_ops;
       const double atol = P.atol;
-      ctx->n_seg_fallbacks++;
       ctx->seg_growth = 16.0;
-      // (the observable of this run grows classes no CTA can hold: stay with the per-gate kernels from half this size on)
-      ctx->seg_block_rows = std::max<u64>(P.n_start / 2, 64);
+      const bool can_cut = n_ops >= 2 * std::max(ctx->seg_min_gates, 2);
+      if (can_cut) {
+        // Too many rows share a partition: with fewer gates per run the partition map has fewer generators to
+        // vanish on, so the classes shrink.  Later runs of this observable are cut into pieces a quarter as long.
+        ctx->seg_max_gates = std::max(ctx->seg_min_gates, (n_ops + 3) / 4);
+        if (P.n_start >= (1ull << 17)) {  // a big table: worth repeating this very run in pieces
+          ctx->n_seg_retries++;
+          return apply_in_pieces(ctx, ops.data(), n_ops, atol, stats, false, ctx->seg_max_gates);
+        }
+      } else {
+        // (even the shortest run grows classes no CTA can hold: stay with the per-gate kernels from half this size on)
+        ctx->seg_block_rows = std::max<u64>(P.n_start / 2, 64);
+      }
+      ctx->n_seg_fallbacks++;
       const bool keep = ctx->use_segments;
       ctx->use_segments = false;
       rc = apply_ops_impl(ctx, ops.data(), n_ops, atol, stats, nullptr, nullptr, false);  // the per-gate kernels
@@ -1321,7 +1338,6 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
     std::swap(ctx->hash, ctx->alt_hash);
     ctx->index_stale = true;
     ctx->n_seg_runs++;
-    ctx->n_seg_retries += ctx->h_ops[P.n_slots].keys_present;  // partitions that needed the big CTAs
     ctx->seg_growth = (double)ctx->n_live / (double)std::max<u64>(P.n_start, 1);
   }
   if (ctx->trace_host) {
@@ -1362,6 +1378,11 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
   ctx->last_op_sizes.assign((size_t)P.n_ops, 0);
   for (int k = 0; k < P.n_ops; ++k)
     if (P.slot_of_op[k] >= 0 && P.slot_of_op[k] < P.n_slots) ctx->last_op_sizes[k] = ctx->h_ops[P.slot_of_op[k]].n_out;
+  // a run that was cut into pieces: this is its last piece, the earlier ones are accounted here
+  updates += ctx->carry_updates;
+  if (!ctx->carry_sizes.empty()) ctx->last_op_sizes.insert(ctx->last_op_sizes.begin(), ctx->carry_sizes.begin(), ctx->carry_sizes.end());
+  ctx->carry_updates = 0;
+  ctx->carry_sizes.clear();
   if (sync_rc) {
     if (stats) {
       stats->updates = updates;      // work done before the overflow was noticed (the caller rolls the slice back)
@@ -1405,6 +1426,43 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
   if (stats) {
     stats->n_out = ctx->n_live;
     stats->n_dense = ctx->n_dense;
+  }
+  return OBP_OK;
+}
+
+// A run of rotations too long for one pass in shared memory (more gates than the parameter block holds, or a run that
+// failed because too many rows shared a partition): pieces of at most `piece` gates, one after the other.  Every piece
+// is a gate program of its own (its own partition map, one read and one write of the table); the statistics of the
+// call are those of the last piece plus the update counts of the pieces before it.
+static int apply_in_pieces(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats, bool defer, int piece) {
+  // (called for a piece that failed and is cut again: what was carried for that piece is carried on)
+  u64 updates = ctx->carry_updates;
+  std::vector<u64> sizes = ctx->carry_sizes;
+  const int stub = std::min(ctx->seg_min_gates, 8);  // no piece shorter than this: the one before it takes its gates
+  piece = std::max(1, std::min(piece, OBP_SEG_MAXG - stub));
+  for (int a = 0; a < n_ops;) {
+    int b = std::min(n_ops, a + piece);
+    if (n_ops - b > 0 && n_ops - b < stub) b = n_ops;
+    const bool last = b == n_ops;
+    if (last) {
+      // the last piece carries the call: deferred if the caller asked for that, its statistics complete the call's
+      ctx->carry_updates = updates;
+      ctx->carry_sizes = sizes;
+      return apply_segment(ctx, ops + a, b - a, atol, stats, defer, 0, 0);  // (finish_ops adds the carry)
+    }
+    std::vector<obp_op> part(ops + a, ops + b);
+    for (obp_op& o : part) o.flags &= ~(unsigned)OBP_FLAG_EXACT_COUNTERS;
+    obp_stats st;
+    ctx->carry_updates = 0;
+    ctx->carry_sizes.clear();
+    const int rc = apply_segment(ctx, part.data(), b - a, atol, &st, false, 0, 0);
+    if (rc) {
+      if (stats) { memset(stats, 0, sizeof(*stats)); stats->updates = updates + st.updates; stats->n_out = st.n_out; }
+      return rc;
+    }
+    updates += st.updates;
+    sizes.insert(sizes.end(), ctx->last_op_sizes.begin(), ctx->last_op_sizes.end());
+    a = b;
   }
   return OBP_OK;
 }
@@ -1577,7 +1635,11 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     const int vrc = validate_op(ctx, ops[k]);
     if (vrc) return vrc;
   }
-  if (segment_eligible(ctx, ops, n_ops) && !n_done) return apply_segment(ctx, ops, n_ops, atol, stats, defer, 0, 0);
+  if (segment_eligible(ctx, ops, n_ops) && !n_done) {
+    const int piece = std::max(ctx->seg_min_gates, std::min(ctx->seg_max_gates, OBP_SEG_MAXG - 8));
+    if (n_ops <= piece) return apply_segment(ctx, ops, n_ops, atol, stats, defer, 0, 0);
+    return apply_in_pieces(ctx, ops, n_ops, atol, stats, defer, piece);
+  }
   {
     // rows this program can reach: every rotation may double the table
     int n_rot = 0;
@@ -2038,6 +2100,7 @@ static const char* kRowOrderMsg =
 int obp_apply_ops(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats) {
   OBP_NO_PENDING(ctx, "obp_apply_ops");
   if (ctx && ctx->row_order) return ctx->fail(OBP_ERR_UNSUPPORTED, kRowOrderMsg);
+  if (ctx) { ctx->carry_updates = 0; ctx->carry_sizes.clear(); }
   return apply_ops_impl(ctx, ops, n_ops, atol, stats, nullptr, nullptr);
 }
 
@@ -2045,6 +2108,9 @@ int obp_apply_ops_submit(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   OBP_NO_PENDING(ctx, "obp_apply_ops_submit");
   if (ctx && ctx->row_order) return ctx->fail(OBP_ERR_UNSUPPORTED, kRowOrderMsg);
   if (ctx && ctx->n_ranks > 1) return ctx->fail(OBP_ERR_UNSUPPORTED, "obp_apply_ops_submit: not available on a sharded table");
+  if (!ctx) return OBP_ERR_BADARG;
+  ctx->carry_updates = 0;
+  ctx->carry_sizes.clear();
   return apply_ops_impl(ctx, ops, n_ops, atol, nullptr, nullptr, nullptr, true);
 }
 

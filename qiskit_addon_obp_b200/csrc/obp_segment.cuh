@@ -321,6 +321,10 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
     int add_i = 1;  // s_add slot the current pass appends to (the next one is cleared meanwhile)
     bool failed = false;
     for (int g = 0; g < s.ng && !failed; ++g) {
+      int* add_w = &s_add[add_i];
+      if (threadIdx.x == 0) s_add[add_i == 2 ? 0 : add_i + 1] = 0;
+      // a warp whose rows all lie beyond the partition only keeps the barrier company (most warps of most partitions)
+      if ((int)(threadIdx.x & ~31u) < n_pass) {
       const SegGate& G = sgate[g];
       RotP pg;  // the fields rot_rows() reads
       pg.u0r = G.u0r; pg.u0i = G.u0i; pg.u1r = G.u1r; pg.u1i = G.u1i;
@@ -333,8 +337,6 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
       for (int w = 0; w < W; ++w) { gx[w] = G.gx[w]; gz[w] = G.gz[w]; }
       const int yG = G.yG;
       const double thr_self = G.thr_self, thr_all = G.thr_all;
-      int* add_w = &s_add[add_i];
-      if (threadIdx.x == 0) s_add[add_i == 2 ? 0 : add_i + 1] = 0;
       int dlive = 0;
       for (int base = (int)(threadIdx.x & ~31u); base < n_pass; base += NT) {
         const int r = base + (int)lane;
@@ -491,6 +493,7 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
       if (lane == 0 && dl) {
         atomicAdd(&dgp[g], dl);
         atomicAdd(&s_live, dl);
+      }
       }
       __syncthreads();
       n_pass += *add_w;

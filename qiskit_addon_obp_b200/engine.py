@@ -588,7 +588,7 @@ class TermTable:
         self._check(self._lib.obp_set_shard(self._h, int(n_ranks), int(rank)), "obp_set_shard")
 
     def segment_stats(self) -> tuple[int, int, int]:
-        """``(runs of rotations applied in shared memory, runs retried with smaller partitions, runs handed to the
+        """``(runs of rotations applied in shared memory, failed runs repeated in shorter pieces, runs handed to the
         per-gate kernels)`` since the context was created."""
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(self._lib.obp_segment_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "obp_segment_stats")
