@@ -210,6 +210,12 @@ int obp_configure(obp_ctx* ctx, int32_t option, int64_t value);
  * shorter pieces (too many rows shared a partition), runs handed to the per-gate kernels. */
 int obp_segment_stats(obp_ctx* ctx, uint64_t* n_runs, uint64_t* n_retries, uint64_t* n_fallbacks);
 
+/* The partition map of a run (host only, no device needed; exposed for tests): n_gen rotation generators as packed
+ * words (gen_x / gen_z: n_gen x n_words, n_words = 1 or 2).  fmask (16 x 4 words) receives a GF(2)-linear map
+ * keys -> 16 bits, bit j = parity of (x0 & fmask[4j]) ^ (z0 & fmask[4j+1]) ^ (x1 & fmask[4j+2]) ^ (z1 & fmask[4j+3]),
+ * that vanishes on every generator: a key and the key xor any product of generators land in the same partition. */
+int obp_segment_partition_map(int32_t n_words, int32_t n_gen, const uint64_t* gen_x, const uint64_t* gen_z, uint64_t* fmask);
+
 /* Row-order mode (off by default).  The reference's simplify() returns rows in the order of each
  * key's first appearance among the gate's k*k raw rows (utils/simplify.py:126,160-165 on top of the
  * compose order of utils/operations.py:103-105); the in-place gate kernels of obp_apply_ops do not

@@ -127,6 +127,8 @@ struct obp_ctx {
   double2* alt_coef = nullptr;
   u64* alt_hash = nullptr;
   unsigned char* d_seg = nullptr;  // [cnt | off | cur] (OBP_SEG_MAXP + 1 u32 each) | SegRes
+  bool index_touched = true;       // a program consulted the index since the last run committed: the next run fills it in its output stage
+  u64 seg_T_new = 0;               // ... slots that run cleared (0: it did not touch the index)
   bool index_stale = false;        // the table's columns were replaced by a run: the index is rebuilt before its next use
   u64 T_eff = 0;                   // index slots in use (a power of two <= T): a lazy rebuild after a run sizes the index to the rows
   u64 n_seg_runs = 0, n_seg_retries = 0, n_seg_fallbacks = 0;
@@ -338,6 +340,7 @@ int rebuild_index(obp_ctx* ctx) {
 // rebuild that follows a run clears and fills only as many slots as those rows want (a 10^4-row table in a context
 // sized for 4 * 10^6 terms would otherwise pay a 64 MB memset per slice).
 int ensure_index(obp_ctx* ctx, u64 need_rows = 0) {
+  ctx->index_touched = true;
   if (need_rows == 0 || need_rows > ctx->cap) need_rows = ctx->cap;
   const u64 want = std::min<u64>(ctx->T, next_pow2(std::max<u64>(4 * need_rows, 1ull << 16)));
   if (!ctx->index_stale && (ctx->T_eff == 0 || ctx->T_eff >= std::min<u64>(ctx->T, 2 * need_rows))) return OBP_OK;
@@ -1337,6 +1340,11 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
     std::swap(ctx->coef, ctx->alt_coef);
     std::swap(ctx->hash, ctx->alt_hash);
     ctx->index_stale = true;
+    if (ctx->seg_T_new && ctx->h_ops[P.n_slots].cancelled == 0) {  // the run published every row it wrote
+      ctx->index_stale = false;
+      ctx->T_eff = ctx->seg_T_new;
+    }
+    ctx->index_touched = false;  // (set again by the next program that consults the index)
     ctx->n_seg_runs++;
     ctx->seg_growth = (double)ctx->n_live / (double)std::max<u64>(P.n_start, 1);
   }
@@ -1455,7 +1463,7 @@ static int apply_in_pieces(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, doubl
     obp_stats st;
     ctx->carry_updates = 0;
     ctx->carry_sizes.clear();
-    const int rc = apply_segment(ctx, part.data(), b - a, atol, &st, false, 0, 0);
+    const int rc = apply_segment(ctx, part.data(), b - a, atol, &st, false, 0, 1);
     if (rc) {
       if (stats) { memset(stats, 0, sizeof(*stats)); stats->updates = updates + st.updates; stats->n_out = st.n_out; }
       return rc;
@@ -1566,6 +1574,20 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   out.xz[1] = ctx->alt_xz[1];
   out.coef = ctx->alt_coef;
   out.hash = ctx->alt_hash;
+  out.index = nullptr;
+  out.index_mask = 0;
+  ctx->seg_T_new = 0;
+  if (ctx->index_touched && !n_try) {  // (n_try != 0: a piece of a cut run that is not the last one)
+    // the programs after a run of this observable look keys up: the run's output stage fills the index itself (cleared
+    // here, sized to the rows expected; the input table's entries are gone either way once the run commits)
+    const double growth = std::min(32.0, std::max(1.5, ctx->seg_growth));
+    const u64 want = std::min<u64>(ctx->T, next_pow2(std::max<u64>((u64)(8.0 * growth * (double)ctx->n_live), 1ull << 16)));
+    CU(cudaMemsetAsync(ctx->index, 0xFF, want * sizeof(u64), ctx->stream));
+    ctx->index_stale = true;  // (until the run reports that every row was published)
+    ctx->seg_T_new = want;
+    out.index = ctx->index;
+    out.index_mask = want - 1;
+  }
   unsigned* part = ctx->dest;
   unsigned* perm = (unsigned*)ctx->spare8;
   {
@@ -3218,6 +3240,23 @@ int obp_segment_stats(obp_ctx* ctx, uint64_t* n_runs, uint64_t* n_retries, uint6
   if (n_runs) *n_runs = ctx->n_seg_runs;
   if (n_retries) *n_retries = ctx->n_seg_retries;
   if (n_fallbacks) *n_fallbacks = ctx->n_seg_fallbacks;
+  return OBP_OK;
+}
+
+int obp_segment_partition_map(int32_t n_words, int32_t n_gen, const uint64_t* gen_x, const uint64_t* gen_z, uint64_t* fmask) {
+  if ((n_words != 1 && n_words != 2) || n_gen < 0 || (n_gen && (!gen_x || !gen_z)) || !fmask) return OBP_ERR_BADARG;
+  std::vector<SegGate> gates((size_t)n_gen);
+  for (int k = 0; k < n_gen; ++k) {
+    memset(&gates[(size_t)k], 0, sizeof(SegGate));
+    for (int w = 0; w < n_words; ++w) {
+      gates[(size_t)k].gx[w] = gen_x[(size_t)k * n_words + w];
+      gates[(size_t)k].gz[w] = gen_z[(size_t)k * n_words + w];
+    }
+  }
+  u64 fm[OBP_SEG_FBITS][4];
+  seg_partition_map(gates, n_words, fm);
+  for (int j = 0; j < OBP_SEG_FBITS; ++j)
+    for (int q = 0; q < 4; ++q) fmask[4 * j + q] = fm[j][q];
   return OBP_OK;
 }
 

@@ -74,7 +74,7 @@ struct SegRes {  // device-side result of a run (zeroed before)
   unsigned overflow;     // 1: a partition outgrew shared memory, 2: the output outgrew its columns, 4: a local index filled up
   unsigned n_redo;       // partitions that outgrew the small CTAs and were run again by the big ones
   unsigned ticket;       // last-block-done counter (k_seg_count, second k_seg_main)
-  unsigned pad;
+  unsigned index_skipped; // the output outgrew the cleared part of the index: rows were not published
   long long delta[OBP_SEG_MAXG];  // change of the live-row count by every gate
 };
 
@@ -82,6 +82,8 @@ struct SegOut {
   ulonglong2* xz[2];
   double2* coef;
   u64* hash;
+  u64* index;      // the table's hash index, cleared for this run: the output stage publishes the rows it writes
+  u64 index_mask;  // (nullptr: the index is rebuilt later, if anybody needs it)
 };
 
 template <int W>
@@ -514,6 +516,9 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
       __syncthreads();
       continue;
     }
+    // publish the rows in the table's index while it stays at most half full
+    const bool publish = out.index != nullptr && 2 * (obase + (u64)s_live) <= out.index_mask + 1;
+    if (out.index != nullptr && !publish && threadIdx.x == 0) res->index_skipped = 1u;
     for (int base = (int)(threadIdx.x & ~31u); base < n_pass; base += NT) {
       const int r = base + (int)lane;
       const bool alive = r < n_pass && m.died[r] == OBP_SEG_ALIVE;
@@ -527,7 +532,16 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
 #pragma unroll
         for (int w = 0; w < W; ++w) out.xz[w][o] = m.xz[w][r];
         out.coef[o] = m.coef[r];
-        out.hash[o] = m.hash[r];
+        const u64 h = m.hash[r];
+        out.hash[o] = h;
+        if (publish) {
+          const u64 entry = ((h >> 32) << 32) | o;
+          u64 sl = h & out.index_mask;
+          for (u64 probes = 0; probes <= out.index_mask; ++probes) {
+            if (atomicCAS(&out.index[sl], OBP_EMPTY, entry) == OBP_EMPTY) break;
+            sl = (sl + 1) & out.index_mask;
+          }
+        }
       }
     }
     // the partition is done: its counters join the CTA's
@@ -588,6 +602,7 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
     f->n_out = ovf;
     f->rows_surv = n_rows;
     f->keys_present = __ldcg(&res->n_redo);
+    f->cancelled = __ldcg(&res->index_skipped);
     if (ovf == 0u) {
       fin.st->n_scan = n_rows;
       fin.st->n_append = n_rows;

@@ -152,6 +152,7 @@ def lib() -> C.CDLL:
         "obp_record_bytes": ([C.c_int], C.c_uint64),
         "obp_shard_stats": ([vp, u64p, u64p], C.c_int),
         "obp_segment_stats": ([vp, u64p, u64p, u64p], C.c_int),
+        "obp_segment_partition_map": ([C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "obp_shard_split": ([vp, C.c_int32, C.c_int32, vp, C.c_int32, u64p, C.POINTER(C.c_int32)], C.c_int),
         "obp_apply_ops_sharded": (
             [vp, vp, C.c_int32, C.c_double, C.POINTER(ObpStats), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
@@ -190,7 +191,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count obp_shard_stats obp_segment_stats"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count obp_shard_stats obp_segment_stats obp_segment_partition_map"
 ).split()
 
 

@@ -359,3 +359,58 @@ def test_slice_program_cache_follows_in_place_edits():
     assert ins.matrix[0, 0] == 1
     with pytest.raises(ValueError):
         ins.matrix[0, 0] = 5
+
+
+def test_segment_partition_map_vanishes_on_every_generator():
+    """The host step of the slice-in-shared-memory path (csrc/obp_segment.cuh): a GF(2)-linear map keys -> 16 bits
+    that vanishes on every rotation generator of the run, so that P and P xor (any product of generators) share a
+    partition — for generators on disjoint qubits (an RX / RZZ layer), for overlapping and for dependent ones — and
+    that still tells keys apart that differ outside the generators' span."""
+    import ctypes as C
+
+    from qiskit_addon_obp_b200 import engine
+
+    lib = engine.lib()
+    rng = np.random.default_rng(7)
+
+    def fmap(fm, x, z):
+        v = 0
+        for j in range(16):
+            a = 0
+            for w in range(len(x)):
+                a ^= (int(x[w]) & int(fm[4 * j + 2 * w])) ^ (int(z[w]) & int(fm[4 * j + 2 * w + 1]))
+            v |= (bin(a).count("1") & 1) << j
+        return v
+
+    for n_words, nq in ((1, 40), (2, 127)):
+        layers = {
+            "rx": [({q: "X"}) for q in range(nq)],
+            "rzz": [({q: "Z", q + 1: "Z"}) for q in range(0, nq - 1, 2)],
+            "xx+yy same bonds": [({q: p, q + 1: p}) for q in range(0, nq - 1, 2) for p in "XY"],
+            "overlapping chain": [({q: "X", q + 1: "Z", q + 2: "Y"}) for q in range(0, nq - 2)],
+            "random": [dict(zip(rng.choice(nq, 3, replace=False).tolist(), rng.choice(list("XYZ"), 3))) for _ in range(60)],
+        }
+        for name, gens in layers.items():
+            gx = np.zeros((len(gens), n_words), dtype=np.uint64)
+            gz = np.zeros((len(gens), n_words), dtype=np.uint64)
+            for k, g in enumerate(gens):
+                for q, p in g.items():
+                    if p in "XY":
+                        gx[k, q // 64] |= np.uint64(1 << (q % 64))
+                    if p in "ZY":
+                        gz[k, q // 64] |= np.uint64(1 << (q % 64))
+            fm = np.zeros(64, dtype=np.uint64)
+            rc = lib.obp_segment_partition_map(n_words, len(gens), gx.ctypes.data_as(C.c_void_p), gz.ctypes.data_as(C.c_void_p),
+                                               fm.ctypes.data_as(C.c_void_p))
+            assert rc == 0, name
+            for k in range(len(gens)):
+                assert fmap(fm, gx[k], gz[k]) == 0, (name, k)
+            # linear: f(P xor G) == f(P); and not degenerate unless the generators span (almost) everything
+            seen = set()
+            for _ in range(200):
+                x = rng.integers(0, 1 << 63, size=n_words, dtype=np.uint64)
+                z = rng.integers(0, 1 << 63, size=n_words, dtype=np.uint64)
+                k = int(rng.integers(len(gens)))
+                assert fmap(fm, x ^ gx[k], z ^ gz[k]) == fmap(fm, x, z), name
+                seen.add(fmap(fm, x, z))
+            assert len(seen) > 150, (name, len(seen))
