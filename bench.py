@@ -276,6 +276,18 @@ def run_reference(args, rank: int, world: int) -> None:
         tot_t += t
     value = tot_u / tot_t
     sample = f"first {tot_u // max(1, args.steps)} term-gate updates of the workload per step (oracle stopped by max_updates)"
+    full = None
+    if args.workload == "config2" and not args.no_full_run:
+        # one member of the sweep run to COMPLETION (same work as the engine's `other_configs["config2@theta=pi/4"]`):
+        # a wall-time comparison beside the rate comparison of the bounded samples
+        from qiskit_addon_obp_b200 import workloads as wl_mod
+
+        w = wl_mod.config2_kicked_ising(theta_h=np.pi / 4, steps=20, max_paulis=args.max_paulis)
+        t0 = time.perf_counter()
+        u, _ = cpu_sample([w], 10**15)
+        t_full = time.perf_counter() - t0
+        full = {"workload": w.name, "updates": u, "wall_s": t_full, "updates_per_s": u / t_full, "same_work": True,
+                "engine_counterpart": "other_configs['config2@theta=pi/4'] of the engine arm's line (e2e_ms)"}
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -301,6 +313,7 @@ def run_reference(args, rank: int, world: int) -> None:
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "full_workload": full,
     }
     print(json.dumps(line), flush=True)
 
@@ -387,6 +400,8 @@ def other_configs(backpropagate, bpmod, torch, device, flush_buf, peak: float) -
         ("config3", wl.config3_square_lattice(), 2, True),
         ("config4@2e7", wl.config4_near_clifford(depth=200, max_paulis=20_000_000), 2, False),
         ("config5@1e6", wl.config5_magic_sweep(theta=np.pi / 16, depth=40, max_paulis=1_000_000), 2, True),
+        # the one member of the headline sweep the CPU arm runs to completion (`full_workload` of --impl reference)
+        ("config2@theta=pi/4", wl.config2_kicked_ising(theta_h=np.pi / 4, steps=20, max_paulis=1_000_000), 3, True),
     ]
     out = {}
     for name, w, reps, download in cases:
@@ -858,6 +873,7 @@ def main() -> None:
     ap.add_argument("--no-download", action="store_true", help="leave the result on the device(s): for 1e8-term tables whose "
                     "host copy would be tens of GB (e2e is then not an end-to-end number and is reported as null)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-run", action="store_true", help="--impl reference: skip the one workload run to completion (~70 s)")
     ap.add_argument("--no-large-table", action="store_true", help="skip the extra HBM-regime roofline pass")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the configs 1/3/4/5 side measurements (N = 1)")
     ap.add_argument("--no-sharded-block", action="store_true", help="skip the config-4 hash-sharded strong-scaling measurement")
