@@ -83,13 +83,12 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) {
   return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y));
 }
 // a * (-i)^e, exact
+// (branch-free: the exponent differs from lane to lane, a switch would run its four cases one after the other)
 __device__ __forceinline__ double2 mul_mi_pow(double2 a, int e) {
-  switch (e & 3) {
-    case 0: return a;
-    case 1: return make_double2(a.y, -a.x);
-    case 2: return make_double2(-a.x, -a.y);
-    default: return make_double2(-a.y, a.x);
-  }
+  const bool odd = (e & 1) != 0, neg = (e & 2) != 0;
+  const double re = odd ? a.y : a.x;    // e = 1: (y, -x)
+  const double im = odd ? -a.x : a.y;
+  return make_double2(neg ? -re : re, neg ? -im : im);  // e = 2: (-x, -y), e = 3: (-y, x)
 }
 // np.isclose(c, 0, atol, rtol) == (|c| <= atol) with |c| = hypot(re, im); NaN compares false, i.e.
 // the row is kept.  hypot() is ~60 instructions in fp64, so the squared magnitude decides unless it
