@@ -198,12 +198,15 @@ int obp_is_broken(const obp_ctx* ctx);
  *                             0: one pass over the table per gate.  Results are identical either way.
  *   OBP_OPT_SEGMENT_MIN_GATES shorter runs use the per-gate kernels (default 6).
  *   OBP_OPT_SEGMENT_CAP_ROWS  rows a partition may hold, 0 = what the shared memory allows (test hook: small values
- *                             force the retry with more partitions and the fall-back to the per-gate kernels). */
+ *                             force the cut into shorter pieces and the fall-back to the per-gate kernels).
+ *   OBP_OPT_SEGMENT_PIECES_MIN_ROWS  a failed run on at least this many rows is repeated in shorter pieces, a failed
+ *                             run on fewer rows goes to the per-gate kernels (default 2^17). */
 #define OBP_OPT_PROGRAM 1
 #define OBP_OPT_PROGRAM_MAX_ROWS 2
 #define OBP_OPT_SEGMENTS 3
 #define OBP_OPT_SEGMENT_MIN_GATES 4
 #define OBP_OPT_SEGMENT_CAP_ROWS 5
+#define OBP_OPT_SEGMENT_PIECES_MIN_ROWS 6
 int obp_configure(obp_ctx* ctx, int32_t option, int64_t value);
 
 /* Runs of rotations applied in shared memory since the context was created: committed runs, failed runs repeated in

@@ -116,6 +116,7 @@ struct obp_ctx {
   bool use_segments = true;
   int seg_min_gates = 6;        // shorter runs go through the per-gate kernels
   int seg_cap_rows = 0;         // test hook: rows a partition may hold (0: what the shared memory allows)
+  u64 seg_pieces_min_rows = 1ull << 17;  // a failed run on at least this many rows is repeated in pieces (below: per-gate kernels)
   int seg_smem_max = 0;         // opt-in shared memory per CTA of k_seg_main (0: path unavailable)
   double seg_growth = 4.0;      // rows out / rows in of the last run (sizes the next run's partitions)
   int seg_max_gates = OBP_SEG_MAXG;  // longer runs are cut into pieces of at most this many gates (halved when a run fails:
@@ -985,6 +986,7 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
       if (const char* e8 = getenv("OBP_B200_NO_SEGMENTS")) ctx->use_segments = !(e8[0] && e8[0] != '0');
       if (const char* e9 = getenv("OBP_B200_SEG_MIN_GATES")) ctx->seg_min_gates = std::max(1, atoi(e9));
       if (const char* e10 = getenv("OBP_B200_SEG_CAP_ROWS")) ctx->seg_cap_rows = std::max(0, atoi(e10));
+      if (const char* e11 = getenv("OBP_B200_SEG_PIECES_MIN_ROWS")) ctx->seg_pieces_min_rows = (u64)std::max(0ll, atoll(e11));
     }
     init_frame(ctx);
     return set_counts(ctx, 0);
@@ -1320,7 +1322,7 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
         // Too many rows share a partition: with fewer gates per run the partition map has fewer generators to
         // vanish on, so the classes shrink.  Later runs of this observable are cut into pieces a quarter as long.
         ctx->seg_max_gates = std::max(ctx->seg_min_gates, (n_ops + 3) / 4);
-        if (P.n_start >= (1ull << 17)) {  // a big table: worth repeating this very run in pieces
+        if (P.n_start >= ctx->seg_pieces_min_rows) {  // a big table: worth repeating this very run in pieces
           ctx->n_seg_retries++;
           return apply_in_pieces(ctx, ops.data(), n_ops, atol, stats, false, ctx->seg_max_gates);
         }
@@ -3231,6 +3233,7 @@ int obp_configure(obp_ctx* ctx, int32_t option, int64_t value) {
     case OBP_OPT_SEGMENTS: ctx->use_segments = value != 0; return OBP_OK;
     case OBP_OPT_SEGMENT_MIN_GATES: ctx->seg_min_gates = value < 1 ? 1 : (int)std::min<int64_t>(value, 1 << 20); return OBP_OK;
     case OBP_OPT_SEGMENT_CAP_ROWS: ctx->seg_cap_rows = value < 0 ? 0 : (int)std::min<int64_t>(value, 4096); return OBP_OK;
+    case OBP_OPT_SEGMENT_PIECES_MIN_ROWS: ctx->seg_pieces_min_rows = value < 0 ? 0 : (u64)value; return OBP_OK;
     default: return ctx->fail(OBP_ERR_BADARG, "obp_configure: unknown option");
   }
 }

@@ -172,7 +172,7 @@ def test_random_circuit_truncation(nq, p):
 
 
 @pytest.mark.parametrize("nq", [5, 40, 70, 127])
-@pytest.mark.parametrize("mode", ["slice-in-smem", "tiny-partitions", "gate-by-gate"])
+@pytest.mark.parametrize("mode", ["slice-in-smem", "tiny-partitions", "cut-into-pieces", "gate-by-gate"])
 def test_rotation_layers(nq, mode, monkeypatch):
     """Slices made of rotations only (RX / RY / RZ / RZZ / RXX layers): the slice-in-shared-memory path
     (k_slice_smem: the table partitioned so that whole cosets live in one CTA, all gates between __syncthreads)
@@ -181,8 +181,10 @@ def test_rotation_layers(nq, mode, monkeypatch):
     monkeypatch.setenv("OBP_B200_NO_SEGMENTS", "1" if mode == "gate-by-gate" else "0")
     # partitions of 24 rows: runs outgrow them, are retried with four times as many partitions and finally fall
     # back to the per-gate kernels (the input table must come through untouched)
-    monkeypatch.setenv("OBP_B200_SEG_CAP_ROWS", "24" if mode == "tiny-partitions" else "0")
+    monkeypatch.setenv("OBP_B200_SEG_CAP_ROWS", {"tiny-partitions": "24", "cut-into-pieces": "48"}.get(mode, "0"))
     monkeypatch.setenv("OBP_B200_SEG_MIN_GATES", "2")
+    # cut-into-pieces: a failed run is repeated in shorter pieces whatever the table size (default: only from 2^17 rows)
+    monkeypatch.setenv("OBP_B200_SEG_PIECES_MIN_ROWS", "1" if mode == "cut-into-pieces" else str(1 << 17))
     rng = np.random.default_rng(4000 + nq)
     slices = []
     for k in range(6):
@@ -204,6 +206,13 @@ def test_rotation_layers(nq, mode, monkeypatch):
     _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=20000))
     _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=20000, atol=1e-4))
     _compare(obs, slices, truncation_error_budget=TruncationErrorBudget([0.01], 0.1, 2, 1e-8))
+    if mode != "gate-by-gate":
+        from qiskit_addon_obp_b200 import backpropagation as bpmod
+
+        runs, cut, fell_back = bpmod.last_run.segments
+        assert runs > 0, "the slice-in-shared-memory path did not run"
+        if mode == "cut-into-pieces" and nq >= 40:
+            assert cut > 0, "no run was cut into pieces: the case does not test what it says"
 
 
 def test_clifford_only_counters():
