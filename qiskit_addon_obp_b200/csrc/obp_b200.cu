@@ -714,8 +714,6 @@ struct PendingOps {
   u64 n_start = 0;
   bool prog_mode = false;
   bool segment = false;   // a run of rotations in shared memory (slot n_slots reports its outcome)
-  int seg_P = 0;          // its partition count
-  int seg_try = 0;
   double atol = 0.0;
   std::chrono::steady_clock::time_point t_host0;
 };
@@ -1299,7 +1297,7 @@ static void seg_partition_map(const std::vector<SegGate>& gates, int W, u64 fmas
 static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats,
                           int32_t* n_done, int32_t* peer_xor, bool defer);
 static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats, bool defer,
-                         int force_P, int n_try);
+                         bool inner_piece);
 static int apply_in_pieces(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats, bool defer, int piece);
 
 static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
@@ -1458,14 +1456,14 @@ static int apply_in_pieces(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, doubl
       // the last piece carries the call: deferred if the caller asked for that, its statistics complete the call's
       ctx->carry_updates = updates;
       ctx->carry_sizes = sizes;
-      return apply_segment(ctx, ops + a, b - a, atol, stats, defer, 0, 0);  // (finish_ops adds the carry)
+      return apply_segment(ctx, ops + a, b - a, atol, stats, defer, false);  // (finish_ops adds the carry)
     }
     std::vector<obp_op> part(ops + a, ops + b);
     for (obp_op& o : part) o.flags &= ~(unsigned)OBP_FLAG_EXACT_COUNTERS;
     obp_stats st;
     ctx->carry_updates = 0;
     ctx->carry_sizes.clear();
-    const int rc = apply_segment(ctx, part.data(), b - a, atol, &st, false, 0, 1);
+    const int rc = apply_segment(ctx, part.data(), b - a, atol, &st, false, true);
     if (rc) {
       if (stats) { memset(stats, 0, sizeof(*stats)); stats->updates = updates + st.updates; stats->n_out = st.n_out; }
       return rc;
@@ -1480,8 +1478,9 @@ static int apply_in_pieces(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, doubl
 // A run of rotations (the whole call) applied in shared memory: partition the table by a linear map that vanishes on
 // every generator, one CTA per partition applies all gates, the survivors go to the second set of columns
 // (obp_segment.cuh).  The table is committed in finish_ops once the outcome is known.
+// inner_piece: a piece of a cut run that is not the last one (nobody looks keys up before the next piece).
 static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double atol, obp_stats* stats, bool defer,
-                         int force_P, int n_try) {
+                         bool inner_piece) {
   const auto t_host0 = std::chrono::steady_clock::now();
   const int W = ctx->W, ng = n_ops;
   int rc = ensure_ops(ctx, ng + 2);
@@ -1543,8 +1542,8 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   seg_geometry(W, ng, (size_t)ctx->seg_smem_max, 4 * ctx->seg_cap_rows, &sp2.cap_rows, &sp2.n_index);
   const size_t smem1 = seg_smem_bytes(W, sp.cap_rows, sp.n_index, ng), smem2 = seg_smem_bytes(W, sp2.cap_rows, sp2.n_index, ng);
   const int n_ctas1 = 4 * ctx->n_sm, n_ctas2 = ctx->n_sm;
-  int P = force_P;
-  if (P <= 0) {
+  int P;
+  {
     const double growth = std::min(32.0, std::max(1.5, ctx->seg_growth));
     const double rows_per_part = std::min(256.0, 0.35 * sp.cap_rows);
     const double want = (double)ctx->n_live * growth / rows_per_part;
@@ -1579,7 +1578,7 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   out.index = nullptr;
   out.index_mask = 0;
   ctx->seg_T_new = 0;
-  if (ctx->index_touched && !n_try) {  // (n_try != 0: a piece of a cut run that is not the last one)
+  if (ctx->index_touched && !inner_piece) {
     // the programs after a run of this observable look keys up: the run's output stage fills the index itself (cleared
     // here, sized to the rows expected; the input table's entries are gone either way once the run commits)
     const double growth = std::min(32.0, std::max(1.5, ctx->seg_growth));
@@ -1631,8 +1630,6 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   P_.n_start = ctx->n_live;
   P_.prog_mode = false;
   P_.segment = true;
-  P_.seg_P = P;
-  P_.seg_try = n_try;
   P_.atol = atol;
   P_.t_host0 = t_host0;
   if (defer) {
@@ -1661,7 +1658,7 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
   }
   if (segment_eligible(ctx, ops, n_ops) && !n_done) {
     const int piece = std::max(ctx->seg_min_gates, std::min(ctx->seg_max_gates, OBP_SEG_MAXG - 8));
-    if (n_ops <= piece) return apply_segment(ctx, ops, n_ops, atol, stats, defer, 0, 0);
+    if (n_ops <= piece) return apply_segment(ctx, ops, n_ops, atol, stats, defer, false);
     return apply_in_pieces(ctx, ops, n_ops, atol, stats, defer, piece);
   }
   {
