@@ -114,6 +114,7 @@ struct obp_ctx {
   bool broken = false;  // a failed obp_reserve could not restore the table: every entry point fails fast
   // ---- runs of rotations applied in shared memory (obp_segment.cuh) ----
   bool use_segments = true;
+  bool seg_mixed = true;        // runs may hold Clifford-class gates between their rotations (OBP_B200_SEG_MIXED=0: rotations only)
   int seg_min_gates = 6;        // shorter runs go through the per-gate kernels
   int seg_cap_rows = 0;         // test hook: rows a partition may hold (0: what the shared memory allows)
   u64 seg_pieces_min_rows = 1ull << 17;  // a failed run on at least this many rows is repeated in pieces (below: per-gate kernels)
@@ -714,6 +715,7 @@ struct PendingOps {
   u64 n_start = 0;
   bool prog_mode = false;
   bool segment = false;   // a run of rotations in shared memory (slot n_slots reports its outcome)
+  std::vector<u64> frame_hx, frame_hz;  // the hash frame before the run, if the run holds Clifford-class gates (restored when it fails)
   double atol = 0.0;
   std::chrono::steady_clock::time_point t_host0;
 };
@@ -982,6 +984,7 @@ int obp_create(int device, int n_qubits, uint64_t capacity, obp_ctx** out) {
       if (const char* e6 = getenv("OBP_B200_PROG_DEBUG")) ctx->prog_debug = atoi(e6) & ~1;
       if (const char* e7 = getenv("OBP_B200_PROG_MAX_ROWS")) ctx->prog_max_rows = (u64)std::max(0ll, atoll(e7));
       if (const char* e8 = getenv("OBP_B200_NO_SEGMENTS")) ctx->use_segments = !(e8[0] && e8[0] != '0');
+      if (const char* e12 = getenv("OBP_B200_SEG_MIXED")) ctx->seg_mixed = e12[0] && e12[0] != '0';
       if (const char* e9 = getenv("OBP_B200_SEG_MIN_GATES")) ctx->seg_min_gates = std::max(1, atoi(e9));
       if (const char* e10 = getenv("OBP_B200_SEG_CAP_ROWS")) ctx->seg_cap_rows = std::max(0, atoi(e10));
       if (const char* e11 = getenv("OBP_B200_SEG_PIECES_MIN_ROWS")) ctx->seg_pieces_min_rows = (u64)std::max(0ll, atoll(e11));
@@ -1214,16 +1217,24 @@ int obp_download(obp_ctx* ctx, uint64_t* x_words, uint64_t* z_words, double* coe
 // Second half of a gate program: wait for the device, account, compact if needed, fill the statistics.
 
 // ---- runs of rotations in shared memory (obp_segment.cuh) -------------------------------------------------------
-static bool segment_eligible(const obp_ctx* ctx, const obp_op* ops, int n_ops) {
-  if (!ctx->use_segments || ctx->seg_smem_max <= 0 || ctx->W > 2 || ctx->n_ranks != 1 || ctx->row_order || ctx->flag_sync) return false;
-  if (n_ops < ctx->seg_min_gates || ctx->n_live == 0 || ctx->n_dense >= (1ull << 31)) return false;
-  if (ctx->n_live >= ctx->seg_block_rows) return false;
+// A gate program (or its prefix) that can run in shared memory: rotations and Clifford-class gates only, at least
+// seg_min_gates rotations, no per-gate counter requests except the reference's counters on a LAST gate that is a rotation.
+// Returns the number of leading ops the run covers (0: not eligible): everything, or everything up to and including the
+// last rotation when Clifford-class gates with counters of their own follow it.
+static int segment_span(const obp_ctx* ctx, const obp_op* ops, int n_ops) {
+  if (!ctx->use_segments || ctx->seg_smem_max <= 0 || ctx->W > 2 || ctx->n_ranks != 1 || ctx->row_order || ctx->flag_sync) return 0;
+  if (ctx->n_live == 0 || ctx->n_dense >= (1ull << 31) || ctx->n_live >= ctx->seg_block_rows) return 0;
+  int n_rot = 0, last_rot = -1;
   for (int k = 0; k < n_ops; ++k) {
-    if (ops[k].kind != OBP_OP_ROTATION) return false;
+    if (ops[k].kind != OBP_OP_ROTATION && ops[k].kind != OBP_OP_CLIFFORD) return 0;
     const unsigned allowed = (k == n_ops - 1) ? OBP_FLAG_EXACT_COUNTERS : 0u;
-    if (ops[k].flags & ~allowed) return false;
+    if (ops[k].flags & ~allowed) return 0;
+    if (ops[k].kind == OBP_OP_ROTATION) { n_rot++; last_rot = k; }
   }
-  return true;
+  if (n_rot < ctx->seg_min_gates) return 0;
+  if (!ctx->seg_mixed && n_rot != n_ops) return 0;
+  const bool tail_counts = ops[n_ops - 1].kind == OBP_OP_CLIFFORD && (ops[n_ops - 1].flags & OBP_FLAG_EXACT_COUNTERS);
+  return tail_counts ? last_rot + 1 : n_ops;
 }
 
 // bytes of dynamic shared memory k_seg_main needs for `cap` rows per partition
@@ -1315,6 +1326,11 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
       const int n_ops = P.n_ops;
       const double atol = P.atol;
       ctx->seg_growth = 16.0;
+      if (!P.frame_hx.empty()) {  // the gates are applied again, by other kernels: back to the frame the run started in
+        ctx->hx = P.frame_hx;
+        ctx->hz = P.frame_hz;
+        ctx->cols_dirty = true;
+      }
       const bool can_cut = n_ops >= 2 * std::max(ctx->seg_min_gates, 2);
       if (can_cut) {
         // Too many rows share a partition: with fewer gates per run the partition map has fewer generators to
@@ -1509,12 +1525,45 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   unsigned* d_redo = d_cur + (OBP_SEG_MAXP + 1);
   SegRes* d_res = (SegRes*)(ctx->d_seg + part_bytes);
 
-  // gate parameters
-  std::vector<SegGate> gates((size_t)ng);
+  // gate parameters.  Clifford-class gates re-express the hash frame as they go (the generator hashes of the rotations
+  // after them are taken in the frame of their place in the program) and, for the partition map, the generators are
+  // pulled back through them to the keys the run starts from: a row P becomes C(P), a later rotation mixes C(P) with
+  // C(P) xor G = C(P xor C^-1(G)), so the map has to vanish on C^-1(G) — the same column update as the hash frame,
+  // on 256-bit columns that start as the identity.
+  std::vector<SegGate> gates((size_t)ng), gens;
+  bool has_cliff = false;
+  for (int k = 0; k < ng; ++k) has_cliff = has_cliff || ops[k].kind == OBP_OP_CLIFFORD;
+  std::vector<u64> hx0, hz0;
+  std::vector<WideCol> sx, sz;
+  if (has_cliff) {
+    hx0 = ctx->hx;
+    hz0 = ctx->hz;
+    sx.resize((size_t)ctx->nq);
+    sz.resize((size_t)ctx->nq);
+    for (int q = 0; q < ctx->nq; ++q) {
+      memset(&sx[(size_t)q], 0, sizeof(WideCol));
+      memset(&sz[(size_t)q], 0, sizeof(WideCol));
+      sx[(size_t)q].w[2 * (q / 64)] = 1ull << (q % 64);
+      sz[(size_t)q].w[2 * (q / 64) + 1] = 1ull << (q % 64);
+    }
+  }
   for (int k = 0; k < ng; ++k) {
-    const RotP p = build_rotp(ctx, ops[k], atol);
     SegGate& g = gates[k];
     memset(&g, 0, sizeof(g));
+    if (ops[k].kind == OBP_OP_CLIFFORD) {
+      const obp_op& op = ops[k];
+      const int qa = op.qubit[0], qb = op.n_qubits == 2 ? op.qubit[1] : op.qubit[0];
+      g.simple = OBP_SEG_CLIFFORD;
+      g.gx[0] = op.lut;
+      g.gx[1] = (u64)(op.sign_mask & 0xffffu) | ((u64)op.n_qubits << 16) | ((u64)(qa / 64) << 24) | ((u64)(qa % 64) << 32) |
+                ((u64)(qb / 64) << 40) | ((u64)(qb % 64) << 48);
+      g.u0r = op.row_scale;
+      g.thr_self = g.thr_all = HUGE_VAL;
+      frame_update(ctx, op);
+      wide_frame_update(sx, sz, op);
+      continue;
+    }
+    const RotP p = build_rotp(ctx, ops[k], atol);
     for (int q = 0; q < p.ngw; ++q) { g.gx[p.gw[q]] = p.gx[q]; g.gz[p.gw[q]] = p.gz[q]; }
     g.hG = p.hG;
     g.u0r = p.u0r; g.u0i = p.u0i; g.u1r = p.u1r; g.u1i = p.u1i;
@@ -1524,17 +1573,29 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
     // min(|u0|^2, |u1|^2) (|u0||u1| lies between them)
     const double f0 = p.u0r * p.u0r + p.u0i * p.u0i, f1 = p.u1r * p.u1r + p.u1i * p.u1i, fmin = std::min(f0, f1);
     g.thr_self = g.thr_all = atol < 0.0 ? -1.0 : (fmin > 0.0 ? atol * atol * (1.0 + 1e-6) / (fmin * fmin) : HUGE_VAL);
+    SegGate gen = g;
+    if (has_cliff) {
+      WideCol v;
+      memset(&v, 0, sizeof(v));
+      for (int j = 0; j < ops[k].n_qubits; ++j) {
+        const unsigned code = (ops[k].gen_local >> (2 * j)) & 3u;
+        if (code & 1u) v ^= sx[(size_t)ops[k].qubit[j]];
+        if (code & 2u) v ^= sz[(size_t)ops[k].qubit[j]];
+      }
+      gen.gx[0] = v.w[0]; gen.gz[0] = v.w[1]; gen.gx[1] = v.w[2]; gen.gz[1] = v.w[3];
+    }
+    gens.push_back(gen);
   }
   SegP sp;
   memset(&sp, 0, sizeof(sp));
   sp.ng = ng;
-  sp.exact_last = (ops[ng - 1].flags & OBP_FLAG_EXACT_COUNTERS) ? 1 : 0;
+  sp.exact_last = (ops[ng - 1].kind == OBP_OP_ROTATION && (ops[ng - 1].flags & OBP_FLAG_EXACT_COUNTERS)) ? 1 : 0;
   sp.slot0 = 0;
   if (const char* e = getenv("OBP_B200_SEG_DEBUG")) sp.dbg = atoi(e);
   sp.n_dense = ctx->n_dense;
   sp.out_cap = ctx->cap;
   sp.atol = atol;
-  seg_partition_map(gates, W, sp.fmask);
+  seg_partition_map(gens, W, sp.fmask);
   // Geometry.  First launch: 128-thread CTAs, four per SM (a quarter of the shared memory each), partitions sized for
   // ~256 rows after the run's growth; second launch: the partitions that outgrew those, one 512-thread CTA per SM.
   SegP sp2 = sp;
@@ -1630,6 +1691,8 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   P_.n_start = ctx->n_live;
   P_.prog_mode = false;
   P_.segment = true;
+  P_.frame_hx = std::move(hx0);
+  P_.frame_hz = std::move(hz0);
   P_.atol = atol;
   P_.t_host0 = t_host0;
   if (defer) {
@@ -1656,10 +1719,37 @@ static int apply_ops_impl(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double
     const int vrc = validate_op(ctx, ops[k]);
     if (vrc) return vrc;
   }
-  if (segment_eligible(ctx, ops, n_ops) && !n_done) {
-    const int piece = std::max(ctx->seg_min_gates, std::min(ctx->seg_max_gates, OBP_SEG_MAXG - 8));
-    if (n_ops <= piece) return apply_segment(ctx, ops, n_ops, atol, stats, defer, false);
-    return apply_in_pieces(ctx, ops, n_ops, atol, stats, defer, piece);
+  if (!n_done) {
+    const int span = segment_span(ctx, ops, n_ops);
+    if (span > 0) {
+      const int piece = std::max(ctx->seg_min_gates, std::min(ctx->seg_max_gates, OBP_SEG_MAXG - 8));
+      if (span == n_ops) {
+        if (n_ops <= piece) return apply_segment(ctx, ops, n_ops, atol, stats, defer, false);
+        return apply_in_pieces(ctx, ops, n_ops, atol, stats, defer, piece);
+      }
+      // Clifford-class gates with counters of their own follow the last rotation: the run covers the gates before
+      // them, they go through the program kernel (its coset count needs the global index) and complete the statistics
+      obp_stats st;
+      u64 carry_u = ctx->carry_updates;
+      std::vector<u64> carry_s = ctx->carry_sizes;
+      ctx->carry_updates = 0;
+      ctx->carry_sizes.clear();
+      const bool keep = ctx->use_segments;
+      std::vector<obp_op> head(ops, ops + span);
+      const int rc1 = span <= piece ? apply_segment(ctx, head.data(), span, atol, &st, false, false)
+                                    : apply_in_pieces(ctx, head.data(), span, atol, &st, false, piece);
+      if (rc1) {
+        if (stats) { memset(stats, 0, sizeof(*stats)); stats->updates = carry_u + st.updates; stats->n_out = st.n_out; }
+        return rc1;
+      }
+      carry_s.insert(carry_s.end(), ctx->last_op_sizes.begin(), ctx->last_op_sizes.end());
+      ctx->carry_updates = carry_u + st.updates;
+      ctx->carry_sizes = carry_s;
+      ctx->use_segments = false;  // (the tail holds no rotation: it is not a run)
+      const int rc2 = apply_ops_impl(ctx, ops + span, n_ops - span, atol, stats, nullptr, nullptr, defer);
+      ctx->use_segments = keep;
+      return rc2;
+    }
   }
   {
     // rows this program can reach: every rotation may double the table

@@ -36,13 +36,16 @@
 #define OBP_SEG_MAXP 65536  // partitions per run
 #define OBP_SEG_FBITS 16    // output bits of the partition map
 #define OBP_SEG_ALIVE 255u
+#define OBP_SEG_CLIFFORD 2
 
 struct SegGate {  // 96 bytes
   u64 gx[2], gz[2];  // generator on table words 0 and 1 (zero where it is the identity)
   u64 hG;            // hash of the generator
   double u0r, u0i, u1r, u1i;
   int yG;
-  int simple;
+  int simple;        // rotation: 1 = u0 real and u1 imaginary, 0 = general; OBP_SEG_CLIFFORD: a Clifford-class gate —
+                     // gx[0] = its 16-entry table, gx[1] = sign mask | nq << 16 | word a << 24 | bit a << 32 | word b << 40 |
+                     // bit b << 48, u0r = its row scale (k_clifford_reg's gate, applied to the rows of the partition)
   // |c|^2 above which no raw row of a term can fall under the zero filter (1e-6 relative margin; rows below take the
   // exact path): thr_self for the two rows of the term's own key (|c||u0|^2, |c||u1|^2), thr_all for all four
   double thr_self, thr_all;
@@ -325,6 +328,62 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
     for (int g = 0; g < s.ng && !failed; ++g) {
       int* add_w = &s_add[add_i];
       if (threadIdx.x == 0) s_add[add_i == 2 ? 0 : add_i + 1] = 0;
+      if (sgate[g].simple == OBP_SEG_CLIFFORD) {
+        // A group of consecutive Clifford-class gates: they map every row on its own (key bits through a 16-entry
+        // table, a sign, the raw-row zero filter |c| * row_scale <= atol, utils/operations.py:103-105 +
+        // simplify for a signed-permutation gate), so the whole group is ONE pass without a barrier in between.
+        // The rows' stored hashes stay valid: the host re-expresses the hash frame (frame_update).
+        int g2 = g + 1;
+        while (g2 < s.ng && sgate[g2].simple == OBP_SEG_CLIFFORD) ++g2;
+        for (int r = threadIdx.x; r < n_pass; r += NT) {
+          if (m.died[r] != OBP_SEG_ALIVE) continue;
+          double2 c = m.coef[r];
+          ulonglong2 key[W];
+#pragma unroll
+          for (int w = 0; w < W; ++w) key[w] = m.xz[w][r];
+          unsigned flip = 0;
+          int dead_at = -1;
+          for (int gg = g; gg < g2; ++gg) {
+            const SegGate& C = sgate[gg];
+            if (s.atol >= 0.0 && is_small_scaled(c, C.u0r, s.atol)) { dead_at = gg; break; }
+            const u64 lut = C.gx[0], pos = C.gx[1];
+            const unsigned nq = (unsigned)(pos >> 16) & 0xffu;
+            const unsigned wa = (unsigned)(pos >> 24) & 0xffu, ba = (unsigned)(pos >> 32) & 0xffu;
+            const unsigned wb = (unsigned)(pos >> 40) & 0xffu, bb = (unsigned)(pos >> 48) & 0xffu;
+            const ulonglong2 ka = (W == 2 && wa) ? key[W - 1] : key[0];
+            const ulonglong2 kb = (W == 2 && wb) ? key[W - 1] : key[0];
+            unsigned v = (unsigned)((ka.x >> ba) & 1ull) | ((unsigned)((ka.y >> ba) & 1ull) << 1);
+            if (nq == 2) v |= ((unsigned)((kb.x >> bb) & 1ull) << 2) | ((unsigned)((kb.y >> bb) & 1ull) << 3);
+            const unsigned d = ((unsigned)(lut >> (4 * v)) & 15u) ^ v;
+            flip ^= (unsigned)(pos >> v) & 1u;
+            const u64 fxa = (u64)(d & 1u) << ba, fza = (u64)((d >> 1) & 1u) << ba;
+            const u64 fxb = (u64)((d >> 2) & 1u) << bb, fzb = (u64)((d >> 3) & 1u) << bb;
+            if (W == 2) {
+              key[0].x ^= (wa ? 0ull : fxa) ^ (wb ? 0ull : fxb);
+              key[0].y ^= (wa ? 0ull : fza) ^ (wb ? 0ull : fzb);
+              key[W - 1].x ^= (wa ? fxa : 0ull) ^ (wb ? fxb : 0ull);
+              key[W - 1].y ^= (wa ? fza : 0ull) ^ (wb ? fzb : 0ull);
+            } else {
+              key[0].x ^= fxa ^ fxb;
+              key[0].y ^= fza ^ fzb;
+            }
+          }
+          if (dead_at >= 0) {
+            m.died[r] = (unsigned char)dead_at;
+            atomicAdd(&dgp[dead_at], -1);
+            atomicAdd(&s_live, -1);
+          } else {
+#pragma unroll
+            for (int w = 0; w < W; ++w) m.xz[w][r] = key[w];
+            if (flip & 1u) m.coef[r] = make_double2(-c.x, -c.y);
+          }
+        }
+        __syncthreads();
+        n_pass += *add_w;  // (nothing is appended by a Clifford group: the slot was cleared by the pass before)
+        add_i = add_i == 2 ? 0 : add_i + 1;
+        g = g2 - 1;
+        continue;
+      }
       // a warp whose rows all lie beyond the partition only keeps the barrier company (most warps of most partitions)
       if ((int)(threadIdx.x & ~31u) < n_pass) {
       const SegGate& G = sgate[g];

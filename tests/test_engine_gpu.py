@@ -215,6 +215,40 @@ def test_rotation_layers(nq, mode, monkeypatch):
             assert cut > 0, "no run was cut into pieces: the case does not test what it says"
 
 
+@pytest.mark.parametrize("nq", [6, 40, 70, 127])
+@pytest.mark.parametrize("mode", ["slice-in-smem", "tiny-partitions", "cut-into-pieces", "rotations-only-runs"])
+def test_mixed_runs(nq, mode, monkeypatch):
+    """Slices that mix rotations with Clifford-class gates (one- and two-qubit, with sign flips): the whole slice is one
+    run in shared memory — the Clifford gates are applied to the rows of each partition, the partition map vanishes on
+    the generators pulled back through them — against the oracle, counters included; slices that end on a Clifford gate
+    (its coset count goes through the program kernel) and on a rotation both occur."""
+    monkeypatch.setenv("OBP_B200_SEG_MIN_GATES", "2")
+    monkeypatch.setenv("OBP_B200_SEG_MIXED", "0" if mode == "rotations-only-runs" else "1")
+    monkeypatch.setenv("OBP_B200_SEG_CAP_ROWS", {"tiny-partitions": "24", "cut-into-pieces": "48"}.get(mode, "0"))
+    monkeypatch.setenv("OBP_B200_SEG_PIECES_MIN_ROWS", "1" if mode == "cut-into-pieces" else str(1 << 17))
+    rng = np.random.default_rng(9000 + nq)
+    slices = random_slices(nq, 6, rng, p_rot=0.45, angles=[0.1, 0.3, -0.7, 1e-3, 0.25])
+    obs = random_observable(nq, 3, rng, weight=min(nq, 4))
+    _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=30000))
+    _compare(obs, slices, operator_budget=OperatorBudget(max_paulis=30000, atol=1e-4))
+    _compare(obs, slices, truncation_error_budget=TruncationErrorBudget([0.01], 0.1, 2, 1e-8))
+    if mode != "rotations-only-runs" and nq >= 40:
+        from qiskit_addon_obp_b200 import backpropagation as bpmod
+
+        assert bpmod.last_run.segments[0] > 0, "no slice ran in shared memory"
+
+
+def test_mixed_runs_config5():
+    """BASELINE config 5 (Clifford + RZ brickwork) at oracle size: every slice is a mixed run."""
+    from qiskit_addon_obp_b200 import backpropagation as bpmod
+    from qiskit_addon_obp_b200 import workloads as wl
+
+    for seed in (0, 1):
+        w = wl.config5_magic_sweep(theta=np.pi / 8, depth=14, max_paulis=4_000, seed=seed)
+        _compare(w.observables, w.slices, **w.kwargs())
+        assert bpmod.last_run.segments[0] > 0
+
+
 def test_clifford_only_counters():
     """Clifford gates: keys move, nothing merges; counters come from the coset count kernel."""
     rng = np.random.default_rng(5)
