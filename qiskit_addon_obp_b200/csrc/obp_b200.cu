@@ -114,7 +114,8 @@ struct obp_ctx {
   bool broken = false;  // a failed obp_reserve could not restore the table: every entry point fails fast
   // ---- runs of rotations applied in shared memory (obp_segment.cuh) ----
   bool use_segments = true;
-  bool seg_mixed = true;        // runs may hold Clifford-class gates between their rotations (OBP_B200_SEG_MIXED=0: rotations only)
+  bool seg_mixed = false;       // OBP_B200_SEG_MIXED=1: runs may hold Clifford-class gates between their rotations (parity-green; measured
+                                // slower than the program kernel's fused Clifford batches on config 5, so off by default)
   int seg_min_gates = 6;        // shorter runs go through the per-gate kernels
   int seg_cap_rows = 0;         // test hook: rows a partition may hold (0: what the shared memory allows)
   u64 seg_pieces_min_rows = 1ull << 17;  // a failed run on at least this many rows is repeated in pieces (below: per-gate kernels)

@@ -238,11 +238,12 @@ def test_mixed_runs(nq, mode, monkeypatch):
         assert bpmod.last_run.segments[0] > 0, "no slice ran in shared memory"
 
 
-def test_mixed_runs_config5():
+def test_mixed_runs_config5(monkeypatch):
     """BASELINE config 5 (Clifford + RZ brickwork) at oracle size: every slice is a mixed run."""
     from qiskit_addon_obp_b200 import backpropagation as bpmod
     from qiskit_addon_obp_b200 import workloads as wl
 
+    monkeypatch.setenv("OBP_B200_SEG_MIXED", "1")
     for seed in (0, 1):
         w = wl.config5_magic_sweep(theta=np.pi / 8, depth=14, max_paulis=4_000, seed=seed)
         _compare(w.observables, w.slices, **w.kwargs())
