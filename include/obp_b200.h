@@ -200,13 +200,17 @@ int obp_is_broken(const obp_ctx* ctx);
  *   OBP_OPT_SEGMENT_CAP_ROWS  rows a partition may hold, 0 = what the shared memory allows (test hook: small values
  *                             force the cut into shorter pieces and the fall-back to the per-gate kernels).
  *   OBP_OPT_SEGMENT_PIECES_MIN_ROWS  a failed run on at least this many rows is repeated in shorter pieces, a failed
- *                             run on fewer rows goes to the per-gate kernels (default 2^17). */
+ *                             run on fewer rows goes to the per-gate kernels (default 2^17).
+ *   OBP_OPT_SEGMENT_MIXED     1: a run may also hold Clifford-class gates between its rotations (applied to the rows
+ *                             of each partition; the partition map vanishes on the generators pulled back through
+ *                             them).  0 (default): rotation-only gate programs.  Results are identical either way. */
 #define OBP_OPT_PROGRAM 1
 #define OBP_OPT_PROGRAM_MAX_ROWS 2
 #define OBP_OPT_SEGMENTS 3
 #define OBP_OPT_SEGMENT_MIN_GATES 4
 #define OBP_OPT_SEGMENT_CAP_ROWS 5
 #define OBP_OPT_SEGMENT_PIECES_MIN_ROWS 6
+#define OBP_OPT_SEGMENT_MIXED 7
 int obp_configure(obp_ctx* ctx, int32_t option, int64_t value);
 
 /* Runs of rotations applied in shared memory since the context was created: committed runs, failed runs repeated in

@@ -3321,6 +3321,7 @@ int obp_configure(obp_ctx* ctx, int32_t option, int64_t value) {
     case OBP_OPT_SEGMENTS: ctx->use_segments = value != 0; return OBP_OK;
     case OBP_OPT_SEGMENT_MIN_GATES: ctx->seg_min_gates = value < 1 ? 1 : (int)std::min<int64_t>(value, 1 << 20); return OBP_OK;
     case OBP_OPT_SEGMENT_CAP_ROWS: ctx->seg_cap_rows = value < 0 ? 0 : (int)std::min<int64_t>(value, 4096); return OBP_OK;
+    case OBP_OPT_SEGMENT_MIXED: ctx->seg_mixed = value != 0; return OBP_OK;
     case OBP_OPT_SEGMENT_PIECES_MIN_ROWS: ctx->seg_pieces_min_rows = value < 0 ? 0 : (u64)value; return OBP_OK;
     default: return ctx->fail(OBP_ERR_BADARG, "obp_configure: unknown option");
   }

@@ -36,6 +36,7 @@ OBP_OPT_SEGMENTS = 3
 OBP_OPT_SEGMENT_MIN_GATES = 4
 OBP_OPT_SEGMENT_CAP_ROWS = 5
 OBP_OPT_SEGMENT_PIECES_MIN_ROWS = 6
+OBP_OPT_SEGMENT_MIXED = 7
 OBP_K_NAMES = ("rotate", "clifford", "truncate", "compact", "index", "other", "program", "segment")
 
 #: numpy mirror of ``obp_op`` (104 bytes, natural C alignment)
@@ -277,6 +278,7 @@ class TermTable:
         self.configure(OBP_OPT_SEGMENT_MIN_GATES, int(os.environ.get("OBP_B200_SEG_MIN_GATES", "6")))
         self.configure(OBP_OPT_SEGMENT_CAP_ROWS, int(os.environ.get("OBP_B200_SEG_CAP_ROWS", "0")))
         self.configure(OBP_OPT_SEGMENT_PIECES_MIN_ROWS, int(os.environ.get("OBP_B200_SEG_PIECES_MIN_ROWS", str(1 << 17))))
+        self.configure(OBP_OPT_SEGMENT_MIXED, 1 if os.environ.get("OBP_B200_SEG_MIXED", "0") not in ("", "0") else 0)
 
     def configure(self, option: int, value: int) -> None:
         self._check(self._lib.obp_configure(self._h, int(option), int(value)), "obp_configure")
