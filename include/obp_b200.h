@@ -140,6 +140,12 @@ int obp_apply_ops_wait(obp_ctx* ctx, obp_stats* stats);
  * carried OBP_FLAG_OWN_SLOT.  Writes min(n_ops, max_ops) values, returns the number of ops in *n_ops. */
 int obp_last_op_sizes(obp_ctx* ctx, uint64_t* sizes, int32_t max_ops, int32_t* n_ops);
 
+/* The reference's simplify counters (and n_in / raw_rows / n_out) of op `op_index` of the gate program just finished,
+ * for every op that carried OBP_FLAG_EXACT_COUNTERS — not only the last one: several slices whose gates are all
+ * Clifford-class can then travel as ONE program, each slice's last gate flagged (the driver does that when the term
+ * count cannot grow and nothing can be rejected in between).  Not available after a run in shared memory. */
+int obp_last_op_stats(obp_ctx* ctx, int32_t op_index, obp_stats* out);
+
 /* Any other gate on 1-4 qubits (cp, crz, arbitrary unitaries): U = sum_j u_j * Pauli(codes[j]) with
  * codes[j] = local Pauli code (bit 2q = x, bit 2q+1 = z on qubits[q]) and coeffs[j] = (re, im).  Runs
  * the reference's literal k*k raw-row expansion (utils/operations.py:103-105) followed by simplify

@@ -20,7 +20,7 @@ from collections.abc import Sequence
 import numpy as np
 
 from . import engine
-from .engine import (OBP_ATOL_RAW, OBP_FLAG_EXACT_COUNTERS, OBP_FLAG_OWN_SLOT, OBP_OP_GENERIC, OP_DTYPE, CapacityError,
+from .engine import (OBP_ATOL_RAW, OBP_FLAG_EXACT_COUNTERS, OBP_FLAG_OWN_SLOT, OBP_OP_CLIFFORD, OBP_OP_GENERIC, OP_DTYPE, CapacityError,
                      TermTable)
 from .gates import program_for, raw_program_for
 from .ir import QuantumCircuit, SparsePauliOp, topological_op_order
@@ -177,8 +177,28 @@ def backpropagate(
         try:
             reversed_slices = slices_ir[::-1]
             log_info = LOGGER.isEnabledFor(logging.INFO)
+            merged_until = 0  # slices before this position were handled as part of a merged Clifford group
+            # Several Clifford-only slices as one gate program (OBP_B200_MERGE_CLIFFORD_SLICES=1; off by default: it
+            # halves the host round trips of the 127-qubit workload and was measured to gain nothing, the time of such a
+            # slice is on the device side of its program): only where nothing between them can stop the run or
+            # needs the operator on the host (one unsharded observable, no truncation, no QWC budget, no timeout, no
+            # per-gate DEBUG log, fast path)
+            can_merge = (
+                n_obs == 1 and comm is None and not raw and not ordered and not trunc_active and max_seconds is None
+                and operator_budget.max_qwc_groups is None and not LOGGER.isEnabledFor(logging.DEBUG)
+                and os.environ.get("OBP_B200_MERGE_CLIFFORD_SLICES", "0") not in ("0", "")
+            )
             for slice_pos, slice_ in enumerate(reversed_slices):
+                if slice_pos < merged_until:
+                    continue
                 next_slice = reversed_slices[slice_pos + 1] if slice_pos + 1 < len(reversed_slices) else None
+                if can_merge and loaded[0] and not tables[0].zero_operator:
+                    group = _merge_clifford_slices(tables[0], reversed_slices, slice_pos, support_mask[0], expand_all)
+                    if len(group) >= 2 and _run_clifford_group(tables[0], group, atol, metadata, operator_budget, info,
+                                                               lengths, support_mask, log_info):
+                        merged_until = slice_pos + len(group)
+                        loaded_committed = list(loaded)
+                        continue
                 sm = SliceMetadata(
                     slice_errors=[0.0] * n_obs,
                     raw_num_paulis=[0] * n_obs,
@@ -368,6 +388,102 @@ def backpropagate(
     last_run.segments = info.segments
     obs_out = [restore_types(o) for o in obs_out]
     return (obs_out[0] if single else obs_out), slices_out, metadata
+
+
+def _clifford_only(plan: "SlicePlan") -> bool:
+    """The slice's applied gates are one gate program of Clifford-class gates only (the term count cannot grow)."""
+    if len(plan.steps) != 1 or plan.steps[0][0] != "ops":
+        return False
+    ops = plan.steps[0][1]
+    cached = getattr(plan, "_clifford_only", None)
+    if cached is None:
+        cached = bool(len(ops)) and bool((ops["kind"] == OBP_OP_CLIFFORD).all())
+        try:
+            plan._clifford_only = cached
+        except AttributeError:  # (__slots__: no cache)
+            pass
+    return cached
+
+
+def _merge_clifford_slices(table, reversed_slices, slice_pos, support, expand_all, max_group: int = 8):
+    """Consecutive slices from ``slice_pos`` on whose applied gates are all Clifford-class, with their plans.
+
+    Such slices permute the terms (the raw-row filter can only remove some): none of them can exceed an operator
+    budget the slice before them met, so they travel as ONE gate program with the last gate of each slice flagged
+    for the reference's counters (``obp_last_op_stats``) instead of one host round trip each."""
+    group = []
+    pos = slice_pos
+    while pos < len(reversed_slices) and len(group) < max_group:
+        prog = _slice_program(reversed_slices[pos], expand_all)
+        plan = prog.plan(support)
+        if not plan.applied or not _clifford_only(plan):
+            break
+        group.append((prog, plan))
+        support = plan.support_after
+        pos += 1
+    return group
+
+
+
+def _run_clifford_group(table, group, atol, metadata, operator_budget, info, lengths, support_mask, log_info) -> bool:
+    """Run a group of Clifford-only slices (one observable) as one gate program and book each slice exactly as the
+    slice-by-slice loop would.  Returns False — with the table restored to the last commit and nothing booked — if
+    anything unusual happens (the operator vanishes, the table overflows): the caller then takes the slices one by one."""
+    parts = []
+    ends = []
+    for _, plan in group:
+        ops = plan.steps[0][1]  # (its last gate already carries OBP_FLAG_EXACT_COUNTERS)
+        parts.append(ops)
+        ends.append((ends[-1] if ends else 0) + len(ops))
+    merged = np.concatenate(parts)
+    t0 = time.perf_counter() if TRACE else 0.0
+    n_before = table.n
+    try:
+        table.apply_ops_submit(merged, atol)
+        total = table.apply_ops_wait()
+    except CapacityError:
+        table.restore()
+        return False
+    stats = []
+    try:
+        stats = [table.last_op_stats(e - 1) for e in ends]
+    except engine.EngineError:
+        stats = []
+    if not stats or any(int(st.n_out) == 0 for st in stats) or table.zero_operator:
+        table.restore()  # (the all-trimmed operator has its own conventions: let the ordinary loop meet it)
+        return False
+    if TRACE:
+        dt = time.perf_counter() - t0
+        print(f"[obp trace] ops {len(merged):4d} (rot   0, {len(group)} Clifford-only slices) n {n_before:>10d} -> {int(total.n_out):>10d} "
+              f"dense {int(total.n_dense):>10d} updates {int(total.updates):>12d} {dt * 1e3:9.3f} ms", flush=True)
+    info.updates += int(total.updates)
+    for (prog, plan), st in zip(group, stats):
+        sm = SliceMetadata(
+            slice_errors=[0.0],
+            raw_num_paulis=[int(st.raw_rows)],
+            num_unique_paulis=[int(st.num_unique)],
+            num_duplicate_paulis=[int(st.num_duplicate)],
+            num_trimmed_paulis=[int(st.num_trimmed)],
+            sum_trimmed_coeffs=[0],
+            num_truncated_paulis=[0],
+            num_paulis=[int(st.n_out)],
+            sum_paulis=None,
+            num_qwc_groups=None,
+        )
+        c = complex(st.sum_trimmed[0], st.sum_trimmed[1])
+        sm.sum_trimmed_coeffs[0] = c if c != 0 else 0.0
+        metadata.backpropagation_history.append(sm)
+        info.applied_gates += len(plan.applied)
+        support_mask[0] = plan.support_after
+        lengths[0] = int(st.n_out)
+        if log_info:
+            LOGGER.info(f"[{metadata.num_backpropagated_slices:3}] size of the 0-th observable: {sm.num_paulis[0]}")
+        if operator_budget.max_paulis is not None:
+            sm.sum_paulis = int(st.n_out)  # one observable: its keys are distinct; it cannot exceed what the slice before met
+        metadata.num_backpropagated_slices += 1
+    table.snapshot()  # the commit after the group's last slice (nothing can roll back to a point inside the group)
+    return True
+
 
 
 def _stop_on_overflow(operator_budget: OperatorBudget, trunc_active: bool, peak_live: int) -> bool:

@@ -109,6 +109,10 @@ struct obp_ctx {
   u64* d_tbegin = nullptr;
   u64* h_tbegin = nullptr;  // pinned
   std::vector<u64> last_op_sizes;  // live rows after every op of the last finished program
+  std::vector<obp_op> last_ops;    // ... its ops, the counter slot of each and the row count it started from (obp_last_op_stats)
+  std::vector<int> last_slot_of_op;
+  int last_n_slots = 0;
+  u64 last_n_start = 0;
   bool use_program = true;
   u64 prog_max_rows = 1ull << 18;  // tables of at least this many rows run their gates as stand-alone kernels
   bool broken = false;  // a failed obp_reserve could not restore the table: every entry point fails fast
@@ -1403,6 +1407,14 @@ static int finish_ops(obp_ctx* ctx, PendingOps& P, obp_stats* stats) {
   ctx->last_op_sizes.assign((size_t)P.n_ops, 0);
   for (int k = 0; k < P.n_ops; ++k)
     if (P.slot_of_op[k] >= 0 && P.slot_of_op[k] < P.n_slots) ctx->last_op_sizes[k] = ctx->h_ops[P.slot_of_op[k]].n_out;
+  if (!P.segment && ctx->carry_sizes.empty()) {
+    ctx->last_ops = P.ops;
+    ctx->last_slot_of_op = P.slot_of_op;
+    ctx->last_n_slots = P.n_slots;
+    ctx->last_n_start = P.n_start;
+  } else {
+    ctx->last_ops.clear();  // (runs in shared memory report the counters of their last gate only)
+  }
   // a run that was cut into pieces: this is its last piece, the earlier ones are accounted here
   updates += ctx->carry_updates;
   if (!ctx->carry_sizes.empty()) ctx->last_op_sizes.insert(ctx->last_op_sizes.begin(), ctx->carry_sizes.begin(), ctx->carry_sizes.end());
@@ -2249,6 +2261,39 @@ int obp_last_op_sizes(obp_ctx* ctx, uint64_t* sizes, int32_t max_ops, int32_t* n
   *n_ops = (int32_t)ctx->last_op_sizes.size();
   if (sizes)
     for (int k = 0; k < *n_ops && k < max_ops; ++k) sizes[k] = ctx->last_op_sizes[k];
+  return OBP_OK;
+}
+
+int obp_last_op_stats(obp_ctx* ctx, int32_t op_index, obp_stats* out) {
+  if (!ctx || !out) return OBP_ERR_BADARG;
+  if (ctx->last_ops.empty() || op_index < 0 || op_index >= (int32_t)ctx->last_ops.size())
+    return ctx->fail(OBP_ERR_BADARG, "obp_last_op_stats: no such op in the last gate program");
+  const obp_op& op = ctx->last_ops[(size_t)op_index];
+  const int s = ctx->last_slot_of_op[(size_t)op_index];
+  if (!(op.flags & OBP_FLAG_EXACT_COUNTERS) || s < 0 || s >= ctx->last_n_slots)
+    return ctx->fail(OBP_ERR_BADARG, "obp_last_op_stats: the op did not ask for exact counters");
+  memset(out, 0, sizeof(*out));
+  const OpStat& o = ctx->h_ops[s];
+  const u64 n_in = s == 0 ? ctx->last_n_start : ctx->h_ops[s - 1].n_out;
+  const u64 k2 = (u64)op.n_components * op.n_components;
+  out->n_in = n_in;
+  out->raw_rows = n_in * k2;
+  out->n_out = o.n_out;
+  if (op.kind == OBP_OP_ROTATION) {
+    out->num_unique = o.keys_present;
+    out->num_duplicate = o.rows_surv - o.keys_present;
+    out->num_trimmed = (out->raw_rows - o.rows_surv) + o.cancelled;
+    out->sum_trimmed[0] = o.sum_re;
+    out->sum_trimmed[1] = o.sum_im;
+  } else {
+    u64 cosets = 0;
+    for (unsigned c = 1; c <= 16; ++c) cosets += o.ncnt[c] / c;
+    const u64 rows = o.n_surv * k2;
+    const u64 uniq = (u64)op.group_size * cosets;
+    out->num_unique = uniq;
+    out->num_duplicate = rows - uniq;
+    out->num_trimmed = (out->raw_rows - rows) + (uniq - o.n_surv);
+  }
   return OBP_OK;
 }
 

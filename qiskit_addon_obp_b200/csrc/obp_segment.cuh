@@ -264,16 +264,16 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
   __shared__ u64 s_base;         // first output row of the partition
   const unsigned idx_mask = (unsigned)s.n_index - 1u;
   const unsigned lane = threadIdx.x & 31u;
-  for (int k = threadIdx.x; k < ngp; k += NT) m.dg[k] = 0;
-  for (int k = threadIdx.x; k < s.ng * (int)(sizeof(SegGate) / 16); k += NT)
-    reinterpret_cast<uint4*>(sgate)[k] = reinterpret_cast<const uint4*>(gates)[k];
   // exact counters of the last gate: thread-local, over all partitions this CTA completes
   unsigned rows_surv = 0, keys_present = 0, cancelled = 0;
   double sum_re = 0.0, sum_im = 0.0;
   // a run that has already failed (a partition too big for any CTA, or a partition of the second launch) is not continued;
   // one thread looks, so that the whole CTA takes the same decision
-  __shared__ int s_abort;
-  if (threadIdx.x == 0) s_abort = __ldcg(&res->overflow) != 0u;
+  __shared__ int s_abort, s_nlist;
+  if (threadIdx.x == 0) {
+    s_abort = __ldcg(&res->overflow) != 0u;
+    s_nlist = s_abort ? 0 : (plist ? (int)__ldcg(plist_n) : s.P);
+  }
   auto redo = [&](int part) {
     if (threadIdx.x == 0) {
       if (redo_list) redo_list[atomicAdd(&res->n_redo, 1u)] = (unsigned)part;
@@ -281,7 +281,15 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
     }
   };
   __syncthreads();
-  const int n_list = s_abort ? 0 : (plist ? (int)*plist_n : s.P);
+  const int n_list = s_nlist;
+  // a CTA without a partition (every CTA of the second launch when nothing outgrew the small ones) stages nothing
+  const bool has_work = (int)blockIdx.x < n_list;
+  if (has_work) {
+    for (int k = threadIdx.x; k < ngp; k += NT) m.dg[k] = 0;
+    for (int k = threadIdx.x; k < s.ng * (int)(sizeof(SegGate) / 16); k += NT)
+      reinterpret_cast<uint4*>(sgate)[k] = reinterpret_cast<const uint4*>(gates)[k];
+  }
+  __syncthreads();
 
   for (int it = blockIdx.x; it < n_list; it += gridDim.x) {
     const int part = plist ? (int)plist[it] : it;
@@ -614,9 +622,11 @@ k_seg_main(Tab t, SegOut out, const __grid_constant__ SegP s, const SegGate* __r
   }
   // ---- counters ---------------------------------------------------------------------------------------------------
   __syncthreads();
-  for (int k = threadIdx.x; k < s.ng; k += NT)
-    if (m.dg[k]) atomicAdd(reinterpret_cast<unsigned long long*>(&res->delta[k]), (unsigned long long)(long long)m.dg[k]);
-  if (s.exact_last) {
+  if (has_work) {
+    for (int k = threadIdx.x; k < s.ng; k += NT)
+      if (m.dg[k]) atomicAdd(reinterpret_cast<unsigned long long*>(&res->delta[k]), (unsigned long long)(long long)m.dg[k]);
+  }
+  if (s.exact_last && has_work) {
     const u64 a = warp_sum_u64(rows_surv), b = warp_sum_u64(keys_present), cz = warp_sum_u64(cancelled);
     const double sr = warp_sum_f64(sum_re), si = warp_sum_f64(sum_im);
     if (lane == 0) {

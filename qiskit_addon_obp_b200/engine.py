@@ -154,6 +154,7 @@ def lib() -> C.CDLL:
         "obp_record_bytes": ([C.c_int], C.c_uint64),
         "obp_shard_stats": ([vp, u64p, u64p], C.c_int),
         "obp_segment_stats": ([vp, u64p, u64p, u64p], C.c_int),
+        "obp_last_op_stats": ([vp, C.c_int32, C.POINTER(ObpStats)], C.c_int),
         "obp_segment_partition_map": ([C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "obp_shard_split": ([vp, C.c_int32, C.c_int32, vp, C.c_int32, u64p, C.POINTER(C.c_int32)], C.c_int),
         "obp_apply_ops_sharded": (
@@ -193,7 +194,7 @@ EXPORTED_SYMBOLS = (
     "obp_timer_start obp_timer_stop obp_set_shard obp_record_bytes obp_apply_ops_sharded obp_rotate_emit "
     "obp_rotate_merge obp_trunc_begin obp_trunc_masked_sum obp_trunc_finish obp_inbox_create obp_inbox_release "
     "obp_inbox_export obp_inbox_attach obp_rotate_emit_p2p obp_rotate_merge_inbox obp_set_shard_sync "
-    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count obp_shard_stats obp_segment_stats obp_segment_partition_map"
+    "obp_last_split_counters obp_reset_emit obp_reset_merge obp_configure obp_is_broken obp_last_op_sizes obp_shard_split obp_qwc_group_count obp_shard_stats obp_segment_stats obp_segment_partition_map obp_last_op_stats"
 ).split()
 
 
@@ -466,6 +467,12 @@ class TermTable:
         self.n, self.n_dense = st.n_out, st.n_dense
         if self.n == 0:
             self.zero_operator = self.track_zero
+        return st
+
+    def last_op_stats(self, op_index: int) -> ObpStats:
+        """Counters of one op of the program just waited for (it must have carried ``OBP_FLAG_EXACT_COUNTERS``)."""
+        st = ObpStats()
+        self._check(self._lib.obp_last_op_stats(self._h, int(op_index), C.byref(st)), "obp_last_op_stats")
         return st
 
     def last_op_sizes(self, n_ops: int) -> list[int]:

@@ -70,6 +70,18 @@ def test_engine_matches_the_golden_vectors(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
+def test_engine_with_merged_clifford_slices_matches_the_golden_vectors(name, monkeypatch):
+    """OBP_B200_MERGE_CLIFFORD_SLICES=1: consecutive Clifford-only slices travel as one gate program, each slice's
+    counters read back with obp_last_op_stats — every per-slice number must come out as slice by slice."""
+    from qiskit_addon_obp_b200 import backpropagate
+
+    monkeypatch.setenv("OBP_B200_MERGE_CLIFFORD_SLICES", "1")
+    wl = MAKERS[name]()
+    _check(CASES[name], *backpropagate(wl.observables, wl.slices, **wl.kwargs()), ordered=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
 def test_engine_row_order_mode_matches_the_golden_row_order(name, monkeypatch):
     from qiskit_addon_obp_b200 import backpropagate
 
