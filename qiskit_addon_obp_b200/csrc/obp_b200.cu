@@ -1619,7 +1619,8 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   int P;
   {
     const double growth = std::min(32.0, std::max(1.5, ctx->seg_growth));
-    const double rows_per_part = std::min(256.0, 0.35 * sp.cap_rows);
+    double rows_per_part = std::min(256.0, 0.35 * sp.cap_rows);
+    if (const char* e = getenv("OBP_B200_SEG_ROWS_PER_PART")) rows_per_part = std::max(8.0, std::min(atof(e), 0.8 * sp.cap_rows));  // (tuning experiment)
     const double want = (double)ctx->n_live * growth / rows_per_part;
     P = (int)std::min<double>((double)OBP_SEG_MAXP, std::max<double>((double)n_ctas1, std::ceil(want)));
   }
