@@ -1560,6 +1560,7 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
       sz[(size_t)q].w[2 * (q / 64) + 1] = 1ull << (q % 64);
     }
   }
+  auto build_gates = [&]() {
   for (int k = 0; k < ng; ++k) {
     SegGate& g = gates[k];
     memset(&g, 0, sizeof(g));
@@ -1597,7 +1598,26 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
       }
       gen.gx[0] = v.w[0]; gen.gz[0] = v.w[1]; gen.gx[1] = v.w[2]; gen.gz[1] = v.w[3];
     }
-    gens.push_back(gen);
+    if (has_cliff) gens.push_back(gen);
+  }
+  };
+  if (has_cliff) {
+    build_gates();  // (the pulled-back generators come out of the same pass as the frames)
+  } else {
+    // rotations only: the partition map needs nothing but the generators, so the partition kernels are launched
+    // before the host fills in the rest of the gate parameters (the device is idle until the first launch)
+    for (int k = 0; k < ng; ++k) {
+      SegGate gen;
+      memset(&gen, 0, sizeof(gen));
+      for (int j = 0; j < ops[k].n_qubits; ++j) {
+        const unsigned code = (ops[k].gen_local >> (2 * j)) & 3u;
+        const int w = ops[k].qubit[j] / 64;
+        const u64 bit = 1ull << (ops[k].qubit[j] % 64);
+        if (code & 1u) gen.gx[w] |= bit;
+        if (code & 2u) gen.gz[w] |= bit;
+      }
+      gens.push_back(gen);
+    }
   }
   SegP sp;
   memset(&sp, 0, sizeof(sp));
@@ -1628,22 +1648,6 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
   sp.P = sp2.P = P;
   sp.cap_rows_big = sp2.cap_rows_big = sp2.cap_rows;
 
-  // upload the gates through the program staging buffer
-  const size_t need = gates.size() * sizeof(SegGate);
-  if (need > ctx->prog_alloc) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_prog);
-    if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
-    ctx->d_prog = ctx->h_prog = nullptr;
-    ctx->prog_alloc = 0;
-    const size_t na = std::max<size_t>(2 * need, 1 << 16);
-    CU(cudaMalloc(&ctx->d_prog, na));
-    CU(cudaMallocHost(&ctx->h_prog, na));
-    ctx->prog_alloc = na;
-  }
-  memcpy(ctx->h_prog, gates.data(), need);
-  CU(cudaMemcpyAsync(ctx->d_prog, ctx->h_prog, need, cudaMemcpyHostToDevice, ctx->stream));
-  const SegGate* gs = (const SegGate*)ctx->d_prog;
   Tab t = make_tab(ctx);
   SegOut out;
   out.xz[0] = ctx->alt_xz[0];
@@ -1671,6 +1675,27 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
     ctx->prof.passes[OBP_K_SEGMENT] += (u64)(ng - 1);  // (one pass per gate, in shared memory)
     const int g1 = grid_for(ctx, ctx->n_dense);
     const int gm = std::min(P, n_ctas1);
+    if (W == 1) k_seg_count<1><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt, d_off, d_cur, d_res);
+    else k_seg_count<2><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt, d_off, d_cur, d_res);
+    k_seg_scatter<<<g1, OBP_BS, 0, ctx->stream>>>(part, d_off, d_cur, perm, ctx->n_dense);
+    if (!has_cliff) build_gates();
+    // upload the gates through the program staging buffer
+    const size_t need = gates.size() * sizeof(SegGate);
+    if (need > ctx->prog_alloc) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_prog);
+      if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
+      ctx->d_prog = ctx->h_prog = nullptr;
+      ctx->prog_alloc = 0;
+      const size_t na = std::max<size_t>(2 * need, 1 << 16);
+      CU(cudaMalloc(&ctx->d_prog, na));
+      CU(cudaMallocHost(&ctx->h_prog, na));
+      ctx->prog_alloc = na;
+    }
+    memcpy(ctx->h_prog, gates.data(), need);
+    CU(cudaMemcpyAsync(ctx->d_prog, ctx->h_prog, need, cudaMemcpyHostToDevice, ctx->stream));
+    const SegGate* gs = (const SegGate*)ctx->d_prog;
+
     const unsigned* none = nullptr;
     SegFin fin0;
     memset(&fin0, 0, sizeof(fin0));
@@ -1681,13 +1706,9 @@ static int apply_segment(obp_ctx* ctx, const obp_op* ops, int32_t n_ops, double 
     fin.host_res = ctx->h_res_dev;
     fin.n_res_ops = ng + 1;
     if (W == 1) {
-      k_seg_count<1><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt, d_off, d_cur, d_res);
-      k_seg_scatter<<<g1, OBP_BS, 0, ctx->stream>>>(part, d_off, d_cur, perm, ctx->n_dense);
       k_seg_main<1, 128, 4><<<gm, 128, smem1, ctx->stream>>>(t, out, sp, gs, d_off, perm, d_res, none, none, d_redo, fin0);
       k_seg_main<1, 512, 1><<<n_ctas2, 512, smem2, ctx->stream>>>(t, out, sp2, gs, d_off, perm, d_res, d_redo, &d_res->n_redo, nullptr, fin);
     } else {
-      k_seg_count<2><<<g1, OBP_BS, 0, ctx->stream>>>(t, sp, part, d_cnt, d_off, d_cur, d_res);
-      k_seg_scatter<<<g1, OBP_BS, 0, ctx->stream>>>(part, d_off, d_cur, perm, ctx->n_dense);
       k_seg_main<2, 128, 4><<<gm, 128, smem1, ctx->stream>>>(t, out, sp, gs, d_off, perm, d_res, none, none, d_redo, fin0);
       k_seg_main<2, 512, 1><<<n_ctas2, 512, smem2, ctx->stream>>>(t, out, sp2, gs, d_off, perm, d_res, d_redo, &d_res->n_redo, nullptr, fin);
     }
