@@ -26,9 +26,13 @@
 // Four launches per run: k_seg_count (partition id per live row + histogram; its last CTA turns the histogram into
 // offsets), k_seg_scatter (row ids in partition order), k_seg_main<W, 128, 4> (the run), k_seg_main<W, 512, 1> (the
 // listed partitions again; its last CTA writes the per-gate row counts, the table state and the host's result
-// block).  One small upload (the gates) precedes them; nothing is cleared in between.
+// block).  One small upload (the gates) sits between the partition kernels and the run; nothing is cleared in between
+// (the table's hash index is, before the run, when the run is to publish its output rows in it).
 // The input table is never modified: if a partition outgrows even the big CTA (or the output its capacity) the run
-// reports it and the host applies the same gates through the per-gate kernels instead.
+// reports it and the host repeats it in shorter pieces (fewer generators: a finer partition map) or applies the same
+// gates through the per-gate kernels instead.
+// Opt-in (OBP_OPT_SEGMENT_MIXED): a run may also hold Clifford-class gates; they are applied to the rows of each
+// partition in groups without a barrier, and the partition map vanishes on the generators pulled back through them.
 #pragma once
 #include "obp_kernels.cuh"
 
