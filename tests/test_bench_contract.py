@@ -47,3 +47,23 @@ def test_engine_arm_has_no_cpu_fallback():
     assert out.returncode != 0
     assert "no CPU fallback" in (out.stderr + out.stdout)
     assert not any(ln.startswith("{") for ln in out.stdout.splitlines())
+
+
+def test_rotation_roofline_picks_the_dominant_rotation_kernel():
+    """bench.rotation_roofline: SURVEY 8(d)'s algorithmic figure for whichever rotation kernel took more device time."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    prof = {
+        "rotate": {"launches": 10, "passes": 10, "ms": 2.0, "term_updates": 1_000_000},
+        "segment": {"launches": 8, "passes": 200, "ms": 6.0, "term_updates": 30_000_000},
+    }
+    r = bench.rotation_roofline(prof, 96, 6531.0)
+    assert r["kernel"] == "k_seg_main" and r["bound"] == "hbm" and r["unit"] == "GB/s" and r["traffic"] is None
+    assert abs(r["achieved"] - 30_000_000 * 96 / 6.0e-3 / 1e9) < 1e-9
+    assert abs(r["frac"] - r["achieved"] / 6531.0) < 1e-12
+    assert r["gates_per_launch"] == 100.0 and "not DRAM bytes" in r["note"]
+    prof["segment"]["ms"] = 1.0
+    r = bench.rotation_roofline(prof, 96, 6531.0)
+    assert r["kernel"] == "k_rotate" and "note" not in r
+    assert bench.rotation_roofline({}, 96, 6531.0)["achieved"] is None

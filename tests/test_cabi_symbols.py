@@ -93,3 +93,26 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "obp_oracle" in text:
                     offenders.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
     assert offenders == []
+
+
+def test_option_and_class_constants_match_the_header():
+    """``OBP_OPT_*`` / ``OBP_K_*`` / ``OBP_FLAG_*`` in engine.py are the header's values."""
+    import re
+
+    from qiskit_addon_obp_b200 import engine
+
+    text = open(HEADER).read()
+    defines = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(OBP_(?:OPT|FLAG|OP)_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)u?\b", text)}
+    assert {"OBP_OPT_PROGRAM", "OBP_OPT_SEGMENTS", "OBP_OPT_SEGMENT_MIXED"} <= set(defines)
+    for name, value in defines.items():
+        if hasattr(engine, name):
+            assert getattr(engine, name) == value, name
+    for name in ("OBP_OPT_PROGRAM", "OBP_OPT_PROGRAM_MAX_ROWS", "OBP_OPT_SEGMENTS", "OBP_OPT_SEGMENT_MIN_GATES",
+                 "OBP_OPT_SEGMENT_CAP_ROWS", "OBP_OPT_SEGMENT_PIECES_MIN_ROWS", "OBP_OPT_SEGMENT_MIXED"):
+        assert getattr(engine, name) == defines[name], name
+    enum = re.search(r"enum \{ OBP_K_ROTATE = 0,(.*?)\};", text, re.S).group(0)
+    classes = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"OBP_K_([A-Z]+) = (\d+)", enum)}
+    count = classes.pop("count")
+    assert len(engine.OBP_K_NAMES) == count
+    for name, k in classes.items():
+        assert engine.OBP_K_NAMES[k] == name
