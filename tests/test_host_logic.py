@@ -414,3 +414,27 @@ def test_segment_partition_map_vanishes_on_every_generator():
                 assert fmap(fm, x ^ gx[k], z ^ gz[k]) == fmap(fm, x, z), name
                 seen.add(fmap(fm, x, z))
             assert len(seen) > 150, (name, len(seen))
+
+
+def test_clifford_only_slices_are_grouped_structurally():
+    """``_merge_clifford_slices`` (the opt-in OBP_B200_MERGE_CLIFFORD_SLICES path): consecutive slices whose applied
+    gates are all Clifford-class form a group that ends at the first slice with a rotation — decided on the compiled
+    plans alone (light cone included), no device needed."""
+    from qiskit_addon_obp_b200 import backpropagation as bp
+    from qiskit_addon_obp_b200 import workloads as wl
+
+    w = wl.config2_kicked_ising(theta_h=0.3, steps=2, max_paulis=1000)
+    rev = w.slices[::-1]  # backpropagation order: RX layer first, then the three RZZ(-pi/2) colour layers
+    support = (1 << w.num_qubits) - 1  # every qubit in the light cone
+    assert bp._merge_clifford_slices(None, rev, 0, support, False) == []  # the RX slice is not Clifford-only
+    group = bp._merge_clifford_slices(None, rev, 1, support, False)
+    assert len(group) == 3
+    for prog, plan in group:
+        ops = plan.steps[0][1]
+        assert (ops["kind"] == bp.OBP_OP_CLIFFORD).all()
+        assert ops["flags"][-1] & bp.OBP_FLAG_EXACT_COUNTERS and not (ops["flags"][:-1] & bp.OBP_FLAG_EXACT_COUNTERS).any()
+    assert len(bp._merge_clifford_slices(None, rev, 1, support, False, max_group=2)) == 2
+    # a slice outside the light cone (no applied gate) ends a group
+    one = 1 << 62
+    g1 = bp._merge_clifford_slices(None, rev, 1, one, False)
+    assert all(plan.applied for _, plan in g1)
